@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — 4-stage LWSNet inference throughput (stereo pairs/s) on N B200s of one node, plus the per-kernel roofline.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (torch-CPU restatement of the Paddle model)
+
+Workload (BASELINE.json configs[2], the configuration the metric "stereo pairs/sec, 4-stage KITTI 1232x368" is quoted
+on): full 4-stage inference on synthetic KITTI-shaped pairs [64,3,368,1232] per GPU, random-init weights (seed 0).
+One step = one pass over one 64-pair batch.  Weak scaling: every rank owns its own 64 pairs, no collective on the
+data path.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H_IMG, W_IMG = 368, 1232
+BATCH = 64
+METRIC = "stereo pairs/sec, 4-stage KITTI 1232x368"
+GFLOP_PER_PAIR = 91.6
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops"], tensor_sustained=p.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path.  Paddle cannot be installed in this image, so this is the
+    torch-CPU restatement (oracle/) — the only other place bench.py may execute oracle/ — on all host threads."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import lwsnet_torch as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build_oracle(seed=0)
+    sample_pairs = 1
+    left, right = O.synthetic_pair(sample_pairs, H_IMG, W_IMG, seed=1234)
+    with torch.no_grad():
+        for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
+            model(left, right)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model(left, right)
+        dt = time.perf_counter() - t0
+    value = sample_pairs * args.steps / dt
+    sample = f"{sample_pairs} KITTI-shaped pair per step (of the 64-pair batch), torch-CPU restatement of the Paddle model, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: full 4-stage LWSNet inference, KITTI 1232x368", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------- kernel probes
+def time_rotating(fn, nsets, iters=20, warm=5):
+    """Average device time (us) of fn(i % nsets) with CUDA events on the current stream; buffer sets rotate so inputs
+    are not L2 resident."""
+    import torch
+    for i in range(warm):
+        fn(i % nsets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % nsets)
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / iters
+
+
+def kernel_probes(model, pk):
+    """Per-kernel achieved HBM GB/s (streaming kernels) / TFLOP/s (conv kernels), each timed alone on KITTI shapes at
+    batch 16 with >= 3 rotating buffer sets (> 126 MB in total, so nothing is L2 resident)."""
+    import torch
+    from lwsnet_b200 import ops
+    dev = torch.device("cuda")
+    out = []
+    B = 16
+
+    def sets(n, *shapes, scale=2.0):
+        return [[torch.randn(s, device=dev) * scale for s in shapes] for _ in range(n)]
+
+    def add(name, us, bytes_=None, flops=None):
+        rec = {"kernel": name, "us": round(us, 2)}
+        if bytes_ is not None:
+            rec.update(bytes=bytes_, gbs=round(bytes_ / us / 1e3, 1), frac_hbm=round(bytes_ / us / 1e3 / pk["hbm"], 3))
+        if flops is not None:
+            rec.update(flops=flops, tflops=round(flops / us / 1e6, 2))
+        out.append(rec)
+
+    # K1 stage-1 volume: (2*C + D) * h*w*4 bytes
+    h, w, C, D = 46, 154, 16, 24
+    s = sets(12, (B, C, h, w), (B, C, h, w))
+    us = time_rotating(lambda i: ops.cost_volume_l1(s[i][0], s[i][1], D), len(s))
+    add("K1 cost_volume_l1 [16,16,46,154] D=24", us, B * (2 * C + D) * h * w * 4)
+    # K2 stages 2 and 3
+    for (h, w, C) in ((92, 308, 16), (184, 616, 8)):
+        s = sets(6, (B, C, h, w), (B, C, h, w))
+        d = [torch.rand((B, 1, h, w), device=dev) * 20 for _ in s]
+        us = time_rotating(lambda i: ops.warp_residual_volume_l1(s[i][0], s[i][1], d[i], 5), len(s))
+        add(f"K2 warp_residual_volume_l1 [16,{C},{h},{w}] m=5", us, B * (2 * C + 1 + 9) * h * w * 4)
+    # K4
+    for (D, h, w) in ((24, 46, 154), (9, 92, 308), (9, 184, 616)):
+        n = 12 if h < 100 else 4
+        s = sets(n, (B, D, h, w), scale=8.0)
+        us = time_rotating(lambda i: ops.softmax_regression(s[i][0], 0.0), len(s))
+        add(f"K4 softmax_regression [16,{D},{h},{w}]", us, B * (D + 1) * h * w * 4)
+    # K5
+    s = sets(4, (B, 1, 184, 616), (B, 1, H_IMG, W_IMG))
+    o = torch.empty((B, 1, H_IMG, W_IMG), device=dev)
+    us = time_rotating(lambda i: ops.scale_upsample_add(s[i][0], s[i][1], H_IMG, W_IMG, out=o), len(s))
+    add("K5 scale_upsample_add [16,1,184,616]->[16,1,368,1232]", us, B * (184 * 616 + 2 * H_IMG * W_IMG) * 4)
+    # K3 dominant layers
+    for (C, D, h, w, b) in ((32, 24, 46, 154, 4), (8, 9, 184, 616, 4)):
+        xs = sets(3, (b, C, D, h, w), scale=1.0)
+        wt = torch.randn((C * 27 * C,), device=dev) * 0.05
+        bias = torch.zeros((C,), device=dev)
+        o3 = torch.empty((b, C, D, h, w), device=dev)
+        us = time_rotating(lambda i: ops.conv3d_bnrelu_layer(xs[i][0], wt, bias, out=o3), len(xs), iters=10, warm=3)
+        add(f"K3 conv3d_k3 {C}->{C} [{b},{C},{D},{h},{w}] (fp32 FFMA)", us, flops=2 * 27 * C * C * D * h * w * b)
+    # whole refinement (a8+a9), batch 2
+    left = [torch.randn((2, 3, H_IMG, W_IMG), device=dev) for _ in range(2)]
+    p3 = [torch.rand((2, 1, H_IMG, W_IMG), device=dev) * 100 for _ in range(2)]
+    rp = model._refinement_packed(dev)
+    us = time_rotating(lambda i: ops.refinement(left[i], p3[i], rp), 2, iters=6, warm=2)
+    add("K6 refinement a8+a9 [2,*,368,1232] (16 launches)", us, flops=int(2 * 71232 * H_IMG * W_IMG))
+    return out
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from oracle import lwsnet_torch as O   # input/weight generation + cpu_baseline leg only (never on the timed GPU path)
+    from lwsnet_b200 import LWSNet, ops
+    from lwsnet_b200.runner import StereoEngine
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    oracle_model = O.build_oracle(seed=0)
+    model = LWSNet(O.default_args())
+    model.load_state_dict(oracle_model.state_dict(), strict=True)
+    model = model.to(dev)
+    engine = StereoEngine(model, micro_batch=args.micro_batch, device=dev, use_graphs=not args.no_graphs)
+
+    # synthetic batch: 8 distinct pairs tiled to 64 (content does not change the work); rank-dependent seed
+    base_l, base_r = O.synthetic_pair(8, H_IMG, W_IMG, seed=1234 + 8 * rank)
+    left_h = base_l.repeat(BATCH // 8, 1, 1, 1).pin_memory()
+    right_h = base_r.repeat(BATCH // 8, 1, 1, 1).pin_memory()
+    left_d, right_d = left_h.to(dev), right_h.to(dev)
+    out_d = torch.empty((BATCH, 4, H_IMG, W_IMG), device=dev)
+    out_h = torch.empty((BATCH, 4, H_IMG, W_IMG)).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------------
+    for _ in range(args.warmup):
+        engine.infer_device(left_d, right_d, out_d)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.LAUNCHES[0]
+    ms = timed(lambda: engine.infer_device(left_d, right_d, out_d), args.steps)
+    launches = ops.LAUNCHES[0] - n0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers ("e2e") --------------------------------------------
+    for _ in range(max(1, min(2, args.warmup))):
+        engine.infer_host(left_h, right_h, out_h)
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e = timed(lambda: engine.infer_host(left_h, right_h, out_h), e2e_steps)
+    e2e_value = world * BATCH * e2e_steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the kernels (rank 0, timed alone) ----------------------------------------------------------------
+    kernels, roofline = [], None
+    if not args.skip_probes:
+        kernels = kernel_probes(model, pk)
+        dom = max((k for k in kernels if k["kernel"].startswith("K3 conv3d_k3 32")), key=lambda k: k["us"])
+        roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": pk["tensor"],
+                    "unit": "TFLOP/s", "frac": round(dom["tflops"] / pk["tensor"], 4), "traffic": None,
+                    "peak_source": pk["source"] + " bf16 burst",
+                    "note": "dominant kernel by time (4 launches per pair, 37.6 of 91.6 GFLOP); fp32 FFMA on the CUDA "
+                            "cores this round, so the fraction of the tensor roofline is small by construction; "
+                            "see the `kernels` table for the HBM-bound kernels"}
+
+    # ---- CPU baseline beside it (N=1 only): the oracle port on the host cores, bounded sample -----------------------
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        l1, r1 = base_l[:1], base_r[:1]
+        with torch.no_grad():
+            oracle_model(l1, r1)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                oracle_model(l1, r1)
+            dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": f"{reps} forwards of 1 KITTI-shaped pair (of the 64-pair batch), torch-CPU restatement of the Paddle reference, fp32"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: full 4-stage LWSNet inference (volume build + warp + residual volumes + 3D stacks "
+                               "+ regression + colour-guidance refinement), KITTI 1232x368, batch 64 per GPU",
+                   "batch_per_gpu": BATCH, "micro_batch": args.micro_batch, "maxdisplist": [24, 5, 5],
+                   "weights": "random init (KaimingNormal, seed 0)", "cuda_graphs": not args.no_graphs,
+                   "l2": "inputs (697 MB per step) and per-step activations exceed the 126 MB L2",
+                   "feature_extractor": "torch/cuDNN (off the north-star hot path, SURVEY.md 8(f))",
+                   "tflops_equiv": round(value * GFLOP_PER_PAIR / 1e3, 2)},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(left_h.nbytes + right_h.nbytes),
+                "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--micro-batch", type=int, default=2)
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--skip-probes", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+/*
+ * lws.h — C ABI of the B200-native LWSNet stereo hot path (liblws_b200.so).
+ *
+ * The reference (PrinceVictor/LWSNet) has no FFI / operator-plugin layer: its hot path is a chain of
+ * PaddlePaddle operator calls made from models/models.py and models/submodules.py.  Each entry point
+ * below replaces the operator chain of one reference function (file:line given per function); the
+ * Python host in lwsnet_b200/ keeps the reference's class / method names and calls these through ctypes,
+ * and INTEGRATION.md shows the Paddle custom-op binding a maintainer would add on top of the same symbols.
+ *
+ * Contract (all functions unless noted):
+ *   - every tensor pointer is a DEVICE pointer to contiguous fp32, NCHW (NCDHW for volumes);
+ *   - the caller owns every buffer including workspaces; nothing is allocated or freed here;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no synchronisation;
+ *   - re-entrant, no global mutable state;
+ *   - return 0 on success, <0 = LWS_ERR_*, >0 = the cudaError_t of a failed launch.
+ *   - lws_pack_* functions are pure HOST functions (host pointers in, host blob out).
+ */
+#ifndef LWS_H_
+#define LWS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lws_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define LWS_API __attribute__((visibility("default")))
+#else
+#define LWS_API
+#endif
+
+enum {
+  LWS_OK = 0,
+  LWS_ERR_BAD_SHAPE = -1,
+  LWS_ERR_BAD_ALIGN = -2,
+  LWS_ERR_NULL_PTR = -3,
+  LWS_ERR_WORKSPACE_TOO_SMALL = -4,
+  LWS_ERR_UNSUPPORTED = -5
+};
+
+LWS_API const char* lws_status_string(int status);
+/* "lws_b200 <semver> sm_100a" */
+LWS_API const char* lws_version(void);
+
+/* ---- a1: LWSNet._build_volume_2d  (models/models.py:58-76) ------------------------------------------
+ * cost[b,d/stride,y,x] = sum_c | L[b,c,y,x] - (x-d >= 0 ? R[b,c,y,x-d] : 0) |,  d = 0,stride,..,maxdisp-stride.
+ * L,R [B,C,H,W] -> cost [B,maxdisp/stride,H,W].  LWS_ERR_BAD_SHAPE if maxdisp % stride != 0 (the reference asserts). */
+LWS_API int lws_cost_volume_l1_f32(const float* L, const float* R, float* cost, int B, int C, int H, int W, int maxdisp,
+                           int stride, lws_stream_t stream);
+
+/* ---- a2: wflow, LWSNet.forward (models/models.py:119-121) -------------------------------------------
+ * wflow = (bilinear_resize_halfpixel(pred_full, h, w) * float(h)) * fl32(1/H).  pred_full [B,1,H,W] -> wflow [B,1,h,w]. */
+LWS_API int lws_disp_to_scale_f32(const float* pred_full, float* wflow, int B, int H, int W, int h, int w, lws_stream_t stream);
+
+/* ---- a3: LWSNet.warp  (models/models.py:28-55) -------------------------------------------------------
+ * out[n,c,y,x] = bilinear sample of x[n,c] at (x - disp[n,0,y,x], y), zero padding, grid_sample(align_corners=True)
+ * semantics with the reference's fp32 normalise/un-normalise round trip replayed op by op (no FMA contraction). */
+LWS_API int lws_warp_bilinear_f32(const float* x, const float* disp, float* out, int N, int C, int H, int W, lws_stream_t stream);
+
+/* Test hook for "warp sampling indices must be bit-exact": runs the same device function the warp kernels use and
+ * exports, for warp argument (disp - shift): x0 [N,H,W] int32 (clamped to [-2, W+1]), y0 [H] int32,
+ * wx [N,H,W,2] = (x1-ix, ix-x0), wy [H,2] = (y1-iy, iy-y0). */
+LWS_API int lws_warp_taps_f32(const float* disp, float shift, int32_t* x0, int32_t* y0, float* wx, float* wy, int N, int H,
+                      int W, lws_stream_t stream);
+
+/* ---- a4: LWSNet._build_volume_2d3  (models/models.py:78-104) ---------------------------------------
+ * cost[b,k,y,x] = sum_c | L[b,c,y,x] - warp(R[b], disp[b] - (k-(m-1))*stride)[c,y,x] |,  k = 0..2m-2.
+ * L,R [B,C,H,W], disp [B,1,H,W] -> cost [B,2m-1,H,W].  The 9x replicated batch of the reference is never materialised. */
+LWS_API int lws_warp_residual_volume_l1_f32(const float* L, const float* R, const float* disp, float* cost, int B, int C,
+                                    int H, int W, int m, int stride, lws_stream_t stream);
+
+/* ---- a5: post_3dconvs + skip  (models/submodules.py:190-221, models/models.py:136-138) ---------------
+ * out = cost + Conv_{n-1}(ReLU(BN_{n-1}( ... Conv_0(ReLU(BN_0(cost))) ... ))),  n = layers + 2 convs,
+ * channels 1 -> C -> ... -> C -> 1, every conv 3x3x3 / stride 1 / zero pad 1 / no bias, BN in inference mode.
+ * cost,out [B,D,H,W] (the singleton channel is implicit).  C must be 8, 16 or 32.
+ * add_skip != 0 fuses the `+ cost` of models/models.py:137 into the last conv; add_skip == 0 returns the bare
+ * post_3dconvs(cost) (what calling the reference's nn.Sequential alone returns). */
+LWS_API size_t lws_conv3d_stack_packed_floats(int C, int layers);
+/* HOST: fold BN into the conv weights and lay them out for the kernels.
+ * conv_w[i]  : [Cout_i, Cin_i, 3,3,3] fp32 (Paddle Conv3D layout), i = 0..layers+1
+ * bn_*[i]    : [Cin_i] weight / bias / _mean / _variance of the BatchNorm3D in front of conv i
+ * packed     : host buffer of lws_conv3d_stack_packed_floats(C, layers) floats */
+LWS_API int lws_pack_conv3d_stack_weights(const float* const* conv_w, const float* const* bn_weight,
+                                  const float* const* bn_bias, const float* const* bn_mean,
+                                  const float* const* bn_var, float eps, int C, int layers, float* packed);
+LWS_API size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, int C, int layers);
+LWS_API int lws_conv3d_stack_f32(const float* cost, const float* packed_weights, float* out, void* ws, size_t ws_bytes, int B,
+                         int D, int H, int W, int C, int layers, int add_skip, lws_stream_t stream);
+
+/* One BN-folded C -> C layer of the stack (out = ReLU(conv3x3x3(in, w_folded) + bias)), in/out [B,C,D,H,W] post-activation,
+ * w_folded [Cin][27][Cout].  The stack's dominant kernel on its own: for per-layer tests and for timing it in isolation. */
+LWS_API int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folded, const float* bias, float* out, int B, int C,
+                                        int D, int H, int W, lws_stream_t stream);
+
+/* ---- a6: F.softmax(-cost, axis=1) + disparity_regression  (models/models.py:142,151-152,167-179) ----
+ * low[b,0,y,x] = sum_j softmax_j(-cost[b,:,y,x]) * (start + j*step).  One pass over the volume. */
+LWS_API int lws_softmax_regression_f32(const float* cost, float* low, int B, int D, int H, int W, float start, float step,
+                               lws_stream_t stream);
+
+/* ---- a7: rescale + upsample + skip  (models/models.py:145-148,153-156) ------------------------------
+ * pred = bilinear_resize_halfpixel((low * float(H)) * fl32(1/h), H, W) (+ prev if prev != NULL).
+ * low [B,1,h,w], prev/pred [B,1,H,W]. */
+LWS_API int lws_scale_upsample_add_f32(const float* low, const float* prev_or_null, float* pred, int B, int h, int w, int H,
+                               int W, lws_stream_t stream);
+
+/* ---- a8+a9: refinement1_left / refinement1_disp / refinement2 + skip
+ *             (models/submodules.py:223-327, models/models.py:158-162) --------------------------------
+ * pred4 = pred3 + R2(concat[R1_left(left), R1_disp(pred3)]).  left [B,3,H,W], pred3/pred4 [B,1,H,W]. */
+LWS_API size_t lws_refinement_packed_floats(void);
+/* HOST.  Tensor order in `tensors` (each a host fp32 pointer), with BN = (weight, bias, _mean, _variance):
+ *   R1_left : conv0 [32,3,3,3];  then for blocks 1..4: BN(32) x4 tensors, dw [32,1,3,3], pw [32,32,1,1]   -> 25 tensors
+ *   R1_disp : conv0 [32,1,3,3];  blocks 1..4 as above                                                      -> 25 tensors
+ *   R2      : BN(64) x4 tensors, conv [32,64,3,3]; blocks 1..4 as above; conv_last [1,32,3,3]               -> 30 tensors
+ * n_tensors must be 80. */
+LWS_API int lws_pack_refinement_weights(const float* const* tensors, int n_tensors, float eps, float* packed);
+LWS_API size_t lws_refinement_workspace_bytes(int B, int H, int W);
+LWS_API int lws_refinement_f32(const float* left, const float* pred3, const float* packed_weights, float* pred4, void* ws,
+                       size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWS_H_ */

@@ -1,0 +1,344 @@
+// K3: the residual 3D-conv stack  out = cost + Conv_{n-1}(ReLU(BN_{n-1}(... Conv_0(ReLU(BN_0(cost))) ...)))
+// (reference models/submodules.py:190-221 post_3dconvs / batch_relu_conv3d, skip at models/models.py:136-138;
+//  18 cuDNN conv3d + 18 batch_norm + 18 relu launches per forward in the reference, 6 launches per stage here).
+//
+// BatchNorm (inference) is folded on the host (lws_pack_conv3d_stack_weights): BN_{i+1}'s scale goes into conv i's
+// output channels, its shift becomes a bias, and every kernel stores the *post-activation* tensor
+// ReLU(BN_{i+1}(conv_i(.))) so that the consumer's zero padding is the reference's padding of the ReLU output
+// (SURVEY.md A.5).  BN_0 is a scalar affine applied while the raw cost tile is staged.
+//
+// Direct convolution on the FP32 pipes, NCDHW:
+//   block  : output tile TD x 8 x TW voxels, all Cout; input channels streamed in chunks of CK through shared memory
+//   thread : 8 consecutive w  x  Q output channels = 64 accumulators; per (ci,kd,kh) it reads a 10-wide input row
+//            segment (2 LDS.128 + 2 LDS.32) and 3*Q weights (warp-uniform broadcast LDS.128) for 24*Q FFMA.
+//   lanes run over h first, rows are TW+4 floats apart (== 4 mod 32), so the 128-bit row loads are conflict-free.
+// These layers are compute-bound (54-216 flop/B): the bound is the FP32 FFMA rate, not HBM.
+#include <math.h>
+#include <string.h>
+
+#include "lws_common.cuh"
+
+namespace lws {
+
+struct Conv3dArgs {
+  const float* in;      // [B,Cin,D,H,W]  post-activation (or raw cost when FIRST)
+  const float* w;       // [Cin][27][Cout] folded weights
+  const float* bias;    // [Cout] (unused when LAST)
+  const float* skip;    // raw cost [B,D,H,W] (LAST only)
+  float* out;           // [B,Cout,D,H,W]
+  int Cin, D, H, W;
+  int tiles_w, tiles_h, tiles_d;
+  const float* affine;  // device [s0, t0]: BN_0 scalar affine (FIRST only)
+};
+
+template <int CK, int COUT, int Q, int TD, int TW, bool FIRST, bool LAST>
+struct Conv3dCfg {
+  static constexpr int TH = 8;
+  static constexpr int P = 8;
+  static constexpr int WQ = TW / P;
+  static constexpr int NVT = TD * TH * WQ;
+  static constexpr int NCG = COUT / Q;
+  static constexpr int THREADS = NVT * NCG;
+  static constexpr int PITCH = TW + 4;
+  static constexpr int ROWS = (TD + 2) * (TH + 2);
+  static constexpr int IN_FLOATS = CK * ROWS * PITCH + 4;  // +4: right halo of the very last row
+  static constexpr int WT_STRIDE = (COUT + 3) / 4 * 4;      // floats per (ci,tap) in shared memory
+  static constexpr int WT_FLOATS = CK * 27 * WT_STRIDE;
+  static constexpr size_t SMEM = (size_t)(IN_FLOATS + WT_FLOATS) * sizeof(float);
+  static constexpr int MIN_BLOCKS = THREADS <= 256 ? 2 : 1;
+  static_assert(NVT % 32 == 0, "cout group must be warp-uniform");
+  static_assert(TW % 32 == 0, "row pitch must be 4 mod 32");
+};
+
+template <int CK, int COUT, int Q, int TD, int TW, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>::THREADS,
+                                  Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>::MIN_BLOCKS)
+    conv3d_k3_kernel(const Conv3dArgs a) {
+  using Cfg = Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>;
+  constexpr int TH = Cfg::TH, P = Cfg::P, PITCH = Cfg::PITCH, ROWS = Cfg::ROWS;
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;
+  float* sW = smem + Cfg::IN_FLOATS;
+
+  const int tid = threadIdx.x;
+  const int vt = tid % Cfg::NVT;
+  const int cg = tid / Cfg::NVT;
+  const int th = vt % TH;
+  const int twq = (vt / TH) % Cfg::WQ;
+  const int td = vt / (TH * Cfg::WQ);
+
+  int tile = blockIdx.x;
+  const int tw_i = tile % a.tiles_w;
+  tile /= a.tiles_w;
+  const int th_i = tile % a.tiles_h;
+  const int td_i = tile / a.tiles_h;
+  const int b = blockIdx.y;
+  const int w0 = tw_i * TW, h0 = th_i * TH, d0 = td_i * TD;
+  const int D = a.D, H = a.H, W = a.W;
+  const long long hw = (long long)H * W;
+  const long long dhw = (long long)D * hw;
+
+  float acc[P][Q];
+#pragma unroll
+  for (int p = 0; p < P; ++p)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[p][q] = 0.f;
+
+  float s0 = 1.f, t0 = 0.f;
+  if constexpr (FIRST) s0 = __ldg(a.affine), t0 = __ldg(a.affine + 1);
+  const float* in_b = a.in + (long long)b * a.Cin * dhw;
+  for (int c0 = 0; c0 < a.Cin; c0 += CK) {
+    // ---- stage the input tile (halo 1, zero padded) and this chunk's weights --------------------------
+    constexpr int ROW_E = TW + 2;
+    for (int idx = tid; idx < CK * ROWS * ROW_E; idx += Cfg::THREADS) {
+      const int e = idx % ROW_E;
+      const int row = idx / ROW_E;
+      const int hh = row % (TH + 2);
+      const int dd = (row / (TH + 2)) % (TD + 2);
+      const int ci = row / ((TH + 2) * (TD + 2));
+      const int gd = d0 - 1 + dd, gh = h0 - 1 + hh, gw = w0 - 1 + e;
+      float v = 0.f;
+      if (c0 + ci < a.Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+        v = __ldg(in_b + (long long)(c0 + ci) * dhw + (long long)gd * hw + (long long)gh * W + gw);
+        if constexpr (FIRST) v = fmaxf(fmaf(v, s0, t0), 0.f);
+      }
+      sIn[row * PITCH + 3 + e] = v;
+    }
+    {
+      const float* wsrc = a.w + (long long)c0 * 27 * COUT;
+      const int nvalid = min(CK, a.Cin - c0) * 27;
+      for (int idx = tid; idx < CK * 27 * Cfg::WT_STRIDE; idx += Cfg::THREADS) {
+        const int co = idx % Cfg::WT_STRIDE;
+        const int ct = idx / Cfg::WT_STRIDE;
+        sW[idx] = (co < COUT && ct < nvalid) ? __ldg(wsrc + ct * COUT + co) : 0.f;
+      }
+    }
+    __syncthreads();
+
+    // ---- FFMA main loop ---------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int ci = 0; ci < CK; ++ci) {
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float* row = sIn + ((ci * (TD + 2) + td + kd) * (TH + 2) + th + kh) * PITCH + twq * P;
+          float x[P + 2];
+          x[0] = row[3];
+          const float4 x1 = *reinterpret_cast<const float4*>(row + 4);
+          const float4 x2 = *reinterpret_cast<const float4*>(row + 8);
+          x[1] = x1.x, x[2] = x1.y, x[3] = x1.z, x[4] = x1.w;
+          x[5] = x2.x, x[6] = x2.y, x[7] = x2.z, x[8] = x2.w;
+          x[9] = row[12];
+          const float* wrow = sW + (ci * 27 + (kd * 3 + kh) * 3) * Cfg::WT_STRIDE + cg * Q;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            float wv[Q];
+            if constexpr (Q % 4 == 0) {
+#pragma unroll
+              for (int q4 = 0; q4 < Q / 4; ++q4) {
+                const float4 t = *reinterpret_cast<const float4*>(wrow + kw * Cfg::WT_STRIDE + q4 * 4);
+                wv[q4 * 4] = t.x, wv[q4 * 4 + 1] = t.y, wv[q4 * 4 + 2] = t.z, wv[q4 * 4 + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < Q; ++q) wv[q] = wrow[kw * Cfg::WT_STRIDE + q];
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+              for (int q = 0; q < Q; ++q) acc[p][q] = fmaf(x[p + kw], wv[q], acc[p][q]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue -----------------------------------------------------------------------------------------
+  const int gd = d0 + td, gh = h0 + th, gw = w0 + twq * P;
+  if (gd >= D || gh >= H || gw >= W) return;
+  const long long vox = (long long)gd * hw + (long long)gh * W + gw;
+  if constexpr (LAST) {
+    const float* sk = a.skip + (long long)b * dhw + vox;
+    float* o = a.out + (long long)b * dhw + vox;
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+      if (gw + p < W) o[p] = acc[p][0] + (a.skip ? __ldg(sk + p) : 0.f);
+  } else {
+    const int nvec = (gw + P <= W) ? (((W & 3) == 0) ? 4 : (((W & 1) == 0) ? 2 : 1)) : 1;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int co = cg * Q + q;
+      const float bias = __ldg(a.bias + co);
+      float* o = a.out + ((long long)b * COUT + co) * dhw + vox;
+      float r[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) r[p] = fmaxf(acc[p][q] + bias, 0.f);
+      if (nvec == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+      } else if (nvec == 2) {
+#pragma unroll
+        for (int p = 0; p < P; p += 2) *reinterpret_cast<float2*>(o + p) = make_float2(r[p], r[p + 1]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (gw + p < W) o[p] = r[p];
+      }
+    }
+  }
+}
+
+template <int CK, int COUT, int Q, int TD, int TW, bool FIRST, bool LAST>
+static int launch_conv3d(Conv3dArgs a, int B, cudaStream_t st) {
+  using Cfg = Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>;
+  auto kern = conv3d_k3_kernel<CK, COUT, Q, TD, TW, FIRST, LAST>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  a.tiles_w = cdiv(a.W, TW);
+  a.tiles_h = cdiv(a.H, Cfg::TH);
+  a.tiles_d = cdiv(a.D, TD);
+  dim3 grid(a.tiles_w * a.tiles_h * a.tiles_d, B);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(a);
+  cudaError_t e2 = cudaPeekAtLastError();
+  return e2 == cudaSuccess ? LWS_OK : (int)e2;
+}
+
+// packed layout (floats): [s0, t0, 0, 0] then per conv i: weights [Cin_i][27][Cout_i] (rounded up to 4 floats),
+// bias [Cout_i] (rounded up to 4; zeros for the last conv)
+static size_t conv_w_floats(int cin, int cout) { return (size_t)round_up(cin * 27 * cout, 4); }
+static size_t packed_offset(int C, int layers, int conv, bool bias) {
+  size_t off = 4;
+  const int n = layers + 2;
+  for (int i = 0; i < n; ++i) {
+    const int cin = i == 0 ? 1 : C, cout = i == n - 1 ? 1 : C;
+    if (i == conv && !bias) return off;
+    off += conv_w_floats(cin, cout);
+    if (i == conv && bias) return off;
+    off += (size_t)round_up(cout, 4);
+  }
+  return off;
+}
+
+template <int C>
+static int run_stack(const float* cost, const float* pk, float* out, float* bufA, float* bufB, int B, int D, int H,
+                     int W, int layers, int add_skip, cudaStream_t st) {
+  constexpr int TD = (C == 32) ? 2 : 3;
+  constexpr int TW = (C == 32) ? 32 : 64;
+  constexpr int CK = (C == 32) ? 8 : 4;
+  constexpr int Q = 8;
+  Conv3dArgs a;
+  memset(&a, 0, sizeof(a));
+  a.D = D, a.H = H, a.W = W;
+  int rc;
+  // conv 0: 1 -> C on the raw cost
+  a.in = cost, a.Cin = 1, a.out = bufA, a.affine = pk;
+  a.w = pk + packed_offset(C, layers, 0, false), a.bias = pk + packed_offset(C, layers, 0, true);
+  rc = launch_conv3d<1, C, Q, TD, TW, true, false>(a, B, st);
+  if (rc) return rc;
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int i = 1; i <= layers; ++i) {
+    a.in = cur, a.Cin = C, a.out = nxt;
+    a.w = pk + packed_offset(C, layers, i, false), a.bias = pk + packed_offset(C, layers, i, true);
+    rc = launch_conv3d<CK, C, Q, TD, TW, false, false>(a, B, st);
+    if (rc) return rc;
+    float* t = cur;
+    cur = nxt, nxt = t;
+  }
+  a.in = cur, a.Cin = C, a.out = out, a.skip = add_skip ? cost : nullptr;
+  a.w = pk + packed_offset(C, layers, layers + 1, false), a.bias = nullptr;
+  return launch_conv3d<4, 1, 1, 4, 64, false, true>(a, B, st);
+}
+
+}  // namespace lws
+
+extern "C" size_t lws_conv3d_stack_packed_floats(int C, int layers) {
+  if (C <= 0 || layers < 0) return 0;
+  return lws::packed_offset(C, layers, layers + 2, false);
+}
+
+extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const float* const* bn_weight,
+                                             const float* const* bn_bias, const float* const* bn_mean,
+                                             const float* const* bn_var, float eps, int C, int layers,
+                                             float* packed) {
+  using namespace lws;
+  if (!conv_w || !bn_weight || !bn_bias || !bn_mean || !bn_var || !packed) return LWS_ERR_NULL_PTR;
+  if (C <= 0 || layers < 0) return LWS_ERR_BAD_SHAPE;
+  const int n = layers + 2;
+  memset(packed, 0, lws_conv3d_stack_packed_floats(C, layers) * sizeof(float));
+  auto bn_scale = [&](int i, int c) { return (double)bn_weight[i][c] / sqrt((double)bn_var[i][c] + (double)eps); };
+  auto bn_shift = [&](int i, int c) { return (double)bn_bias[i][c] - (double)bn_mean[i][c] * bn_scale(i, c); };
+  packed[0] = (float)bn_scale(0, 0);
+  packed[1] = (float)bn_shift(0, 0);
+  for (int i = 0; i < n; ++i) {
+    const int cin = i == 0 ? 1 : C, cout = i == n - 1 ? 1 : C;
+    float* w = packed + packed_offset(C, layers, i, false);
+    float* bias = packed + packed_offset(C, layers, i, true);
+    for (int co = 0; co < cout; ++co) {
+      const double s = (i < n - 1) ? bn_scale(i + 1, co) : 1.0;
+      if (i < n - 1) bias[co] = (float)bn_shift(i + 1, co);
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < 27; ++t)
+          w[((size_t)ci * 27 + t) * cout + co] = (float)((double)conv_w[i][((size_t)co * cin + ci) * 27 + t] * s);
+    }
+  }
+  return LWS_OK;
+}
+
+extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, int C, int layers) {
+  (void)layers;
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
+  const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
+  return 2 * act;
+}
+
+extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weights, float* out, void* ws,
+                                    size_t ws_bytes, int B, int D, int H, int W, int C, int layers, int add_skip,
+                                    lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(cost);
+  LWS_CHECK_PTR(packed_weights);
+  LWS_CHECK_PTR(out);
+  LWS_CHECK_PTR(ws);
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || layers < 0 || B > 65535) return LWS_ERR_BAD_SHAPE;
+  if (C != 8 && C != 16 && C != 32) return LWS_ERR_UNSUPPORTED;
+  if (ws_bytes < lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers)) return LWS_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)ws) | ((uintptr_t)packed_weights)) & 15) return LWS_ERR_BAD_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t act = lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers) / 2;
+  float* bufA = (float*)ws;
+  float* bufB = (float*)((char*)ws + act);
+  // BN_0's scalar affine is the first two floats of the device blob; the first conv kernel reads it from there.
+  switch (C) {
+    case 8:
+      return run_stack<8>(cost, packed_weights, out, bufA, bufB, B, D, H, W, layers, add_skip, st);
+    case 16:
+      return run_stack<16>(cost, packed_weights, out, bufA, bufB, B, D, H, W, layers, add_skip, st);
+    default:
+      return run_stack<32>(cost, packed_weights, out, bufA, bufB, B, D, H, W, layers, add_skip, st);
+  }
+}
+
+// One BN-folded C -> C layer of the stack on its own (the kernel the stack spends its time in): used by bench.py to
+// time the dominant kernel in isolation and by tests to check a single layer.
+extern "C" int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folded, const float* bias, float* out,
+                                           int B, int C, int D, int H, int W, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(in);
+  LWS_CHECK_PTR(w_folded);
+  LWS_CHECK_PTR(bias);
+  LWS_CHECK_PTR(out);
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535) return LWS_ERR_BAD_SHAPE;
+  Conv3dArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in, a.w = w_folded, a.bias = bias, a.out = out, a.Cin = C, a.D = D, a.H = H, a.W = W;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 8: return launch_conv3d<4, 8, 8, 3, 64, false, false>(a, B, st);
+    case 16: return launch_conv3d<4, 16, 8, 3, 64, false, false>(a, B, st);
+    case 32: return launch_conv3d<8, 32, 8, 2, 32, false, false>(a, B, st);
+    default: return LWS_ERR_UNSUPPORTED;
+  }
+}

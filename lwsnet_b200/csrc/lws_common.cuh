@@ -1,0 +1,103 @@
+// Shared helpers for the lws_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lws.h"
+
+#define LWS_CHECK_PTR(p) \
+  do {                   \
+    if ((p) == nullptr) return LWS_ERR_NULL_PTR; \
+  } while (0)
+
+#define LWS_RETURN_LAUNCH_STATUS()            \
+  do {                                        \
+    cudaError_t e__ = cudaPeekAtLastError();  \
+    return e__ == cudaSuccess ? LWS_OK : (int)e__; \
+  } while (0)
+
+namespace lws {
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+// ---- cp.async (LDGSTS) ------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// streaming (evict-first) 128-bit store for write-once outputs
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+
+// ---- reference coordinate replay (models/models.py:44-53) ------------------------
+// Every operation is an explicitly rounded intrinsic so ptxas can never contract them into FMAs: the reference
+// issues one Paddle operator per arithmetic step and the tap indices must match it bit for bit.
+struct WarpAxis {
+  float recip;  // fl32(1 / max(size-1, 1))
+  float half;   // (size-1) * 0.5
+};
+
+__host__ inline WarpAxis make_warp_axis(int size) {
+  WarpAxis a;
+  a.recip = (float)(1.0 / (double)(size - 1 > 1 ? size - 1 : 1));
+  a.half = (float)((double)(size - 1) * 0.5);
+  return a;
+}
+
+// un-normalised sampling coordinate for pixel coordinate `pix` displaced by `dsp`
+__device__ __forceinline__ float warp_coord(float pix, float dsp, WarpAxis a) {
+  float v = __fsub_rn(pix, dsp);
+  float g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, v), a.recip), 1.0f);
+  return __fmul_rn(__fadd_rn(g, 1.0f), a.half);
+}
+__device__ __forceinline__ float warp_coord_nodisp(float pix, WarpAxis a) {
+  float g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, pix), a.recip), 1.0f);
+  return __fmul_rn(__fadd_rn(g, 1.0f), a.half);
+}
+
+struct Tap {
+  int i0;      // floor(coord), clamped to [-2, size+1]
+  float w0;    // (i0+1) - coord : weight of tap i0
+  float w1;    // coord - i0     : weight of tap i0+1
+};
+__device__ __forceinline__ Tap make_tap(float coord, int size) {
+  Tap t;
+  float f = floorf(coord);
+  t.w1 = __fsub_rn(coord, f);
+  t.w0 = __fsub_rn(__fadd_rn(f, 1.0f), coord);
+  f = fminf(fmaxf(f, -2.0f), (float)(size + 1));
+  t.i0 = (int)f;
+  return t;
+}
+
+// ---- half-pixel bilinear resize index (paddle F.interpolate defaults) -------------------
+struct ResizeTap {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ ResizeTap resize_tap(int dst, float scale, int in_size) {
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  src = fmaxf(src, 0.0f);
+  ResizeTap t;
+  t.i0 = min((int)src, in_size - 1);
+  t.i1 = min(t.i0 + 1, in_size - 1);
+  t.l1 = __fsub_rn(src, (float)t.i0);
+  t.l0 = __fsub_rn(1.0f, t.l1);
+  return t;
+}
+
+}  // namespace lws

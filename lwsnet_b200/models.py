@@ -1,0 +1,115 @@
+"""Mirror of the reference's models/models.py: same class / method names and signatures, B200 kernels underneath.
+
+``LWSNet(args)`` reads the same four attributes (``maxdisplist, layers_3d, channels_3d, growth_rate``; reference
+models/models.py:11-14), owns sub-layers under the same attribute names (``feature_extraction``,
+``volume_postprocess``, ``refinement1_left``, ``refinement1_disp``, ``refinement2``; models.py:16-26) so state-dict keys
+match the Paddle checkpoint grammar, and ``forward(left, right)`` returns the same list of four ``[B,1,H,W]``
+disparity maps.  Every hot-path function runs through the C ABI (``ops``); there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import LwsError
+from .submodules import BN_EPS, feature_extraction, post_3dconvs, refinement1, refinement2, refinement_tensor_list
+
+
+class LWSNet(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.maxdisplist = args.maxdisplist
+        self.layers_3d = args.layers_3d
+        self.channels_3d = args.channels_3d
+        self.growth_rate = args.growth_rate
+
+        self.feature_extraction = feature_extraction()
+        self.volume_postprocess = nn.ModuleList(
+            [post_3dconvs(self.layers_3d, self.channels_3d * self.growth_rate[i]) for i in range(3)])
+        self.refinement1_left = refinement1(in_channels=3, out_channels=32)
+        self.refinement1_disp = refinement1(in_channels=1, out_channels=32)
+        self.refinement2 = refinement2(in_channels=64, out_channels=32)
+        self._ref_packed = None
+        self._ref_key = None
+        self.eval()  # inference only: BatchNorm always uses its running statistics
+
+    # -- reference models/models.py:28-55 ------------------------------------------------------------------------
+    def warp(self, x, disp):
+        """x [B,C,H,W] (right features), disp [B,1,H,W] -> x sampled at (x - disp, y), bilinear, zero padding."""
+        return ops.warp_bilinear(x, disp)
+
+    # -- reference models/models.py:58-76 ------------------------------------------------------------------------
+    def _build_volume_2d(self, feat_l, feat_r, maxdisp, stride=1):
+        assert maxdisp % stride == 0
+        return ops.cost_volume_l1(feat_l, feat_r, maxdisp, stride)
+
+    # -- reference models/models.py:78-104 -----------------------------------------------------------------------
+    def _build_volume_2d3(self, feat_l, feat_r, maxdisp, disp, stride=1):
+        return ops.warp_residual_volume_l1(feat_l, feat_r, disp, maxdisp, stride)
+
+    def _refinement_packed(self, device):
+        mods = (self.refinement1_left, self.refinement1_disp, self.refinement2)
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for m in mods
+                                     for p in list(m.parameters()) + list(m.buffers()))
+        if self._ref_packed is None or self._ref_key != key:
+            self._ref_packed = ops.pack_refinement(refinement_tensor_list(*mods), BN_EPS).to(device)
+            self._ref_key = key
+        return self._ref_packed
+
+    # one iteration of the stage loop, reference models/models.py:115-156
+    def _stage(self, scale, feat_l, feat_r, prev_pred, img_h, img_w):
+        if scale > 0:
+            wflow = ops.disp_to_scale(prev_pred, feat_l.shape[2], feat_l.shape[3])                 # models.py:119-121
+            cost = self._build_volume_2d3(feat_l, feat_r, self.maxdisplist[scale], wflow, stride=1)  # :123-127
+            start = float(-self.maxdisplist[scale] + 1)
+        else:
+            cost = self._build_volume_2d(feat_l, feat_r, self.maxdisplist[scale], stride=1)          # :131-134
+            start = 0.0
+        cost = self.volume_postprocess[scale].run(cost, add_skip=True)                               # :136-138
+        low = ops.softmax_regression(cost, start, 1.0)                                              # :142 / :151-152
+        return ops.scale_upsample_add(low, prev_pred if scale > 0 else None, img_h, img_w)          # :145-148 / :153-156
+
+    def _refine(self, left_input, pred3):
+        return ops.refinement(left_input, pred3, self._refinement_packed(left_input.device))        # :158-162
+
+    # -- reference models/models.py:106-164 ----------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, left_input, right_input):
+        if not (left_input.is_cuda and right_input.is_cuda):
+            raise LwsError("LWSNet.forward: lwsnet_b200 has no CPU path; inputs must be CUDA tensors")
+        if left_input.shape != right_input.shape or left_input.dim() != 4 or left_input.shape[1] != 3:
+            raise ValueError("left_input / right_input must be equal-shape [B,3,H,W]")
+        img_h, img_w = left_input.shape[2], left_input.shape[3]
+        if img_h % 8 or img_w % 8:
+            raise ValueError("H and W must be multiples of 8 (hourglass skip adds, reference models/submodules.py:103)")
+        left_input = left_input.contiguous()
+        feats_l = self.feature_extraction(left_input)
+        feats_r = self.feature_extraction(right_input)
+        pred = []
+        for scale in range(len(feats_l)):
+            pred.append(self._stage(scale, feats_l[scale].contiguous(), feats_r[scale].contiguous(),
+                                    pred[scale - 1] if scale > 0 else None, img_h, img_w))
+        pred.append(self._refine(left_input, pred[2]))
+        return pred
+
+
+class disparity_regression(nn.Module):
+    """reference models/models.py:167-179: expectation of arange(start*stride, end*stride, stride) under `input`.
+
+    `input` is the already soft-maxed volume (as in the reference).  Inside LWSNet the softmax and this expectation run
+    as one fused kernel (ops.softmax_regression); this stand-alone class is kept for API compatibility and evaluates
+    the same fused kernel on log(input), which is mathematically the identity softmax(log p) = p for a normalised p.
+    """
+
+    def __init__(self, start, end, stride=1):
+        super().__init__()
+        self.start, self.end, self.stride = start, end, stride
+        self.my_steplength = len(range(start * stride, end * stride, stride))
+
+    def forward(self, input):
+        if not input.is_cuda:
+            raise LwsError("disparity_regression: no CPU path")
+        if input.shape[1] != self.my_steplength:
+            raise ValueError(f"expected {self.my_steplength} disparity planes, got {input.shape[1]}")
+        return ops.softmax_regression(-torch.log(input), float(self.start * self.stride), float(self.stride))

@@ -1,0 +1,257 @@
+"""Torch-tensor front end of the lws_b200 C ABI (include/lws.h).
+
+torch is used for device memory, streams and nothing else: every function below validates its arguments, allocates
+the output with torch and enqueues exactly the C-ABI call on torch's current stream.  CPU tensors are rejected —
+there is no CPU or PyTorch fallback for any hot-path op.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import LwsError, check, lib
+
+LAUNCHES = [0]  # kernels of liblws_b200 enqueued through this module (bench.py reports it as gpu_launches)
+_workspaces: dict = {}
+_retired: list = []  # outgrown buffers stay alive: captured CUDA graphs may still hold their addresses
+
+
+def _ptr(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise LwsError(f"{name}: lwsnet_b200 ops run on CUDA tensors only (got device {t.device}); there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag).  Reuse is stream-ordered, so use one stream per tag."""
+    key = (device.index, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _retired.append(buf)
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    """Drop all scratch buffers (only safe once no captured CUDA graph that used them will be replayed)."""
+    _workspaces.clear()
+    _retired.clear()
+
+
+# ------------------------------------------------------------------------------------------------ a1
+def cost_volume_l1(feat_l: torch.Tensor, feat_r: torch.Tensor, maxdisp: int, stride: int = 1) -> torch.Tensor:
+    """LWSNet._build_volume_2d (reference models/models.py:58-76)."""
+    assert maxdisp % stride == 0  # the reference's own assert (models.py:63)
+    feat_l, feat_r = _f32c(feat_l), _f32c(feat_r)
+    if feat_l.shape != feat_r.shape or feat_l.dim() != 4:
+        raise ValueError(f"feat_l/feat_r must be equal-shape [B,C,H,W], got {tuple(feat_l.shape)} {tuple(feat_r.shape)}")
+    B, C, H, W = feat_l.shape
+    cost = torch.empty((B, maxdisp // stride, H, W), dtype=torch.float32, device=feat_l.device)
+    if cost.numel() == 0:
+        return cost
+    with torch.cuda.device(feat_l.device):
+        check(lib.lws_cost_volume_l1_f32(_ptr(feat_l, "feat_l"), _ptr(feat_r, "feat_r"), _ptr(cost, "cost"), B, C, H, W,
+                                         maxdisp, stride, _stream(feat_l)), "lws_cost_volume_l1_f32")
+    LAUNCHES[0] += 1
+    return cost
+
+
+# ------------------------------------------------------------------------------------------------ a2
+def disp_to_scale(pred_full: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """wflow of LWSNet.forward (reference models/models.py:119-121)."""
+    pred_full = _f32c(pred_full)
+    B, one, H, W = pred_full.shape
+    if one != 1:
+        raise ValueError("pred_full must be [B,1,H,W]")
+    out = torch.empty((B, 1, h, w), dtype=torch.float32, device=pred_full.device)
+    with torch.cuda.device(pred_full.device):
+        check(lib.lws_disp_to_scale_f32(_ptr(pred_full, "pred_full"), _ptr(out, "wflow"), B, H, W, h, w,
+                                        _stream(pred_full)), "lws_disp_to_scale_f32")
+    LAUNCHES[0] += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a3
+def warp_bilinear(x: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+    """LWSNet.warp (reference models/models.py:28-55)."""
+    x, disp = _f32c(x), _f32c(disp)
+    N, C, H, W = x.shape
+    if tuple(disp.shape) != (N, 1, H, W):
+        raise ValueError(f"disp must be [N,1,H,W]={(N, 1, H, W)}, got {tuple(disp.shape)}")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.lws_warp_bilinear_f32(_ptr(x, "x"), _ptr(disp, "disp"), _ptr(out, "out"), N, C, H, W, _stream(x)),
+              "lws_warp_bilinear_f32")
+    LAUNCHES[0] += 1
+    return out
+
+
+def warp_taps(disp: torch.Tensor, shift: float = 0.0):
+    """Test hook: tap indices / weights of warp(., disp - shift).  Returns x0 [N,H,W] i32, y0 [H] i32, wx [N,H,W,2], wy [H,2]."""
+    disp = _f32c(disp)
+    N, one, H, W = disp.shape
+    dev = disp.device
+    x0 = torch.empty((N, H, W), dtype=torch.int32, device=dev)
+    y0 = torch.empty((H,), dtype=torch.int32, device=dev)
+    wx = torch.empty((N, H, W, 2), dtype=torch.float32, device=dev)
+    wy = torch.empty((H, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.lws_warp_taps_f32(_ptr(disp, "disp"), float(shift), _ptr(x0, "x0", torch.int32),
+                                    _ptr(y0, "y0", torch.int32), _ptr(wx, "wx"), _ptr(wy, "wy"), N, H, W,
+                                    _stream(disp)), "lws_warp_taps_f32")
+    return x0, y0, wx, wy
+
+
+# ------------------------------------------------------------------------------------------------ a4
+def warp_residual_volume_l1(feat_l: torch.Tensor, feat_r: torch.Tensor, disp: torch.Tensor, maxdisp: int,
+                            stride: int = 1) -> torch.Tensor:
+    """LWSNet._build_volume_2d3 (reference models/models.py:78-104)."""
+    feat_l, feat_r, disp = _f32c(feat_l), _f32c(feat_r), _f32c(disp)
+    B, C, H, W = feat_l.shape
+    if feat_r.shape != feat_l.shape or tuple(disp.shape) != (B, 1, H, W):
+        raise ValueError("shape mismatch between feat_l, feat_r and disp")
+    cost = torch.empty((B, 2 * maxdisp - 1, H, W), dtype=torch.float32, device=feat_l.device)
+    with torch.cuda.device(feat_l.device):
+        check(lib.lws_warp_residual_volume_l1_f32(_ptr(feat_l, "feat_l"), _ptr(feat_r, "feat_r"), _ptr(disp, "disp"),
+                                                  _ptr(cost, "cost"), B, C, H, W, maxdisp, stride, _stream(feat_l)),
+              "lws_warp_residual_volume_l1_f32")
+    LAUNCHES[0] += 1
+    return cost
+
+
+# ------------------------------------------------------------------------------------------------ a5
+def _host_f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to("cpu", torch.float32).contiguous()
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def pack_conv3d_stack(conv_weights: Sequence[torch.Tensor], bns: Sequence[Sequence[torch.Tensor]], eps: float, C: int,
+                      layers: int) -> torch.Tensor:
+    """Fold BN into the convs (host).  bns[i] = (weight, bias, _mean, _variance) of the BN in front of conv i."""
+    n = layers + 2
+    if len(conv_weights) != n or len(bns) != n:
+        raise ValueError(f"expected {n} convs and BNs")
+    cw = [_host_f32(w) for w in conv_weights]
+    for i, w in enumerate(cw):
+        cin, cout = (1 if i == 0 else C), (1 if i == n - 1 else C)
+        if tuple(w.shape) != (cout, cin, 3, 3, 3):
+            raise ValueError(f"conv {i}: expected weight {(cout, cin, 3, 3, 3)}, got {tuple(w.shape)}")
+    parts = [[_host_f32(b[j]) for b in bns] for j in range(4)]
+    packed = torch.zeros(int(lib.lws_conv3d_stack_packed_floats(C, layers)), dtype=torch.float32)
+    check(lib.lws_pack_conv3d_stack_weights(_ptr_array(cw), _ptr_array(parts[0]), _ptr_array(parts[1]),
+                                            _ptr_array(parts[2]), _ptr_array(parts[3]), float(eps), C, layers,
+                                            ctypes.c_void_p(packed.data_ptr())), "lws_pack_conv3d_stack_weights")
+    return packed
+
+
+def conv3d_stack(cost: torch.Tensor, packed: torch.Tensor, C: int, layers: int, add_skip: bool = True) -> torch.Tensor:
+    """post_3dconvs (+ skip) (reference models/submodules.py:190-221, models/models.py:136-138).  cost [B,D,H,W]."""
+    cost = _f32c(cost)
+    B, D, H, W = cost.shape
+    out = torch.empty_like(cost)
+    nbytes = int(lib.lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers))
+    ws = workspace(cost.device, "conv3d", nbytes)
+    with torch.cuda.device(cost.device):
+        check(lib.lws_conv3d_stack_f32(_ptr(cost, "cost"), _ptr(packed, "packed"), _ptr(out, "out"),
+                                       ctypes.c_void_p(ws.data_ptr()), nbytes, B, D, H, W, C, layers, int(add_skip),
+                                       _stream(cost)), "lws_conv3d_stack_f32")
+    LAUNCHES[0] += layers + 2
+    return out
+
+
+def conv3d_bnrelu_layer(x: torch.Tensor, w_folded: torch.Tensor, bias: torch.Tensor,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One BN-folded C->C layer: ReLU(conv3x3x3(x, w) + bias); x [B,C,D,H,W], w_folded [C][27][C]."""
+    B, C, D, H, W = x.shape
+    out = out if out is not None else torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.lws_conv3d_bnrelu_layer_f32(_ptr(x, "x"), _ptr(w_folded, "w"), _ptr(bias, "bias"), _ptr(out, "out"),
+                                              B, C, D, H, W, _stream(x)), "lws_conv3d_bnrelu_layer_f32")
+    LAUNCHES[0] += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a6 / a7
+def softmax_regression(cost: torch.Tensor, start: float, step: float = 1.0) -> torch.Tensor:
+    """disparity_regression(start, end)(softmax(-cost, axis=1)) (reference models/models.py:142,151-152,167-179)."""
+    cost = _f32c(cost)
+    B, D, H, W = cost.shape
+    low = torch.empty((B, 1, H, W), dtype=torch.float32, device=cost.device)
+    with torch.cuda.device(cost.device):
+        check(lib.lws_softmax_regression_f32(_ptr(cost, "cost"), _ptr(low, "low"), B, D, H, W, float(start),
+                                             float(step), _stream(cost)), "lws_softmax_regression_f32")
+    LAUNCHES[0] += 1
+    return low
+
+
+def scale_upsample_add(low: torch.Tensor, prev: Optional[torch.Tensor], H: int, W: int,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """low * H / h -> bilinear upsample to (H, W) (+ prev)  (reference models/models.py:145-148,153-156)."""
+    low = _f32c(low)
+    B, one, h, w = low.shape
+    if prev is not None:
+        prev = _f32c(prev)
+        if tuple(prev.shape) != (B, 1, H, W):
+            raise ValueError("prev must be [B,1,H,W]")
+    pred = out if out is not None else torch.empty((B, 1, H, W), dtype=torch.float32, device=low.device)
+    with torch.cuda.device(low.device):
+        check(lib.lws_scale_upsample_add_f32(_ptr(low, "low"), _ptr(prev, "prev"), _ptr(pred, "pred"), B, h, w, H, W,
+                                             _stream(low)), "lws_scale_upsample_add_f32")
+    LAUNCHES[0] += 1
+    return pred
+
+
+# ------------------------------------------------------------------------------------------------ a8 + a9
+def pack_refinement(tensors: Sequence[torch.Tensor], eps: float) -> torch.Tensor:
+    """Fold the BNs of refinement1_left / refinement1_disp / refinement2 (host); tensor order: include/lws.h."""
+    hs = [_host_f32(t) for t in tensors]
+    packed = torch.zeros(int(lib.lws_refinement_packed_floats()), dtype=torch.float32)
+    check(lib.lws_pack_refinement_weights(_ptr_array(hs), len(hs), float(eps), ctypes.c_void_p(packed.data_ptr())),
+          "lws_pack_refinement_weights")
+    return packed
+
+
+def refinement(left: torch.Tensor, pred3: torch.Tensor, packed: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pred3 + refinement2(concat[refinement1_left(left), refinement1_disp(pred3)]) (reference models/models.py:158-162)."""
+    left, pred3 = _f32c(left), _f32c(pred3)
+    B, three, H, W = left.shape
+    if three != 3 or tuple(pred3.shape) != (B, 1, H, W):
+        raise ValueError("left must be [B,3,H,W] and pred3 [B,1,H,W]")
+    pred4 = out if out is not None else torch.empty_like(pred3)
+    nbytes = int(lib.lws_refinement_workspace_bytes(B, H, W))
+    ws = workspace(left.device, "refine", nbytes)
+    with torch.cuda.device(left.device):
+        check(lib.lws_refinement_f32(_ptr(left, "left"), _ptr(pred3, "pred3"), _ptr(packed, "packed"),
+                                     _ptr(pred4, "pred4"), ctypes.c_void_p(ws.data_ptr()), nbytes, B, H, W,
+                                     _stream(left)), "lws_refinement_f32")
+    LAUNCHES[0] += 16
+    return pred4

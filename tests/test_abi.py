@@ -1,0 +1,102 @@
+"""CPU: the C-ABI library loads, exports every symbol include/lws.h declares, and its host-only entry points
+(weight packing, size queries, argument validation that returns before any CUDA call) behave."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "lws.h")).read()
+    return sorted(set(re.findall(r"LWS_API\s+[\w\s\*]+?\b(lws_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lwsnet_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in lws.h but not exported by {_lib.LIB_PATH}"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert "sm_100a" in _lib.version()
+
+
+def test_status_strings_and_validation_without_gpu():
+    from lwsnet_b200 import _lib
+    lib = _lib.lib
+    assert lib.lws_status_string(0) == b"LWS_OK"
+    assert lib.lws_status_string(-1) == b"LWS_ERR_BAD_SHAPE"
+    assert lib.lws_status_string(-4) == b"LWS_ERR_WORKSPACE_TOO_SMALL"
+    # argument validation happens before any CUDA call
+    assert lib.lws_cost_volume_l1_f32(None, None, None, 1, 1, 1, 1, 1, 1, None) == -3
+    dummy = ctypes.c_void_p(16)
+    assert lib.lws_cost_volume_l1_f32(dummy, dummy, dummy, 1, 4, 4, 8, 13, 2, None) == -1  # maxdisp % stride
+    assert lib.lws_conv3d_stack_f32(dummy, dummy, dummy, dummy, 0, 1, 4, 4, 4, 8, 4, 1, None) == -4
+    assert lib.lws_conv3d_stack_f32(dummy, dummy, dummy, dummy, 1 << 40, 1, 4, 4, 4, 7, 4, 1, None) == -5
+    assert lib.lws_refinement_f32(dummy, dummy, dummy, dummy, dummy, 0, 1, 8, 8, None) == -4
+    assert lib.lws_conv3d_stack_workspace_bytes(2, 24, 46, 154, 32, 4) >= 2 * 2 * 32 * 24 * 46 * 154 * 4
+    assert lib.lws_refinement_workspace_bytes(1, 368, 1232) == 128 * 368 * 1232 * 4
+
+
+def test_pack_conv3d_stack_folds_bn():
+    """Host packing: w'[ci][tap][co] = w[co][ci][tap] * s_{i+1}[co], bias = t_{i+1}, [s0,t0] first."""
+    from lwsnet_b200 import ops
+    from lwsnet_b200.submodules import BN_EPS
+    C, layers = 8, 4
+    g = torch.Generator().manual_seed(0)
+    convs, bns = [], []
+    for i in range(layers + 2):
+        cin, cout = (1 if i == 0 else C), (1 if i == layers + 1 else C)
+        convs.append(torch.randn(cout, cin, 3, 3, 3, generator=g))
+        bns.append((torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g), torch.randn(cin, generator=g),
+                    torch.rand(cin, generator=g) + 0.5))
+    packed = ops.pack_conv3d_stack(convs, bns, BN_EPS, C, layers).numpy()
+    s = [(b[0].double() / torch.sqrt(b[3].double() + BN_EPS)).numpy() for b in bns]
+    t = [(b[1].double() - b[2].double() * torch.from_numpy(s[i])).numpy() for i, b in enumerate(bns)]
+    assert np.allclose(packed[0], s[0][0]) and np.allclose(packed[1], t[0][0])
+    off = 4
+    for i in range(layers + 2):
+        cin, cout = (1 if i == 0 else C), (1 if i == layers + 1 else C)
+        w = convs[i].double().numpy().reshape(cout, cin, 27)
+        scale = s[i + 1] if i < layers + 1 else np.ones(1)
+        exp = (w * scale[:, None, None]).transpose(1, 2, 0).reshape(-1)
+        n = cin * 27 * cout
+        assert np.allclose(packed[off:off + n], exp, rtol=1e-6, atol=1e-7), i
+        off += (n + 3) // 4 * 4
+        if i < layers + 1:
+            assert np.allclose(packed[off:off + cout], t[i + 1], rtol=1e-6, atol=1e-7)
+        off += (cout + 3) // 4 * 4
+    assert off == packed.size
+
+
+def test_pack_refinement_folds_bn():
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200 import ops
+    from lwsnet_b200.submodules import BN_EPS, refinement1, refinement2, refinement_tensor_list
+    m = O.build_oracle(seed=3, random_bn=True)
+    r1l, r1d, r2 = refinement1(3, 32), refinement1(1, 32), refinement2(64, 32)
+    r1l.load_state_dict(m.refinement1_left.state_dict())
+    r1d.load_state_dict(m.refinement1_disp.state_dict())
+    r2.load_state_dict(m.refinement2.state_dict())
+    packed = ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2), BN_EPS).numpy()
+    from lwsnet_b200._lib import lib
+    assert packed.size == lib.lws_refinement_packed_floats() == 36096
+    # first section: conv0 of R1_left [3][9][32] scaled by block-1 BN; then its bias
+    bn = m.refinement1_left[1][0]
+    s = (bn.weight.double() / torch.sqrt(bn._variance.double() + BN_EPS)).detach().numpy()
+    t = (bn.bias.double() - bn._mean.double() * torch.from_numpy(s)).detach().numpy()
+    w = m.refinement1_left[0].weight.detach().double().numpy().reshape(32, 3, 9)
+    exp = (w * s[:, None, None]).transpose(1, 2, 0).reshape(-1)
+    assert np.allclose(packed[:864], exp, rtol=1e-6, atol=1e-7)
+    assert np.allclose(packed[864:896], t, rtol=1e-6, atol=1e-7)
+    # last section: conv_last [32][9][1], unscaled
+    wl = m.refinement2[5].weight.detach().numpy().reshape(32 * 9)
+    assert np.allclose(packed[-288:], wl)
+    with pytest.raises(Exception):
+        ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2)[:-1], BN_EPS)

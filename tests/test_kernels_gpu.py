@@ -1,0 +1,242 @@
+"""GPU parity tests: every hot-path kernel, called through the C ABI, against the CPU oracle (SURVEY.md 8(c) protocol 1).
+
+Tolerances (fp32 kernels, stated per test):
+  K1/K2 volumes     |d| <= 1e-5 * max(1, |cost|)      (summation order differs from the oracle's)
+  warp taps         indices and both weights BIT-EXACT
+  K4 regression     |d| <= 2e-5 low-res px
+  K5 / wflow        |d| <= 1e-5 * max(1, |x|)
+  K3 / K6 convs     |d| <= 1e-4 * (1 + |y|) against the fp64 oracle
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import cu, golden, rnd
+
+pytestmark = pytest.mark.gpu
+
+
+def ops():
+    from lwsnet_b200 import ops as o
+    return o
+
+
+def close_rel(a, b, tol, floor=1.0):
+    a, b = a.double().cpu(), torch.as_tensor(b).double()
+    bound = tol * torch.clamp(b.abs(), min=floor)
+    bad = (a - b).abs() > bound
+    assert not bad.any(), f"{int(bad.sum())} / {bad.numel()} beyond tol; max err {(a - b).abs().max().item():.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ a1
+@pytest.mark.parametrize("case,D", [("odd", 24), ("d12", 12), ("dgtw", 16)])
+def test_cost_volume_golden(case, D):
+    g = golden("cost_volume")
+    out = ops().cost_volume_l1(cu(g[f"{case}_L"]), cu(g[f"{case}_R"]), D)
+    close_rel(out, g[f"{case}_cost"], 1e-5)
+
+
+@pytest.mark.parametrize("B,C,H,W,D", [(2, 16, 46, 154, 24), (1, 16, 23, 77, 12), (1, 16, 20, 64, 48), (1, 8, 9, 33, 20),
+                                        (1, 16, 4, 1300, 24), (3, 6, 5, 31, 8), (1, 3, 4, 9, 7)])
+def test_cost_volume_vs_spec(B, C, H, W, D):
+    from oracle import spec_np as S
+    L, R = rnd(1, B, C, H, W, scale=2.0), rnd(2, B, C, H, W, scale=2.0)
+    out = ops().cost_volume_l1(L.cuda(), R.cuda(), D)
+    close_rel(out, S.cost_volume_l1(L.numpy(), R.numpy(), D), 1e-5)
+
+
+def test_cost_volume_stride2_and_assert():
+    from oracle import lwsnet_torch as O
+    L, R = rnd(3, 1, 8, 6, 40), rnd(4, 1, 8, 6, 40)
+    out = ops().cost_volume_l1(L.cuda(), R.cuda(), 12, stride=2)
+    close_rel(out, O.build_volume_2d(L, R, 12, stride=2), 1e-5)
+    with pytest.raises(AssertionError):  # reference: assert maxdisp % stride == 0 (models.py:63)
+        ops().cost_volume_l1(L.cuda(), R.cuda(), 13, stride=2)
+
+
+def test_cost_volume_linearity_fullsize():
+    """Size-independent property at the BASELINE configs[1] size: cost(aL, aR) == a * cost(L, R) exactly for a = 2."""
+    L, R = rnd(5, 8, 16, 46, 154, scale=2.0).cuda(), rnd(6, 8, 16, 46, 154, scale=2.0).cuda()
+    c1 = ops().cost_volume_l1(L, R, 24)
+    c2 = ops().cost_volume_l1(2 * L, 2 * R, 24)
+    assert torch.equal(c2, 2 * c1)
+    # plane 0 is the plain L1 distance; plane d at x < d is |L|_1 (occlusion branch)
+    close_rel(c1[:, 0], (L - R).abs().sum(1).cpu(), 1e-5)
+    close_rel(c1[:, 23, :, :23], L[..., :23].abs().sum(1).cpu(), 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ a2 / a3 / a4
+def test_warp_taps_bit_exact_golden():
+    g = golden("warp_volume")
+    x0, y0, wx, wy = ops().warp_taps(cu(g["disp"]), float(g["taps_shift"]))
+    assert torch.equal(x0.cpu(), torch.from_numpy(g["x0"]))
+    assert torch.equal(y0.cpu(), torch.from_numpy(g["y0"]))
+    assert np.array_equal(wx.cpu().numpy().view(np.uint32), g["wx"].view(np.uint32))
+    assert np.array_equal(wy.cpu().numpy().view(np.uint32), g["wy"].view(np.uint32))
+
+
+@pytest.mark.parametrize("H,W", [(92, 308), (184, 616), (46, 154), (136, 240), (272, 480), (7, 2), (1, 1)])
+def test_warp_taps_bit_exact(H, W):
+    from oracle import spec_np as S
+    disp = rnd(7, 2, 1, H, W, scale=40.0) + 30.0
+    disp[0, 0, 0, 0] = 0.0
+    disp[1, 0, -1, -1] = 1e9   # wildly out of range both ways
+    disp[1, 0, 0, -1] = -1e9
+    for shift in (-4.0, 0.0, 3.0):
+        x0, y0, wx, wy = ops().warp_taps(disp.cuda(), shift)
+        ex0, ey0, (ewx0, ewx1), (ewy0, ewy1) = S.warp_taps(disp[:, 0].numpy() - np.float32(shift), H, W)
+        assert np.array_equal(x0.cpu().numpy(), ex0)
+        assert np.array_equal(y0.cpu().numpy(), ey0)
+        assert np.array_equal(wx.cpu().numpy().view(np.uint32), np.stack([ewx0, ewx1], -1).view(np.uint32))
+        assert np.array_equal(wy.cpu().numpy().view(np.uint32), np.stack([ewy0, ewy1], -1).view(np.uint32))
+
+
+def test_warp_and_residual_volume_golden():
+    g = golden("warp_volume")
+    L, R, disp = cu(g["L"]), cu(g["R"]), cu(g["disp"])
+    close_rel(ops().warp_bilinear(R, disp), g["warped"], 1e-5)
+    close_rel(ops().warp_residual_volume_l1(L, R, disp, 5), g["cost"], 1e-5)
+    close_rel(ops().disp_to_scale(cu(g["pred_full"]), 7, 38), g["wflow"], 1e-5)
+
+
+@pytest.mark.parametrize("B,C,H,W,m", [(2, 16, 92, 308, 5), (1, 8, 184, 616, 5), (1, 16, 12, 40, 3), (2, 4, 9, 17, 1),
+                                        (1, 8, 10, 33, 7)])
+def test_residual_volume_vs_oracle(B, C, H, W, m):
+    from oracle import lwsnet_torch as O
+    L, R = rnd(8, B, C, H, W, scale=2.0), rnd(9, B, C, H, W, scale=2.0)
+    disp = rnd(10, B, 1, H, W, scale=W / 8.0) + W / 6.0
+    out = ops().warp_residual_volume_l1(L.cuda(), R.cuda(), disp.cuda(), m)
+    close_rel(out, O.build_volume_2d3(L, R, m, disp), 1e-5)
+
+
+def test_residual_volume_integer_disp_matches_shifted_l1():
+    """Property: with zero disparity plane k = m-1 of the residual volume is the plain L1 distance, up to the y-row
+    blend weights of the reference's fp32 coordinate round trip (|iy - y| <= 6.1e-5)."""
+    B, C, H, W = 2, 16, 92, 308
+    L, R = rnd(11, B, C, H, W).cuda(), rnd(12, B, C, H, W).cuda()
+    out = ops().warp_residual_volume_l1(L, R, torch.zeros(B, 1, H, W, device="cuda"), 5)
+    ref = (L - R).abs().sum(1)
+    assert (out[:, 4] - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("B,H,W,h,w", [(2, 368, 1232, 92, 308), (1, 368, 1232, 184, 616), (1, 64, 128, 16, 32), (1, 30, 50, 7, 11)])
+def test_disp_to_scale(B, H, W, h, w):
+    from oracle import spec_np as S
+    p = rnd(13, B, 1, H, W, scale=40.0)
+    close_rel(ops().disp_to_scale(p.cuda(), h, w), S.disp_to_scale(p.numpy(), h, w), 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ a6 / a7
+def test_regression_golden():
+    g = golden("regression")
+    out24 = ops().softmax_regression(cu(g["c24"]), 0.0)
+    out9 = ops().softmax_regression(cu(g["c9"]), -4.0)
+    assert (out24.cpu() - torch.from_numpy(g["low24"])).abs().max().item() <= 2e-5
+    assert (out9.cpu() - torch.from_numpy(g["low9"])).abs().max().item() <= 2e-5
+    up = ops().scale_upsample_add(cu(g["low"]), None, 48, 160)
+    close_rel(up, g["up"], 1e-5)
+    close_rel(ops().scale_upsample_add(cu(g["low"]), cu(g["prev"]), 48, 160), g["up_prev"], 1e-5)
+
+
+@pytest.mark.parametrize("B,D,H,W,start", [(2, 24, 46, 154, 0.0), (1, 9, 92, 308, -4.0), (1, 9, 7, 9, -4.0), (1, 48, 17, 24, 0.0),
+                                            (1, 1, 4, 4, 0.0), (1, 13, 3, 5, -6.0)])
+def test_regression_vs_spec(B, D, H, W, start):
+    from oracle import spec_np as S
+    for scale in (1.0, 10.0, 100.0):  # soft, sharp, arg-min-like volumes
+        c = rnd(14, B, D, H, W, scale=scale)
+        out = ops().softmax_regression(c.cuda(), start)
+        ref = S.softmax_regression(c.double().numpy(), start)
+        assert (out.cpu().double() - torch.from_numpy(ref)).abs().max().item() <= 2e-5
+
+
+def test_regression_shift_invariance_fullsize():
+    """Property: softmax regression is invariant to adding a per-pixel constant to the cost column."""
+    c = rnd(15, 8, 24, 46, 154, scale=8.0).cuda()
+    a = ops().softmax_regression(c, 0.0)
+    b = ops().softmax_regression(c + 64.0, 0.0)
+    assert (a - b).abs().max().item() <= 2e-5
+    assert a.min().item() >= 0.0 and a.max().item() <= 23.0
+
+
+@pytest.mark.parametrize("B,h,w,H,W", [(2, 46, 154, 368, 1232), (1, 184, 616, 368, 1232), (1, 5, 7, 40, 56), (1, 6, 9, 13, 31)])
+def test_scale_upsample_add(B, h, w, H, W):
+    from oracle import spec_np as S
+    low, prev = rnd(16, B, 1, h, w, scale=5.0), rnd(17, B, 1, H, W, scale=30.0)
+    close_rel(ops().scale_upsample_add(low.cuda(), None, H, W), S.scale_upsample_add(low.numpy(), None, H, W), 1e-5)
+    close_rel(ops().scale_upsample_add(low.cuda(), prev.cuda(), H, W), S.scale_upsample_add(low.numpy(), prev.numpy(), H, W), 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ a5
+def _stack_from_golden(prefix, C):
+    from lwsnet_b200.submodules import post_3dconvs
+    g = golden("conv3d_stack")
+    net = post_3dconvs(4, C)
+    sd = {k[len(prefix) + 3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix + "_w_")}
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), g
+
+
+@pytest.mark.parametrize("name,C", [("c8", 8), ("c32", 32)])
+def test_conv3d_stack_golden(name, C):
+    net, g = _stack_from_golden(name, C)
+    cost = cu(g[f"{name}_cost"])
+    out = net.run(cost, add_skip=True)
+    ref = torch.from_numpy(g[f"{name}_out64"])
+    err = (out.cpu().double() - ref).abs()
+    assert (err <= 1e-4 * (1 + ref.abs())).all(), f"max err {err.max().item():.3e}"
+    noskip = net(cost.unsqueeze(1))[:, 0]
+    err2 = (noskip.cpu().double() + g[f"{name}_cost"] - ref).abs()
+    assert (err2 <= 1e-4 * (1 + ref.abs())).all()
+
+
+@pytest.mark.parametrize("C,B,D,H,W", [(32, 2, 24, 46, 154), (8, 1, 9, 92, 308), (8, 1, 9, 40, 70), (16, 1, 5, 11, 30), (32, 1, 3, 5, 9)])
+def test_conv3d_stack_vs_fp64_oracle(C, B, D, H, W):
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200.submodules import post_3dconvs
+    onet = O.post_3dconvs(4, C)
+    holder = torch.nn.Module()
+    holder.net = onet
+    O.kaiming_normal_init_(holder, 21)
+    O.randomize_bn_(holder, 22)
+    net = post_3dconvs(4, C)
+    net.load_state_dict(onet.state_dict(), strict=True)
+    cost = rnd(23, B, D, H, W, scale=6.0).abs()
+    out = net.cuda().run(cost.cuda(), add_skip=True)
+    with torch.no_grad():
+        ref = (onet.double()(cost.double().unsqueeze(1)) + cost.double().unsqueeze(1))[:, 0]
+    err = (out.cpu().double() - ref).abs()
+    assert (err <= 1e-4 * (1 + ref.abs())).all(), f"max err {err.max().item():.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ a8 + a9
+@pytest.mark.parametrize("B,H,W,random_bn", [(1, 64, 128, True), (2, 40, 72, True), (1, 368, 1232, False), (1, 24, 30, True)])
+def test_refinement_vs_fp64_oracle(B, H, W, random_bn):
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    o64 = O.build_oracle(seed=0, random_bn=random_bn, dtype=torch.float64)
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=random_bn))
+    left = rnd(31, B, 3, H, W)
+    pred3 = rnd(32, B, 1, H, W, scale=10.0) + 20.0
+    out = model._refine(left.cuda(), pred3.cuda())
+    with torch.no_grad():
+        ref = o64.refine(left.double(), pred3.double())
+    err = (out.cpu().double() - ref).abs()
+    assert (err <= 1e-4 * (1 + ref.abs())).all(), f"max err {err.max().item():.3e} (|ref| max {ref.abs().max().item():.1f})"
+
+
+def test_refinement_golden():
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    g = golden("model_small")
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=True))
+    out = model._refine(cu(g["left"]), cu(g["pred3"]))
+    ref = torch.from_numpy(g["refine64"])
+    err = (out.cpu().double() - ref).abs()
+    assert (err <= 1e-4 * (1 + ref.abs())).all(), f"max err {err.max().item():.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def test_cpu_tensors_are_refused():
+    from lwsnet_b200._lib import LwsError
+    with pytest.raises(LwsError):
+        ops().cost_volume_l1(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8), 4)

@@ -37,6 +37,10 @@ def _stream(t: torch.Tensor):
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise LwsError(f"lwsnet_b200 ops run on CUDA tensors only (got device {t.device}); there is no CPU path")
     if t.dtype != torch.float32:
         raise TypeError(f"expected float32, got {t.dtype}")
     return t if t.is_contiguous() else t.contiguous()

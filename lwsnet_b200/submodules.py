@@ -76,7 +76,8 @@ class Conv2D(_Conv):
 
     def forward(self, x):  # feature extractor only (off the hot path, see module docstring)
         _require_cuda(x, "Conv2D")
-        return F.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # fp32 operands: TF32 moves disparities by px
+            return F.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
 
 
 class Conv2DTranspose(_Conv):
@@ -85,7 +86,8 @@ class Conv2DTranspose(_Conv):
 
     def forward(self, x):
         _require_cuda(x, "Conv2DTranspose")
-        return F.conv_transpose2d(x, self.weight, None, self.stride, self.padding, self.output_padding)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return F.conv_transpose2d(x, self.weight, None, self.stride, self.padding, self.output_padding)
 
 
 class Conv3D(_Conv):

@@ -121,6 +121,17 @@ LWS_API size_t lws_refinement_workspace_bytes(int B, int H, int W);
 LWS_API int lws_refinement_f32(const float* left, const float* pred3, const float* packed_weights, float* pred4, void* ws,
                        size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
 
+/* ---- n1 (SURVEY.md 8(f) "next"): feature_extraction  (models/submodules.py:5-188) ----------------------------
+ * img [B,3,H,W] -> f8 [B,16,H/8,W/8], f4 [B,16,H/4,W/4], f2 [B,8,H/2,W/2]; H, W multiples of 8.  12 launches, fp32.
+ * HOST pack: tensors = for each of the 12 convs in execution order (dres0.0, dres0.2, dres1.0, dres1.2, dres2.conv1..4,
+ * dres2.conv5, dres2.conv6 (Conv2DTranspose, weight [Cin,Cout,3,3]), classif1.0, classif1.2): conv weight, then — except
+ * for the last conv, which has none — its BatchNorm (weight, bias, _mean, _variance).  n_tensors must be 56. */
+LWS_API size_t lws_feature_extraction_packed_floats(void);
+LWS_API int lws_pack_feature_extraction_weights(const float* const* tensors, int n_tensors, float eps, float* packed);
+LWS_API size_t lws_feature_extraction_workspace_bytes(int B, int H, int W);
+LWS_API int lws_feature_extraction_f32(const float* img, const float* packed_weights, float* f8, float* f4, float* f2,
+                                       void* ws, size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

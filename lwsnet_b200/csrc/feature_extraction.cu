@@ -1,0 +1,257 @@
+// Feature pyramid (reference models/submodules.py:5-188: convbn / deconvbn / hourglass / feature_extraction).
+// SURVEY.md 8(f) "next" row n1: the step in front of the hot path, 2.3 of 91.6 GFLOP per pair, 3..16 channels, so
+// every layer is bandwidth / latency bound rather than FLOP bound.  One generic direct kernel covers the 12 layers:
+// 3x3 conv with stride 1|2 and dilation, or 3x3 stride-2 transposed conv (pad 1, output_padding 1), BatchNorm folded
+// on the host (scale into the weights, shift as bias), optional residual add and ReLU fused in the epilogue.
+// fp32 end to end (TF32 feature maps move the disparities by whole pixels).
+#include <math.h>
+#include <string.h>
+
+#include "lws_common.cuh"
+
+namespace lws {
+
+struct FeConvArgs {
+  const float* in;    // [B,Cin,Hi,Wi]
+  const float* w;     // [Cin][9][COUT] folded
+  const float* bias;  // [COUT]
+  const float* res;   // [B,COUT,Ho,Wo] or null
+  float* out;         // [B,COUT,Ho,Wo]
+  int Cin, Hi, Wi, Ho, Wo;
+  int stride, dil, pad, transposed, relu;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
+  extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
+  for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
+  __syncthreads();
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yo = blockIdx.y;
+  const int b = blockIdx.z;
+  const int x0 = xq * 4;
+  if (x0 >= a.Wo) return;
+  const long long in_hw = (long long)a.Hi * a.Wi;
+  const long long out_hw = (long long)a.Ho * a.Wo;
+  const float* in_b = a.in + (long long)b * a.Cin * in_hw;
+
+  float acc[4][COUT];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < COUT; ++q) acc[p][q] = 0.f;
+
+  // input coordinates of the 3 taps per axis (-1 = contributes nothing)
+  int yi[3], xi[3][4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (a.transposed) {
+      const int t = yo + a.pad - k;  // yo = 2*yi - pad + k
+      yi[k] = (t >= 0 && (t & 1) == 0 && (t >> 1) < a.Hi) ? (t >> 1) : -1;
+    } else {
+      const int t = yo * a.stride - a.pad + k * a.dil;
+      yi[k] = (t >= 0 && t < a.Hi) ? t : -1;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int xo = x0 + p;
+      if (a.transposed) {
+        const int t = xo + a.pad - k;
+        xi[k][p] = (t >= 0 && (t & 1) == 0 && (t >> 1) < a.Wi) ? (t >> 1) : -1;
+      } else {
+        const int t = xo * a.stride - a.pad + k * a.dil;
+        xi[k][p] = (t >= 0 && t < a.Wi) ? t : -1;
+      }
+    }
+  }
+
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float* plane = in_b + ci * in_hw;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      if (yi[ky] < 0) continue;
+      const float* row = plane + (long long)yi[ky] * a.Wi;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float v[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[p] = xi[kx][p] >= 0 ? __ldg(row + xi[kx][p]) : 0.f;
+        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT;
+#pragma unroll
+        for (int q = 0; q < COUT; q += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            acc[p][q] = fmaf(v[p], w4.x, acc[p][q]);
+            acc[p][q + 1] = fmaf(v[p], w4.y, acc[p][q + 1]);
+            acc[p][q + 2] = fmaf(v[p], w4.z, acc[p][q + 2]);
+            acc[p][q + 3] = fmaf(v[p], w4.w, acc[p][q + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  const bool vec = ((a.Wo & 3) == 0);
+#pragma unroll
+  for (int q = 0; q < COUT; ++q) {
+    const float bias = __ldg(a.bias + q);
+    const long long o = ((long long)b * COUT + q) * out_hw + (long long)yo * a.Wo + x0;
+    float r[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
+    if (vec) {
+      if (a.res) {
+        const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
+        r[0] += rv.x, r[1] += rv.y, r[2] += rv.z, r[3] += rv.w;
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) r[p] = fmaxf(r[p], 0.f);
+      }
+      *reinterpret_cast<float4*>(a.out + o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (x0 + p < a.Wo) {
+          float t = r[p] + (a.res ? a.res[o + p] : 0.f);
+          a.out[o + p] = a.relu ? fmaxf(t, 0.f) : t;
+        }
+      }
+    }
+  }
+}
+
+static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
+  dim3 grid(cdiv(cdiv(a.Wo, 4), 128), a.Ho, B);
+  const size_t smem = (size_t)a.Cin * 9 * cout * sizeof(float);
+  switch (cout) {
+    case 4: fe_conv_kernel<4><<<grid, 128, smem, st>>>(a); break;
+    case 8: fe_conv_kernel<8><<<grid, 128, smem, st>>>(a); break;
+    case 16: fe_conv_kernel<16><<<grid, 128, smem, st>>>(a); break;
+    default: return LWS_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
+// layer table of feature_extraction (reference models/submodules.py:113-188 and hourglass :35-109)
+struct FeLayer {
+  int cin, cout, stride, dil, transposed, relu, has_bn;
+};
+static const FeLayer kFe[12] = {
+    {3, 4, 2, 2, 0, 1, 1},    // 0 dres0.0   pad = dil
+    {4, 8, 1, 4, 0, 1, 1},    // 1 dres0.2
+    {8, 4, 1, 2, 0, 1, 1},    // 2 dres1.0
+    {4, 8, 1, 2, 0, 0, 1},    // 3 dres1.2   + out0
+    {8, 16, 2, 1, 0, 1, 1},   // 4 dres2.conv1
+    {16, 16, 1, 1, 0, 1, 1},  // 5 dres2.conv2 -> pre
+    {16, 16, 2, 1, 0, 1, 1},  // 6 dres2.conv3
+    {16, 16, 1, 1, 0, 1, 1},  // 7 dres2.conv4 -> feature 1/8
+    {16, 16, 2, 1, 1, 1, 1},  // 8 dres2.conv5 (transposed) + pre, relu -> feature 1/4
+    {16, 8, 2, 1, 1, 0, 1},   // 9 dres2.conv6 (transposed) + out1
+    {8, 8, 1, 1, 0, 1, 1},    // 10 classif1.0
+    {8, 8, 1, 1, 0, 0, 0},    // 11 classif1.2 -> feature 1/2
+};
+static size_t fe_w_off(int layer, bool bias) {
+  size_t off = 0;
+  for (int i = 0; i < 12; ++i) {
+    if (i == layer && !bias) return off;
+    off += (size_t)round_up(kFe[i].cin * 9 * kFe[i].cout, 4);
+    if (i == layer && bias) return off;
+    off += (size_t)round_up(kFe[i].cout, 4);
+  }
+  return off;
+}
+
+}  // namespace lws
+
+extern "C" size_t lws_feature_extraction_packed_floats(void) { return lws::fe_w_off(12, false); }
+
+extern "C" int lws_pack_feature_extraction_weights(const float* const* t, int n_tensors, float eps, float* packed) {
+  using namespace lws;
+  if (!t || !packed) return LWS_ERR_NULL_PTR;
+  if (n_tensors != 12 + 11 * 4) return LWS_ERR_BAD_SHAPE;
+  for (int i = 0; i < n_tensors; ++i)
+    if (!t[i]) return LWS_ERR_NULL_PTR;
+  memset(packed, 0, lws_feature_extraction_packed_floats() * sizeof(float));
+  int ti = 0;
+  for (int l = 0; l < 12; ++l) {
+    const FeLayer& L = kFe[l];
+    const float* w = t[ti++];
+    const float *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+    if (L.has_bn) g = t[ti++], be = t[ti++], mu = t[ti++], var = t[ti++];
+    float* dw = packed + fe_w_off(l, false);
+    float* db = packed + fe_w_off(l, true);
+    for (int co = 0; co < L.cout; ++co) {
+      const double s = L.has_bn ? (double)g[co] / sqrt((double)var[co] + (double)eps) : 1.0;
+      db[co] = L.has_bn ? (float)((double)be[co] - (double)mu[co] * s) : 0.f;
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int k = 0; k < 9; ++k) {
+          // Conv2D weight [Cout,Cin,3,3]; Conv2DTranspose weight [Cin,Cout,3,3]
+          const size_t src = L.transposed ? ((size_t)ci * L.cout + co) * 9 + k : ((size_t)co * L.cin + ci) * 9 + k;
+          dw[((size_t)ci * 9 + k) * L.cout + co] = (float)((double)w[src] * s);
+        }
+    }
+  }
+  return LWS_OK;
+}
+
+extern "C" size_t lws_feature_extraction_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0 || (H & 7) || (W & 7)) return 0;
+  const size_t p2 = (size_t)(H / 2) * (W / 2), p4 = (size_t)(H / 4) * (W / 4), p8 = (size_t)(H / 8) * (W / 8);
+  return (size_t)B * (40 * p2 + 32 * p4 + 16 * p8) * sizeof(float);
+}
+
+extern "C" int lws_feature_extraction_f32(const float* img, const float* pk, float* f8, float* f4, float* f2, void* ws,
+                                          size_t ws_bytes, int B, int H, int W, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(img);
+  LWS_CHECK_PTR(pk);
+  LWS_CHECK_PTR(f8);
+  LWS_CHECK_PTR(f4);
+  LWS_CHECK_PTR(f2);
+  LWS_CHECK_PTR(ws);
+  if (B <= 0 || H <= 0 || W <= 0 || (H & 7) || (W & 7) || B > 65535 || H / 2 > 65535) return LWS_ERR_BAD_SHAPE;
+  if (ws_bytes < lws_feature_extraction_workspace_bytes(B, H, W)) return LWS_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)ws) | ((uintptr_t)pk) | ((uintptr_t)f8) | ((uintptr_t)f4) | ((uintptr_t)f2)) & 15) return LWS_ERR_BAD_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+  const size_t p2 = (size_t)H2 * W2, p4 = (size_t)H4 * W4, p8 = (size_t)H8 * W8;
+  float* base = (float*)ws;
+  float* t0 = base;                      // [B,4,1/2]
+  float* out0 = t0 + (size_t)B * 4 * p2;   // [B,8,1/2]
+  float* t2 = out0 + (size_t)B * 8 * p2;   // [B,4,1/2]
+  float* out1 = t2 + (size_t)B * 4 * p2;   // [B,8,1/2]
+  float* c6 = out1 + (size_t)B * 8 * p2;   // [B,8,1/2]
+  float* cl = c6 + (size_t)B * 8 * p2;     // [B,8,1/2]
+  float* c1 = cl + (size_t)B * 8 * p2;     // [B,16,1/4]
+  float* pre = c1 + (size_t)B * 16 * p4;   // [B,16,1/4]
+  float* c3 = pre + (size_t)B * 16 * p4;   // [B,16,1/8]
+  (void)p8;
+
+  struct Step {
+    int layer;
+    const float* in;
+    int Hi, Wi;
+    float* out;
+    int Ho, Wo;
+    const float* res;
+  };
+  const Step steps[12] = {
+      {0, img, H, W, t0, H2, W2, nullptr},   {1, t0, H2, W2, out0, H2, W2, nullptr}, {2, out0, H2, W2, t2, H2, W2, nullptr},
+      {3, t2, H2, W2, out1, H2, W2, out0},   {4, out1, H2, W2, c1, H4, W4, nullptr}, {5, c1, H4, W4, pre, H4, W4, nullptr},
+      {6, pre, H4, W4, c3, H8, W8, nullptr}, {7, c3, H8, W8, f8, H8, W8, nullptr},   {8, f8, H8, W8, f4, H4, W4, pre},
+      {9, f4, H4, W4, c6, H2, W2, out1},     {10, c6, H2, W2, cl, H2, W2, nullptr},  {11, cl, H2, W2, f2, H2, W2, nullptr},
+  };
+  for (const Step& s : steps) {
+    const FeLayer& L = kFe[s.layer];
+    FeConvArgs a;
+    a.in = s.in, a.w = pk + fe_w_off(s.layer, false), a.bias = pk + fe_w_off(s.layer, true), a.res = s.res, a.out = s.out;
+    a.Cin = L.cin, a.Hi = s.Hi, a.Wi = s.Wi, a.Ho = s.Ho, a.Wo = s.Wo;
+    a.stride = L.stride, a.dil = L.dil, a.pad = L.dil > 1 ? L.dil : 1, a.transposed = L.transposed, a.relu = L.relu;
+    int rc = launch_fe(a, L.cout, B, st);
+    if (rc) return rc;
+  }
+  return LWS_OK;
+}

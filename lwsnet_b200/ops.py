@@ -259,3 +259,33 @@ def refinement(left: torch.Tensor, pred3: torch.Tensor, packed: torch.Tensor,
                                      _stream(left)), "lws_refinement_f32")
     LAUNCHES[0] += 16
     return pred4
+
+
+# ------------------------------------------------------------------------------------------------ n1 feature pyramid
+def pack_feature_extraction(tensors: Sequence[torch.Tensor], eps: float) -> torch.Tensor:
+    """Fold the BNs of feature_extraction (host); tensor order: include/lws.h."""
+    hs = [_host_f32(t) for t in tensors]
+    packed = torch.zeros(int(lib.lws_feature_extraction_packed_floats()), dtype=torch.float32)
+    check(lib.lws_pack_feature_extraction_weights(_ptr_array(hs), len(hs), float(eps),
+                                                  ctypes.c_void_p(packed.data_ptr())), "lws_pack_feature_extraction_weights")
+    return packed
+
+
+def feature_extraction(img: torch.Tensor, packed: torch.Tensor):
+    """feature_extraction.forward (reference models/submodules.py:176-188) -> [f 1/8 (16ch), f 1/4 (16ch), f 1/2 (8ch)]."""
+    img = _f32c(img)
+    B, three, H, W = img.shape
+    if three != 3 or H % 8 or W % 8:
+        raise ValueError("img must be [B,3,H,W] with H, W multiples of 8")
+    dev = img.device
+    f8 = torch.empty((B, 16, H // 8, W // 8), dtype=torch.float32, device=dev)
+    f4 = torch.empty((B, 16, H // 4, W // 4), dtype=torch.float32, device=dev)
+    f2 = torch.empty((B, 8, H // 2, W // 2), dtype=torch.float32, device=dev)
+    nbytes = int(lib.lws_feature_extraction_workspace_bytes(B, H, W))
+    ws = workspace(dev, "fe", nbytes)
+    with torch.cuda.device(dev):
+        check(lib.lws_feature_extraction_f32(_ptr(img, "img"), _ptr(packed, "packed"), _ptr(f8, "f8"), _ptr(f4, "f4"),
+                                             _ptr(f2, "f2"), ctypes.c_void_p(ws.data_ptr()), nbytes, B, H, W,
+                                             _stream(img)), "lws_feature_extraction_f32")
+    LAUNCHES[0] += 12
+    return [f8, f4, f2]

@@ -6,8 +6,8 @@ parameter containers whose ``forward`` enqueues the hand-written sm_100a kernels
 * ``post_3dconvs``                      -> lws_conv3d_stack_f32         (reference models/submodules.py:190-221)
 * ``refinement1`` / ``refinement2``      -> lws_refinement_f32 (fused, driven from models.LWSNet.forward)
                                            (reference models/submodules.py:223-327)
-* ``feature_extraction`` / ``hourglass`` (reference models/submodules.py:35-188) is NOT on the north-star hot path
-  (SURVEY.md section 8(f) "next"): until its kernels land it runs on the GPU through torch's conv ops.
+* ``feature_extraction`` / ``hourglass`` -> lws_feature_extraction_f32   (reference models/submodules.py:35-188;
+  SURVEY.md section 8(f) row n1, the step in front of the hot path)
 
 State-dict keys follow the Paddle key grammar: Sequential children by index, BatchNorm
 tensors ``weight, bias, _mean, _variance``.  There is no CPU path: CPU tensors raise.
@@ -145,7 +145,7 @@ class hourglass(nn.Module):
 
 
 class feature_extraction(nn.Module):
-    """reference models/submodules.py:113-188."""
+    """reference models/submodules.py:113-188, executed by lws_feature_extraction_f32 (12 fused conv+BN(+ReLU/+skip) launches)."""
 
     def __init__(self):
         super().__init__()
@@ -153,8 +153,34 @@ class feature_extraction(nn.Module):
         self.dres1 = nn.Sequential(convbn(8, 4, 3, 1, 1, 2), ReLU(), convbn(4, 8, 3, 1, 1, 2))
         self.dres2 = hourglass(8)
         self.classif1 = nn.Sequential(convbn(8, 8, 3, 1, 1, 1), ReLU(), Conv2D(8, 8, 3, 1, 1))
+        self._packed = None
+        self._packed_key = None
+
+    def tensor_list(self):
+        """The 56 tensors of include/lws.h:lws_pack_feature_extraction_weights, in execution order."""
+        h = self.dres2
+        cbs = [self.dres0[0], self.dres0[2], self.dres1[0], self.dres1[2], h.conv1[0], h.conv2[0], h.conv3[0], h.conv4[0],
+               h.conv5, h.conv6, self.classif1[0]]
+        out = []
+        for cb in cbs:
+            out += [cb[0].weight] + list(cb[1].tensors())
+        out.append(self.classif1[2].weight)
+        return out
+
+    def packed(self, device):
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        if self._packed is None or self._packed_key != key:
+            self._packed = ops.pack_feature_extraction(self.tensor_list(), BN_EPS).to(device)
+            self._packed_key = key
+        return self._packed
 
     def forward(self, input):
+        _require_cuda(input, "feature_extraction")
+        return ops.feature_extraction(input, self.packed(input.device))
+
+    def forward_torch(self, input):
+        """The same graph through torch's conv ops (cuDNN, fp32).  Not used by the product path; kept as a GPU-side
+        cross-check for the tests of the feature-pyramid kernel."""
         _require_cuda(input, "feature_extraction")
         output = self.dres0(input)
         output = self.dres1(output) + output

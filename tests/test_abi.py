@@ -100,3 +100,30 @@ def test_pack_refinement_folds_bn():
     assert np.allclose(packed[-288:], wl)
     with pytest.raises(Exception):
         ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2)[:-1], BN_EPS)
+
+
+def test_pack_feature_extraction_folds_bn():
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200 import ops
+    from lwsnet_b200._lib import lib
+    from lwsnet_b200.submodules import BN_EPS, feature_extraction
+    m = O.build_oracle(seed=5, random_bn=True)
+    fe = feature_extraction()
+    fe.load_state_dict(m.feature_extraction.state_dict())
+    tl = fe.tensor_list()
+    assert len(tl) == 56
+    packed = ops.pack_feature_extraction(tl, BN_EPS).numpy()
+    assert packed.size == lib.lws_feature_extraction_packed_floats()
+    # layer 0: dres0.0 conv [4,3,3,3] scaled by its BN -> [3][9][4]
+    conv, bn = m.feature_extraction.dres0[0][0], m.feature_extraction.dres0[0][1]
+    s = (bn.weight.double() / torch.sqrt(bn._variance.double() + BN_EPS)).detach().numpy()
+    exp = (conv.weight.detach().double().numpy().reshape(4, 3, 9) * s[:, None, None]).transpose(1, 2, 0).reshape(-1)
+    assert np.allclose(packed[:108], exp, rtol=1e-6, atol=1e-7)
+    t = (bn.bias.double() - bn._mean.double() * torch.from_numpy(s)).detach().numpy()
+    assert np.allclose(packed[108:112], t, rtol=1e-6, atol=1e-7)
+    # last layer: classif1.2 plain conv [8,8,3,3] -> [8][9][8], zero bias
+    wl = m.feature_extraction.classif1[2].weight.detach().numpy().reshape(8, 8, 9).transpose(1, 2, 0).reshape(-1)
+    assert np.allclose(packed[-(576 + 8):-8], wl)
+    assert np.all(packed[-8:] == 0)
+    assert lib.lws_feature_extraction_workspace_bytes(1, 368, 1232) > 0
+    assert lib.lws_feature_extraction_workspace_bytes(1, 370, 1232) == 0  # H, W must be multiples of 8

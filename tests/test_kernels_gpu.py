@@ -249,6 +249,28 @@ def test_refinement_golden():
     _check_refine(out, ref, None)
 
 
+# ------------------------------------------------------------------------------------------------ n1 feature pyramid
+@pytest.mark.parametrize("B,H,W,random_bn", [(1, 64, 128, True), (2, 40, 72, True), (1, 368, 1232, False), (1, 24, 40, True)])
+def test_feature_extraction_vs_fp64_oracle(B, H, W, random_bn):
+    """|d| <= 1e-4 * (1 + |y|) + 2e-6 * max|y| against the fp64 oracle (reference models/submodules.py:176-188)."""
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    o64 = O.build_oracle(seed=0, random_bn=random_bn, dtype=torch.float64)
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=random_bn))
+    img = rnd(41, B, 3, H, W)
+    out = model.feature_extraction(img.cuda())
+    with torch.no_grad():
+        ref = o64.feature_extraction(img.double())
+    shapes = [(B, 16, H // 8, W // 8), (B, 16, H // 4, W // 4), (B, 8, H // 2, W // 2)]
+    for o, r, shp in zip(out, ref, shapes):
+        assert tuple(o.shape) == shp
+        err = (o.cpu().double() - r).abs()
+        assert (err <= 1e-4 * (1 + r.abs()) + 2e-6 * r.abs().max()).all(), f"max err {err.max().item():.3e}"
+    # same graph through torch/cuDNN fp32 on the GPU: an independent second opinion
+    for o, t in zip(out, model.feature_extraction.forward_torch(img.cuda())):
+        assert (o - t).abs().max().item() <= 1e-4 * (1 + t.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ error behaviour
 def test_cpu_tensors_are_refused():
     from lwsnet_b200._lib import LwsError

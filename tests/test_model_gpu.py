@@ -33,7 +33,7 @@ def test_feature_extractor_matches_oracle(models):
         ref = o64.feature_extraction(left.double())
         out = prod.feature_extraction(left.cuda())
     for a, b in zip(out, ref):
-        assert (a.cpu().double() - b).abs().max().item() <= 1e-4 * (1 + b.abs().max().item())
+        assert (a.cpu().double() - b).abs().max().item() <= 1e-5 * (1 + b.abs().max().item())
 
 
 @pytest.mark.parametrize("H,W", [(64, 128), (368, 1232)])
@@ -88,30 +88,15 @@ def test_end_to_end_golden(models):
 
 
 def test_batch_shard_equivalence(models):
-    """concatenated per-shard outputs == whole-batch outputs, bitwise (pairs are independent).
-    The hot path (stages + refinement) is checked bitwise on shared features; the full model (whose feature extractor
-    still runs through torch/cuDNN, which may pick batch-size dependent algorithms) to 1e-4 relative."""
+    """concatenated per-shard outputs == whole-batch outputs, BITWISE (pairs are independent and no
+    kernel's arithmetic depends on the batch size)."""
     O, o32, o64, prod = models
     left, right = O.synthetic_pair(4, 64, 128, seed=21, max_disp=20.0)
     left, right = left.cuda(), right.cuda()
-    fl, fr = prod.feature_extraction(left), prod.feature_extraction(right)
-
-    def hot(sl):
-        pred = []
-        for s in range(3):
-            pred.append(prod._stage(s, fl[s][sl].contiguous(), fr[s][sl].contiguous(), pred[s - 1] if s else None, 64, 128))
-        pred.append(prod._refine(left[sl].contiguous(), pred[2]))
-        return pred
-
-    whole = hot(slice(0, 4))
-    parts = [hot(slice(0, 1)), hot(slice(1, 4))]
-    for s in range(4):
-        assert torch.equal(whole[s], torch.cat([p[s] for p in parts]))
     full = prod(left, right)
-    halves = [prod(left[i:i + 2].contiguous(), right[i:i + 2].contiguous()) for i in (0, 2)]
+    parts = [prod(left[lo:hi].contiguous(), right[lo:hi].contiguous()) for lo, hi in ((0, 1), (1, 4))]
     for s in range(4):
-        cat = torch.cat([p[s] for p in halves])
-        assert (full[s] - cat).abs().max().item() <= 1e-4 * (1 + full[s].abs().max().item())
+        assert torch.equal(full[s], torch.cat([p[s] for p in parts]))
 
 
 def test_cpu_input_raises(models):

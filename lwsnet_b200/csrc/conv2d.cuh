@@ -73,26 +73,37 @@ __global__ void __launch_bounds__(Conv2dCfg<CK, COUT, Q, RG, TW, DIL, EPI>::THRE
   const float* in_b = a.in + (long long)b * a.in_bs;
   for (int c0 = 0; c0 < a.Cin; c0 += CK) {
     constexpr int ROW_E = TW + 2 * DIL;
+    // cp.async: every copy of the chunk is in flight at once (see conv3d_stack.cu)
     for (int idx = tid; idx < CK * ROWS * ROW_E; idx += Cfg::THREADS) {
       const int e = idx % ROW_E;
       const int row = idx / ROW_E;
       const int hh = row % ROWS;
       const int ci = row / ROWS;
       const int gh = h0 - DIL + hh, gw = w0 - DIL + e;
-      float v = 0.f;
+      float* dst = sIn + row * PITCH + (PADL - DIL) + e;
       if (c0 + ci < a.Cin && gh >= 0 && gh < H && gw >= 0 && gw < W)
-        v = __ldg(in_b + (long long)(c0 + ci) * hw + (long long)gh * W + gw);
-      sIn[row * PITCH + (PADL - DIL) + e] = v;
+        cp_async_4(dst, in_b + (long long)(c0 + ci) * hw + (long long)gh * W + gw);
+      else
+        *dst = 0.f;
     }
     {
       const float* wsrc = a.w + (long long)c0 * 9 * COUT;
       const int nvalid = min(CK, a.Cin - c0) * 9;
-      for (int idx = tid; idx < CK * 9 * Cfg::WT_STRIDE; idx += Cfg::THREADS) {
-        const int co = idx % Cfg::WT_STRIDE;
-        const int ct = idx / Cfg::WT_STRIDE;
-        sW[idx] = (co < COUT && ct < nvalid) ? __ldg(wsrc + ct * COUT + co) : 0.f;
+      if constexpr (COUT % 4 == 0) {
+        for (int idx = tid; idx < CK * 9 * COUT / 4; idx += Cfg::THREADS) {
+          if (idx * 4 < nvalid * COUT) cp_async_16(sW + idx * 4, wsrc + idx * 4);
+          else *reinterpret_cast<float4*>(sW + idx * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        for (int idx = tid; idx < CK * 9 * Cfg::WT_STRIDE; idx += Cfg::THREADS) {
+          const int co = idx % Cfg::WT_STRIDE;
+          const int ct = idx / Cfg::WT_STRIDE;
+          sW[idx] = (co < COUT && ct < nvalid) ? __ldg(wsrc + ct * COUT + co) : 0.f;
+        }
       }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
 
 #pragma unroll 1

@@ -89,30 +89,64 @@ __global__ void __launch_bounds__(Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>::T
   const float* in_b = a.in + (long long)b * a.Cin * dhw;
   for (int c0 = 0; c0 < a.Cin; c0 += CK) {
     // ---- stage the input tile (halo 1, zero padded) and this chunk's weights --------------------------
+    // cp.async keeps every copy of the chunk in flight at once (a register-staged loop exposes one L2 round trip
+    // per element); the raw-cost layer needs BN_0 + ReLU on the way in, so it batches plain loads instead.
     constexpr int ROW_E = TW + 2;
-    for (int idx = tid; idx < CK * ROWS * ROW_E; idx += Cfg::THREADS) {
-      const int e = idx % ROW_E;
-      const int row = idx / ROW_E;
-      const int hh = row % (TH + 2);
-      const int dd = (row / (TH + 2)) % (TD + 2);
-      const int ci = row / ((TH + 2) * (TD + 2));
-      const int gd = d0 - 1 + dd, gh = h0 - 1 + hh, gw = w0 - 1 + e;
-      float v = 0.f;
-      if (c0 + ci < a.Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
-        v = __ldg(in_b + (long long)(c0 + ci) * dhw + (long long)gd * hw + (long long)gh * W + gw);
-        if constexpr (FIRST) v = fmaxf(fmaf(v, s0, t0), 0.f);
+    constexpr int N_IN = CK * ROWS * ROW_E;
+    if constexpr (FIRST) {
+      constexpr int UNR = 4;
+      for (int base = tid; base < N_IN; base += Cfg::THREADS * UNR) {
+        float v[UNR];
+        int dst[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int idx = base + u * Cfg::THREADS;
+          const int e = idx % ROW_E;
+          const int row = idx / ROW_E;
+          const int hh = row % (TH + 2);
+          const int dd = (row / (TH + 2)) % (TD + 2);
+          const int gd = d0 - 1 + dd, gh = h0 - 1 + hh, gw = w0 - 1 + e;
+          dst[u] = idx < N_IN ? row * PITCH + 3 + e : -1;
+          const bool inb = idx < N_IN && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;
+          v[u] = inb ? fmaxf(fmaf(__ldg(in_b + (long long)gd * hw + (long long)gh * W + gw), s0, t0), 0.f) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          if (dst[u] >= 0) sIn[dst[u]] = v[u];
       }
-      sIn[row * PITCH + 3 + e] = v;
+    } else {
+      for (int idx = tid; idx < N_IN; idx += Cfg::THREADS) {
+        const int e = idx % ROW_E;
+        const int row = idx / ROW_E;
+        const int hh = row % (TH + 2);
+        const int dd = (row / (TH + 2)) % (TD + 2);
+        const int ci = row / ((TH + 2) * (TD + 2));
+        const int gd = d0 - 1 + dd, gh = h0 - 1 + hh, gw = w0 - 1 + e;
+        float* dst = sIn + row * PITCH + 3 + e;
+        if (c0 + ci < a.Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)
+          cp_async_4(dst, in_b + (long long)(c0 + ci) * dhw + (long long)gd * hw + (long long)gh * W + gw);
+        else
+          *dst = 0.f;
+      }
     }
     {
       const float* wsrc = a.w + (long long)c0 * 27 * COUT;
       const int nvalid = min(CK, a.Cin - c0) * 27;
-      for (int idx = tid; idx < CK * 27 * Cfg::WT_STRIDE; idx += Cfg::THREADS) {
-        const int co = idx % Cfg::WT_STRIDE;
-        const int ct = idx / Cfg::WT_STRIDE;
-        sW[idx] = (co < COUT && ct < nvalid) ? __ldg(wsrc + ct * COUT + co) : 0.f;
+      if constexpr (COUT % 4 == 0) {
+        for (int idx = tid; idx < CK * 27 * COUT / 4; idx += Cfg::THREADS) {
+          if (idx * 4 < nvalid * COUT) cp_async_16(sW + idx * 4, wsrc + idx * 4);
+          else *reinterpret_cast<float4*>(sW + idx * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        for (int idx = tid; idx < CK * 27 * Cfg::WT_STRIDE; idx += Cfg::THREADS) {
+          const int co = idx % Cfg::WT_STRIDE;
+          const int ct = idx / Cfg::WT_STRIDE;
+          sW[idx] = (co < COUT && ct < nvalid) ? __ldg(wsrc + ct * COUT + co) : 0.f;
+        }
       }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
 
     // ---- FFMA main loop ---------------------------------------------------------------------------------

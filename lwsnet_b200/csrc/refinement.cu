@@ -6,8 +6,7 @@
 // concat is never materialised separately (the two R1 branches write their halves of the 64-channel buffer), and the
 // final interpolate (same size => identity) is dropped.
 //   dense 3x3 convs  : conv2d.cuh (FP32 direct, smem tiled)
-//   BN-ReLU-DW-PW    : dwsep_block_kernel below: depthwise dilated 3x3 into shared memory, then the 32x32 pointwise
-//                      product out of shared memory with a 4 px x 8 cout register tile.
+//   BN-ReLU-DW-PW    : dwsep_block_kernel below (phase-row tiling, depthwise result kept in registers)
 #include <math.h>
 #include <string.h>
 
@@ -25,103 +24,154 @@ struct DwsepArgs {
   int H, W, dil, relu;
 };
 
-constexpr int DW_TH = 8, DW_TW = 32, DW_C = 32;
+// BN-ReLU-DW(dil)-PW block.  "Phase-row" tiling: a block owns 8 output rows spaced `dil` apart (same row phase) x 128
+// consecutive columns, so the dilated 3x3 needs only 10 input rows and a +-dil column halo whatever the dilation is
+// (1.56x read amplification at dil 16 instead of 9x for a square tile).  A thread owns 2 vertically adjacent
+// phase-rows x 1 column x all 32 output channels: the depthwise result never leaves registers, the 32x32 pointwise
+// weights are warp-uniform broadcast LDS.128.  Input channels stream through shared memory in cp.async double-buffered
+// chunks of 8.
+constexpr int DW_TI = 8, DW_TX = 128, DW_C = 32, DW_CK = 8, DW_THREADS = 512, DW_ROWS = DW_TI + 2;
+constexpr int DW_PWMAX = DW_TX + 2 * 16;
 
-__global__ void __launch_bounds__(256, 2) dwsep_block_kernel(const DwsepArgs a) {
-  __shared__ __align__(16) float sDW[DW_C][DW_TH * DW_TW];  // 32 KB
-  __shared__ __align__(16) float sPW[DW_C][DW_C];           // 4 KB
-  __shared__ float sK[DW_C][9];
+__global__ void __launch_bounds__(DW_THREADS, 1) dwsep_block_kernel(const DwsepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* sIn = smem;                                       // [2][CK][ROWS][pw]
+  const int dil = a.dil;
+  const int pw = (DW_TX + 2 * dil + 3) & ~3;
+  float* sPW = smem + 2 * DW_CK * DW_ROWS * DW_PWMAX;      // [32][32]
+  float* sK = sPW + DW_C * DW_C;                           // [32][12]
   const int tid = threadIdx.x;
-  const int tiles_w = (a.W + DW_TW - 1) / DW_TW;
-  const int w0 = (blockIdx.x % tiles_w) * DW_TW, h0 = (blockIdx.x / tiles_w) * DW_TH;
+  const int tiles_x = (a.W + DW_TX - 1) / DW_TX;
+  const int x0 = (blockIdx.x % tiles_x) * DW_TX;
+  const int rb = blockIdx.x / tiles_x;
+  const int grp = rb / dil, py = rb - grp * dil;
   const int b = blockIdx.y;
-  const int H = a.H, W = a.W, dil = a.dil;
+  const int H = a.H, W = a.W;
   const long long hw = (long long)H * W;
-  for (int i = tid; i < DW_C * DW_C; i += 256) sPW[i / DW_C][i % DW_C] = __ldg(a.pw + i);
-  for (int i = tid; i < DW_C * 9; i += 256) sK[i / 9][i % 9] = __ldg(a.dw + i);
-  __syncthreads();
+  const float* in_b = a.in + (long long)b * a.in_bs;
+  const bool vec16 = ((dil & 3) == 0) && ((W & 3) == 0) && ((((uintptr_t)a.in) & 15) == 0) && ((a.in_bs & 3) == 0);
 
-  // phase 1: depthwise dilated 3x3, one pixel per thread, channels in a loop (coalesced along w)
-  {
-    const int lx = tid % DW_TW, ly = tid / DW_TW;
-    const int gx = w0 + lx, gy = h0 + ly;
-    const float* in_b = a.in + (long long)b * a.in_bs;
-    bool okx[3], oky[3];
-    long long off[3][3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      okx[k] = gx + (k - 1) * dil >= 0 && gx + (k - 1) * dil < W;
-      oky[k] = gy + (k - 1) * dil >= 0 && gy + (k - 1) * dil < H;
+  for (int i = tid; i < DW_C * DW_C; i += DW_THREADS) sPW[i] = __ldg(a.pw + i);
+  for (int i = tid; i < DW_C * 12; i += DW_THREADS) sK[i] = (i % 12 < 9) ? __ldg(a.dw + (i / 12) * 9 + (i % 12)) : 0.f;
+
+  auto issue = [&](int chunk, int buf) {
+    float* dst = sIn + buf * DW_CK * DW_ROWS * DW_PWMAX;
+    const int c0 = chunk * DW_CK;
+    if (vec16) {
+      const int pw4 = pw >> 2;
+      for (int idx = tid; idx < DW_CK * DW_ROWS * pw4; idx += DW_THREADS) {
+        const int e4 = idx % pw4;
+        const int row = idx / pw4;
+        const int r = row % DW_ROWS, cl = row / DW_ROWS;
+        const int gy = (grp * DW_TI + r - 1) * dil + py;
+        const int gx = x0 - dil + e4 * 4;
+        float* d = dst + row * DW_PWMAX + e4 * 4;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+          cp_async_16(d, in_b + (long long)(c0 + cl) * hw + (long long)gy * W + gx);
+        else
+          *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int idx = tid; idx < DW_CK * DW_ROWS * pw; idx += DW_THREADS) {
+        const int e = idx % pw;
+        const int row = idx / pw;
+        const int r = row % DW_ROWS, cl = row / DW_ROWS;
+        const int gy = (grp * DW_TI + r - 1) * dil + py;
+        const int gx = x0 - dil + e;
+        float* d = dst + row * DW_PWMAX + e;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+          cp_async_4(d, in_b + (long long)(c0 + cl) * hw + (long long)gy * W + gx);
+        else
+          *d = 0.f;
+      }
     }
+    cp_async_commit();
+  };
+
+  const int lx = tid % DW_TX;
+  const int i0 = (tid / DW_TX) * 2;  // first of this thread's two phase-rows
+  float acc[2][DW_C];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+  for (int p = 0; p < 2; ++p)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-        off[ky][kx] = (long long)(gy + (ky - 1) * dil) * W + (gx + (kx - 1) * dil);
-#pragma unroll 4
-    for (int c = 0; c < DW_C; ++c) {
-      const float* p = in_b + c * hw;
-      float s = 0.f;
+    for (int q = 0; q < DW_C; ++q) acc[p][q] = 0.f;
+
+  constexpr int NCH = DW_C / DW_CK;
+  issue(0, 0);
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch + 1 < NCH) {
+      issue(ch + 1, (ch + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* src = sIn + (ch & 1) * DW_CK * DW_ROWS * DW_PWMAX + i0 * DW_PWMAX + lx;
+#pragma unroll 2
+    for (int cl = 0; cl < DW_CK; ++cl) {
+      const int ci = ch * DW_CK + cl;
+      const float* rowp = src + cl * DW_ROWS * DW_PWMAX;
+      float v[4][3];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        v[r][0] = rowp[r * DW_PWMAX];
+        v[r][1] = rowp[r * DW_PWMAX + dil];
+        v[r][2] = rowp[r * DW_PWMAX + 2 * dil];
+      }
+      const float4 k0 = *reinterpret_cast<const float4*>(sK + ci * 12);
+      const float4 k1 = *reinterpret_cast<const float4*>(sK + ci * 12 + 4);
+      const float4 k2 = *reinterpret_cast<const float4*>(sK + ci * 12 + 8);
+      const float k[9] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x};
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float v = (okx[kx] && oky[ky]) ? __ldg(p + off[ky][kx]) : 0.f;
-          s = fmaf(v, sK[c][ky * 3 + kx], s);
+          d0 = fmaf(v[ky][kx], k[ky * 3 + kx], d0);
+          d1 = fmaf(v[ky + 1][kx], k[ky * 3 + kx], d1);
         }
-      sDW[c][tid] = s;
+      const float4* wp = reinterpret_cast<const float4*>(sPW + ci * DW_C);
+#pragma unroll
+      for (int q4 = 0; q4 < DW_C / 4; ++q4) {
+        const float4 w4 = wp[q4];
+        acc[0][q4 * 4] = fmaf(d0, w4.x, acc[0][q4 * 4]);
+        acc[0][q4 * 4 + 1] = fmaf(d0, w4.y, acc[0][q4 * 4 + 1]);
+        acc[0][q4 * 4 + 2] = fmaf(d0, w4.z, acc[0][q4 * 4 + 2]);
+        acc[0][q4 * 4 + 3] = fmaf(d0, w4.w, acc[0][q4 * 4 + 3]);
+        acc[1][q4 * 4] = fmaf(d1, w4.x, acc[1][q4 * 4]);
+        acc[1][q4 * 4 + 1] = fmaf(d1, w4.y, acc[1][q4 * 4 + 1]);
+        acc[1][q4 * 4 + 2] = fmaf(d1, w4.z, acc[1][q4 * 4 + 2]);
+        acc[1][q4 * 4 + 3] = fmaf(d1, w4.w, acc[1][q4 * 4 + 3]);
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
-  // phase 2: pointwise 32 -> 32; thread = 4 consecutive px x 8 cout
-  const int pq = tid % 64, cg = tid / 64;
-  float acc[4][8];
+  const int gx = x0 + lx;
+  if (gx >= W) return;
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 2; ++p) {
+    const int gy = (grp * DW_TI + i0 + p) * dil + py;
+    if (gy >= H) continue;
+    float* o = a.out + (long long)b * a.out_bs + (long long)gy * W + gx;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
-#pragma unroll 8
-  for (int ci = 0; ci < DW_C; ++ci) {
-    const float4 x = *reinterpret_cast<const float4*>(&sDW[ci][pq * 4]);
-    const float4 wa = *reinterpret_cast<const float4*>(&sPW[ci][cg * 8]);
-    const float4 wb = *reinterpret_cast<const float4*>(&sPW[ci][cg * 8 + 4]);
-    const float xv[4] = {x.x, x.y, x.z, x.w};
-    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(xv[p], wv[q], acc[p][q]);
-  }
-  const int lx = (pq * 4) % DW_TW, ly = (pq * 4) / DW_TW;
-  const int gx = w0 + lx, gy = h0 + ly;
-  if (gy >= H || gx >= W) return;
-  const bool vec = ((W & 3) == 0);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int co = cg * 8 + q;
-    const float bias = __ldg(a.bias + co);
-    float r[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      r[p] = acc[p][q] + bias;
-      if (a.relu) r[p] = fmaxf(r[p], 0.f);
-    }
-    float* o = a.out + (long long)b * a.out_bs + co * hw + (long long)gy * W + gx;
-    if (vec) {
-      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
-    } else {
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-        if (gx + p < W) o[p] = r[p];
+    for (int q = 0; q < DW_C; ++q) {
+      float r = acc[p][q] + __ldg(a.bias + q);
+      if (a.relu) r = fmaxf(r, 0.f);
+      o[q * hw] = r;
     }
   }
 }
 
+constexpr size_t DW_SMEM = (size_t)(2 * DW_CK * DW_ROWS * DW_PWMAX + DW_C * DW_C + DW_C * 12) * sizeof(float);
+
 static int launch_dwsep(DwsepArgs a, int B, cudaStream_t st) {
-  dim3 grid(cdiv(a.W, DW_TW) * cdiv(a.H, DW_TH), B);
-  dwsep_block_kernel<<<grid, 256, 0, st>>>(a);
-  cudaError_t e = cudaPeekAtLastError();
+  if (a.dil < 1 || a.dil > 16) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(dwsep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(cdiv(a.W, DW_TX) * cdiv(a.H, DW_TI * a.dil) * a.dil, B);
+  dwsep_block_kernel<<<grid, DW_THREADS, DW_SMEM, st>>>(a);
+  e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }
 

@@ -14,11 +14,19 @@
 //   lanes run over h first, rows are TW+4 floats apart (== 4 mod 32), so the 128-bit row loads are conflict-free.
 // These layers are compute-bound (54-216 flop/B): the bound is the FP32 FFMA rate, not HBM.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "lws_common.cuh"
 
 namespace lws {
+
+// conv3d_tc.cu: tcgen05 3xTF32 path for C = 32
+size_t conv3d_tc_workspace_bytes(int B, int D, int H, int W);
+int conv3d_stack_c32_tc(const float* cost, const float* affine, const float* w_first, const float* b_first,
+                        const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last,
+                        float* out, void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
+constexpr int kTcLayerFloats = 9 * 192 * 32;  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
 
 struct Conv3dArgs {
   const float* in;      // [B,Cin,D,H,W]  post-activation (or raw cost when FIRST)
@@ -254,6 +262,15 @@ static size_t packed_offset(int C, int layers, int conv, bool bias) {
   }
   return off;
 }
+// C == 32 only: the tensor-core operand tables follow the generic layout, one per 32 -> 32 layer
+static size_t packed_tc_offset(int C, int layers, int mid_layer) {
+  return packed_offset(C, layers, layers + 2, false) + (size_t)mid_layer * kTcLayerFloats;
+}
+static bool use_tc_path(int C) {
+  if (C != 32) return false;
+  const char* e = getenv("LWS_CONV3D_TC");
+  return !(e && e[0] == '0');
+}
 
 template <int C>
 static int run_stack(const float* cost, const float* pk, float* out, float* bufA, float* bufB, int B, int D, int H,
@@ -290,7 +307,7 @@ static int run_stack(const float* cost, const float* pk, float* out, float* bufA
 
 extern "C" size_t lws_conv3d_stack_packed_floats(int C, int layers) {
   if (C <= 0 || layers < 0) return 0;
-  return lws::packed_offset(C, layers, layers + 2, false);
+  return lws::packed_offset(C, layers, layers + 2, false) + (C == 32 ? (size_t)layers * lws::kTcLayerFloats : 0);
 }
 
 extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const float* const* bn_weight,
@@ -318,6 +335,26 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
           w[((size_t)ci * 27 + t) * cout + co] = (float)((double)conv_w[i][((size_t)co * cin + ci) * 27 + t] * s);
     }
   }
+  if (C == 32) {
+    // 3xTF32 operand tables: row (stage*3 + kw)*64 + n holds, over ci, wh = tf32-truncated folded weight of cout n
+    // (n < 32) or wl = w - wh of cout n-32 (n >= 32); stage = kd*3 + kh
+    for (int l = 0; l < layers; ++l) {
+      const float* wf = packed + packed_offset(C, layers, l + 1, false);  // [ci][27][co]
+      float* tc = packed + packed_tc_offset(C, layers, l);
+      for (int t = 0; t < 27; ++t)
+        for (int co = 0; co < 32; ++co)
+          for (int ci = 0; ci < 32; ++ci) {
+            const float w = wf[((size_t)ci * 27 + t) * 32 + co];
+            uint32_t u;
+            memcpy(&u, &w, 4);
+            u &= 0xFFFFE000u;
+            float hi;
+            memcpy(&hi, &u, 4);
+            tc[((size_t)t * 64 + co) * 32 + ci] = hi;
+            tc[((size_t)t * 64 + 32 + co) * 32 + ci] = w - hi;
+          }
+    }
+  }
   return LWS_OK;
 }
 
@@ -325,7 +362,8 @@ extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, i
   (void)layers;
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
-  return 2 * act;
+  const size_t tc = C == 32 ? lws::conv3d_tc_workspace_bytes(B, D, H, W) : 0;
+  return 2 * act > tc ? 2 * act : tc;
 }
 
 extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weights, float* out, void* ws,
@@ -341,7 +379,20 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
   if (ws_bytes < lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers)) return LWS_ERR_WORKSPACE_TOO_SMALL;
   if ((((uintptr_t)ws) | ((uintptr_t)packed_weights)) & 15) return LWS_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t act = lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers) / 2;
+  if (use_tc_path(C)) {
+    const float* pk = packed_weights;
+    const float* wtc[16];
+    const float* bmid[16];
+    if (layers > 16) return LWS_ERR_UNSUPPORTED;
+    for (int l = 0; l < layers; ++l) {
+      wtc[l] = pk + packed_tc_offset(C, layers, l);
+      bmid[l] = pk + packed_offset(C, layers, l + 1, true);
+    }
+    return conv3d_stack_c32_tc(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
+                               wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
+                               add_skip, st);
+  }
+  const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
   float* bufA = (float*)ws;
   float* bufB = (float*)((char*)ws + act);
   // BN_0's scalar affine is the first two floats of the device blob; the first conv kernel reads it from there.

@@ -1,0 +1,427 @@
+// K3 (C = 32): the 32 -> 32 layers of the stage-1 3D stack as an implicit GEMM on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA), with a 3xTF32 error-compensated split so the
+// result stays at fp32 accuracy (plain TF32 operands move stage-1 disparities by up to 2.5 px).
+// Replaces 4 of the 6 cuDNN conv3d launches of post_3dconvs(4, 32) (reference models/submodules.py:216-221).
+//
+// Layout ("CLP"): activations are channels-last with a one-voxel zero border in y and x:
+//     act[b][d][y][x][32] fp32,  y in [0,H+2), x in [0,W+2)   ->  a voxel = one 128-byte row, R = D*(H+2)*(W+2) rows / b
+// so that a 3x3x3 tap is a constant row offset  off = (kd-1)*(H+2)*(W+2) + (kh-1)*(W+2) + (kw-1)  and an output tile of
+// 128 consecutive rows needs, per (kd,kh), one 136-row TMA box (rows outside [0,R) are zero-filled by TMA = the d
+// padding); the three kw taps are the same shared-memory tile read through UMMA descriptors shifted by 0/1/2 rows
+// (SWIZZLE_128B is a function of the absolute smem address, probe: tools/umma_probe.cu).
+//
+// 3xTF32:  x = xh + xl, w = wh + wl (xh = x with the low 13 mantissa bits cleared — exactly what the tensor core does
+// to an fp32 operand, so the raw x tile *is* xh).  acc = xh*wh + xh*wl + xl*wh in fp32.  Per K=8 step two MMAs:
+//     [acc_hh | acc_hl] (N=64) += x_tile  * [wh | wl]        acc_lh (N=32) += xl_tile * wh
+// (N=64 so the 4 KB A-tile read, which bounds small-N tcgen05.mma, is paid twice instead of three times).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = xl converter
+// (x - trunc(x) into a second smem tile, fence.proxy.async) and, after the last tap, epilogue (tcgen05.ld, sum of the
+// three accumulators, bias + ReLU, zero the border rows, 128-byte row stores).  A CTA owns G consecutive tiles whose
+// accumulators live in TMEM together, so each 24 KB weight stage is fetched once per G tiles.
+#include <math.h>
+#include <string.h>
+
+#include "lws_common.cuh"
+#include "tma_utils.cuh"
+
+namespace lws {
+
+constexpr int TC_M = 128;                 // rows (voxels) per tile
+constexpr int TC_AROWS = 136;             // rows per A stage (128 + 2 halo, rounded to the 8-row swizzle atom)
+constexpr int TC_ABYTES = TC_AROWS * 128;  // 17408
+constexpr int TC_BROWS = 192;             // 3 kw x (32 hi + 32 lo) rows
+constexpr int TC_BBYTES = TC_BROWS * 128;  // 24576
+constexpr int TC_NS = 3;                  // A ring depth
+constexpr int TC_GMAX = 4;                // tiles per CTA group (4 x 96 TMEM columns)
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM = TC_NS * 2 * TC_ABYTES + 2 * TC_BBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcArgs {
+  float* out;         // CLP [B][R][32]
+  const float* bias;  // [32]
+  int R;              // rows per batch element = D*(H+2)*(W+2)
+  int Hp, Wp;         // H+2, W+2
+  int tiles_per_b, groups_per_b, G, total_groups;
+};
+
+__device__ __forceinline__ uint64_t tc_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO (unused: swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 8 rows x 128 B
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    conv3d_c32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                         const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                                   // [NS][17408]  x tiles (= xh as far as the MMA is concerned)
+  uint8_t* sL = smem + TC_NS * TC_ABYTES;               // [NS][17408]  xl tiles
+  uint8_t* sB = smem + 2 * TC_NS * TC_ABYTES;           // [2][24576]   weight stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TC_NS * TC_ABYTES + 2 * TC_BBYTES);
+  uint64_t* a_full = bars;               // [NS] TMA landed
+  uint64_t* a_conv = bars + TC_NS;       // [NS] xl written
+  uint64_t* a_empty = bars + 2 * TC_NS;  // [NS] MMAs that read the slot retired
+  uint64_t* b_full = bars + 3 * TC_NS;   // [2]
+  uint64_t* b_empty = b_full + 2;        // [2]
+  uint64_t* acc_full = b_empty + 2;      // all MMAs of the group retired
+  uint64_t* acc_empty = acc_full + 1;    // epilogue drained TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < TC_NS; ++i) mbar_init(a_full + i, 1), mbar_init(a_conv + i, 4), mbar_init(a_empty + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(b_full + i, 1), mbar_init(b_empty + i, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    mbar_fence_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int plane = a.Hp * a.Wp;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t it = 0, bs = 0;
+      for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x) {
+        const int b = grp / a.groups_per_b;
+        const int t0 = (grp - b * a.groups_per_b) * a.G;
+        const int ntile = min(a.G, a.tiles_per_b - t0);
+        for (int st = 0; st < 9; ++st, ++bs) {
+          const int kd = st / 3, kh = st - kd * 3;
+          mbar_wait(b_empty + (bs & 1), ((bs >> 1) & 1) ^ 1);
+          mbar_expect_tx(b_full + (bs & 1), TC_BBYTES);
+          tma_load_2d(sB + (bs & 1) * TC_BBYTES, &mapB, b_full + (bs & 1), 0, st * TC_BROWS);
+          const int off = (kd - 1) * plane + (kh - 1) * a.Wp - 1;
+          for (int g = 0; g < ntile; ++g, ++it) {
+            const uint32_t slot = it % TC_NS;
+            mbar_wait(a_empty + slot, ((it / TC_NS) & 1) ^ 1);
+            mbar_expect_tx(a_full + slot, TC_ABYTES);
+            // 3D map {32, R, B}: rows outside [0, R) come back as zeros (the depth padding)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+                "[%2];" ::"r"(smem_u32(sX + slot * TC_ABYTES)),
+                "l"(reinterpret_cast<uint64_t>(&mapA)), "r"(smem_u32(a_full + slot)), "r"(0),
+                "r"((t0 + g) * TC_M + off), "r"(b)
+                : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // M=128, K-major A and B, fp32 accumulate, tf32 operands; N = 64 / 32
+      const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t it = 0, bs = 0, gi = 0;
+      for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x, ++gi) {
+        const int b = grp / a.groups_per_b;
+        const int t0 = (grp - b * a.groups_per_b) * a.G;
+        const int ntile = min(a.G, a.tiles_per_b - t0);
+        mbar_wait(acc_empty, (gi & 1) ^ 1);  // previous group's accumulators drained
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int st = 0; st < 9; ++st, ++bs) {
+          mbar_wait(b_full + (bs & 1), (bs >> 1) & 1);
+          const uint32_t b_addr = smem_u32(sB + (bs & 1) * TC_BBYTES);
+          for (int g = 0; g < ntile; ++g, ++it) {
+            const uint32_t slot = it % TC_NS;
+            mbar_wait(a_conv + slot, (it / TC_NS) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t x_addr = smem_u32(sX + slot * TC_ABYTES), l_addr = smem_u32(sL + slot * TC_ABYTES);
+            const uint32_t d_hh = tmem + g * 96, d_lh = tmem + g * 96 + 64;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (st | kw | k) != 0;
+                const uint64_t db = tc_sdesc(b_addr + kw * 8192 + k * 32);
+                tc_mma_tf32(d_hh, tc_sdesc(x_addr + kw * 128 + k * 32), db, idesc64, acc);
+                tc_mma_tf32(d_lh, tc_sdesc(l_addr + kw * 128 + k * 32), db, idesc32, acc);
+              }
+            }
+            tc_commit(a_empty + slot);
+          }
+          tc_commit(b_empty + (bs & 1));
+        }
+        tc_commit(acc_full);
+      }
+    }
+  } else {
+    // ================================ xl converter + epilogue (warps 2..5) ================================
+    const int ct = tid - 64;  // 0..127
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    uint32_t it = 0, gi = 0;
+    float bias[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias[j] = __ldg(a.bias + j);
+    for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x, ++gi) {
+      const int b = grp / a.groups_per_b;
+      const int t0 = (grp - b * a.groups_per_b) * a.G;
+      const int ntile = min(a.G, a.tiles_per_b - t0);
+      for (int n = 0; n < 9 * ntile; ++n, ++it) {
+        const uint32_t slot = it % TC_NS;
+        mbar_wait(a_full + slot, (it / TC_NS) & 1);
+        const float4* src = reinterpret_cast<const float4*>(sX + slot * TC_ABYTES);
+        float4* dst = reinterpret_cast<float4*>(sL + slot * TC_ABYTES);
+#pragma unroll 3
+        for (int i = ct; i < TC_ABYTES / 16; i += 128) {
+          const float4 x = src[i];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          dst[i] = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_conv + slot);
+      }
+      // ---- epilogue of this group ----
+      mbar_wait(acc_full, gi & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int g = 0; g < ntile; ++g) {
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + g * 96;
+        float acc[32], t[32];
+        tc_ld32(taddr, acc);
+        tc_ld32(taddr + 32, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += t[j];
+        tc_ld32(taddr + 64, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += t[j];
+        const int r = (t0 + g) * TC_M + q * 32 + lane;  // row inside this batch element
+        if (r < a.R) {
+          const int x = r % a.Wp, y = (r / a.Wp) % a.Hp;
+          const bool border = x == 0 || x == a.Wp - 1 || y == 0 || y == a.Hp - 1;
+          float4* o = reinterpret_cast<float4*>(a.out + ((long long)b * a.R + r) * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v;
+            v.x = border ? 0.f : fmaxf(acc[4 * j] + bias[4 * j], 0.f);
+            v.y = border ? 0.f : fmaxf(acc[4 * j + 1] + bias[4 * j + 1], 0.f);
+            v.z = border ? 0.f : fmaxf(acc[4 * j + 2] + bias[4 * j + 2], 0.f);
+            v.w = border ? 0.f : fmaxf(acc[4 * j + 3] + bias[4 * j + 3], 0.f);
+            o[j] = v;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---- 1 -> 32 on the raw cost, writing CLP (incl. the zero border); 8 lanes per voxel, 4 couts per lane -------------
+__global__ void __launch_bounds__(256)
+    conv3d_first_clp_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][32]*/,
+                            const float* __restrict__ bias, const float* __restrict__ affine, float* __restrict__ out,
+                            int D, int H, int W, long long total_rows) {
+  __shared__ __align__(16) float sW[27 * 32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[i] = __ldg(w + i);
+  __syncthreads();
+  const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+  const int sub = threadIdx.x & 7;
+  const int Hp = H + 2, Wp = W + 2;
+  const long long hw = (long long)H * W;
+  const float4 bv = *reinterpret_cast<const float4*>(bias + sub * 4);
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < total_rows;
+       row += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const int x = (int)(row % Wp);
+    long long t = row / Wp;
+    const int y = (int)(t % Hp);
+    t /= Hp;
+    const int d = (int)(t % D);
+    const int b = (int)(t / D);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool border = x == 0 || x == Wp - 1 || y == 0 || y == Hp - 1;
+    if (!border) {
+      const float* cb = cost + (long long)b * D * hw;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const int gd = d + kd - 1;
+        if (gd < 0 || gd >= D) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int gh = y - 1 + kh - 1;
+          if (gh < 0 || gh >= H) continue;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int gw = x - 1 + kw - 1;
+            if (gw < 0 || gw >= W) continue;
+            const float v = fmaxf(fmaf(__ldg(cb + (long long)gd * hw + (long long)gh * W + gw), s0, t0), 0.f);
+            const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 4);
+            acc.x = fmaf(v, wv.x, acc.x), acc.y = fmaf(v, wv.y, acc.y), acc.z = fmaf(v, wv.z, acc.z),
+            acc.w = fmaf(v, wv.w, acc.w);
+          }
+        }
+      }
+      acc.x = fmaxf(acc.x + bv.x, 0.f), acc.y = fmaxf(acc.y + bv.y, 0.f), acc.z = fmaxf(acc.z + bv.z, 0.f),
+      acc.w = fmaxf(acc.w + bv.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
+  }
+}
+
+// ---- 32 -> 1 from CLP (+ skip), NCDHW output; 8 lanes per voxel, 4 input channels per lane ---------------------------
+__global__ void __launch_bounds__(256)
+    conv3d_last_clp_kernel(const float* __restrict__ act, const float* __restrict__ w /*[32][27] = packed [Cin][27][1]*/,
+                           const float* __restrict__ skip, float* __restrict__ out, int D, int H, int W,
+                           long long total_vox) {
+  __shared__ __align__(16) float sW[27 * 32];  // [tap][ci]
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[(i % 27) * 32 + i / 27] = __ldg(w + i);
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int Hp = H + 2, Wp = W + 2;
+  const long long R = (long long)D * Hp * Wp;
+  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; vox < total_vox;
+       vox += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const int x = (int)(vox % W);
+    long long t = vox / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int d = (int)(t % D);
+    const int b = (int)(t / D);
+    const float* base = act + ((long long)b * R) * 32 + sub * 4;
+    float acc = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int gd = d + kd - 1;
+      if (gd < 0 || gd >= D) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const long long r = ((long long)gd * Hp + (y + kh)) * Wp + (x + kw);  // padded coords: (y+1)+(kh-1), (x+1)+(kw-1)
+          const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * 32));
+          const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 4);
+          acc = fmaf(v.x, wv.x, acc), acc = fmaf(v.y, wv.y, acc), acc = fmaf(v.z, wv.z, acc), acc = fmaf(v.w, wv.w, acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0) out[vox] = acc + (skip ? __ldg(skip + vox) : 0.f);
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+size_t conv3d_tc_workspace_bytes(int B, int D, int H, int W) {
+  const size_t rows = (size_t)B * D * (H + 2) * (W + 2);
+  return 2 * ((rows * 128 + 255) / 256 * 256);
+}
+
+// w_first [27][32], b_first [32]; per mid layer: wtc [9*192][32] (hi/lo rows), bias [32]; w_last [32][27]
+int conv3d_stack_c32_tc(const float* cost, const float* affine, const float* w_first, const float* b_first,
+                        const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last,
+                        float* out, void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st) {
+  const int Hp = H + 2, Wp = W + 2;
+  const long long R = (long long)D * Hp * Wp;
+  if (R >= (1ll << 31) - 4096) return LWS_ERR_BAD_SHAPE;
+  const size_t act_bytes = conv3d_tc_workspace_bytes(B, D, H, W) / 2;
+  float* bufA = (float*)ws;
+  float* bufB = (float*)((char*)ws + act_bytes);
+  const long long rows = (long long)B * R;
+
+  {
+    const int blocks = (int)((rows * 8 + 255) / 256 < 148 * 16 ? (rows * 8 + 255) / 256 : 148 * 16);
+    conv3d_first_clp_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, bufA, D, H, W, rows);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaError_t e = cudaFuncSetAttribute(conv3d_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  TcArgs a;
+  a.R = (int)R, a.Hp = Hp, a.Wp = Wp;
+  a.tiles_per_b = (int)((R + TC_M - 1) / TC_M);
+  // tiles per CTA group: the G in {2,3,4} that minimises (rounds over 148 SMs) x G, i.e. the tail of the last round
+  int bestG = TC_GMAX;
+  long long best = -1;
+  for (int G = TC_GMAX; G >= 2; --G) {
+    const long long groups = (long long)B * ((a.tiles_per_b + G - 1) / G);
+    const long long cost_ = ((groups + kNumSMs - 1) / kNumSMs) * G;
+    if (best < 0 || cost_ < best) best = cost_, bestG = G;
+  }
+  a.G = bestG;
+  a.groups_per_b = (a.tiles_per_b + a.G - 1) / a.G;
+  a.total_groups = B * a.groups_per_b;
+  const int grid = a.total_groups < kNumSMs ? a.total_groups : kNumSMs;
+
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int l = 0; l < layers; ++l) {
+    CUtensorMap mapA, mapB;
+    const uint64_t dimsA[3] = {32, (uint64_t)R, (uint64_t)B}, strA[2] = {128, (uint64_t)R * 128};
+    const uint32_t boxA[3] = {32, TC_AROWS, 1};
+    int rc = make_tensor_map_f32(&mapA, cur, 3, dimsA, strA, boxA, true);
+    if (rc) return rc;
+    const uint64_t dimsB[2] = {32, 9 * TC_BROWS}, strB[1] = {128};
+    const uint32_t boxB[2] = {32, TC_BROWS};
+    rc = make_tensor_map_f32(&mapB, wtc[l], 2, dimsB, strB, boxB, true);
+    if (rc) return rc;
+    a.out = nxt, a.bias = bias_mid[l];
+    conv3d_c32_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA, mapB, a);
+    e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return (int)e;
+    float* t = cur;
+    cur = nxt, nxt = t;
+  }
+  {
+    const long long vox = (long long)B * D * H * W;
+    const int blocks = (int)((vox * 8 + 255) / 256 < 148 * 16 ? (vox * 8 + 255) / 256 : 148 * 16);
+    conv3d_last_clp_kernel<<<blocks, 256, 0, st>>>(cur, w_last, add_skip ? cost : nullptr, out, D, H, W, vox);
+    e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return LWS_OK;
+}
+
+}  // namespace lws

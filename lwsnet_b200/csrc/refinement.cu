@@ -54,35 +54,29 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dwsep_block_kernel(const DwsepA
   for (int i = tid; i < DW_C * DW_C; i += DW_THREADS) sPW[i] = __ldg(a.pw + i);
   for (int i = tid; i < DW_C * 12; i += DW_THREADS) sK[i] = (i % 12 < 9) ? __ldg(a.dw + (i / 12) * 9 + (i % 12)) : 0.f;
 
+  // one warp per (channel, row) of the chunk: the row decode happens once per row, lanes stride over the columns
+  const int warp = tid >> 5, lane = tid & 31;
   auto issue = [&](int chunk, int buf) {
     float* dst = sIn + buf * DW_CK * DW_ROWS * DW_PWMAX;
     const int c0 = chunk * DW_CK;
-    if (vec16) {
-      const int pw4 = pw >> 2;
-      for (int idx = tid; idx < DW_CK * DW_ROWS * pw4; idx += DW_THREADS) {
-        const int e4 = idx % pw4;
-        const int row = idx / pw4;
-        const int r = row % DW_ROWS, cl = row / DW_ROWS;
-        const int gy = (grp * DW_TI + r - 1) * dil + py;
-        const int gx = x0 - dil + e4 * 4;
-        float* d = dst + row * DW_PWMAX + e4 * 4;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-          cp_async_16(d, in_b + (long long)(c0 + cl) * hw + (long long)gy * W + gx);
-        else
-          *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    } else {
-      for (int idx = tid; idx < DW_CK * DW_ROWS * pw; idx += DW_THREADS) {
-        const int e = idx % pw;
-        const int row = idx / pw;
-        const int r = row % DW_ROWS, cl = row / DW_ROWS;
-        const int gy = (grp * DW_TI + r - 1) * dil + py;
-        const int gx = x0 - dil + e;
-        float* d = dst + row * DW_PWMAX + e;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-          cp_async_4(d, in_b + (long long)(c0 + cl) * hw + (long long)gy * W + gx);
-        else
-          *d = 0.f;
+    for (int row = warp; row < DW_CK * DW_ROWS; row += DW_THREADS / 32) {
+      const int cl = row / DW_ROWS, r = row - cl * DW_ROWS;
+      const int gy = (grp * DW_TI + r - 1) * dil + py;
+      float* d = dst + row * DW_PWMAX;
+      const bool yok = gy >= 0 && gy < H;
+      const float* src = in_b + (long long)(c0 + cl) * hw + (long long)(yok ? gy : 0) * W + (x0 - dil);
+      if (vec16) {
+        for (int e = lane * 4; e < pw; e += 128) {
+          const int gx = x0 - dil + e;
+          if (yok && gx >= 0 && gx < W) cp_async_16(d + e, src + e);
+          else *reinterpret_cast<float4*>(d + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        for (int e = lane; e < pw; e += 32) {
+          const int gx = x0 - dil + e;
+          if (yok && gx >= 0 && gx < W) cp_async_4(d + e, src + e);
+          else d[e] = 0.f;
+        }
       }
     }
     cp_async_commit();

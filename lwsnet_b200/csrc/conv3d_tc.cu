@@ -28,8 +28,8 @@
 namespace lws {
 
 constexpr int TC_M = 128;                 // rows (voxels) per tile
-constexpr int TC_AROWS = 136;             // rows per A stage (128 + 2 halo, rounded to the 8-row swizzle atom)
-constexpr int TC_ABYTES = TC_AROWS * 128;  // 17408
+constexpr int TC_AROWS = 144;             // rows per A stage: 128 + the kw halo (2 rows for the 3D conv, 16 for dilation 8)
+constexpr int TC_ABYTES = TC_AROWS * 128;  // 18432 = 18 x 1024 (keeps every slot 1024-byte aligned for SWIZZLE_128B)
 constexpr int TC_BROWS = 192;             // 3 kw x (32 hi + 32 lo) rows
 constexpr int TC_BBYTES = TC_BROWS * 128;  // 24576
 constexpr int TC_NS = 3;                  // A ring depth
@@ -40,9 +40,14 @@ constexpr int TC_SMEM = TC_NS * 2 * TC_ABYTES + 2 * TC_BBYTES + 1024 /*align sla
 struct TcArgs {
   float* out;         // CLP [B][R][32]
   const float* bias;  // [32]
-  int R;              // rows per batch element = D*(H+2)*(W+2)
-  int Hp, Wp;         // H+2, W+2
+  int R;              // rows per batch element
+  int Hp, Wp, pad;    // padded plane height / width and the border width (rows with x or y inside the border are zeroed)
   int tiles_per_b, groups_per_b, G, total_groups;
+  int nstages;        // <= 9 operand stages per tile; stage s reads source st_src[s] at row offset st_off[s]
+  int kw_shift;       // rows between the three kw taps inside a stage (1 for the 3D conv, 8 for the dilated 2D conv)
+  int relu;
+  int st_off[9];
+  int st_src[9];
 };
 
 __device__ __forceinline__ uint64_t tc_sdesc(uint32_t saddr) {
@@ -83,8 +88,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    conv3d_c32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                         const TcArgs a) {
+    conv3d_c32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
+                         const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;                                   // [NS][17408]  x tiles (= xh as far as the MMA is concerned)
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(acc_empty, 4);
     mbar_fence_init();
     tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
   }
   if (warp == 1) {
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const int plane = a.Hp * a.Wp;
+  const int nst = a.nstages;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -128,12 +134,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int b = grp / a.groups_per_b;
         const int t0 = (grp - b * a.groups_per_b) * a.G;
         const int ntile = min(a.G, a.tiles_per_b - t0);
-        for (int st = 0; st < 9; ++st, ++bs) {
-          const int kd = st / 3, kh = st - kd * 3;
+        for (int st = 0; st < nst; ++st, ++bs) {
           mbar_wait(b_empty + (bs & 1), ((bs >> 1) & 1) ^ 1);
           mbar_expect_tx(b_full + (bs & 1), TC_BBYTES);
           tma_load_2d(sB + (bs & 1) * TC_BBYTES, &mapB, b_full + (bs & 1), 0, st * TC_BROWS);
-          const int off = (kd - 1) * plane + (kh - 1) * a.Wp - 1;
+          const int off = a.st_off[st];
+          const CUtensorMap* src = a.st_src[st] ? &mapA1 : &mapA;
           for (int g = 0; g < ntile; ++g, ++it) {
             const uint32_t slot = it % TC_NS;
             mbar_wait(a_empty + slot, ((it / TC_NS) & 1) ^ 1);
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
                 "[%2];" ::"r"(smem_u32(sX + slot * TC_ABYTES)),
-                "l"(reinterpret_cast<uint64_t>(&mapA)), "r"(smem_u32(a_full + slot)), "r"(0),
+                "l"(reinterpret_cast<uint64_t>(src)), "r"(smem_u32(a_full + slot)), "r"(0),
                 "r"((t0 + g) * TC_M + off), "r"(b)
                 : "memory");
           }
@@ -156,13 +162,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
       uint32_t it = 0, bs = 0, gi = 0;
+      const uint32_t kwb = (uint32_t)a.kw_shift * 128u;
       for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x, ++gi) {
         const int b = grp / a.groups_per_b;
         const int t0 = (grp - b * a.groups_per_b) * a.G;
         const int ntile = min(a.G, a.tiles_per_b - t0);
         mbar_wait(acc_empty, (gi & 1) ^ 1);  // previous group's accumulators drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int st = 0; st < 9; ++st, ++bs) {
+        for (int st = 0; st < nst; ++st, ++bs) {
           mbar_wait(b_full + (bs & 1), (bs >> 1) & 1);
           const uint32_t b_addr = smem_u32(sB + (bs & 1) * TC_BBYTES);
           for (int g = 0; g < ntile; ++g, ++it) {
@@ -177,8 +184,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               for (int k = 0; k < 4; ++k) {
                 const uint32_t acc = (st | kw | k) != 0;
                 const uint64_t db = tc_sdesc(b_addr + kw * 8192 + k * 32);
-                tc_mma_tf32(d_hh, tc_sdesc(x_addr + kw * 128 + k * 32), db, idesc64, acc);
-                tc_mma_tf32(d_lh, tc_sdesc(l_addr + kw * 128 + k * 32), db, idesc32, acc);
+                tc_mma_tf32(d_hh, tc_sdesc(x_addr + kw * kwb + k * 32), db, idesc64, acc);
+                tc_mma_tf32(d_lh, tc_sdesc(l_addr + kw * kwb + k * 32), db, idesc32, acc);
               }
             }
             tc_commit(a_empty + slot);
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int b = grp / a.groups_per_b;
       const int t0 = (grp - b * a.groups_per_b) * a.G;
       const int ntile = min(a.G, a.tiles_per_b - t0);
-      for (int n = 0; n < 9 * ntile; ++n, ++it) {
+      for (int n = 0; n < nst * ntile; ++n, ++it) {
         const uint32_t slot = it % TC_NS;
         mbar_wait(a_full + slot, (it / TC_NS) & 1);
         const float4* src = reinterpret_cast<const float4*>(sX + slot * TC_ABYTES);
@@ -235,15 +242,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int r = (t0 + g) * TC_M + q * 32 + lane;  // row inside this batch element
         if (r < a.R) {
           const int x = r % a.Wp, y = (r / a.Wp) % a.Hp;
-          const bool border = x == 0 || x == a.Wp - 1 || y == 0 || y == a.Hp - 1;
+          const bool border = x < a.pad || x >= a.Wp - a.pad || y < a.pad || y >= a.Hp - a.pad;
+          const float lo = a.relu ? 0.f : -INFINITY;
           float4* o = reinterpret_cast<float4*>(a.out + ((long long)b * a.R + r) * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 v;
-            v.x = border ? 0.f : fmaxf(acc[4 * j] + bias[4 * j], 0.f);
-            v.y = border ? 0.f : fmaxf(acc[4 * j + 1] + bias[4 * j + 1], 0.f);
-            v.z = border ? 0.f : fmaxf(acc[4 * j + 2] + bias[4 * j + 2], 0.f);
-            v.w = border ? 0.f : fmaxf(acc[4 * j + 3] + bias[4 * j + 3], 0.f);
+            v.x = border ? 0.f : fmaxf(acc[4 * j] + bias[4 * j], lo);
+            v.y = border ? 0.f : fmaxf(acc[4 * j + 1] + bias[4 * j + 1], lo);
+            v.z = border ? 0.f : fmaxf(acc[4 * j + 2] + bias[4 * j + 2], lo);
+            v.w = border ? 0.f : fmaxf(acc[4 * j + 3] + bias[4 * j + 3], lo);
             o[j] = v;
           }
         }
@@ -359,6 +367,49 @@ size_t conv3d_tc_workspace_bytes(int B, int D, int H, int W) {
   return 2 * ((rows * 128 + 255) / 256 * 256);
 }
 
+// One 32-channel implicit-GEMM layer on CLP tensors: out = act(sum over stages/taps of src[row + off] x W + bias).
+// src0/src1: CLP [B][R][32]; wtc: [nstages*192][32] operand table; stage s reads source st_src[s] at row offset st_off[s]
+// (the three kw taps are kw_shift rows apart inside the stage's 144-row box).
+int launch_tc_implicit_gemm(const float* src0, const float* src1, const float* wtc, const float* bias, float* out, int B,
+                            int R, int Hp, int Wp, int pad, int nstages, const int* st_off, const int* st_src,
+                            int kw_shift, int relu, cudaStream_t st) {
+  if (nstages < 1 || nstages > 9 || 2 * kw_shift + TC_M > TC_AROWS) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(conv3d_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R, a.Hp = Hp, a.Wp = Wp, a.pad = pad, a.nstages = nstages, a.kw_shift = kw_shift, a.relu = relu;
+  for (int s = 0; s < nstages; ++s) a.st_off[s] = st_off[s], a.st_src[s] = st_src[s];
+  a.tiles_per_b = (R + TC_M - 1) / TC_M;
+  // tiles per CTA group: the G in {2,3,4} that minimises (rounds over 148 SMs) x G, i.e. the tail of the last round
+  int bestG = TC_GMAX;
+  long long best = -1;
+  for (int G = TC_GMAX; G >= 2; --G) {
+    const long long groups = (long long)B * ((a.tiles_per_b + G - 1) / G);
+    const long long cost_ = ((groups + kNumSMs - 1) / kNumSMs) * G;
+    if (best < 0 || cost_ < best) best = cost_, bestG = G;
+  }
+  a.G = bestG;
+  a.groups_per_b = (a.tiles_per_b + a.G - 1) / a.G;
+  a.total_groups = B * a.groups_per_b;
+  const int grid = a.total_groups < kNumSMs ? a.total_groups : kNumSMs;
+  CUtensorMap mapA0, mapA1, mapB;
+  const uint64_t dimsA[3] = {32, (uint64_t)R, (uint64_t)B}, strA[2] = {128, (uint64_t)R * 128};
+  const uint32_t boxA[3] = {32, TC_AROWS, 1};
+  int rc = make_tensor_map_f32(&mapA0, src0, 3, dimsA, strA, boxA, true);
+  if (rc) return rc;
+  rc = make_tensor_map_f32(&mapA1, src1, 3, dimsA, strA, boxA, true);
+  if (rc) return rc;
+  const uint64_t dimsB[2] = {32, (uint64_t)nstages * TC_BROWS}, strB[1] = {128};
+  const uint32_t boxB[2] = {32, TC_BROWS};
+  rc = make_tensor_map_f32(&mapB, wtc, 2, dimsB, strB, boxB, true);
+  if (rc) return rc;
+  a.out = out, a.bias = bias;
+  conv3d_c32_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA0, mapA1, mapB, a);
+  e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
 // w_first [27][32], b_first [32]; per mid layer: wtc [9*192][32] (hi/lo rows), bias [32]; w_last [32][27]
 int conv3d_stack_c32_tc(const float* cost, const float* affine, const float* w_first, const float* b_first,
                         const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last,
@@ -377,43 +428,17 @@ int conv3d_stack_c32_tc(const float* cost, const float* affine, const float* w_f
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return (int)e;
   }
-  cudaError_t e = cudaFuncSetAttribute(conv3d_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  TcArgs a;
-  a.R = (int)R, a.Hp = Hp, a.Wp = Wp;
-  a.tiles_per_b = (int)((R + TC_M - 1) / TC_M);
-  // tiles per CTA group: the G in {2,3,4} that minimises (rounds over 148 SMs) x G, i.e. the tail of the last round
-  int bestG = TC_GMAX;
-  long long best = -1;
-  for (int G = TC_GMAX; G >= 2; --G) {
-    const long long groups = (long long)B * ((a.tiles_per_b + G - 1) / G);
-    const long long cost_ = ((groups + kNumSMs - 1) / kNumSMs) * G;
-    if (best < 0 || cost_ < best) best = cost_, bestG = G;
-  }
-  a.G = bestG;
-  a.groups_per_b = (a.tiles_per_b + a.G - 1) / a.G;
-  a.total_groups = B * a.groups_per_b;
-  const int grid = a.total_groups < kNumSMs ? a.total_groups : kNumSMs;
-
   float* cur = bufA;
   float* nxt = bufB;
+  int st_off[9], st_src[9];
+  for (int s = 0; s < 9; ++s) st_off[s] = (s / 3 - 1) * Hp * Wp + (s % 3 - 1) * Wp - 1, st_src[s] = 0;
   for (int l = 0; l < layers; ++l) {
-    CUtensorMap mapA, mapB;
-    const uint64_t dimsA[3] = {32, (uint64_t)R, (uint64_t)B}, strA[2] = {128, (uint64_t)R * 128};
-    const uint32_t boxA[3] = {32, TC_AROWS, 1};
-    int rc = make_tensor_map_f32(&mapA, cur, 3, dimsA, strA, boxA, true);
+    int rc = launch_tc_implicit_gemm(cur, cur, wtc[l], bias_mid[l], nxt, B, (int)R, Hp, Wp, 1, 9, st_off, st_src, 1, 1, st);
     if (rc) return rc;
-    const uint64_t dimsB[2] = {32, 9 * TC_BROWS}, strB[1] = {128};
-    const uint32_t boxB[2] = {32, TC_BROWS};
-    rc = make_tensor_map_f32(&mapB, wtc[l], 2, dimsB, strB, boxB, true);
-    if (rc) return rc;
-    a.out = nxt, a.bias = bias_mid[l];
-    conv3d_c32_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA, mapB, a);
-    e = cudaPeekAtLastError();
-    if (e != cudaSuccess) return (int)e;
     float* t = cur;
     cur = nxt, nxt = t;
   }
+  cudaError_t e;
   {
     const long long vox = (long long)B * D * H * W;
     const int blocks = (int)((vox * 8 + 255) / 256 < 148 * 16 ? (vox * 8 + 255) / 256 : 148 * 16);

@@ -10,9 +10,21 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "conv2d.cuh"
 
 namespace lws {
+
+// refinement_tc.cu: channels-last tensor-core path
+struct RefTcWeights {
+  const float *w0[2], *b0[2];
+  const float *dw[3][4], *pwtc[3][4], *bias[3][4];
+  const float *dense_tc, *dense_bias, *last_w;
+};
+size_t refinement_tc_workspace_bytes(int B, int H, int W);
+int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt, float* pred4, void* ws, int B, int H,
+                  int W, cudaStream_t st);
 
 struct DwsepArgs {
   const float* in;    // [B,32,H,W] post-activation
@@ -176,6 +188,8 @@ struct RefLayout {
   size_t r2_w, r2_b;                    // [64][9][32], bias[32]
   size_t r2_dw[4], r2_pw[4], r2_bb[4];
   size_t last_w;                        // [32][9][1]
+  // tensor-core operand tables (refinement_tc.cu): pointwise [64][32] per block, dense conv [6*192][32]
+  size_t r1_pwtc[2][4], r2_pwtc[4], r2_wtc;
   size_t total;
 };
 static RefLayout ref_layout() {
@@ -195,6 +209,10 @@ static RefLayout ref_layout() {
   L.r2_b = take(32);
   for (int j = 0; j < 4; ++j) L.r2_dw[j] = take(32 * 9), L.r2_pw[j] = take(32 * 32), L.r2_bb[j] = take(32);
   L.last_w = take(32 * 9);
+  for (int br = 0; br < 2; ++br)
+    for (int j = 0; j < 4; ++j) L.r1_pwtc[br][j] = take(64 * 32);
+  for (int j = 0; j < 4; ++j) L.r2_pwtc[j] = take(64 * 32);
+  L.r2_wtc = take(6 * 192 * 32);
   L.total = off;
   return L;
 }
@@ -266,12 +284,42 @@ extern "C" int lws_pack_refinement_weights(const float* const* t, int n_tensors,
     }
     pack_conv(r2(29), 1, 32, nullptr, 0, packed + L.last_w, nullptr);
   }
+  // 3xTF32 operand tables from the folded fp32 weights: hi = low 13 mantissa bits cleared, lo = w - hi
+  auto split = [](float w, float* hi, float* lo) {
+    uint32_t u;
+    memcpy(&u, &w, 4);
+    u &= 0xFFFFE000u;
+    memcpy(hi, &u, 4);
+    *lo = w - *hi;
+  };
+  auto pack_pwtc = [&](const float* pwf /*[ci][co]*/, float* tc /*[64][32]*/) {
+    for (int co = 0; co < 32; ++co)
+      for (int ci = 0; ci < 32; ++ci) split(pwf[ci * 32 + co], tc + co * 32 + ci, tc + (32 + co) * 32 + ci);
+  };
+  for (int br = 0; br < 2; ++br)
+    for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r1_pw[br][j], packed + L.r1_pwtc[br][j]);
+  for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r2_pw[j], packed + L.r2_pwtc[j]);
+  {
+    const float* wf = packed + L.r2_w;  // [64][9][32]
+    float* tc = packed + L.r2_wtc;      // stage = src*3 + kh; row (stage*3 + kw)*64 + n
+    for (int src = 0; src < 2; ++src)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          for (int co = 0; co < 32; ++co)
+            for (int k = 0; k < 32; ++k) {
+              const size_t row = (size_t)((src * 3 + kh) * 3 + kw) * 64;
+              split(wf[((size_t)(src * 32 + k) * 9 + kh * 3 + kw) * 32 + co], tc + (row + co) * 32 + k,
+                    tc + (row + 32 + co) * 32 + k);
+            }
+  }
   return LWS_OK;
 }
 
 extern "C" size_t lws_refinement_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return (size_t)B * 128 * H * W * sizeof(float);  // concat (64 ch) + two 32-channel ping-pong buffers
+  // FFMA path: concat (64 ch) + two 32-channel ping-pong buffers; tensor-core path: four bordered channels-last buffers
+  const size_t ffma = (size_t)B * 128 * H * W * sizeof(float), tc = lws::refinement_tc_workspace_bytes(B, H, W);
+  return ffma > tc ? ffma : tc;
 }
 
 extern "C" int lws_refinement_f32(const float* left, const float* pred3, const float* pk, float* pred4, void* ws,
@@ -287,6 +335,20 @@ extern "C" int lws_refinement_f32(const float* left, const float* pred3, const f
   if ((((uintptr_t)ws) | ((uintptr_t)pk) | ((uintptr_t)pred4)) & 15) return LWS_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   const RefLayout L = ref_layout();
+  {
+    const char* env = getenv("LWS_REFINE_TC");
+    if (!(env && env[0] == '0')) {
+      RefTcWeights wt;
+      for (int br = 0; br < 2; ++br) {
+        wt.w0[br] = pk + L.r1_w0[br], wt.b0[br] = pk + L.r1_b0[br];
+        for (int j = 0; j < 4; ++j)
+          wt.dw[br][j] = pk + L.r1_dw[br][j], wt.pwtc[br][j] = pk + L.r1_pwtc[br][j], wt.bias[br][j] = pk + L.r1_b[br][j];
+      }
+      for (int j = 0; j < 4; ++j) wt.dw[2][j] = pk + L.r2_dw[j], wt.pwtc[2][j] = pk + L.r2_pwtc[j], wt.bias[2][j] = pk + L.r2_bb[j];
+      wt.dense_tc = pk + L.r2_wtc, wt.dense_bias = pk + L.r2_b, wt.last_w = pk + L.last_w;
+      return refinement_tc(left, pred3, wt, pred4, ws, B, H, W, st);
+    }
+  }
   const long long hw = (long long)H * W;
   float* cat = (float*)ws;
   float* bufA = cat + (long long)B * 64 * hw;

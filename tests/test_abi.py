@@ -41,7 +41,7 @@ def test_status_strings_and_validation_without_gpu():
     assert lib.lws_conv3d_stack_f32(dummy, dummy, dummy, dummy, 1 << 40, 1, 4, 4, 4, 7, 4, 1, None) == -5
     assert lib.lws_refinement_f32(dummy, dummy, dummy, dummy, dummy, 0, 1, 8, 8, None) == -4
     assert lib.lws_conv3d_stack_workspace_bytes(2, 24, 46, 154, 32, 4) >= 2 * 2 * 32 * 24 * 46 * 154 * 4
-    assert lib.lws_refinement_workspace_bytes(1, 368, 1232) == 128 * 368 * 1232 * 4
+    assert lib.lws_refinement_workspace_bytes(1, 368, 1232) >= 128 * 368 * 1232 * 4
 
 
 def test_pack_conv3d_stack_folds_bn():
@@ -86,7 +86,7 @@ def test_pack_refinement_folds_bn():
     r2.load_state_dict(m.refinement2.state_dict())
     packed = ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2), BN_EPS).numpy()
     from lwsnet_b200._lib import lib
-    assert packed.size == lib.lws_refinement_packed_floats() == 36096
+    assert packed.size == lib.lws_refinement_packed_floats() == 36096 + 12 * 2048 + 6 * 192 * 32
     # first section: conv0 of R1_left [3][9][32] scaled by block-1 BN; then its bias
     bn = m.refinement1_left[1][0]
     s = (bn.weight.double() / torch.sqrt(bn._variance.double() + BN_EPS)).detach().numpy()
@@ -97,7 +97,12 @@ def test_pack_refinement_folds_bn():
     assert np.allclose(packed[864:896], t, rtol=1e-6, atol=1e-7)
     # last section: conv_last [32][9][1], unscaled
     wl = m.refinement2[5].weight.detach().numpy().reshape(32 * 9)
-    assert np.allclose(packed[-288:], wl)
+    assert np.allclose(packed[36096 - 288:36096], wl)
+    # tensor-core operand tables: first pointwise table = tf32-truncated folded weights [co][ci] + remainders, hi + lo == w
+    pwf = packed[896 + 288:896 + 288 + 1024].reshape(32, 32)           # block 1 of R1_left, [ci][co]
+    tc = packed[36096:36096 + 2048].reshape(64, 32)
+    assert np.array_equal(tc[:32] + tc[32:], pwf.T)
+    assert np.all((tc[:32].view(np.uint32) & 0x1FFF) == 0)
     with pytest.raises(Exception):
         ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2)[:-1], BN_EPS)
 

@@ -106,8 +106,9 @@ def test_batch_shard_equivalence(models):
 
 
 def test_exact_fp32_mode_end_to_end(models, monkeypatch):
-    """LWS_CONV3D_TC=0 selects the fp32 FFMA kernels for the C=32 stack: every stage within 2x the fp32 oracle's floor."""
+    """LWS_CONV3D_TC=0 LWS_REFINE_TC=0 select the fp32 FFMA kernels everywhere: every stage within 2x the fp32 oracle's floor."""
     monkeypatch.setenv("LWS_CONV3D_TC", "0")
+    monkeypatch.setenv("LWS_REFINE_TC", "0")
     O, o32, o64, prod = models
     left, right = O.synthetic_pair(1, 128, 256, seed=3, max_disp=30.0)
     with torch.no_grad():

@@ -26,11 +26,13 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
   extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
   for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
   __syncthreads();
-  const int xq = blockIdx.x * blockDim.x + threadIdx.x;
-  const int yo = blockIdx.y;
-  const int b = blockIdx.z;
-  const int x0 = xq * 4;
-  if (x0 >= a.Wo) return;
+  // flattened (row, 4-pixel group) index so blocks stay full whatever the row length is
+  const int wq = (a.Wo + 3) >> 2;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= wq * a.Ho) return;
+  const int yo = item / wq;
+  const int b = blockIdx.y;
+  const int x0 = (item - yo * wq) * 4;
   const long long in_hw = (long long)a.Hi * a.Wi;
   const long long out_hw = (long long)a.Ho * a.Wo;
   const float* in_b = a.in + (long long)b * a.Cin * in_hw;
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
 }
 
 static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
-  dim3 grid(cdiv(cdiv(a.Wo, 4), 128), a.Ho, B);
+  dim3 grid(cdiv(cdiv(a.Wo, 4) * a.Ho, 128), B);
   const size_t smem = (size_t)a.Cin * 9 * cout * sizeof(float);
   switch (cout) {
     case 4: fe_conv_kernel<4><<<grid, 128, smem, st>>>(a); break;
@@ -212,7 +214,7 @@ extern "C" int lws_feature_extraction_f32(const float* img, const float* pk, flo
   LWS_CHECK_PTR(f4);
   LWS_CHECK_PTR(f2);
   LWS_CHECK_PTR(ws);
-  if (B <= 0 || H <= 0 || W <= 0 || (H & 7) || (W & 7) || B > 65535 || H / 2 > 65535) return LWS_ERR_BAD_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || (H & 7) || (W & 7) || B > 65535) return LWS_ERR_BAD_SHAPE;
   if (ws_bytes < lws_feature_extraction_workspace_bytes(B, H, W)) return LWS_ERR_WORKSPACE_TOO_SMALL;
   if ((((uintptr_t)ws) | ((uintptr_t)pk) | ((uintptr_t)f8) | ((uintptr_t)f4) | ((uintptr_t)f2)) & 15) return LWS_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;

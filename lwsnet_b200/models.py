@@ -84,8 +84,12 @@ class LWSNet(nn.Module):
         if img_h % 8 or img_w % 8:
             raise ValueError("H and W must be multiples of 8 (hourglass skip adds, reference models/submodules.py:103)")
         left_input = left_input.contiguous()
-        feats_l = self.feature_extraction(left_input)
-        feats_r = self.feature_extraction(right_input)
+        # the reference runs the shared-weight extractor twice (models.py:110-111); one launch set over the stacked pair is
+        # the same arithmetic per image (every kernel is batch-independent) and keeps the small 1/8-resolution layers fuller
+        n = left_input.shape[0]
+        feats = self.feature_extraction(torch.cat([left_input, right_input.contiguous()]))
+        feats_l = [f[:n] for f in feats]
+        feats_r = [f[n:] for f in feats]
         pred = []
         for scale in range(len(feats_l)):
             pred.append(self._stage(scale, feats_l[scale].contiguous(), feats_r[scale].contiguous(),

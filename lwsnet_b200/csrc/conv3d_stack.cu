@@ -22,10 +22,10 @@
 namespace lws {
 
 // conv3d_tc.cu: tcgen05 3xTF32 path for C = 32
-size_t conv3d_tc_workspace_bytes(int B, int D, int H, int W);
-int conv3d_stack_c32_tc(const float* cost, const float* affine, const float* w_first, const float* b_first,
-                        const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last,
-                        float* out, void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
+size_t conv3d_tc_workspace_bytes(int B, int C, int D, int H, int W);
+int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,
+                    const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last, float* out,
+                    void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
 constexpr int kTcLayerFloats = 9 * 192 * 32;  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
 
 struct Conv3dArgs {
@@ -266,8 +266,9 @@ static size_t packed_offset(int C, int layers, int conv, bool bias) {
 static size_t packed_tc_offset(int C, int layers, int mid_layer) {
   return packed_offset(C, layers, layers + 2, false) + (size_t)mid_layer * kTcLayerFloats;
 }
+static bool has_tc_tables(int C) { return C == 32 || C == 8; }
 static bool use_tc_path(int C) {
-  if (C != 32) return false;
+  if (!has_tc_tables(C)) return false;
   const char* e = getenv("LWS_CONV3D_TC");
   return !(e && e[0] == '0');
 }
@@ -307,7 +308,7 @@ static int run_stack(const float* cost, const float* pk, float* out, float* bufA
 
 extern "C" size_t lws_conv3d_stack_packed_floats(int C, int layers) {
   if (C <= 0 || layers < 0) return 0;
-  return lws::packed_offset(C, layers, layers + 2, false) + (C == 32 ? (size_t)layers * lws::kTcLayerFloats : 0);
+  return lws::packed_offset(C, layers, layers + 2, false) + (lws::has_tc_tables(C) ? (size_t)layers * lws::kTcLayerFloats : 0);
 }
 
 extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const float* const* bn_weight,
@@ -335,24 +336,43 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
           w[((size_t)ci * 27 + t) * cout + co] = (float)((double)conv_w[i][((size_t)co * cin + ci) * 27 + t] * s);
     }
   }
-  if (C == 32) {
-    // 3xTF32 operand tables: row (stage*3 + kw)*64 + n holds, over ci, wh = tf32-truncated folded weight of cout n
-    // (n < 32) or wl = w - wh of cout n-32 (n >= 32); stage = kd*3 + kh
+  if (has_tc_tables(C)) {
+    // 3xTF32 operand tables, [9 stages = (kd,kh)][3 shifts][64 rows][32]: rows 0..31 hold wh (tf32-truncated folded
+    // weights), rows 32..63 the remainders wl = w - wh.
+    //  C = 32: a GEMM row is one voxel, shift = kw: row n = cout, column k = cin.
+    //  C = 8 : a GEMM row is 4 consecutive voxels u = 0..3 (n = u_out*8 + cout, k = u_in*8 + cin).  Shift 1 (same row)
+    //          carries the taps with u_in - u_out = kw - 1 in {-1,0,1}; shift 0 (previous row) only its last voxel
+    //          (u_in = 3 -> u_out = 0, kw = 0); shift 2 (next row) only its first voxel (u_in = 0 -> u_out = 3, kw = 2).
+    auto split = [](float w, float* hi, float* lo) {
+      uint32_t u;
+      memcpy(&u, &w, 4);
+      u &= 0xFFFFE000u;
+      memcpy(hi, &u, 4);
+      *lo = w - *hi;
+    };
     for (int l = 0; l < layers; ++l) {
       const float* wf = packed + packed_offset(C, layers, l + 1, false);  // [ci][27][co]
       float* tc = packed + packed_tc_offset(C, layers, l);
-      for (int t = 0; t < 27; ++t)
-        for (int co = 0; co < 32; ++co)
-          for (int ci = 0; ci < 32; ++ci) {
-            const float w = wf[((size_t)ci * 27 + t) * 32 + co];
-            uint32_t u;
-            memcpy(&u, &w, 4);
-            u &= 0xFFFFE000u;
-            float hi;
-            memcpy(&hi, &u, 4);
-            tc[((size_t)t * 64 + co) * 32 + ci] = hi;
-            tc[((size_t)t * 64 + 32 + co) * 32 + ci] = w - hi;
-          }
+      memset(tc, 0, kTcLayerFloats * sizeof(float));
+      for (int stg = 0; stg < 9; ++stg)
+        for (int kw = 0; kw < 3; ++kw)
+          for (int co = 0; co < C; ++co)
+            for (int ci = 0; ci < C; ++ci) {
+              const float w = wf[((size_t)ci * 27 + stg * 3 + kw) * C + co];
+              if (C == 32) {
+                float* base = tc + (size_t)(stg * 3 + kw) * 64 * 32;
+                split(w, base + co * 32 + ci, base + (32 + co) * 32 + ci);
+              } else {
+                for (int uo = 0; uo < 4; ++uo) {
+                  const int ui = uo + kw - 1;  // input voxel relative to this row's first voxel
+                  int shift = 1, uin = ui;
+                  if (ui < 0) shift = 0, uin = 3;
+                  else if (ui > 3) shift = 2, uin = 0;
+                  float* base = tc + (size_t)(stg * 3 + shift) * 64 * 32;
+                  split(w, base + (uo * 8 + co) * 32 + uin * 8 + ci, base + (32 + uo * 8 + co) * 32 + uin * 8 + ci);
+                }
+              }
+            }
     }
   }
   return LWS_OK;
@@ -362,7 +382,7 @@ extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, i
   (void)layers;
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
-  const size_t tc = C == 32 ? lws::conv3d_tc_workspace_bytes(B, D, H, W) : 0;
+  const size_t tc = lws::has_tc_tables(C) ? lws::conv3d_tc_workspace_bytes(B, C, D, H, W) : 0;
   return 2 * act > tc ? 2 * act : tc;
 }
 
@@ -388,9 +408,9 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
       wtc[l] = pk + packed_tc_offset(C, layers, l);
       bmid[l] = pk + packed_offset(C, layers, l + 1, true);
     }
-    return conv3d_stack_c32_tc(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
-                               wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
-                               add_skip, st);
+    return conv3d_stack_tc(C, cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
+                           wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
+                           add_skip, st);
   }
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
   float* bufA = (float*)ws;

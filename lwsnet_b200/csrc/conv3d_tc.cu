@@ -32,7 +32,7 @@ constexpr int TC_AROWS = 144;             // rows per A stage: 128 + the kw halo
 constexpr int TC_ABYTES = TC_AROWS * 128;  // 18432 = 18 x 1024 (keeps every slot 1024-byte aligned for SWIZZLE_128B)
 constexpr int TC_BROWS = 192;             // 3 kw x (32 hi + 32 lo) rows
 constexpr int TC_BBYTES = TC_BROWS * 128;  // 24576
-constexpr int TC_NS = 3;                  // A ring depth
+constexpr int TC_NS = 4;                  // A ring depth
 constexpr int TC_GMAX = 4;                // tiles per CTA group (4 x 96 TMEM columns)
 constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM = TC_NS * 2 * TC_ABYTES + 2 * TC_BBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -46,6 +46,8 @@ struct TcArgs {
   int nstages;        // <= 9 operand stages per tile; stage s reads source st_src[s] at row offset st_off[s]
   int kw_shift;       // rows between the three kw taps inside a stage (1 for the 3D conv, 8 for the dilated 2D conv)
   int relu;
+  int Hi, Wi;         // interior (un-padded) plane size: voxels with x or y outside [pad, pad+size) are written as zeros
+  int kmask[3];       // per kw shift: which of the four K=8 steps carry non-zero weights (0xF for 32-channel voxels)
   int st_off[9];
   int st_src[9];
 };
@@ -87,8 +89,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// CPV = channels per voxel.  32: a row is one voxel.  8: a row is 4 consecutive voxels (x fastest) and the kw taps are
+// the rows g-1 / g / g+1 with block-structured weight tables (see pack_tc_table_c8): only the K=8 step holding the
+// neighbouring voxel is issued for the side rows.
+template <int CPV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    conv3d_c32_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
+    tc_implicit_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
                          const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       uint32_t it = 0, bs = 0;
       for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x) {
         const int b = grp / a.groups_per_b;
@@ -157,52 +163,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      // M=128, K-major A and B, fp32 accumulate, tf32 operands; N = 64 / 32
-      const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      uint32_t it = 0, bs = 0, gi = 0;
-      const uint32_t kwb = (uint32_t)a.kw_shift * 128u;
-      for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x, ++gi) {
-        const int b = grp / a.groups_per_b;
-        const int t0 = (grp - b * a.groups_per_b) * a.G;
-        const int ntile = min(a.G, a.tiles_per_b - t0);
-        mbar_wait(acc_empty, (gi & 1) ^ 1);  // previous group's accumulators drained
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int st = 0; st < nst; ++st, ++bs) {
-          mbar_wait(b_full + (bs & 1), (bs >> 1) & 1);
-          const uint32_t b_addr = smem_u32(sB + (bs & 1) * TC_BBYTES);
-          for (int g = 0; g < ntile; ++g, ++it) {
-            const uint32_t slot = it % TC_NS;
-            mbar_wait(a_conv + slot, (it / TC_NS) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t x_addr = smem_u32(sX + slot * TC_ABYTES), l_addr = smem_u32(sL + slot * TC_ABYTES);
+    // The whole warp walks the schedule (so control flow stays converged); one elected lane issues the MMAs and commits.
+    // M=128, K-major A and B, fp32 accumulate, tf32 operands; N = 64 / 32
+    const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
+    const uint32_t km0 = a.kmask[0], km1 = a.kmask[1], km2 = a.kmask[2];
+    uint32_t it = 0, bs = 0, gi = 0;
+    const uint32_t kwq = ((uint32_t)a.kw_shift * 128u) >> 4;  // kw shift in 16-byte descriptor units
+    for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x, ++gi) {
+      const int b = grp / a.groups_per_b;
+      const int t0 = (grp - b * a.groups_per_b) * a.G;
+      const int ntile = min(a.G, a.tiles_per_b - t0);
+      mbar_wait(acc_empty, (gi & 1) ^ 1);  // previous group's accumulators drained
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int st = 0; st < nst; ++st, ++bs) {
+        mbar_wait(b_full + (bs & 1), (bs >> 1) & 1);
+        const uint32_t b_lo = ((smem_u32(sB + (bs & 1) * TC_BBYTES) & 0x3FFFF) >> 4) | (1u << 16);
+        for (int g = 0; g < ntile; ++g, ++it) {
+          const uint32_t slot = it % TC_NS;
+          mbar_wait(a_conv + slot, (it / TC_NS) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one_sync()) {
+            const uint32_t x_lo = ((smem_u32(sX + slot * TC_ABYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t l_lo = ((smem_u32(sL + slot * TC_ABYTES) & 0x3FFFF) >> 4) | (1u << 16);
             const uint32_t d_hh = tmem + g * 96, d_lh = tmem + g * 96 + 64;
+            uint32_t acc = st != 0;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t km = kw == 0 ? km0 : (kw == 1 ? km1 : km2);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t acc = (st | kw | k) != 0;
-                const uint64_t db = tc_sdesc(b_addr + kw * 8192 + k * 32);
-                tc_mma_tf32(d_hh, tc_sdesc(x_addr + kw * kwb + k * 32), db, idesc64, acc);
-                tc_mma_tf32(d_lh, tc_sdesc(l_addr + kw * kwb + k * 32), db, idesc32, acc);
+                if (!((km >> k) & 1)) continue;
+                const uint64_t db = desc_hi | (uint64_t)(b_lo + kw * (8192 >> 4) + k * 2);
+                tc_mma_tf32(d_hh, desc_hi | (uint64_t)(x_lo + kw * kwq + k * 2), db, idesc64, acc);
+                tc_mma_tf32(d_lh, desc_hi | (uint64_t)(l_lo + kw * kwq + k * 2), db, idesc32, acc);
+                acc = 1;
               }
             }
             tc_commit(a_empty + slot);
           }
-          tc_commit(b_empty + (bs & 1));
+          __syncwarp();
         }
-        tc_commit(acc_full);
+        if (elect_one_sync()) tc_commit(b_empty + (bs & 1));
+        __syncwarp();
       }
+      if (elect_one_sync()) tc_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // ================================ xl converter + epilogue (warps 2..5) ================================
     const int ct = tid - 64;  // 0..127
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     uint32_t it = 0, gi = 0;
-    float bias[32];
+    float bias[CPV];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) bias[j] = __ldg(a.bias + j);
+    for (int j = 0; j < CPV; ++j) bias[j] = __ldg(a.bias + j);
     for (int grp = blockIdx.x; grp < a.total_groups; grp += gridDim.x, ++gi) {
       const int b = grp / a.groups_per_b;
       const int t0 = (grp - b * a.groups_per_b) * a.G;
@@ -241,18 +257,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int j = 0; j < 32; ++j) acc[j] += t[j];
         const int r = (t0 + g) * TC_M + q * 32 + lane;  // row inside this batch element
         if (r < a.R) {
-          const int x = r % a.Wp, y = (r / a.Wp) % a.Hp;
-          const bool border = x < a.pad || x >= a.Wp - a.pad || y < a.pad || y >= a.Hp - a.pad;
+          constexpr int VPR = 32 / CPV;  // voxels per row
           const float lo = a.relu ? 0.f : -INFINITY;
           float4* o = reinterpret_cast<float4*>(a.out + ((long long)b * a.R + r) * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v;
-            v.x = border ? 0.f : fmaxf(acc[4 * j] + bias[4 * j], lo);
-            v.y = border ? 0.f : fmaxf(acc[4 * j + 1] + bias[4 * j + 1], lo);
-            v.z = border ? 0.f : fmaxf(acc[4 * j + 2] + bias[4 * j + 2], lo);
-            v.w = border ? 0.f : fmaxf(acc[4 * j + 3] + bias[4 * j + 3], lo);
-            o[j] = v;
+          for (int u = 0; u < VPR; ++u) {
+            const int vi = r * VPR + u;
+            const int x = vi % a.Wp, y = (vi / a.Wp) % a.Hp;
+            const bool border = x < a.pad || x >= a.pad + a.Wi || y < a.pad || y >= a.pad + a.Hi;
+#pragma unroll
+            for (int j = 0; j < CPV / 4; ++j) {
+              const int c = u * CPV + 4 * j;
+              float4 v;
+              v.x = border ? 0.f : fmaxf(acc[c] + bias[c % CPV], lo);
+              v.y = border ? 0.f : fmaxf(acc[c + 1] + bias[(c + 1) % CPV], lo);
+              v.z = border ? 0.f : fmaxf(acc[c + 2] + bias[(c + 2) % CPV], lo);
+              v.w = border ? 0.f : fmaxf(acc[c + 3] + bias[(c + 3) % CPV], lo);
+              o[c / 4] = v;
+            }
           }
         }
       }
@@ -267,29 +289,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// ---- 1 -> 32 on the raw cost, writing CLP (incl. the zero border); 8 lanes per voxel, 4 couts per lane -------------
+// ---- 1 -> C on the raw cost, writing CLP (incl. the zero border); C/4 lanes per voxel, 4 couts per lane ---------------
+// CLP geometry: voxel (d, y, x) with y in [0, H+2), x in [0, Wp); interior = y in [1, H], x in [1, W]; Wp >= W + 2.
+template <int C>
 __global__ void __launch_bounds__(256)
-    conv3d_first_clp_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][32]*/,
+    conv3d_first_clp_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][C]*/,
                             const float* __restrict__ bias, const float* __restrict__ affine, float* __restrict__ out,
-                            int D, int H, int W, long long total_rows) {
-  __shared__ __align__(16) float sW[27 * 32];
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[i] = __ldg(w + i);
+                            int D, int H, int W, int Wp, long long total_vox) {
+  constexpr int LPV = C / 4;
+  __shared__ __align__(16) float sW[27 * C];
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sW[i] = __ldg(w + i);
   __syncthreads();
   const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
-  const int sub = threadIdx.x & 7;
-  const int Hp = H + 2, Wp = W + 2;
+  const int sub = threadIdx.x % LPV;
+  const int Hp = H + 2;
   const long long hw = (long long)H * W;
   const float4 bv = *reinterpret_cast<const float4*>(bias + sub * 4);
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < total_rows;
-       row += ((long long)gridDim.x * blockDim.x) >> 3) {
-    const int x = (int)(row % Wp);
-    long long t = row / Wp;
+  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPV; vox < total_vox;
+       vox += ((long long)gridDim.x * blockDim.x) / LPV) {
+    const int x = (int)(vox % Wp);
+    long long t = vox / Wp;
     const int y = (int)(t % Hp);
     t /= Hp;
     const int d = (int)(t % D);
     const int b = (int)(t / D);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool border = x == 0 || x == Wp - 1 || y == 0 || y == Hp - 1;
+    const bool border = x < 1 || x > W || y < 1 || y > H;
     if (!border) {
       const float* cb = cost + (long long)b * D * hw;
 #pragma unroll
@@ -305,7 +330,7 @@ __global__ void __launch_bounds__(256)
             const int gw = x - 1 + kw - 1;
             if (gw < 0 || gw >= W) continue;
             const float v = fmaxf(fmaf(__ldg(cb + (long long)gd * hw + (long long)gh * W + gw), s0, t0), 0.f);
-            const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 4);
+            const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 4);
             acc.x = fmaf(v, wv.x, acc.x), acc.y = fmaf(v, wv.y, acc.y), acc.z = fmaf(v, wv.z, acc.z),
             acc.w = fmaf(v, wv.w, acc.w);
           }
@@ -314,30 +339,32 @@ __global__ void __launch_bounds__(256)
       acc.x = fmaxf(acc.x + bv.x, 0.f), acc.y = fmaxf(acc.y + bv.y, 0.f), acc.z = fmaxf(acc.z + bv.z, 0.f),
       acc.w = fmaxf(acc.w + bv.w, 0.f);
     }
-    *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
+    *reinterpret_cast<float4*>(out + vox * C + sub * 4) = acc;
   }
 }
 
-// ---- 32 -> 1 from CLP (+ skip), NCDHW output; 8 lanes per voxel, 4 input channels per lane ---------------------------
+// ---- C -> 1 from CLP (+ skip), NCDHW output; C/4 lanes per voxel, 4 input channels per lane --------------------------
+template <int C>
 __global__ void __launch_bounds__(256)
-    conv3d_last_clp_kernel(const float* __restrict__ act, const float* __restrict__ w /*[32][27] = packed [Cin][27][1]*/,
-                           const float* __restrict__ skip, float* __restrict__ out, int D, int H, int W,
+    conv3d_last_clp_kernel(const float* __restrict__ act, const float* __restrict__ w /*[C][27] = packed [Cin][27][1]*/,
+                           const float* __restrict__ skip, float* __restrict__ out, int D, int H, int W, int Wp,
                            long long total_vox) {
-  __shared__ __align__(16) float sW[27 * 32];  // [tap][ci]
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[(i % 27) * 32 + i / 27] = __ldg(w + i);
+  constexpr int LPV = C / 4;
+  __shared__ __align__(16) float sW[27 * C];  // [tap][ci]
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sW[(i % 27) * C + i / 27] = __ldg(w + i);
   __syncthreads();
-  const int sub = threadIdx.x & 7;
-  const int Hp = H + 2, Wp = W + 2;
-  const long long R = (long long)D * Hp * Wp;
-  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; vox < total_vox;
-       vox += ((long long)gridDim.x * blockDim.x) >> 3) {
+  const int sub = threadIdx.x % LPV;
+  const int Hp = H + 2;
+  const long long R = (long long)D * Hp * Wp;  // voxels per batch element
+  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPV; vox < total_vox;
+       vox += ((long long)gridDim.x * blockDim.x) / LPV) {
     const int x = (int)(vox % W);
     long long t = vox / W;
     const int y = (int)(t % H);
     t /= H;
     const int d = (int)(t % D);
     const int b = (int)(t / D);
-    const float* base = act + ((long long)b * R) * 32 + sub * 4;
+    const float* base = act + ((long long)b * R) * C + sub * 4;
     float acc = 0.f;
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
@@ -348,37 +375,42 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const long long r = ((long long)gd * Hp + (y + kh)) * Wp + (x + kw);  // padded coords: (y+1)+(kh-1), (x+1)+(kw-1)
-          const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * 32));
-          const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 4);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * C));
+          const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 4);
           acc = fmaf(v.x, wv.x, acc), acc = fmaf(v.y, wv.y, acc), acc = fmaf(v.z, wv.z, acc), acc = fmaf(v.w, wv.w, acc);
         }
       }
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+#pragma unroll
+    for (int m = 1; m < LPV; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
     if (sub == 0) out[vox] = acc + (skip ? __ldg(skip + vox) : 0.f);
   }
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
-size_t conv3d_tc_workspace_bytes(int B, int D, int H, int W) {
-  const size_t rows = (size_t)B * D * (H + 2) * (W + 2);
-  return 2 * ((rows * 128 + 255) / 256 * 256);
+static int clp_wp(int C, int W) { return C == 32 ? W + 2 : round_up(W + 2, 32 / C); }
+
+size_t conv3d_tc_workspace_bytes(int B, int C, int D, int H, int W) {
+  const size_t vox = (size_t)B * D * (H + 2) * clp_wp(C, W);
+  return 2 * ((vox * C * sizeof(float) + 255) / 256 * 256);
 }
 
-// One 32-channel implicit-GEMM layer on CLP tensors: out = act(sum over stages/taps of src[row + off] x W + bias).
-// src0/src1: CLP [B][R][32]; wtc: [nstages*192][32] operand table; stage s reads source st_src[s] at row offset st_off[s]
-// (the three kw taps are kw_shift rows apart inside the stage's 144-row box).
+// One implicit-GEMM layer on CLP tensors viewed as rows of 32 floats: out = act(sum over stages/taps of src[row + off] x W
+// + bias).  src0/src1: [B][R][32]; wtc: [nstages*192][32] operand table; stage s reads source st_src[s] at row offset
+// st_off[s] (the three kw taps are kw_shift rows apart inside the stage's 144-row box); Hp x Wp voxels per plane,
+// interior Hi x Wi behind a `pad`-wide border; cpv = channels per voxel (32 or 8).
 int launch_tc_implicit_gemm(const float* src0, const float* src1, const float* wtc, const float* bias, float* out, int B,
-                            int R, int Hp, int Wp, int pad, int nstages, const int* st_off, const int* st_src,
-                            int kw_shift, int relu, cudaStream_t st) {
-  if (nstages < 1 || nstages > 9 || 2 * kw_shift + TC_M > TC_AROWS) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(conv3d_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+                            int R, int Hp, int Wp, int pad, int Hi, int Wi, int cpv, int nstages, const int* st_off,
+                            const int* st_src, int kw_shift, int relu, cudaStream_t st) {
+  if (nstages < 1 || nstages > 9 || 2 * kw_shift + TC_M > TC_AROWS || (cpv != 32 && cpv != 8)) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = cpv == 32 ? cudaFuncSetAttribute(tc_implicit_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)
+                            : cudaFuncSetAttribute(tc_implicit_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e != cudaSuccess) return (int)e;
   TcArgs a;
   memset(&a, 0, sizeof(a));
-  a.R = R, a.Hp = Hp, a.Wp = Wp, a.pad = pad, a.nstages = nstages, a.kw_shift = kw_shift, a.relu = relu;
+  a.R = R, a.Hp = Hp, a.Wp = Wp, a.pad = pad, a.Hi = Hi, a.Wi = Wi, a.nstages = nstages, a.kw_shift = kw_shift, a.relu = relu;
+  if (cpv == 32) a.kmask[0] = a.kmask[1] = a.kmask[2] = 0xF;
+  else a.kmask[0] = 0x8, a.kmask[1] = 0xF, a.kmask[2] = 0x1;  // side rows: only the K=8 step of the adjacent voxel
   for (int s = 0; s < nstages; ++s) a.st_off[s] = st_off[s], a.st_src[s] = st_src[s];
   a.tiles_per_b = (R + TC_M - 1) / TC_M;
   // tiles per CTA group: the G in {2,3,4} that minimises (rounds over 148 SMs) x G, i.e. the tail of the last round
@@ -405,48 +437,65 @@ int launch_tc_implicit_gemm(const float* src0, const float* src1, const float* w
   rc = make_tensor_map_f32(&mapB, wtc, 2, dimsB, strB, boxB, true);
   if (rc) return rc;
   a.out = out, a.bias = bias;
-  conv3d_c32_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(mapA0, mapA1, mapB, a);
+  if (cpv == 32) tc_implicit_gemm_kernel<32><<<grid, TC_THREADS, TC_SMEM, st>>>(mapA0, mapA1, mapB, a);
+  else tc_implicit_gemm_kernel<8><<<grid, TC_THREADS, TC_SMEM, st>>>(mapA0, mapA1, mapB, a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }
 
-// w_first [27][32], b_first [32]; per mid layer: wtc [9*192][32] (hi/lo rows), bias [32]; w_last [32][27]
-int conv3d_stack_c32_tc(const float* cost, const float* affine, const float* w_first, const float* b_first,
-                        const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last,
-                        float* out, void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st) {
-  const int Hp = H + 2, Wp = W + 2;
-  const long long R = (long long)D * Hp * Wp;
+// w_first [27][C], b_first [C]; per mid layer: wtc [9*192][32] (hi/lo rows), bias [C]; w_last [C][27]
+template <int C>
+static int conv3d_stack_tc_impl(const float* cost, const float* affine, const float* w_first, const float* b_first,
+                                const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last,
+                                float* out, void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st) {
+  const int Hp = H + 2, Wp = clp_wp(C, W);
+  const long long vox_b = (long long)D * Hp * Wp;      // voxels per batch element
+  const long long R = vox_b * C / 32;                   // 128-byte rows per batch element
   if (R >= (1ll << 31) - 4096) return LWS_ERR_BAD_SHAPE;
-  const size_t act_bytes = conv3d_tc_workspace_bytes(B, D, H, W) / 2;
+  const size_t act_bytes = conv3d_tc_workspace_bytes(B, C, D, H, W) / 2;
   float* bufA = (float*)ws;
   float* bufB = (float*)((char*)ws + act_bytes);
-  const long long rows = (long long)B * R;
-
+  const long long nvox = (long long)B * vox_b;
+  constexpr int LPV = C / 4;
+  cudaError_t e;
   {
-    const int blocks = (int)((rows * 8 + 255) / 256 < 148 * 16 ? (rows * 8 + 255) / 256 : 148 * 16);
-    conv3d_first_clp_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, bufA, D, H, W, rows);
-    cudaError_t e = cudaPeekAtLastError();
-    if (e != cudaSuccess) return (int)e;
+    const long long thr = nvox * LPV;
+    const int blocks = (int)((thr + 255) / 256 < 148 * 16 ? (thr + 255) / 256 : 148 * 16);
+    conv3d_first_clp_kernel<C><<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, bufA, D, H, W, Wp, nvox);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   float* cur = bufA;
   float* nxt = bufB;
   int st_off[9], st_src[9];
-  for (int s = 0; s < 9; ++s) st_off[s] = (s / 3 - 1) * Hp * Wp + (s % 3 - 1) * Wp - 1, st_src[s] = 0;
+  const int rows_line = Wp * C / 32;  // rows per x line
+  for (int s = 0; s < 9; ++s) st_off[s] = ((s / 3 - 1) * Hp + (s % 3 - 1)) * rows_line - 1, st_src[s] = 0;
   for (int l = 0; l < layers; ++l) {
-    int rc = launch_tc_implicit_gemm(cur, cur, wtc[l], bias_mid[l], nxt, B, (int)R, Hp, Wp, 1, 9, st_off, st_src, 1, 1, st);
+    int rc = launch_tc_implicit_gemm(cur, cur, wtc[l], bias_mid[l], nxt, B, (int)R, Hp, Wp, 1, H, W, C, 9, st_off, st_src, 1,
+                                     1, st);
     if (rc) return rc;
     float* t = cur;
     cur = nxt, nxt = t;
   }
-  cudaError_t e;
   {
     const long long vox = (long long)B * D * H * W;
-    const int blocks = (int)((vox * 8 + 255) / 256 < 148 * 16 ? (vox * 8 + 255) / 256 : 148 * 16);
-    conv3d_last_clp_kernel<<<blocks, 256, 0, st>>>(cur, w_last, add_skip ? cost : nullptr, out, D, H, W, vox);
-    e = cudaPeekAtLastError();
-    if (e != cudaSuccess) return (int)e;
+    const long long thr = vox * LPV;
+    const int blocks = (int)((thr + 255) / 256 < 148 * 16 ? (thr + 255) / 256 : 148 * 16);
+    conv3d_last_clp_kernel<C><<<blocks, 256, 0, st>>>(cur, w_last, add_skip ? cost : nullptr, out, D, H, W, Wp, vox);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   return LWS_OK;
+}
+
+int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,
+                    const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last, float* out,
+                    void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st) {
+  if (C == 32)
+    return conv3d_stack_tc_impl<32>(cost, affine, w_first, b_first, wtc, bias_mid, layers, w_last, out, ws, B, D, H, W,
+                                    add_skip, st);
+  if (C == 8)
+    return conv3d_stack_tc_impl<8>(cost, affine, w_first, b_first, wtc, bias_mid, layers, w_last, out, ws, B, D, H, W,
+                                   add_skip, st);
+  return LWS_ERR_UNSUPPORTED;
 }
 
 }  // namespace lws

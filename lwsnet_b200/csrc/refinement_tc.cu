@@ -19,8 +19,8 @@
 namespace lws {
 
 int launch_tc_implicit_gemm(const float* src0, const float* src1, const float* wtc, const float* bias, float* out, int B,
-                            int R, int Hp, int Wp, int pad, int nstages, const int* st_off, const int* st_src,
-                            int kw_shift, int relu, cudaStream_t st);
+                            int R, int Hp, int Wp, int pad, int Hi, int Wi, int cpv, int nstages, const int* st_off,
+                            const int* st_src, int kw_shift, int relu, cudaStream_t st);
 
 constexpr int RP = 16;  // border of the refinement CLP tensors
 
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
     }
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one_sync()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_addr = smem_u32(sA + buf * 16384), l_addr = smem_u32(sL + buf * 16384), b_addr = smem_u32(sB);
       const uint32_t d_hh = tmem + buf * 96, d_lh = d_hh + 64;
@@ -339,8 +339,8 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
   {
     int st_off[6], st_src[6];
     for (int s = 0; s < 6; ++s) st_off[s] = (s % 3 - 1) * 8 * Wp - 8, st_src[s] = s / 3;
-    if ((rc = launch_tc_implicit_gemm(catL, catD, wt.dense_tc, wt.dense_bias, ping, B, (int)R, Hp, Wp, RP, 6, st_off, st_src,
-                                      8, 1, st)))
+    if ((rc = launch_tc_implicit_gemm(catL, catD, wt.dense_tc, wt.dense_bias, ping, B, (int)R, Hp, Wp, RP, H, W, 32, 6, st_off,
+                                      st_src, 8, 1, st)))
       return rc;
   }
   float* cur = ping;

@@ -108,7 +108,8 @@ struct DwTcArgs {
   const float* dw;    // [32][9]
   const float* pwtc;  // [64][32]: rows 0..31 = tf32-truncated folded pointwise weights (row = cout, col = cin), 32..63 = remainder
   const float* bias;  // [32]
-  int R, Hp, Wp, dil, relu, tiles_per_b, total_tiles;
+  int R, Hp, Wp, dil, relu;
+  int nxt, segs, seg_len, total_items;  // strip schedule: item = (b, x tile, row phase, segment of seg_len phase-rows)
 };
 constexpr int DT_THREADS = 256;
 constexpr int DT_SMEM = 4 * 16384 + 8192 + 1024 + 64;
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
   const int dil = a.dil, Wp = a.Wp, Hp = a.Hp, R = a.R;
   const long long tap_step_y = (long long)dil * Wp * 32, tap_step_x = (long long)dil * 32;
 
-  auto epilogue = [&](int j, int tile) {
+  // tile = 128 consecutive pixels of one image line: rows r0 .. r0+127 of batch element b, of which the first `nval` exist
+  auto epilogue = [&](int j, int b, int r0, int nval) {
     const int pbuf = j & 1;
     mbar_wait(mma_bar + pbuf, (j >> 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -192,9 +194,9 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
     dt_ld16(taddr + 64, t);
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] += t[c];
-    const int b = tile / a.tiles_per_b;
-    const int r = (tile - b * a.tiles_per_b) * 128 + quarter * 32 + lane;
-    if (r < R) {
+    const int p = quarter * 32 + lane;
+    if (p < nval) {
+      const int r = r0 + p;
       const int y = r / Wp, x = r - y * Wp;
       const bool border = x < RP || x >= Wp - RP || y < RP || y >= Hp - RP;
       const float lo = a.relu ? 0.f : -INFINITY;
@@ -212,68 +214,82 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
 
-  int i = 0, prev_tile = -1;
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++i) {
-    const int buf = i & 1;
-    const int b = tile / a.tiles_per_b;
-    const int r0 = (tile - b * a.tiles_per_b) * 128;
-    // ---- depthwise phase: 128 pixels x 8 channel quads, 4 items per thread ----
+  // Strip schedule: an item is a run of seg_len image lines of the same row phase (y = py + i*dil) in one 128-pixel
+  // column tile, walked top to bottom, so two of the three tap rows of every tile are L1 hits from the previous tile.
+  int i = 0, pb = 0, pr0 = 0, pnval = 0;
+  for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+    int t = item;
+    const int seg = t % a.segs;
+    t /= a.segs;
+    const int py = t % dil;
+    t /= dil;
+    const int xt = t % a.nxt;
+    const int b = t / a.nxt;
+    const int nval = min(128, Wp - xt * 128);
+    for (int iy = seg * a.seg_len; iy < (seg + 1) * a.seg_len; ++iy) {
+      const int y = py + iy * dil;
+      if (y >= Hp) break;
+      const int buf = i & 1;
+      const int r0 = y * Wp + xt * 128;
+      const bool yin = y >= RP && y < Hp - RP;
+      // ---- depthwise phase: 128 pixels x 8 channel quads, 4 items per thread; loads are unconditional (border pixels
+      //      read their own row and are zeroed afterwards) so all 9 taps of consecutive items can be in flight ----
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int p = (tid >> 3) + 32 * j;
-      const int r = r0 + p;
-      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < R) {
-        const int y = r / Wp, x = r - y * Wp;
-        if (x >= RP && x < Wp - RP && y >= RP && y < Hp - RP) {
-          const float* base = a.in + ((long long)b * R + r) * 32 + q * 4;
+      for (int j = 0; j < 4; ++j) {
+        const int p = (tid >> 3) + 32 * j;
+        const int x = xt * 128 + p;
+        const bool inside = yin && x >= RP && x < Wp - RP;
+        const long long sy = inside ? tap_step_y : 0, sx = inside ? tap_step_x : 0;
+        const float* base = a.in + ((long long)b * R + (p < nval ? r0 + p : r0)) * 32 + q * 4;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(base + (ky - 1) * tap_step_y + (kx - 1) * tap_step_x));
-              const float4 k = kq[ky * 3 + kx];
-              d.x = fmaf(v.x, k.x, d.x), d.y = fmaf(v.y, k.y, d.y), d.z = fmaf(v.z, k.z, d.z), d.w = fmaf(v.w, k.w, d.w);
-            }
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (ky - 1) * sy + (kx - 1) * sx));
+            const float4 k = kq[ky * 3 + kx];
+            d.x = fmaf(v.x, k.x, d.x), d.y = fmaf(v.y, k.y, d.y), d.z = fmaf(v.z, k.z, d.z), d.w = fmaf(v.w, k.w, d.w);
+          }
+        if (!inside) d = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 l;
+        l.x = d.x - __uint_as_float(__float_as_uint(d.x) & 0xFFFFE000u);
+        l.y = d.y - __uint_as_float(__float_as_uint(d.y) & 0xFFFFE000u);
+        l.z = d.z - __uint_as_float(__float_as_uint(d.z) & 0xFFFFE000u);
+        l.w = d.w - __uint_as_float(__float_as_uint(d.w) & 0xFFFFE000u);
+        const int addr = buf * 16384 + p * 128 + ((q ^ (p & 7)) << 4);
+        *reinterpret_cast<float4*>(sA + addr) = d;
+        *reinterpret_cast<float4*>(sL + addr) = l;
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0 && elect_one_sync()) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(sA + buf * 16384), l_addr = smem_u32(sL + buf * 16384), b_addr = smem_u32(sB);
+        const uint32_t d_hh = tmem + buf * 96, d_lh = d_hh + 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t db = dt_sdesc(b_addr + k * 32);
+          const uint32_t accf = k > 0;
+          asm volatile(
+              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_hh),
+              "l"(dt_sdesc(a_addr + k * 32)), "l"(db), "r"(idesc64), "r"(accf)
+              : "memory");
+          asm volatile(
+              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_lh),
+              "l"(dt_sdesc(l_addr + k * 32)), "l"(db), "r"(idesc32), "r"(accf)
+              : "memory");
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mma_bar + buf))
+                     : "memory");
       }
-      float4 l;
-      l.x = d.x - __uint_as_float(__float_as_uint(d.x) & 0xFFFFE000u);
-      l.y = d.y - __uint_as_float(__float_as_uint(d.y) & 0xFFFFE000u);
-      l.z = d.z - __uint_as_float(__float_as_uint(d.z) & 0xFFFFE000u);
-      l.w = d.w - __uint_as_float(__float_as_uint(d.w) & 0xFFFFE000u);
-      const int addr = buf * 16384 + p * 128 + ((q ^ (p & 7)) << 4);
-      *reinterpret_cast<float4*>(sA + addr) = d;
-      *reinterpret_cast<float4*>(sL + addr) = l;
+      if (i > 0) epilogue(i - 1, pb, pr0, pnval);
+      pb = b, pr0 = r0, pnval = nval;
+      ++i;
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 0 && elect_one_sync()) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_addr = smem_u32(sA + buf * 16384), l_addr = smem_u32(sL + buf * 16384), b_addr = smem_u32(sB);
-      const uint32_t d_hh = tmem + buf * 96, d_lh = d_hh + 64;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t db = dt_sdesc(b_addr + k * 32);
-        const uint32_t accf = k > 0;
-        asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_hh),
-            "l"(dt_sdesc(a_addr + k * 32)), "l"(db), "r"(idesc64), "r"(accf)
-            : "memory");
-        asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_lh),
-            "l"(dt_sdesc(l_addr + k * 32)), "l"(db), "r"(idesc32), "r"(accf)
-            : "memory");
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mma_bar + buf))
-                   : "memory");
-    }
-    if (i > 0) epilogue(i - 1, prev_tile);
-    prev_tile = tile;
   }
-  if (i > 0) epilogue(i - 1, prev_tile);
+  if (i > 0) epilogue(i - 1, pb, pr0, pnval);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -284,9 +300,12 @@ static int launch_dwsep_tc(DwTcArgs a, int B, cudaStream_t st) {
   if (a.dil < 1 || a.dil > RP) return LWS_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(dwsep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM);
   if (e != cudaSuccess) return (int)e;
-  a.tiles_per_b = (a.R + 127) / 128;
-  a.total_tiles = B * a.tiles_per_b;
-  const int grid = a.total_tiles < 2 * kNumSMs ? a.total_tiles : 2 * kNumSMs;
+  a.nxt = (a.Wp + 127) / 128;
+  const int rows_per_phase = (a.Hp + a.dil - 1) / a.dil;
+  a.seg_len = 16;
+  a.segs = (rows_per_phase + a.seg_len - 1) / a.seg_len;
+  a.total_items = B * a.nxt * a.dil * a.segs;
+  const int grid = a.total_items < 2 * kNumSMs ? a.total_items : 2 * kNumSMs;
   dwsep_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;

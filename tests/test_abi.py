@@ -72,7 +72,20 @@ def test_pack_conv3d_stack_folds_bn():
         if i < layers + 1:
             assert np.allclose(packed[off:off + cout], t[i + 1], rtol=1e-6, atol=1e-7)
         off += (cout + 3) // 4 * 4
-    assert off == packed.size
+    # C = 8 and C = 32 carry tensor-core operand tables behind the generic layout: [9 stages][3 shifts][64][32] per layer
+    assert packed.size == off + layers * 9 * 192 * 32
+    tc = packed[off:off + 9 * 192 * 32].reshape(9, 3, 64, 32)                  # first 8 -> 8 layer
+    wf = packed[4 + 216 + 8:4 + 216 + 8 + 8 * 27 * 8].reshape(8, 27, 8)         # its folded weights [ci][tap][co]
+    assert np.all((tc[:, :, :32].view(np.uint32) & 0x1FFF) == 0)               # hi rows are tf32-truncated
+    full = tc[:, :, :32] + tc[:, :, 32:]                                       # hi + lo == w, block structure for 4 voxels/row
+    for stg in (0, 4, 8):
+        for kw in range(3):
+            w = wf[:, stg * 3 + kw, :].T                                       # [co][ci]
+            for uo in range(4):
+                ui = uo + kw - 1
+                shift, uin = (0, 3) if ui < 0 else ((2, 0) if ui > 3 else (1, ui))
+                assert np.array_equal(full[stg, shift, uo * 8:uo * 8 + 8, uin * 8:uin * 8 + 8], w)
+    assert np.count_nonzero(full[:, 0, :, :24]) == 0 and np.count_nonzero(full[:, 2, :, 8:]) == 0  # side rows: one K step
 
 
 def test_pack_refinement_folds_bn():

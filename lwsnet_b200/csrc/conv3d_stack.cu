@@ -26,6 +26,8 @@ size_t conv3d_tc_workspace_bytes(int B, int C, int D, int H, int W);
 int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,
                     const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last, float* out,
                     void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
+int conv3d_tc_layer(int C, const float* in_clp, const float* wtc, const float* bias, float* out_clp, int B, int D, int H,
+                    int W, cudaStream_t st);
 constexpr int kTcLayerFloats = 9 * 192 * 32;  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
 
 struct Conv3dArgs {
@@ -446,4 +448,29 @@ extern "C" int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folde
     case 32: return launch_conv3d<8, 32, 8, 2, 32, false, false>(a, B, st);
     default: return LWS_ERR_UNSUPPORTED;
   }
+}
+
+// ---- the tensor-core layer on its own ------------------------------------------------------------------------------------
+extern "C" size_t lws_conv3d_stack_tc_table_offset(int C, int layers, int mid_layer) {
+  if (!lws::has_tc_tables(C) || mid_layer < 0 || mid_layer >= layers) return 0;
+  return lws::packed_tc_offset(C, layers, mid_layer);
+}
+extern "C" size_t lws_conv3d_stack_bias_offset(int C, int layers, int conv) {
+  if (C <= 0 || conv < 0 || conv > layers) return 0;
+  return lws::packed_offset(C, layers, conv, true);
+}
+extern "C" size_t lws_conv3d_clp_floats(int B, int C, int D, int H, int W) {
+  if (!lws::has_tc_tables(C) || B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+  return lws::conv3d_tc_workspace_bytes(B, C, D, H, W) / 2 / sizeof(float);
+}
+extern "C" int lws_conv3d_tc_layer_f32(const float* in_clp, const float* tc_table, const float* bias, float* out_clp, int B,
+                                       int C, int D, int H, int W, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(in_clp);
+  LWS_CHECK_PTR(tc_table);
+  LWS_CHECK_PTR(bias);
+  LWS_CHECK_PTR(out_clp);
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return LWS_ERR_BAD_SHAPE;
+  if (((((uintptr_t)in_clp) | ((uintptr_t)out_clp)) & 127) || (((uintptr_t)tc_table) & 15)) return LWS_ERR_BAD_ALIGN;
+  return conv3d_tc_layer(C, in_clp, tc_table, bias, out_clp, B, D, H, W, (cudaStream_t)stream);
 }

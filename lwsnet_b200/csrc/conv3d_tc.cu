@@ -32,10 +32,11 @@ constexpr int TC_AROWS = 144;             // rows per A stage: 128 + the kw halo
 constexpr int TC_ABYTES = TC_AROWS * 128;  // 18432 = 18 x 1024 (keeps every slot 1024-byte aligned for SWIZZLE_128B)
 constexpr int TC_BROWS = 192;             // 3 kw x (32 hi + 32 lo) rows
 constexpr int TC_BBYTES = TC_BROWS * 128;  // 24576
-constexpr int TC_NS = 4;                  // A ring depth
+constexpr int TC_NSX = 6;                 // x-tile ring (TMA prefetch distance: TMA latency is ~3x one slot's MMA time)
+constexpr int TC_NSL = 2;                 // xl-tile ring (written by the converter warps right before the MMAs need it)
 constexpr int TC_GMAX = 4;                // tiles per CTA group (4 x 96 TMEM columns)
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM = TC_NS * 2 * TC_ABYTES + 2 * TC_BBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM = (TC_NSX + TC_NSL) * TC_ABYTES + 2 * TC_BBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct TcArgs {
   float* out;         // CLP [B][R][32]
@@ -98,14 +99,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                          const __grid_constant__ CUtensorMap mapB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sX = smem;                                   // [NS][17408]  x tiles (= xh as far as the MMA is concerned)
-  uint8_t* sL = smem + TC_NS * TC_ABYTES;               // [NS][17408]  xl tiles
-  uint8_t* sB = smem + 2 * TC_NS * TC_ABYTES;           // [2][24576]   weight stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TC_NS * TC_ABYTES + 2 * TC_BBYTES);
-  uint64_t* a_full = bars;               // [NS] TMA landed
-  uint64_t* a_conv = bars + TC_NS;       // [NS] xl written
-  uint64_t* a_empty = bars + 2 * TC_NS;  // [NS] MMAs that read the slot retired
-  uint64_t* b_full = bars + 3 * TC_NS;   // [2]
+  uint8_t* sX = smem;                                      // [NSX][18432]  x tiles (= xh as far as the MMA is concerned)
+  uint8_t* sL = smem + TC_NSX * TC_ABYTES;                 // [NSL][18432]  xl tiles
+  uint8_t* sB = smem + (TC_NSX + TC_NSL) * TC_ABYTES;      // [2][24576]    weight stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (TC_NSX + TC_NSL) * TC_ABYTES + 2 * TC_BBYTES);
+  uint64_t* a_full = bars;                      // [NSX] TMA landed
+  uint64_t* a_empty = bars + TC_NSX;            // [NSX] MMAs that read the x slot retired
+  uint64_t* a_conv = bars + 2 * TC_NSX;         // [NSL] xl written
+  uint64_t* l_empty = a_conv + TC_NSL;          // [NSL] MMAs that read the xl slot retired
+  uint64_t* b_full = l_empty + TC_NSL;          // [2]
   uint64_t* b_empty = b_full + 2;        // [2]
   uint64_t* acc_full = b_empty + 2;      // all MMAs of the group retired
   uint64_t* acc_empty = acc_full + 1;    // epilogue drained TMEM
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < TC_NS; ++i) mbar_init(a_full + i, 1), mbar_init(a_conv + i, 4), mbar_init(a_empty + i, 1);
+    for (int i = 0; i < TC_NSX; ++i) mbar_init(a_full + i, 1), mbar_init(a_empty + i, 1);
+    for (int i = 0; i < TC_NSL; ++i) mbar_init(a_conv + i, 4), mbar_init(l_empty + i, 1);
     for (int i = 0; i < 2; ++i) mbar_init(b_full + i, 1), mbar_init(b_empty + i, 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4);
@@ -147,8 +150,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int off = a.st_off[st];
           const CUtensorMap* src = a.st_src[st] ? &mapA1 : &mapA;
           for (int g = 0; g < ntile; ++g, ++it) {
-            const uint32_t slot = it % TC_NS;
-            mbar_wait(a_empty + slot, ((it / TC_NS) & 1) ^ 1);
+            const uint32_t slot = it % TC_NSX;
+            mbar_wait(a_empty + slot, ((it / TC_NSX) & 1) ^ 1);
             mbar_expect_tx(a_full + slot, TC_ABYTES);
             // 3D map {32, R, B}: rows outside [0, R) come back as zeros (the depth padding)
             asm volatile(
@@ -181,12 +184,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(b_full + (bs & 1), (bs >> 1) & 1);
         const uint32_t b_lo = ((smem_u32(sB + (bs & 1) * TC_BBYTES) & 0x3FFFF) >> 4) | (1u << 16);
         for (int g = 0; g < ntile; ++g, ++it) {
-          const uint32_t slot = it % TC_NS;
-          mbar_wait(a_conv + slot, (it / TC_NS) & 1);
+          const uint32_t slot = it % TC_NSX, lslot = it % TC_NSL;
+          mbar_wait(a_full + slot, (it / TC_NSX) & 1);
+          mbar_wait(a_conv + lslot, (it / TC_NSL) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one_sync()) {
             const uint32_t x_lo = ((smem_u32(sX + slot * TC_ABYTES) & 0x3FFFF) >> 4) | (1u << 16);
-            const uint32_t l_lo = ((smem_u32(sL + slot * TC_ABYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t l_lo = ((smem_u32(sL + lslot * TC_ABYTES) & 0x3FFFF) >> 4) | (1u << 16);
             const uint32_t d_hh = tmem + g * 96, d_lh = tmem + g * 96 + 64;
             uint32_t acc = st != 0;
 #pragma unroll
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               }
             }
             tc_commit(a_empty + slot);
+            tc_commit(l_empty + lslot);
           }
           __syncwarp();
         }
@@ -224,10 +229,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int t0 = (grp - b * a.groups_per_b) * a.G;
       const int ntile = min(a.G, a.tiles_per_b - t0);
       for (int n = 0; n < nst * ntile; ++n, ++it) {
-        const uint32_t slot = it % TC_NS;
-        mbar_wait(a_full + slot, (it / TC_NS) & 1);
+        const uint32_t slot = it % TC_NSX, lslot = it % TC_NSL;
+        mbar_wait(l_empty + lslot, ((it / TC_NSL) & 1) ^ 1);
+        mbar_wait(a_full + slot, (it / TC_NSX) & 1);
         const float4* src = reinterpret_cast<const float4*>(sX + slot * TC_ABYTES);
-        float4* dst = reinterpret_cast<float4*>(sL + slot * TC_ABYTES);
+        float4* dst = reinterpret_cast<float4*>(sL + lslot * TC_ABYTES);
 #pragma unroll 3
         for (int i = ct; i < TC_ABYTES / 16; i += 128) {
           const float4 x = src[i];
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_conv + slot);
+        if (lane == 0) mbar_arrive(a_conv + lslot);
       }
       // ---- epilogue of this group ----
       mbar_wait(acc_full, gi & 1);
@@ -484,6 +490,19 @@ static int conv3d_stack_tc_impl(const float* cost, const float* affine, const fl
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   return LWS_OK;
+}
+
+// one C -> C tensor-core layer on its own (CLP in, CLP out): tests and per-kernel timing
+int conv3d_tc_layer(int C, const float* in_clp, const float* wtc, const float* bias, float* out_clp, int B, int D, int H,
+                    int W, cudaStream_t st) {
+  if (C != 32 && C != 8) return LWS_ERR_UNSUPPORTED;
+  const int Hp = H + 2, Wp = clp_wp(C, W);
+  const long long R = (long long)D * Hp * Wp * C / 32;
+  if (R >= (1ll << 31) - 4096) return LWS_ERR_BAD_SHAPE;
+  int st_off[9], st_src[9];
+  const int rows_line = Wp * C / 32;
+  for (int s = 0; s < 9; ++s) st_off[s] = ((s / 3 - 1) * Hp + (s % 3 - 1)) * rows_line - 1, st_src[s] = 0;
+  return launch_tc_implicit_gemm(in_clp, in_clp, wtc, bias, out_clp, B, (int)R, Hp, Wp, 1, H, W, C, 9, st_off, st_src, 1, 1, st);
 }
 
 int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,

@@ -111,7 +111,7 @@ struct DwTcArgs {
   int R, Hp, Wp, dil, relu;
   int nxt, segs, seg_len, total_items;  // strip schedule: item = (b, x tile, row phase, segment of seg_len phase-rows)
 };
-constexpr int DT_THREADS = 256;
+constexpr int DT_THREADS = 512;
 constexpr int DT_SMEM = 4 * 16384 + 8192 + 1024 + 64;
 
 __device__ __forceinline__ uint64_t dt_sdesc(uint32_t saddr) {
@@ -136,7 +136,18 @@ __device__ __forceinline__ void dt_ld16(uint32_t taddr, float* v) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs a) {
+__device__ __forceinline__ void dt_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dwsep_tc_kernel(const DwTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;              // [2][16384] depthwise result (= xh for the MMA)
@@ -171,10 +182,10 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
   for (int t = 0; t < 9; ++t)
     kq[t] = make_float4(__ldg(a.dw + (q * 4 + 0) * 9 + t), __ldg(a.dw + (q * 4 + 1) * 9 + t), __ldg(a.dw + (q * 4 + 2) * 9 + t),
                         __ldg(a.dw + (q * 4 + 3) * 9 + t));
-  const int quarter = warp & 3, half = warp >> 2;  // epilogue: TMEM lane quarter / channel half of this warp
-  float bias[16];
+  const int quarter = warp & 3, cgrp = warp >> 2;  // epilogue: TMEM lane quarter / group of 8 channels of this warp
+  float bias[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) bias[j] = __ldg(a.bias + half * 16 + j);
+  for (int j = 0; j < 8; ++j) bias[j] = __ldg(a.bias + cgrp * 8 + j);
   const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
   const int dil = a.dil, Wp = a.Wp, Hp = a.Hp, R = a.R;
@@ -185,24 +196,24 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
     const int pbuf = j & 1;
     mbar_wait(mma_bar + pbuf, (j >> 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + pbuf * 96 + half * 16;
-    float acc[16], t[16];
-    dt_ld16(taddr, acc);
-    dt_ld16(taddr + 32, t);
+    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + pbuf * 96 + cgrp * 8;
+    float acc[8], t[8];
+    dt_ld8(taddr, acc);
+    dt_ld8(taddr + 32, t);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] += t[c];
-    dt_ld16(taddr + 64, t);
+    for (int c = 0; c < 8; ++c) acc[c] += t[c];
+    dt_ld8(taddr + 64, t);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] += t[c];
+    for (int c = 0; c < 8; ++c) acc[c] += t[c];
     const int p = quarter * 32 + lane;
     if (p < nval) {
       const int r = r0 + p;
       const int y = r / Wp, x = r - y * Wp;
       const bool border = x < RP || x >= Wp - RP || y < RP || y >= Hp - RP;
       const float lo = a.relu ? 0.f : -INFINITY;
-      float4* o = reinterpret_cast<float4*>(a.out + ((long long)b * R + r) * 32 + half * 16);
+      float4* o = reinterpret_cast<float4*>(a.out + ((long long)b * R + r) * 32 + cgrp * 8);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float4 v;
         v.x = border ? 0.f : fmaxf(acc[4 * c] + bias[4 * c], lo);
         v.y = border ? 0.f : fmaxf(acc[4 * c + 1] + bias[4 * c + 1], lo);
@@ -232,25 +243,34 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dwsep_tc_kernel(const DwTcArgs 
       const int buf = i & 1;
       const int r0 = y * Wp + xt * 128;
       const bool yin = y >= RP && y < Hp - RP;
-      // ---- depthwise phase: 128 pixels x 8 channel quads, 4 items per thread; loads are unconditional (border pixels
-      //      read their own row and are zeroed afterwards) so all 9 taps of consecutive items can be in flight ----
+      // ---- depthwise phase: 128 pixels x 8 channel quads, 2 items per thread; loads are unconditional (border pixels
+      //      read their own row and are zeroed afterwards) ----
+      float4 v[2][9];
+      bool inside[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = (tid >> 3) + 32 * j;
+      for (int j = 0; j < 2; ++j) {  // issue all 18 tap loads of this thread before touching any of them: one round trip
+        const int p = (tid >> 3) + 64 * j;
         const int x = xt * 128 + p;
-        const bool inside = yin && x >= RP && x < Wp - RP;
-        const long long sy = inside ? tap_step_y : 0, sx = inside ? tap_step_x : 0;
+        inside[j] = yin && x >= RP && x < Wp - RP;
+        const long long sy = inside[j] ? tap_step_y : 0, sx = inside[j] ? tap_step_x : 0;
         const float* base = a.in + ((long long)b * R + (p < nval ? r0 + p : r0)) * 32 + q * 4;
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (ky - 1) * sy + (kx - 1) * sx));
-            const float4 k = kq[ky * 3 + kx];
-            d.x = fmaf(v.x, k.x, d.x), d.y = fmaf(v.y, k.y, d.y), d.z = fmaf(v.z, k.z, d.z), d.w = fmaf(v.w, k.w, d.w);
-          }
-        if (!inside) d = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int kx = 0; kx < 3; ++kx)
+            v[j][ky * 3 + kx] = __ldg(reinterpret_cast<const float4*>(base + (ky - 1) * sy + (kx - 1) * sx));
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p = (tid >> 3) + 64 * j;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 k = kq[t];
+          d.x = fmaf(v[j][t].x, k.x, d.x), d.y = fmaf(v[j][t].y, k.y, d.y), d.z = fmaf(v[j][t].z, k.z, d.z),
+          d.w = fmaf(v[j][t].w, k.w, d.w);
+        }
+        if (!inside[j]) d = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 l;
         l.x = d.x - __uint_as_float(__float_as_uint(d.x) & 0xFFFFE000u);
         l.y = d.y - __uint_as_float(__float_as_uint(d.y) & 0xFFFFE000u);
@@ -305,7 +325,7 @@ static int launch_dwsep_tc(DwTcArgs a, int B, cudaStream_t st) {
   a.seg_len = 16;
   a.segs = (rows_per_phase + a.seg_len - 1) / a.seg_len;
   a.total_items = B * a.nxt * a.dil * a.segs;
-  const int grid = a.total_items < 2 * kNumSMs ? a.total_items : 2 * kNumSMs;
+  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
   dwsep_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;

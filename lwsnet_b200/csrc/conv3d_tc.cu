@@ -32,8 +32,8 @@ constexpr int TC_AROWS = 144;             // rows per A stage: 128 + the kw halo
 constexpr int TC_ABYTES = TC_AROWS * 128;  // 18432 = 18 x 1024 (keeps every slot 1024-byte aligned for SWIZZLE_128B)
 constexpr int TC_BROWS = 192;             // 3 kw x (32 hi + 32 lo) rows
 constexpr int TC_BBYTES = TC_BROWS * 128;  // 24576
-constexpr int TC_NSX = 6;                 // x-tile ring (TMA prefetch distance: TMA latency is ~3x one slot's MMA time)
-constexpr int TC_NSL = 2;                 // xl-tile ring (written by the converter warps right before the MMAs need it)
+constexpr int TC_NSX = 5;                 // x-tile ring (TMA prefetch distance)
+constexpr int TC_NSL = 3;                 // xl-tile ring (written by the converter warps ahead of the MMAs)
 constexpr int TC_GMAX = 4;                // tiles per CTA group (4 x 96 TMEM columns)
 constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM = (TC_NSX + TC_NSL) * TC_ABYTES + 2 * TC_BBYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -232,17 +232,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint32_t slot = it % TC_NSX, lslot = it % TC_NSL;
         mbar_wait(l_empty + lslot, ((it / TC_NSL) & 1) ^ 1);
         mbar_wait(a_full + slot, (it / TC_NSX) & 1);
-        const float4* src = reinterpret_cast<const float4*>(sX + slot * TC_ABYTES);
-        float4* dst = reinterpret_cast<float4*>(sL + lslot * TC_ABYTES);
-#pragma unroll 3
-        for (int i = ct; i < TC_ABYTES / 16; i += 128) {
-          const float4 x = src[i];
+        // 18432 B = 9 float4 per thread: all nine shared loads are issued before the first use (one round trip)
+        const uint32_t src = smem_u32(sX + slot * TC_ABYTES) + ct * 16, dst = smem_u32(sL + lslot * TC_ABYTES) + ct * 16;
+        float4 x[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w)
+                       : "r"(src + j * 2048));
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
           float4 l;
-          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          dst[i] = l;
+          l.x = x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xFFFFE000u);
+          l.y = x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xFFFFE000u);
+          l.z = x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xFFFFE000u);
+          l.w = x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xFFFFE000u);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 2048), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
+                       : "memory");
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -295,14 +301,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// ---- 1 -> C on the raw cost, writing CLP (incl. the zero border); C/4 lanes per voxel, 4 couts per lane ---------------
+// ---- 1 -> C on the raw cost, writing CLP (incl. the zero border); C/8 lanes per voxel, 8 couts per lane ---------------
 // CLP geometry: voxel (d, y, x) with y in [0, H+2), x in [0, Wp); interior = y in [1, H], x in [1, W]; Wp >= W + 2.
 template <int C>
 __global__ void __launch_bounds__(256)
     conv3d_first_clp_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][C]*/,
                             const float* __restrict__ bias, const float* __restrict__ affine, float* __restrict__ out,
                             int D, int H, int W, int Wp, long long total_vox) {
-  constexpr int LPV = C / 4;
+  constexpr int LPV = C / 8;
   __shared__ __align__(16) float sW[27 * C];
   for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sW[i] = __ldg(w + i);
   __syncthreads();
@@ -310,7 +316,9 @@ __global__ void __launch_bounds__(256)
   const int sub = threadIdx.x % LPV;
   const int Hp = H + 2;
   const long long hw = (long long)H * W;
-  const float4 bv = *reinterpret_cast<const float4*>(bias + sub * 4);
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
   for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPV; vox < total_vox;
        vox += ((long long)gridDim.x * blockDim.x) / LPV) {
     const int x = (int)(vox % Wp);
@@ -319,43 +327,47 @@ __global__ void __launch_bounds__(256)
     t /= Hp;
     const int d = (int)(t % D);
     const int b = (int)(t / D);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const bool border = x < 1 || x > W || y < 1 || y > H;
     if (!border) {
-      const float* cb = cost + (long long)b * D * hw;
+      const float* cb = cost + (long long)b * D * hw + (long long)d * hw + (long long)(y - 1) * W + (x - 1);
 #pragma unroll
       for (int kd = 0; kd < 3; ++kd) {
-        const int gd = d + kd - 1;
-        if (gd < 0 || gd >= D) continue;
+        const bool okd = (unsigned)(d + kd - 1) < (unsigned)D;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          const int gh = y - 1 + kh - 1;
-          if (gh < 0 || gh >= H) continue;
+          const bool okh = okd && (unsigned)(y - 1 + kh - 1) < (unsigned)H;
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            const int gw = x - 1 + kw - 1;
-            if (gw < 0 || gw >= W) continue;
-            const float v = fmaxf(fmaf(__ldg(cb + (long long)gd * hw + (long long)gh * W + gw), s0, t0), 0.f);
-            const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 4);
-            acc.x = fmaf(v, wv.x, acc.x), acc.y = fmaf(v, wv.y, acc.y), acc.z = fmaf(v, wv.z, acc.z),
-            acc.w = fmaf(v, wv.w, acc.w);
+            const bool ok = okh && (unsigned)(x - 1 + kw - 1) < (unsigned)W;
+            float v = ok ? __ldg(cb + (kd - 1) * hw + (kh - 1) * W + (kw - 1)) : 0.f;
+            v = ok ? fmaxf(fmaf(v, s0, t0), 0.f) : 0.f;
+            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 8 + 4);
+            acc[0] = fmaf(v, wa.x, acc[0]), acc[1] = fmaf(v, wa.y, acc[1]), acc[2] = fmaf(v, wa.z, acc[2]),
+            acc[3] = fmaf(v, wa.w, acc[3]), acc[4] = fmaf(v, wb.x, acc[4]), acc[5] = fmaf(v, wb.y, acc[5]),
+            acc[6] = fmaf(v, wb.z, acc[6]), acc[7] = fmaf(v, wb.w, acc[7]);
           }
         }
       }
-      acc.x = fmaxf(acc.x + bv.x, 0.f), acc.y = fmaxf(acc.y + bv.y, 0.f), acc.z = fmaxf(acc.z + bv.z, 0.f),
-      acc.w = fmaxf(acc.w + bv.w, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + bv[j], 0.f);
     }
-    *reinterpret_cast<float4*>(out + vox * C + sub * 4) = acc;
+    float4* o = reinterpret_cast<float4*>(out + vox * C + sub * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
-// ---- C -> 1 from CLP (+ skip), NCDHW output; C/4 lanes per voxel, 4 input channels per lane --------------------------
+// ---- C -> 1 from CLP (+ skip), NCDHW output; C/8 lanes per voxel, 8 input channels per lane --------------------------
 template <int C>
 __global__ void __launch_bounds__(256)
     conv3d_last_clp_kernel(const float* __restrict__ act, const float* __restrict__ w /*[C][27] = packed [Cin][27][1]*/,
                            const float* __restrict__ skip, float* __restrict__ out, int D, int H, int W, int Wp,
                            long long total_vox) {
-  constexpr int LPV = C / 4;
+  constexpr int LPV = C / 8;
   __shared__ __align__(16) float sW[27 * C];  // [tap][ci]
   for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sW[(i % 27) * C + i / 27] = __ldg(w + i);
   __syncthreads();
@@ -370,23 +382,25 @@ __global__ void __launch_bounds__(256)
     t /= H;
     const int d = (int)(t % D);
     const int b = (int)(t / D);
-    const float* base = act + ((long long)b * R) * C + sub * 4;
-    float acc = 0.f;
+    const float* base = act + ((long long)b * R + ((long long)d * Hp + (y + 1)) * Wp + (x + 1)) * C + sub * 8;
+    float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
-      const int gd = d + kd - 1;
-      if (gd < 0 || gd >= D) continue;
+      if ((unsigned)(d + kd - 1) >= (unsigned)D) continue;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const long long r = ((long long)gd * Hp + (y + kh)) * Wp + (x + kw);  // padded coords: (y+1)+(kh-1), (x+1)+(kw-1)
-          const float4 v = __ldg(reinterpret_cast<const float4*>(base + r * C));
-          const float4 wv = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 4);
-          acc = fmaf(v.x, wv.x, acc), acc = fmaf(v.y, wv.y, acc), acc = fmaf(v.z, wv.z, acc), acc = fmaf(v.w, wv.w, acc);
+          const float* p = base + (((long long)(kd - 1) * Hp + (kh - 1)) * Wp + (kw - 1)) * C;
+          const float4 va = __ldg(reinterpret_cast<const float4*>(p)), vb = __ldg(reinterpret_cast<const float4*>(p + 4));
+          const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * C + sub * 8 + 4);
+          acc0 = fmaf(va.x, wa.x, acc0), acc0 = fmaf(va.y, wa.y, acc0), acc0 = fmaf(va.z, wa.z, acc0), acc0 = fmaf(va.w, wa.w, acc0);
+          acc1 = fmaf(vb.x, wb.x, acc1), acc1 = fmaf(vb.y, wb.y, acc1), acc1 = fmaf(vb.z, wb.z, acc1), acc1 = fmaf(vb.w, wb.w, acc1);
         }
       }
     }
+    float acc = acc0 + acc1;
 #pragma unroll
     for (int m = 1; m < LPV; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
     if (sub == 0) out[vox] = acc + (skip ? __ldg(skip + vox) : 0.f);
@@ -462,7 +476,7 @@ static int conv3d_stack_tc_impl(const float* cost, const float* affine, const fl
   float* bufA = (float*)ws;
   float* bufB = (float*)((char*)ws + act_bytes);
   const long long nvox = (long long)B * vox_b;
-  constexpr int LPV = C / 4;
+  constexpr int LPV = C / 8;
   cudaError_t e;
   {
     const long long thr = nvox * LPV;

@@ -24,7 +24,7 @@ int launch_tc_implicit_gemm(const float* src0, const float* src1, const float* w
 
 constexpr int RP = 16;  // border of the refinement CLP tensors
 
-// ---- first convs: NCHW [B,CIN,H,W] -> CLP; 8 lanes per pixel, 4 couts per lane ----------------------------------------
+// ---- first convs: NCHW [B,CIN,H,W] -> CLP; 4 lanes per pixel, 8 couts per lane ----------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256)
     ref_conv0_clp_kernel(const float* __restrict__ in, const float* __restrict__ w /*[CIN][9][32]*/,
@@ -32,71 +32,81 @@ __global__ void __launch_bounds__(256)
   __shared__ __align__(16) float sW[CIN * 9 * 32];
   for (int i = threadIdx.x; i < CIN * 9 * 32; i += blockDim.x) sW[i] = __ldg(w + i);
   __syncthreads();
-  const int sub = threadIdx.x & 7;
+  const int sub = threadIdx.x & 3;
   const int Hp = H + 2 * RP, Wp = W + 2 * RP;
   const long long hw = (long long)H * W;
-  const float4 bv = *reinterpret_cast<const float4*>(bias + sub * 4);
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < total_rows;
-       row += ((long long)gridDim.x * blockDim.x) >> 3) {
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; row < total_rows;
+       row += ((long long)gridDim.x * blockDim.x) >> 2) {
     const int x = (int)(row % Wp) - RP;
     const long long t = row / Wp;
     const int y = (int)(t % Hp) - RP;
     const int b = (int)(t / Hp);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (x >= 0 && x < W && y >= 0 && y < H) {
-      const float* ib = in + (long long)b * CIN * hw;
+      const float* ib = in + (long long)b * CIN * hw + (long long)y * W + x;
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci)
+      for (int ky = 0; ky < 3; ++ky) {
+        const bool oky = (unsigned)(y + ky - 1) < (unsigned)H;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int gy = y + ky - 1;
-          if (gy < 0 || gy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const bool ok = oky && (unsigned)(x + kx - 1) < (unsigned)W;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int gx = x + kx - 1;
-            if (gx < 0 || gx >= W) continue;
-            const float v = __ldg(ib + ci * hw + (long long)gy * W + gx);
-            const float4 wv = *reinterpret_cast<const float4*>(sW + (ci * 9 + ky * 3 + kx) * 32 + sub * 4);
-            acc.x = fmaf(v, wv.x, acc.x), acc.y = fmaf(v, wv.y, acc.y), acc.z = fmaf(v, wv.z, acc.z),
-            acc.w = fmaf(v, wv.w, acc.w);
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float v = ok ? __ldg(ib + ci * hw + (ky - 1) * W + (kx - 1)) : 0.f;
+            const float4 wa = *reinterpret_cast<const float4*>(sW + (ci * 9 + ky * 3 + kx) * 32 + sub * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sW + (ci * 9 + ky * 3 + kx) * 32 + sub * 8 + 4);
+            acc[0] = fmaf(v, wa.x, acc[0]), acc[1] = fmaf(v, wa.y, acc[1]), acc[2] = fmaf(v, wa.z, acc[2]),
+            acc[3] = fmaf(v, wa.w, acc[3]), acc[4] = fmaf(v, wb.x, acc[4]), acc[5] = fmaf(v, wb.y, acc[5]),
+            acc[6] = fmaf(v, wb.z, acc[6]), acc[7] = fmaf(v, wb.w, acc[7]);
           }
         }
-      acc.x = fmaxf(acc.x + bv.x, 0.f), acc.y = fmaxf(acc.y + bv.y, 0.f), acc.z = fmaxf(acc.z + bv.z, 0.f),
-      acc.w = fmaxf(acc.w + bv.w, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + bv[j], 0.f);
     }
-    *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
+    float4* o = reinterpret_cast<float4*>(out + row * 32 + sub * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
-// ---- last conv: CLP -> NCHW [B,1,H,W] (+ skip); 8 lanes per pixel, 4 input channels per lane ----------------------------
+// ---- last conv: CLP -> NCHW [B,1,H,W] (+ skip); 4 lanes per pixel, 8 input channels per lane ----------------------------
 __global__ void __launch_bounds__(256)
     ref_last_clp_kernel(const float* __restrict__ act, const float* __restrict__ w /*[32][9]*/,
                         const float* __restrict__ skip, float* __restrict__ out, int H, int W, long long total_px) {
   __shared__ __align__(16) float sW[9 * 32];  // [tap][ci]
   for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) sW[(i % 9) * 32 + i / 9] = __ldg(w + i);
   __syncthreads();
-  const int sub = threadIdx.x & 7;
+  const int sub = threadIdx.x & 3;
   const int Hp = H + 2 * RP, Wp = W + 2 * RP;
   const long long R = (long long)Hp * Wp;
-  for (long long px = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; px < total_px;
-       px += ((long long)gridDim.x * blockDim.x) >> 3) {
+  for (long long px = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; px < total_px;
+       px += ((long long)gridDim.x * blockDim.x) >> 2) {
     const int x = (int)(px % W);
     const long long t = px / W;
     const int y = (int)(t % H);
     const int b = (int)(t / H);
-    const float* base = act + ((long long)b * R + (long long)(y + RP) * Wp + (x + RP)) * 32 + sub * 4;
-    float acc = 0.f;
+    const float* base = act + ((long long)b * R + (long long)(y + RP) * Wp + (x + RP)) * 32 + sub * 8;
+    float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)(ky - 1) * Wp + (kx - 1)) * 32));
-        const float4 wv = *reinterpret_cast<const float4*>(sW + (ky * 3 + kx) * 32 + sub * 4);
-        acc = fmaf(v.x, wv.x, acc), acc = fmaf(v.y, wv.y, acc), acc = fmaf(v.z, wv.z, acc), acc = fmaf(v.w, wv.w, acc);
+        const float* p = base + ((long long)(ky - 1) * Wp + (kx - 1)) * 32;
+        const float4 va = __ldg(reinterpret_cast<const float4*>(p)), vb = __ldg(reinterpret_cast<const float4*>(p + 4));
+        const float4 wa = *reinterpret_cast<const float4*>(sW + (ky * 3 + kx) * 32 + sub * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(sW + (ky * 3 + kx) * 32 + sub * 8 + 4);
+        acc0 = fmaf(va.x, wa.x, acc0), acc0 = fmaf(va.y, wa.y, acc0), acc0 = fmaf(va.z, wa.z, acc0), acc0 = fmaf(va.w, wa.w, acc0);
+        acc1 = fmaf(vb.x, wb.x, acc1), acc1 = fmaf(vb.y, wb.y, acc1), acc1 = fmaf(vb.z, wb.z, acc1), acc1 = fmaf(vb.w, wb.w, acc1);
       }
+    float acc = acc0 + acc1;
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     if (sub == 0) out[px] = acc + __ldg(skip + px);
   }
 }
@@ -355,7 +365,7 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
   static const int r1_dil[4] = {2, 4, 8, 16};
   static const int r2_dil[4] = {8, 4, 2, 1};
   const long long rows = (long long)B * R;
-  const int cblocks = (int)((rows * 8 + 255) / 256 < 148 * 16 ? (rows * 8 + 255) / 256 : 148 * 16);
+  const int cblocks = (int)((rows * 4 + 255) / 256 < 148 * 16 ? (rows * 4 + 255) / 256 : 148 * 16);
   int rc;
   cudaError_t e;
   for (int br = 0; br < 2; ++br) {
@@ -394,7 +404,7 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
     cur = nxt, nxt = t;
   }
   const long long px = (long long)B * H * W;
-  const int lblocks = (int)((px * 8 + 255) / 256 < 148 * 16 ? (px * 8 + 255) / 256 : 148 * 16);
+  const int lblocks = (int)((px * 4 + 255) / 256 < 148 * 16 ? (px * 4 + 255) / 256 : 148 * 16);
   ref_last_clp_kernel<<<lblocks, 256, 0, st>>>(cur, wt.last_w, pred3, pred4, H, W, px);
   if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   return LWS_OK;

@@ -1,0 +1,399 @@
+// K6: the BN-ReLU-DW3x3(dil)-PW1x1 block of the colour-guidance refinement (reference models/submodules.py:236-261, used by
+// refinement1 / refinement2, :282-327) on channels-last bordered ("CLP") tensors  act[b][y][x][32] fp32, border RP = 16.
+//
+// HBM-bound by design (reads and writes each 32-channel pixel once: 256 B / pixel); everything else is arranged so that it
+// stays under that:
+//   * TMA producer warp: one input line segment ((128 + 2*dil) pixels x 128 B) per step into a 5-slot shared-memory ring.
+//   * 8 depthwise warps: a thread owns one channel quad of 4 pixels `dil` apart and walks down image lines of one row phase
+//     (y = py + i*dil), so the 3x3 dilated window lives in registers: per output line it reads 6 float4 from the ring
+//     (1.5 loads per output instead of 9) and issues 144 FFMA.  The result is split x = hi + lo*2^-11 into two fp16 values
+//     and written as the A operand (row = pixel: [32 hi | 32 lo] halves = 128 B, SWIZZLE_128B).
+//   * MMA warp: the 32x32 pointwise product as 4 tcgen05.mma kind::f16 (M=128): hi x [wh | wl] (N=64) and lo x wh (N=32,
+//     accumulated onto the hi*wl columns, both carry the 2^-11 weight); products of 11-bit significands are exact in the
+//     fp32 accumulator, so the result has the accuracy of an fp32 FMA chain (the dropped lo*lo term is 2^-22 relative).
+//     One tcgen05.mma costs ~40 + N/2 cycles with both operands in shared memory (tools/umma_bench.cu), hence few, wide MMAs.
+//   * 4 epilogue warps: tcgen05.ld, rescale + bias + ReLU, zero the x border, stage the 128 x 128 B tile in shared memory and
+//     TMA-store it (clipped at the line end by the tensor map).
+// The y-border lines of the output are zero-filled by all threads at kernel start.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include "lws_common.cuh"
+#include "tma_utils.cuh"
+
+namespace lws {
+
+constexpr int DS_RP = 16;          // border of the refinement CLP tensors
+constexpr int DS_DW_WARPS = 8;     // warps 0..7
+constexpr int DS_EPI_WARP0 = 8;    // warps 8..11 (warp % 4 = TMEM lane quarter)
+constexpr int DS_PROD_WARP = 12;
+constexpr int DS_MMA_WARP = 13;
+constexpr int DS_THREADS = 14 * 32;
+constexpr int DS_NIN = 5;                   // input ring slots
+constexpr int DS_INBYTES = 160 * 128;       // (128 + 2*16) pixels x 128 B
+constexpr int DS_NA = 3;                    // A-operand tiles
+constexpr int DS_NT = 2;                    // TMEM accumulators (64 columns each)
+constexpr int DS_NOUT = 2;                  // output staging tiles
+constexpr int DS_TILE = 128 * 128;          // 16 KB
+constexpr int DS_OFF_A = 0;
+constexpr int DS_OFF_OUT = DS_OFF_A + DS_NA * DS_TILE;
+constexpr int DS_OFF_B = DS_OFF_OUT + DS_NOUT * DS_TILE;
+constexpr int DS_OFF_IN = DS_OFF_B + 8192;
+constexpr int DS_OFF_W = DS_OFF_IN + DS_NIN * DS_INBYTES;   // depthwise weights [9][32] fp32
+constexpr int DS_OFF_BAR = DS_OFF_W + 9 * 32 * 4;
+constexpr int DS_SMEM = DS_OFF_BAR + 256 + 1024 /*align slack*/;
+constexpr float DS_ACT_SCALE = kDwsepActScale;
+
+struct DsArgs {
+  const float* dw;      // [32][9] depthwise weights
+  const __half* pwh;    // [64][32]: rows 0..31 = fp16(w*sw) (row = cout, col = cin), rows 32..63 = fp16((w*sw - hi) * 2^11)
+  const float* scales;  // [2]: c0 = 1 / (DS_ACT_SCALE * sw), c1 = c0 * 2^-11
+  const float* bias;    // [32]
+  float* out;           // CLP [B][Hp][Wp][32] (for the y-border zero fill; the interior goes through the TMA store map)
+  int B, Hp, Wp, H, dil, relu;
+  int nxt, segs, seg_len, total_items;
+};
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void ds_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// Work item = (b, x tile, row phase py, segment): image lines yi = py + i*dil, i in [seg*seg_len, (seg+1)*seg_len) clipped to
+// the phase.  All warp roles walk the same static schedule.
+struct DsItem {
+  int b, x0, yi0, nrows;
+};
+__device__ __forceinline__ DsItem ds_decode(const DsArgs& a, int item) {
+  int t = item;
+  const int seg = t % a.segs;
+  t /= a.segs;
+  const int py = t % a.dil;
+  t /= a.dil;
+  const int xt = t % a.nxt;
+  DsItem it;
+  it.b = t / a.nxt;
+  it.x0 = xt * 128;
+  const int rows_phase = py < a.H ? (a.H - py + a.dil - 1) / a.dil : 0;
+  const int i0 = seg * a.seg_len;
+  it.nrows = max(0, min(a.seg_len, rows_phase - i0));
+  it.yi0 = py + i0 * a.dil;
+  return it;
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 1)
+    dwsep_f16_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, const DsArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DS_OFF_BAR);
+  uint64_t* in_full = bars;                 // [NIN]
+  uint64_t* in_empty = in_full + DS_NIN;    // [NIN]
+  uint64_t* a_full = in_empty + DS_NIN;     // [NA]
+  uint64_t* a_empty = a_full + DS_NA;       // [NA]
+  uint64_t* t_full = a_empty + DS_NA;       // [NT]
+  uint64_t* t_empty = t_full + DS_NT;       // [NT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + DS_NT);
+  float* sW = reinterpret_cast<float*>(smem + DS_OFF_W);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dil = a.dil;
+
+  if (tid == 0) {
+    for (int i = 0; i < DS_NIN; ++i) mbar_init(in_full + i, 1), mbar_init(in_empty + i, DS_DW_WARPS);
+    for (int i = 0; i < DS_NA; ++i) mbar_init(a_full + i, DS_DW_WARPS), mbar_init(a_empty + i, 1);
+    for (int i = 0; i < DS_NT; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
+    mbar_fence_init();
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == DS_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(DS_NT * 64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // pointwise operand tile: 64 rows x 64 B used of a 128-byte SWIZZLE_128B row
+  for (int idx = tid; idx < 64 * 4; idx += DS_THREADS) {
+    const int n = idx >> 2, c = idx & 3;
+    *reinterpret_cast<uint4*>(smem + DS_OFF_B + n * 128 + ((c ^ (n & 7)) << 4)) =
+        __ldg(reinterpret_cast<const uint4*>(a.pwh + n * 32 + c * 8));
+  }
+  for (int idx = tid; idx < 9 * 32; idx += DS_THREADS) sW[idx] = __ldg(a.dw + (idx & 31) * 9 + (idx >> 5)) * DS_ACT_SCALE;
+  // zero the y-border lines of the output
+  {
+    const long long line4 = (long long)a.Wp * 8;  // float4 per line
+    const long long total = (long long)a.B * 2 * DS_RP * line4;
+    float4* o = reinterpret_cast<float4*>(a.out);
+    for (long long i = (long long)blockIdx.x * DS_THREADS + tid; i < total; i += (long long)gridDim.x * DS_THREADS) {
+      const long long ln = i / line4, r = i - ln * line4;
+      const int b = (int)(ln / (2 * DS_RP)), k = (int)(ln % (2 * DS_RP));
+      const int y = k < DS_RP ? k : a.Hp - 2 * DS_RP + k;
+      o[((long long)b * a.Hp + y) * line4 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  fence_proxy_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == DS_PROD_WARP) {
+    // ================================ TMA producer ================================
+    if (elect_one_sync()) {
+      uint32_t it = 0;
+      const uint32_t bytes = (uint32_t)(128 + 2 * dil) * 128;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const DsItem w = ds_decode(a, item);
+        if (w.nrows == 0) continue;
+        const int line0 = w.b * a.Hp + DS_RP + w.yi0 - dil;  // first line needed: y - dil
+        for (int k = 0; k < w.nrows + 2; ++k, ++it) {
+          const uint32_t slot = it % DS_NIN;
+          mbar_wait(in_empty + slot, ((it / DS_NIN) & 1) ^ 1);
+          mbar_expect_tx(in_full + slot, bytes);
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                  smem_u32(smem + DS_OFF_IN + slot * DS_INBYTES)),
+              "l"(reinterpret_cast<uint64_t>(&map_in)), "r"(smem_u32(in_full + slot)), "r"(0), "r"(w.x0 - dil),
+              "r"(line0 + k * dil)
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == DS_MMA_WARP) {
+    // ================================ MMA issuer ================================
+    // kind::f16, fp32 accumulate, K-major A and B, M = 128, N = 64 / 32
+    const uint32_t idesc64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
+    const uint32_t b_lo = ((smem_u32(smem + DS_OFF_B) & 0x3FFFF) >> 4) | (1u << 16);
+    uint32_t t = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const DsItem w = ds_decode(a, item);
+      for (int i = 0; i < w.nrows; ++i, ++t) {
+        const uint32_t ab = t % DS_NA, tb = t % DS_NT;
+        mbar_wait(t_empty + tb, ((t / DS_NT) & 1) ^ 1);
+        mbar_wait(a_full + ab, (t / DS_NA) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one_sync()) {
+          const uint32_t a_lo = ((smem_u32(smem + DS_OFF_A + ab * DS_TILE) & 0x3FFFF) >> 4) | (1u << 16);
+          const uint32_t d = tmem + tb * 64;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t acc = k > 0;
+            asm volatile(
+                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+                "l"(desc_hi | (uint64_t)(a_lo + k * 2)), "l"(desc_hi | (uint64_t)(b_lo + k * 2)), "r"(idesc64), "r"(acc)
+                : "memory");
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            asm volatile(
+                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d + 32),
+                "l"(desc_hi | (uint64_t)(a_lo + 4 + k * 2)), "l"(desc_hi | (uint64_t)(b_lo + k * 2)), "r"(idesc32), "r"(1u)
+                : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(a_empty + ab))
+                       : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(t_full + tb))
+                       : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= DS_EPI_WARP0) {
+    // ================================ epilogue (warps 8..11) ================================
+    const int quarter = warp & 3;
+    const int p = quarter * 32 + lane;  // pixel of the tile = TMEM lane
+    const bool issuer = warp == DS_EPI_WARP0 && lane == 0;
+    float bias[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bias[c] = __ldg(a.bias + c);
+    const float c0 = __ldg(a.scales), c1 = __ldg(a.scales + 1);
+    const float lo = a.relu ? 0.f : -INFINITY;
+    uint32_t t = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const DsItem w = ds_decode(a, item);
+      const int xpix = w.x0 + p;
+      const bool border = xpix < DS_RP || xpix >= a.Wp - DS_RP;
+      for (int i = 0; i < w.nrows; ++i, ++t) {
+        const uint32_t tb = t % DS_NT, ob = t % DS_NOUT;
+        mbar_wait(t_full + tb, (t / DS_NT) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + tb * 64;
+        float m[32], c[32];
+        ds_ld32(taddr, m);
+        ds_ld32(taddr + 32, c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + tb);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = fmaxf(fmaf(c[j], c1, fmaf(m[j], c0, bias[j])), lo);
+          m[j] = border ? 0.f : v;
+        }
+        // staging tile `ob` was last read by the TMA store issued DS_NOUT tiles ago
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DS_NOUT - 1) : "memory");
+        named_bar_sync(1, 128);
+        const uint32_t so = smem_u32(smem + DS_OFF_OUT + ob * DS_TILE) + p * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(so + ((j ^ (p & 7)) << 4), make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]));
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&map_out)),
+                       "r"(smem_u32(smem + DS_OFF_OUT + ob * DS_TILE)), "r"(0), "r"(w.x0),
+                       "r"(w.b * a.Hp + DS_RP + w.yi0 + i * dil)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // ================================ depthwise warps (0..7) ================================
+    const int q = tid & 7;    // channel quad
+    const int pg = tid >> 3;  // 0..31: pixel group = (block of 4*dil pixels, offset g inside the stride)
+    const int blk = pg / dil, g = pg - blk * dil;
+    const int pbase = blk * 4 * dil + g;                      // first of this thread's 4 pixels (stride dil)
+    const uint32_t in_off = (uint32_t)pbase * 128 + q * 16;   // ring column of tap kx = 0 of pixel 0 is pbase (box starts at x0 - dil)
+    const uint32_t jstep = (uint32_t)dil * 128;
+    const uint32_t in_base = smem_u32(smem + DS_OFF_IN), a_base = smem_u32(smem + DS_OFF_A);
+    const uint32_t w_base = smem_u32(sW) + q * 16;
+    uint32_t a_off[4];  // byte offsets of the hi halves of this thread's 4 pixels inside an A tile (lo = chunk + 4)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = pbase + j * dil;
+      a_off[j] = (uint32_t)p * 128 + (q & 1) * 8 + ((uint32_t)((q >> 1) ^ (p & 7)) << 4);
+    }
+    uint32_t it = 0, t = 0;
+    float4 win[3][6];
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const DsItem w = ds_decode(a, item);
+      if (w.nrows == 0) continue;
+      int npend = 0;  // ring slots read but not yet released (released once their values have been consumed)
+      auto load_line = [&](float4(&dst)[6]) {
+        const uint32_t slot = it % DS_NIN;
+        mbar_wait(in_full + slot, (it / DS_NIN) & 1);
+        const uint32_t s = in_base + slot * DS_INBYTES + in_off;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dst[j] = lds128(s + j * jstep);
+        ++it, ++npend;
+      };
+      auto emit = [&](const float4(&top)[6], const float4(&mid)[6], const float4(&bot)[6]) {
+        float4 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4(&row)[6] = ky == 0 ? top : (ky == 1 ? mid : bot);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 k = lds128(w_base + (ky * 3 + kx) * 128);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j].x = fmaf(row[j + kx].x, k.x, acc[j].x), acc[j].y = fmaf(row[j + kx].y, k.y, acc[j].y);
+              acc[j].z = fmaf(row[j + kx].z, k.z, acc[j].z), acc[j].w = fmaf(row[j + kx].w, k.w, acc[j].w);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          for (; npend > 0; --npend) mbar_arrive(in_empty + (it - npend) % DS_NIN);
+        npend = 0;
+        const uint32_t ab = t % DS_NA;
+        mbar_wait(a_empty + ab, ((t / DS_NA) & 1) ^ 1);
+        const uint32_t dst = a_base + ab * DS_TILE;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2 h01 = __floats2half2_rn(acc[j].x, acc[j].y), h23 = __floats2half2_rn(acc[j].z, acc[j].w);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn((acc[j].x - f01.x) * 2048.f, (acc[j].y - f01.y) * 2048.f);
+          const __half2 l23 = __floats2half2_rn((acc[j].z - f23.x) * 2048.f, (acc[j].w - f23.y) * 2048.f);
+          sts64(dst + a_off[j], h2_bits(h01), h2_bits(h23));
+          sts64(dst + (a_off[j] ^ 64u), h2_bits(l01), h2_bits(l23));  // chunk + 4 (bit 6 of the swizzled offset)
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + ab);
+        ++t;
+      };
+      load_line(win[0]);
+      load_line(win[1]);
+      for (int i = 0; i < w.nrows; i += 3) {
+        load_line(win[2]);
+        emit(win[0], win[1], win[2]);
+        if (i + 1 >= w.nrows) break;
+        load_line(win[0]);
+        emit(win[1], win[2], win[0]);
+        if (i + 2 >= w.nrows) break;
+        load_line(win[1]);
+        emit(win[2], win[0], win[1]);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == DS_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(DS_NT * 64));
+}
+
+// in/out: CLP [B][H + 2*RP][W + 2*RP][32]; dw [32][9]; pwh/scales: see DsArgs; dil in {1,2,4,8,16}
+int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
+                     int H, int W, int dil, int relu, cudaStream_t st) {
+  if (dil < 1 || dil > DS_RP || (32 % dil) != 0) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(dwsep_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  DsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dw = dw, a.pwh = (const __half*)pwh, a.scales = scales, a.bias = bias, a.out = out;
+  a.B = B, a.Hp = H + 2 * DS_RP, a.Wp = W + 2 * DS_RP, a.H = H, a.dil = dil, a.relu = relu;
+  a.nxt = (a.Wp + 127) / 128;
+  const int rows_phase = (H + dil - 1) / dil;
+  // segments of ~16 lines (two warm-up line loads each); at least ~4 items per SM so the static round-robin balances
+  a.seg_len = rows_phase < 16 ? rows_phase : 16;
+  a.segs = (rows_phase + a.seg_len - 1) / a.seg_len;
+  a.seg_len = (rows_phase + a.segs - 1) / a.segs;
+  a.total_items = B * a.nxt * dil * a.segs;
+  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+  CUtensorMap map_in, map_out;
+  const uint64_t dims[3] = {32, (uint64_t)a.Wp, (uint64_t)B * a.Hp}, strides[2] = {128, (uint64_t)a.Wp * 128};
+  const uint32_t box_in[3] = {32, (uint32_t)(128 + 2 * dil), 1}, box_out[3] = {32, 128, 1};
+  int rc = make_tensor_map_f32(&map_in, in, 3, dims, strides, box_in, false);
+  if (rc) return rc;
+  rc = make_tensor_map_f32(&map_out, out, 3, dims, strides, box_out, true);
+  if (rc) return rc;
+  dwsep_f16_kernel<<<grid, DS_THREADS, DS_SMEM, st>>>(map_in, map_out, a);
+  e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
+}  // namespace lws

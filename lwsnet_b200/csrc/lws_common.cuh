@@ -19,6 +19,9 @@
 namespace lws {
 
 constexpr int kNumSMs = 148;  // B200
+// split-fp16 tensor-core operands (x = hi + lo * 2^-11, both fp16): activations are pre-scaled by this power of two so that
+// values up to 4.19e6 stay finite in fp16; weights carry their own per-layer power-of-two scale (see the pack functions)
+constexpr float kDwsepActScale = 0.015625f;  // 2^-6
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return cdiv(a, b) * b; }

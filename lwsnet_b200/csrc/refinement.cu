@@ -7,6 +7,7 @@
 // final interpolate (same size => identity) is dropped.
 //   dense 3x3 convs  : conv2d.cuh (FP32 direct, smem tiled)
 //   BN-ReLU-DW-PW    : dwsep_block_kernel below (phase-row tiling, depthwise result kept in registers)
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 
@@ -292,9 +293,25 @@ extern "C" int lws_pack_refinement_weights(const float* const* t, int n_tensors,
     memcpy(hi, &u, 4);
     *lo = w - *hi;
   };
-  auto pack_pwtc = [&](const float* pwf /*[ci][co]*/, float* tc /*[64][32]*/) {
+  // split-fp16 pointwise operand table (dwsep_tc.cu): [64][32] halves, rows 0..31 = fp16(w * sw), rows 32..63 =
+  // fp16((w * sw - hi) * 2^11), sw = the power of two that puts max|w| into [256, 512); then the two epilogue scales
+  // c0 = 1 / (act_scale * sw) and c1 = c0 * 2^-11 at float offsets 1024 / 1025 of the slot
+  auto pack_pwtc = [&](const float* pwf /*[ci][co]*/, float* slot /*2048 floats*/) {
+    float mx = 0.f;
+    for (int i = 0; i < 32 * 32; ++i) mx = fmaxf(mx, fabsf(pwf[i]));
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+    __half* h = reinterpret_cast<__half*>(slot);
     for (int co = 0; co < 32; ++co)
-      for (int ci = 0; ci < 32; ++ci) split(pwf[ci * 32 + co], tc + co * 32 + ci, tc + (32 + co) * 32 + ci);
+      for (int ci = 0; ci < 32; ++ci) {
+        const float w = pwf[ci * 32 + co] * sw;
+        const __half hi = __float2half_rn(w);
+        h[co * 32 + ci] = hi;
+        h[(32 + co) * 32 + ci] = __float2half_rn((w - __half2float(hi)) * 2048.f);
+      }
+    slot[1024] = 1.f / (kDwsepActScale * sw);
+    slot[1025] = slot[1024] / 2048.f;
   };
   for (int br = 0; br < 2; ++br)
     for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r1_pw[br][j], packed + L.r1_pwtc[br][j]);

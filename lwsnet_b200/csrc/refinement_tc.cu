@@ -1,12 +1,8 @@
 // K6 on the tensor cores: the colour-guidance refinement (reference models/submodules.py:223-327, models/models.py:158-162)
 // in channels-last "CLP" layout  act[b][y][x][32] fp32 with a 16-pixel zero border (the largest dilation), so every
 // 32-channel pixel is one 128-byte row and every dilated tap is a constant row offset.
-//   * BN-ReLU-DW(dil)-PW block  -> dwsep_tc_kernel: the depthwise 3x3 runs on the CUDA cores straight from global memory
-//     (8 lanes per pixel, 128-bit coalesced loads), its result is written as the A operand (x and x - trunc(x)) into
-//     SWIZZLE_128B shared-memory tiles, and the 32x32 pointwise product is 8 tcgen05.mma (3xTF32 split, see conv3d_tc.cu)
-//     against a weight tile that stays resident in shared memory; accumulators ping-pong in TMEM so the MMA of tile i
-//     overlaps the depthwise phase of tile i+1 and the epilogue of tile i-1.  Only 4 accumulation steps per output, so
-//     the result is fp32-exact to a couple of ulps.
+//   * BN-ReLU-DW(dil)-PW block  -> dwsep_f16_kernel (dwsep_tc.cu): TMA-fed depthwise on the CUDA cores with the 3x3 window in
+//     registers, pointwise product on tcgen05 with split-fp16 operands.
 //   * dense 64->32 dilation-8 3x3 -> the implicit-GEMM kernel of conv3d_tc.cu with 6 stages (2 sources x 3 kh), kw taps 8
 //     rows apart in the stage tile; the concat is never formed (the two refinement1 branches are the two sources).
 //   * 3->32 / 1->32 first convs and the 32->1 last conv (+ skip) are small FP32 kernels reading / writing CLP.
@@ -111,235 +107,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---- BN-ReLU-DW(dil)-PW block on CLP, pointwise product on tcgen05 -------------------------------------------------------
-struct DwTcArgs {
-  const float* in;    // CLP [B][R][32] post-activation
-  float* out;         // CLP [B][R][32]
-  const float* dw;    // [32][9]
-  const float* pwtc;  // [64][32]: rows 0..31 = tf32-truncated folded pointwise weights (row = cout, col = cin), 32..63 = remainder
-  const float* bias;  // [32]
-  int R, Hp, Wp, dil, relu;
-  int nxt, segs, seg_len, total_items;  // strip schedule: item = (b, x tile, row phase, segment of seg_len phase-rows)
-};
-constexpr int DT_THREADS = 512;
-constexpr int DT_SMEM = 4 * 16384 + 8192 + 1024 + 64;
-
-__device__ __forceinline__ uint64_t dt_sdesc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void dt_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-}
-
-__device__ __forceinline__ void dt_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-}
-
-__global__ void __launch_bounds__(DT_THREADS, 1) dwsep_tc_kernel(const DwTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;              // [2][16384] depthwise result (= xh for the MMA)
-  uint8_t* sL = smem + 32768;      // [2][16384] x - trunc(x)
-  uint8_t* sB = smem + 65536;      // [64][128 B] pointwise operand, SWIZZLE_128B
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 65536 + 8192);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    mbar_init(mma_bar, 1);
-    mbar_init(mma_bar + 1, 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  for (int idx = tid; idx < 64 * 8; idx += DT_THREADS) {
-    const int n = idx >> 3, c = idx & 7;
-    *reinterpret_cast<float4*>(sB + n * 128 + ((c ^ (n & 7)) << 4)) = __ldg(reinterpret_cast<const float4*>(a.pwtc + n * 32 + c * 4));
-  }
-  fence_proxy_async_smem();
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
-
-  const int q = tid & 7;  // channel quad of the depthwise phase
-  float4 kq[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-    kq[t] = make_float4(__ldg(a.dw + (q * 4 + 0) * 9 + t), __ldg(a.dw + (q * 4 + 1) * 9 + t), __ldg(a.dw + (q * 4 + 2) * 9 + t),
-                        __ldg(a.dw + (q * 4 + 3) * 9 + t));
-  const int quarter = warp & 3, cgrp = warp >> 2;  // epilogue: TMEM lane quarter / group of 8 channels of this warp
-  float bias[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bias[j] = __ldg(a.bias + cgrp * 8 + j);
-  const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-  const int dil = a.dil, Wp = a.Wp, Hp = a.Hp, R = a.R;
-  const long long tap_step_y = (long long)dil * Wp * 32, tap_step_x = (long long)dil * 32;
-
-  // tile = 128 consecutive pixels of one image line: rows r0 .. r0+127 of batch element b, of which the first `nval` exist
-  auto epilogue = [&](int j, int b, int r0, int nval) {
-    const int pbuf = j & 1;
-    mbar_wait(mma_bar + pbuf, (j >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + pbuf * 96 + cgrp * 8;
-    float acc[8], t[8];
-    dt_ld8(taddr, acc);
-    dt_ld8(taddr + 32, t);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] += t[c];
-    dt_ld8(taddr + 64, t);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] += t[c];
-    const int p = quarter * 32 + lane;
-    if (p < nval) {
-      const int r = r0 + p;
-      const int y = r / Wp, x = r - y * Wp;
-      const bool border = x < RP || x >= Wp - RP || y < RP || y >= Hp - RP;
-      const float lo = a.relu ? 0.f : -INFINITY;
-      float4* o = reinterpret_cast<float4*>(a.out + ((long long)b * R + r) * 32 + cgrp * 8);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float4 v;
-        v.x = border ? 0.f : fmaxf(acc[4 * c] + bias[4 * c], lo);
-        v.y = border ? 0.f : fmaxf(acc[4 * c + 1] + bias[4 * c + 1], lo);
-        v.z = border ? 0.f : fmaxf(acc[4 * c + 2] + bias[4 * c + 2], lo);
-        v.w = border ? 0.f : fmaxf(acc[4 * c + 3] + bias[4 * c + 3], lo);
-        o[c] = v;
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  };
-
-  // Strip schedule: an item is a run of seg_len image lines of the same row phase (y = py + i*dil) in one 128-pixel
-  // column tile, walked top to bottom, so two of the three tap rows of every tile are L1 hits from the previous tile.
-  int i = 0, pb = 0, pr0 = 0, pnval = 0;
-  for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-    int t = item;
-    const int seg = t % a.segs;
-    t /= a.segs;
-    const int py = t % dil;
-    t /= dil;
-    const int xt = t % a.nxt;
-    const int b = t / a.nxt;
-    const int nval = min(128, Wp - xt * 128);
-    for (int iy = seg * a.seg_len; iy < (seg + 1) * a.seg_len; ++iy) {
-      const int y = py + iy * dil;
-      if (y >= Hp) break;
-      const int buf = i & 1;
-      const int r0 = y * Wp + xt * 128;
-      const bool yin = y >= RP && y < Hp - RP;
-      // ---- depthwise phase: 128 pixels x 8 channel quads, 2 items per thread; loads are unconditional (border pixels
-      //      read their own row and are zeroed afterwards) ----
-      float4 v[2][9];
-      bool inside[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {  // issue all 18 tap loads of this thread before touching any of them: one round trip
-        const int p = (tid >> 3) + 64 * j;
-        const int x = xt * 128 + p;
-        inside[j] = yin && x >= RP && x < Wp - RP;
-        const long long sy = inside[j] ? tap_step_y : 0, sx = inside[j] ? tap_step_x : 0;
-        const float* base = a.in + ((long long)b * R + (p < nval ? r0 + p : r0)) * 32 + q * 4;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-            v[j][ky * 3 + kx] = __ldg(reinterpret_cast<const float4*>(base + (ky - 1) * sy + (kx - 1) * sx));
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int p = (tid >> 3) + 64 * j;
-        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 k = kq[t];
-          d.x = fmaf(v[j][t].x, k.x, d.x), d.y = fmaf(v[j][t].y, k.y, d.y), d.z = fmaf(v[j][t].z, k.z, d.z),
-          d.w = fmaf(v[j][t].w, k.w, d.w);
-        }
-        if (!inside[j]) d = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 l;
-        l.x = d.x - __uint_as_float(__float_as_uint(d.x) & 0xFFFFE000u);
-        l.y = d.y - __uint_as_float(__float_as_uint(d.y) & 0xFFFFE000u);
-        l.z = d.z - __uint_as_float(__float_as_uint(d.z) & 0xFFFFE000u);
-        l.w = d.w - __uint_as_float(__float_as_uint(d.w) & 0xFFFFE000u);
-        const int addr = buf * 16384 + p * 128 + ((q ^ (p & 7)) << 4);
-        *reinterpret_cast<float4*>(sA + addr) = d;
-        *reinterpret_cast<float4*>(sL + addr) = l;
-      }
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (warp == 0 && elect_one_sync()) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(sA + buf * 16384), l_addr = smem_u32(sL + buf * 16384), b_addr = smem_u32(sB);
-        const uint32_t d_hh = tmem + buf * 96, d_lh = d_hh + 64;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t db = dt_sdesc(b_addr + k * 32);
-          const uint32_t accf = k > 0;
-          asm volatile(
-              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_hh),
-              "l"(dt_sdesc(a_addr + k * 32)), "l"(db), "r"(idesc64), "r"(accf)
-              : "memory");
-          asm volatile(
-              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_lh),
-              "l"(dt_sdesc(l_addr + k * 32)), "l"(db), "r"(idesc32), "r"(accf)
-              : "memory");
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mma_bar + buf))
-                     : "memory");
-      }
-      if (i > 0) epilogue(i - 1, pb, pr0, pnval);
-      pb = b, pr0 = r0, pnval = nval;
-      ++i;
-    }
-  }
-  if (i > 0) epilogue(i - 1, pb, pr0, pnval);
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
-}
-
-static int launch_dwsep_tc(DwTcArgs a, int B, cudaStream_t st) {
-  if (a.dil < 1 || a.dil > RP) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(dwsep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  a.nxt = (a.Wp + 127) / 128;
-  const int rows_per_phase = (a.Hp + a.dil - 1) / a.dil;
-  a.seg_len = 16;
-  a.segs = (rows_per_phase + a.seg_len - 1) / a.seg_len;
-  a.total_items = B * a.nxt * a.dil * a.segs;
-  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-  dwsep_tc_kernel<<<grid, DT_THREADS, DT_SMEM, st>>>(a);
-  e = cudaPeekAtLastError();
-  return e == cudaSuccess ? LWS_OK : (int)e;
-}
+// BN-ReLU-DW(dil)-PW block on CLP (dwsep_tc.cu)
+int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
+                     int H, int W, int dil, int relu, cudaStream_t st);
 
 // ---- host ------------------------------------------------------------------------------------------------------------------
 struct RefTcWeights {
@@ -375,12 +145,10 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
     float* cur = ping;
     float* nxt = pong;
     for (int j = 0; j < 4; ++j) {
-      DwTcArgs d;
-      memset(&d, 0, sizeof(d));
-      d.in = cur, d.out = j < 3 ? nxt : (br == 0 ? catL : catD);
-      d.dw = wt.dw[br][j], d.pwtc = wt.pwtc[br][j], d.bias = wt.bias[br][j];
-      d.R = (int)R, d.Hp = Hp, d.Wp = Wp, d.dil = r1_dil[j], d.relu = 1;
-      if ((rc = launch_dwsep_tc(d, B, st))) return rc;
+      float* dst = j < 3 ? nxt : (br == 0 ? catL : catD);
+      if ((rc = launch_dwsep_f16(cur, dst, wt.dw[br][j], wt.pwtc[br][j], wt.pwtc[br][j] + 1024, wt.bias[br][j], B, H, W,
+                                 r1_dil[j], 1, st)))
+        return rc;
       float* t = cur;
       cur = nxt, nxt = t;
     }
@@ -395,11 +163,9 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
   float* cur = ping;
   float* nxt = pong;
   for (int j = 0; j < 4; ++j) {
-    DwTcArgs d;
-    memset(&d, 0, sizeof(d));
-    d.in = cur, d.out = nxt, d.dw = wt.dw[2][j], d.pwtc = wt.pwtc[2][j], d.bias = wt.bias[2][j];
-    d.R = (int)R, d.Hp = Hp, d.Wp = Wp, d.dil = r2_dil[j], d.relu = j < 3;
-    if ((rc = launch_dwsep_tc(d, B, st))) return rc;
+    if ((rc = launch_dwsep_f16(cur, nxt, wt.dw[2][j], wt.pwtc[2][j], wt.pwtc[2][j] + 1024, wt.bias[2][j], B, H, W, r2_dil[j],
+                               j < 3, st)))
+      return rc;
     float* t = cur;
     cur = nxt, nxt = t;
   }

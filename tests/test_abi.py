@@ -111,11 +111,16 @@ def test_pack_refinement_folds_bn():
     # last section: conv_last [32][9][1], unscaled
     wl = m.refinement2[5].weight.detach().numpy().reshape(32 * 9)
     assert np.allclose(packed[36096 - 288:36096], wl)
-    # tensor-core operand tables: first pointwise table = tf32-truncated folded weights [co][ci] + remainders, hi + lo == w
+    # tensor-core operand tables: first pointwise table = split-fp16 folded weights [co][ci]: hi = fp16(w * sw),
+    # lo = fp16((w * sw - hi) * 2^11) with sw the power of two that puts max|w| into [256, 512); then the epilogue scales
     pwf = packed[896 + 288:896 + 288 + 1024].reshape(32, 32)           # block 1 of R1_left, [ci][co]
-    tc = packed[36096:36096 + 2048].reshape(64, 32)
-    assert np.array_equal(tc[:32] + tc[32:], pwf.T)
-    assert np.all((tc[:32].view(np.uint32) & 0x1FFF) == 0)
+    slot = packed[36096:36096 + 2048]
+    tc = slot[:1024].view(np.float16).reshape(64, 32).astype(np.float64)
+    c0, c1 = float(slot[1024]), float(slot[1025])
+    sw = 1.0 / (c0 * 2.0 ** -6)
+    assert 256 <= np.abs(pwf).max() * sw < 512 and np.log2(sw) == int(np.log2(sw)) and c1 == c0 / 2048
+    rec = (tc[:32] + tc[32:] / 2048) / sw
+    assert np.abs(rec - pwf.T.astype(np.float64)).max() <= 2.0 ** -22 * np.abs(pwf).max()   # 22-bit significand
     with pytest.raises(Exception):
         ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2)[:-1], BN_EPS)
 

@@ -51,6 +51,13 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
 struct BenchCfg {
   int kind, N, layout, a_slots, nmma, two_acc;
 };
@@ -78,22 +85,31 @@ __global__ void __launch_bounds__(128) rate_kernel(BenchCfg c, long long* cycles
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
+  if (warp == 1) {
     const uint32_t idesc = (1u << 4) | ((uint32_t)c.kind << 7) | ((uint32_t)c.kind << 10) | ((uint32_t)(c.N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t lbo = c.layout == 0 ? 128 : 16, sbo = c.layout == 0 ? 256 : 1024;
-    long long t0 = clock64();
-    for (int i = 0; i < c.nmma; ++i) {
-      const uint32_t slot = i % c.a_slots;
-      const uint64_t da = make_desc(smem_u32(sA + slot * 16384) + (c.layout == 2 ? (i & 3) * 32 : 0), lbo, sbo, c.layout);
-      const uint64_t db = make_desc(smem_u32(sB) + (c.layout == 2 ? (i & 3) * 32 : 0), lbo, sbo, c.layout);
-      const uint32_t d = tmem + (c.two_acc ? (i & 1) * 256 : 0);
-      if (c.kind == 2) mma<2>(d, da, db, idesc, i > 1);
-      else mma<0>(d, da, db, idesc, i > 1);
+    const uint64_t hi = make_desc(0, lbo, sbo, c.layout);
+    const uint32_t a_lo = (smem_u32(sA) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+    const uint32_t slot_step = c.a_slots > 1 ? (16384 >> 4) : 0;
+    const uint32_t kstep = c.layout == 2 ? 2 : 0;
+    long long t0 = 0;
+    if (elect_one_sync()) {
+      t0 = clock64();
+      for (int i = 0; i < c.nmma; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint64_t da = hi | (uint64_t)(a_lo + u * slot_step + (u & 3) * kstep);
+          const uint64_t db = hi | (uint64_t)(b_lo + (u & 3) * kstep);
+          const uint32_t d = tmem + (c.two_acc ? (u & 1) * 256 : 0);
+          if (c.kind == 2) mma<2>(d, da, db, idesc, 1);
+          else mma<0>(d, da, db, idesc, 1);
+        }
+      }
+      commit(bar);
+      mbar_wait(bar, 0);
+      cycles[blockIdx.x] = clock64() - t0;
     }
-    commit(bar);
-    mbar_wait(bar, 0);
-    long long t1 = clock64();
-    cycles[blockIdx.x] = t1 - t0;
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -249,6 +265,7 @@ int main() {
             CK(cudaMemcpy(cy.data(), dcy, grid * 8, cudaMemcpyDeviceToHost));
             long long mx = 0;
             for (auto v : cy) mx = v > mx ? v : mx;
+            fflush(stdout);
             printf("rate grid=%3d kind=%s layout=%s N=%3d a_slots=%d: %.1f cyc/MMA (ideal N/2=%d)\n", grid, kind == 2 ? "tf32" : "f16 ",
                    layout == 2 ? "SW128" : "NONE ", N, slots, (double)mx / c.nmma, N / 2);
           }

@@ -96,16 +96,6 @@ LWS_API int lws_conv3d_stack_f32(const float* cost, const float* packed_weights,
 LWS_API int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folded, const float* bias, float* out, int B, int C,
                                         int D, int H, int W, lws_stream_t stream);
 
-/* The tensor-core (tcgen05, 3xTF32) form of one C -> C layer, C = 32 or 8, on its own: channels-last bordered tensors
- * ("CLP": act[b][d][y in 0..H+1][x in 0..Wp-1][C], interior y in 1..H, x in 1..W, Wp = W+2 rounded up to a multiple of
- * 32/C, borders zero; lws_conv3d_clp_floats gives the element count).  tc_table / bias point into the packed blob at
- * lws_conv3d_stack_tc_table_offset / lws_conv3d_stack_bias_offset(C, layers, mid_layer + 1) floats. */
-LWS_API size_t lws_conv3d_stack_tc_table_offset(int C, int layers, int mid_layer);
-LWS_API size_t lws_conv3d_stack_bias_offset(int C, int layers, int conv);
-LWS_API size_t lws_conv3d_clp_floats(int B, int C, int D, int H, int W);
-LWS_API int lws_conv3d_tc_layer_f32(const float* in_clp, const float* tc_table, const float* bias, float* out_clp, int B,
-                                    int C, int D, int H, int W, lws_stream_t stream);
-
 /* ---- a6: F.softmax(-cost, axis=1) + disparity_regression  (models/models.py:142,151-152,167-179) ----
  * low[b,0,y,x] = sum_j softmax_j(-cost[b,:,y,x]) * (start + j*step).  One pass over the volume. */
 LWS_API int lws_softmax_regression_f32(const float* cost, float* low, int B, int D, int H, int W, float start, float step,

@@ -33,10 +33,6 @@ SIGNATURES = {
     "lws_conv3d_stack_f32": (c_int, [_fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "lws_conv3d_bnrelu_layer_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "lws_conv3d_stack_tc_table_offset": (c_size_t, [c_int, c_int, c_int]),
-    "lws_conv3d_stack_bias_offset": (c_size_t, [c_int, c_int, c_int]),
-    "lws_conv3d_clp_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "lws_conv3d_tc_layer_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_softmax_regression_f32": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "lws_scale_upsample_add_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_refinement_packed_floats": (c_size_t, []),

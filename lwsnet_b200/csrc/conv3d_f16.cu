@@ -1,0 +1,546 @@
+// K3 (C = 32) and the dense refinement conv on the 5th-generation tensor cores with split-fp16 operands.
+//
+// Replaces the 32 -> 32 layers of post_3dconvs(4, 32) (reference models/submodules.py:190-221) and, with TZ = 8, the dense
+// 64 -> 32 dilation-8 conv of refinement2 (models/submodules.py:302-312).
+//
+// Numerics: every activation x and folded weight w is carried as two fp16 values, x*sa = xh + xl * 2^-11 (sa = 2^-6),
+// w*sw = wh + wl * 2^-11 (sw = per-layer power of two).  acc_main = sum xh*wh, acc_corr = sum (xh*wl + xl*wh) in fp32 (TMEM);
+// products of two 11-bit significands are exact in fp32, the dropped xl*wl term is 2^-22 relative: fp32-grade results at the
+// fp16 tensor rate (plain TF32/BF16 operands move stage-1 disparities by whole pixels).
+//
+// Cost model (tools/umma_bench.cu): one tcgen05.mma with both operands in shared memory takes ~40 + N/2 cycles at M = 128,
+// whatever the kind, so the work is arranged as few, wide MMAs ("Toeplitz-N"):
+//   * a GEMM row is one voxel = 128 bytes [32 hi | 32 lo] halves; voxels are stored with the Toeplitz axis fastest
+//     (3D stack: act[b][y][x][d], d padded by one zero voxel each side, x padded, y padding = TMA out-of-bounds zero fill);
+//   * the three taps along the fastest axis are folded into N: D[r', t*32+co] = sum_ci x[r', ci] * w[t][ci][co], t = 0..2, and
+//     the epilogue adds the three column blocks of three neighbouring rows: out[r] = D[r-TZ, 0] + D[r, 1] + D[r+TZ, 2].
+//     With the hi/lo weight halves side by side, N = 192 for the xh operand and N = 96 (accumulated onto the wl columns) for
+//     the xl operand: 4 MMAs per (stage, window) instead of 24;
+//   * the taps along the middle axis are row-shifted windows (UMMA descriptor offsets) of ONE TMA box per stage, the taps
+//     along the slowest axis are the stages: 3 TMA loads of 23 KB per 126 output voxels for the 3D stack;
+//   * all weights of the layer (27 x 32 x 32 hi + lo = 108 KB) stay resident in shared memory.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (2 accumulators x 192 columns),
+// warps 2-5 = epilogue (tcgen05.ld, Toeplitz row shifts by warp shuffles + a small shared-memory exchange at the warp
+// boundaries, bias + ReLU, border zeroing, re-split into hi/lo, staged through shared memory into one TMA store).
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include "lws_common.cuh"
+#include "tma_utils.cuh"
+
+namespace lws {
+
+constexpr int TZ_THREADS = 192;
+constexpr int TZ_MAXST = 6;
+constexpr int TZ_BTILE = 192 * 128;  // one weight tile: 192 rows x [block 2i | block 2i+1] x 32 halves
+constexpr int TZ_NSLOT = 3;
+
+struct TzArgs {
+  const float* bias;    // [32]
+  const float* scales;  // [2] device: 1/sw, 1/(sw * 2^11)
+  float out_mul;        // epilogue multiplier on top of scales: 1 for split-fp16 output (values stay scaled by sa), 1/sa for fp32
+  float bias_mul;       // sa for split-fp16 output, 1 for fp32
+  int out_split;        // 1: rows [32 hi | 32 lo] halves; 0: rows of 32 fp32
+  int relu;
+  int R;                // rows per batch element
+  int n0, p0, i0;       // fastest axis: length (padded), pad, interior length  -> rows outside the interior are written as 0
+  int n1, p1, i1;       // middle axis
+  int tiles_per_b, total_tiles;
+  int nstages, nshift, nbtiles;
+  int slot_bytes, box_bytes;
+  int st_off[TZ_MAXST];  // row offset of the stage's box relative to the tile's first GEMM row
+  int st_src[TZ_MAXST];
+  int shift_rows[3];     // row offset of window k inside the box
+};
+
+__device__ __forceinline__ void tz_mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tz_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// TZ = Toeplitz row shift (1: 3D stack along d; 8: dilated 2D conv along x).  Output rows per tile: 128 - 2*TZ.
+template <int TZ>
+__global__ void __launch_bounds__(TZ_THREADS, 1)
+    tz_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut, const TzArgs a) {
+  constexpr int OUTR = 128 - 2 * TZ;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;                                   // [nbtiles][24576]
+  uint8_t* sOut = sB + a.nbtiles * TZ_BTILE;             // [16384] staging tile
+  uint8_t* sA = sOut + 16384;                            // [NSLOT][slot_bytes]
+  uint8_t* tail = sA + TZ_NSLOT * a.slot_bytes;
+  float* xch = reinterpret_cast<float*>(tail);           // [4 quarters][3*TZ rows][32] boundary rows for the Toeplitz shifts
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4 * 3 * TZ * 32 * 4);
+  uint64_t* a_full = bars;                 // [NSLOT]
+  uint64_t* a_empty = a_full + TZ_NSLOT;   // [NSLOT]
+  uint64_t* b_full = a_empty + TZ_NSLOT;   // [1]
+  uint64_t* t_full = b_full + 1;           // [2]
+  uint64_t* t_empty = t_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < TZ_NSLOT; ++i) mbar_init(a_full + i, 1), mbar_init(a_empty + i, 1);
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
+    mbar_fence_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapOut);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int nst = a.nstages;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one_sync()) {
+      mbar_expect_tx(b_full, (uint32_t)a.nbtiles * TZ_BTILE);
+      for (int i = 0; i < a.nbtiles; ++i) tma_load_2d(sB + i * TZ_BTILE, &mapB, b_full, 0, i * 192);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_b;
+        const int row0 = (tile - b * a.tiles_per_b) * OUTR - TZ;  // GEMM row 0 of the tile
+        for (int s = 0; s < nst; ++s, ++it) {
+          const uint32_t slot = it % TZ_NSLOT;
+          mbar_wait(a_empty + slot, ((it / TZ_NSLOT) & 1) ^ 1);
+          mbar_expect_tx(a_full + slot, (uint32_t)a.box_bytes);
+          const CUtensorMap* src = a.st_src[s] ? &mapA1 : &mapA0;
+          // 3D map {32 words, R, B}: rows outside [0, R) come back as zeros (the padding of the slowest axis)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+              "[%2];" ::"r"(smem_u32(sA + slot * a.slot_bytes)),
+              "l"(reinterpret_cast<uint64_t>(src)), "r"(smem_u32(a_full + slot)), "r"(0), "r"(row0 + a.st_off[s]), "r"(b)
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc192 = (1u << 4) | ((192u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128
+    const uint32_t idesc96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
+    const uint32_t b_lo = ((smem_u32(sB) & 0x3FFFF) >> 4) | (1u << 16);
+    const int nsh = a.nshift;
+    const uint32_t sh0 = (uint32_t)a.shift_rows[0] * 8, sh1 = (uint32_t)a.shift_rows[1] * 8, sh2 = (uint32_t)a.shift_rows[2] * 8;
+    mbar_wait(b_full, 0);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t tb = ti & 1;
+      mbar_wait(t_empty + tb, ((ti >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_main = tmem + tb * 256;
+      for (int s = 0; s < nst; ++s, ++it) {
+        const uint32_t slot = it % TZ_NSLOT;
+        mbar_wait(a_full + slot, (it / TZ_NSLOT) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one_sync()) {
+          const uint32_t x_lo = ((smem_u32(sA + slot * a.slot_bytes) & 0x3FFFF) >> 4) | (1u << 16);
+          for (int k = 0; k < nsh; ++k) {
+            const int blk = s * nsh + k;
+            const uint32_t wa = x_lo + (k == 0 ? sh0 : (k == 1 ? sh1 : sh2));                   // window base (16-byte units)
+            const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE >> 4) + (blk & 1) * 4;  // weight block
+            const uint32_t first = (s | k) == 0 ? 0u : 1u;
+            tz_mma(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, first);
+            tz_mma(d_main, desc_hi | (uint64_t)(wa + 2), desc_hi | (uint64_t)(wb + 2), idesc192, 1u);
+            tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 4), desc_hi | (uint64_t)(wb + 0), idesc96, 1u);
+            tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wb + 2), idesc96, 1u);
+          }
+          tz_commit(a_empty + slot);
+          if (s == nst - 1) tz_commit(t_full + tb);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;           // TMEM lane quarter
+    const int j = q * 32 + lane;      // GEMM row of the tile; this thread produces output row j + TZ -> staging row j
+    const bool issuer = warp == 2 && lane == 0;
+    const float c0 = __ldg(a.scales) * a.out_mul, c1 = __ldg(a.scales + 1) * a.out_mul;
+    const float relu_lo = a.relu ? 0.f : -INFINITY;
+    const bool has1 = lane + TZ < 32, has2 = lane + 2 * TZ < 32;
+    float bias[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bias[c] = __ldg(a.bias + c) * a.bias_mul;
+    float* xq = xch + q * (3 * TZ * 32);         // this quarter publishes: rows [0,TZ) E1 of lanes 0..TZ-1, [TZ,3TZ) E2 of lanes 0..2TZ-1
+    const float* xn = xch + ((q + 1) & 3) * (3 * TZ * 32);  // next quarter's rows
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t tb = ti & 1;
+      const int b = tile / a.tiles_per_b;
+      const int orow0 = (tile - b * a.tiles_per_b) * OUTR;  // first output row of the tile
+      mbar_wait(t_full + tb, (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tb * 256;
+      float out[32];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // 8 output channels at a time
+        float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];
+        tz_ld8(taddr + cc * 8, m0);
+        tz_ld8(taddr + 32 + cc * 8, m1);
+        tz_ld8(taddr + 64 + cc * 8, m2);
+        tz_ld8(taddr + 96 + cc * 8, k0);
+        tz_ld8(taddr + 128 + cc * 8, k1);
+        tz_ld8(taddr + 160 + cc * 8, k2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // tap t of GEMM row j contributes to staging row j - t*TZ:
+        // staging row j = e0 of GEMM row j + e1 of GEMM row j + TZ + e2 of GEMM row j + 2 TZ
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float e0 = fmaf(k0[c], c1, m0[c] * c0);
+          m1[c] = fmaf(k1[c], c1, m1[c] * c0);
+          m2[c] = fmaf(k2[c], c1, m2[c] * c0);
+          const float s1 = __shfl_down_sync(0xffffffffu, m1[c], TZ);
+          const float s2 = __shfl_down_sync(0xffffffffu, m2[c], (2 * TZ) & 31);
+          out[cc * 8 + c] = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
+        }
+        if (lane < 2 * TZ) {  // rows the previous quarter needs
+          float4* d2 = reinterpret_cast<float4*>(xq + (TZ + lane) * 32 + cc * 8);
+          d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
+          if (lane < TZ) {
+            float4* d1 = reinterpret_cast<float4*>(xq + lane * 32 + cc * 8);
+            d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
+          }
+        }
+        __syncwarp();
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + tb);
+      // previous tile's TMA store must have finished reading the staging tile before anyone overwrites it
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      named_bar_sync(1, 128);
+      if (q < 3) {  // rows of the next quarter (the last quarter's missing rows belong to the next tile)
+        if (!has1) {
+          const float4* p1 = reinterpret_cast<const float4*>(xn + (lane + TZ - 32) * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = p1[c];
+            out[4 * c] += v.x, out[4 * c + 1] += v.y, out[4 * c + 2] += v.z, out[4 * c + 3] += v.w;
+          }
+        }
+        if (!has2) {
+          const float4* p2 = reinterpret_cast<const float4*>(xn + (TZ + lane + 2 * TZ - 32) * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = p2[c];
+            out[4 * c] += v.x, out[4 * c + 1] += v.y, out[4 * c + 2] += v.z, out[4 * c + 3] += v.w;
+          }
+        }
+      }
+      // bias, ReLU, border; output row index inside the batch element
+      const int r = orow0 + j;
+      const int c0i = r % a.n0, c1i = (r / a.n0) % a.n1;
+      const bool border = c0i < a.p0 || c0i >= a.p0 + a.i0 || c1i < a.p1 || c1i >= a.p1 + a.i1;
+      const uint32_t so = smem_u32(sOut) + j * 128;
+      if (a.out_split) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int c = c8 * 8 + 2 * p;
+            float v0 = fmaxf(out[c] + bias[c], relu_lo);
+            float v1 = fmaxf(out[c + 1] + bias[c + 1], relu_lo);
+            v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+            hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c8 ^ (j & 7)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                       "r"(hi[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + (((c8 + 4) ^ (j & 7)) << 4)), "r"(lo[0]), "r"(lo[1]),
+                       "r"(lo[2]), "r"(lo[3])
+                       : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float v[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int c = c4 * 4 + p;
+            const float t = fmaxf(out[c] + bias[c], relu_lo);
+            v[p] = border ? 0.f : t;
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c4 ^ (j & 7)) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&mapOut)),
+                     "r"(smem_u32(sOut)), "r"(0), "r"(orow0), "r"(b)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---- host: one Toeplitz-N GEMM layer -------------------------------------------------------------------------------------
+struct TzLayer {
+  const float* src0;    // rows [B][R][128 B]
+  const float* src1;    // second source (dense refinement conv) or src0
+  const float* wtab;    // device: [nbtiles][192][32 words] operand table, then scales[2]
+  const float* bias;
+  float* out;           // rows [B][R][128 B]
+  int B, R;
+  int n0, p0, i0, n1, p1, i1;
+  int tz;               // 1 or 8
+  int nstages, nshift;
+  int st_off[TZ_MAXST], st_src[TZ_MAXST], shift_rows[3];
+  int box_rows;         // rows per TMA box (<= 256)
+  int out_split, relu;
+};
+
+static size_t tz_smem_bytes(int nbtiles, int slot_bytes, int tz) {
+  return (size_t)nbtiles * TZ_BTILE + 16384 + (size_t)TZ_NSLOT * slot_bytes + 4 * 3 * tz * 32 * 4 + 256 + 1024;
+}
+
+int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
+  if ((L.tz != 1 && L.tz != 8) || L.nstages < 1 || L.nstages > TZ_MAXST || L.nshift < 1 || L.nshift > 3 || L.box_rows > 256)
+    return LWS_ERR_UNSUPPORTED;
+  TzArgs a;
+  memset(&a, 0, sizeof(a));
+  const int nblk = L.nstages * L.nshift;
+  a.nbtiles = (nblk + 1) / 2;
+  a.box_bytes = L.box_rows * 128;
+  a.slot_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  const size_t smem = tz_smem_bytes(a.nbtiles, a.slot_bytes, L.tz);
+  if (smem > 232448) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = L.tz == 1 ? cudaFuncSetAttribute(tz_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(tz_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int outr = 128 - 2 * L.tz;
+  a.bias = L.bias, a.scales = L.wtab + (size_t)a.nbtiles * 192 * 32;
+  a.out_split = L.out_split, a.relu = L.relu;
+  a.out_mul = L.out_split ? 1.f : 1.f / kDwsepActScale;
+  a.bias_mul = L.out_split ? kDwsepActScale : 1.f;
+  a.R = L.R, a.n0 = L.n0, a.p0 = L.p0, a.i0 = L.i0, a.n1 = L.n1, a.p1 = L.p1, a.i1 = L.i1;
+  a.tiles_per_b = (L.R + outr - 1) / outr;
+  a.total_tiles = L.B * a.tiles_per_b;
+  a.nstages = L.nstages, a.nshift = L.nshift;
+  for (int s = 0; s < L.nstages; ++s) a.st_off[s] = L.st_off[s], a.st_src[s] = L.st_src[s];
+  for (int k = 0; k < 3; ++k) a.shift_rows[k] = k < L.nshift ? L.shift_rows[k] : 0;
+  CUtensorMap mapA0, mapA1, mapB, mapOut;
+  const uint64_t dimsA[3] = {32, (uint64_t)L.R, (uint64_t)L.B}, strA[2] = {128, (uint64_t)L.R * 128};
+  const uint32_t boxA[3] = {32, (uint32_t)L.box_rows, 1}, boxO[3] = {32, (uint32_t)outr, 1};
+  int rc = make_tensor_map_f32(&mapA0, L.src0, 3, dimsA, strA, boxA, true);
+  if (rc) return rc;
+  rc = make_tensor_map_f32(&mapA1, L.src1, 3, dimsA, strA, boxA, true);
+  if (rc) return rc;
+  rc = make_tensor_map_f32(&mapOut, L.out, 3, dimsA, strA, boxO, true);
+  if (rc) return rc;
+  const uint64_t dimsB[2] = {32, (uint64_t)a.nbtiles * 192}, strB[1] = {128};
+  const uint32_t boxB[2] = {32, 192};
+  rc = make_tensor_map_f32(&mapB, L.wtab, 2, dimsB, strB, boxB, true);
+  if (rc) return rc;
+  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+  if (L.tz == 1) tz_gemm_kernel<1><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  else tz_gemm_kernel<8><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
+// ---- 3D stack, C = 32: rows ordered (y, x, d) with x and d padded by one zero voxel each side -------------------------------
+// first conv 1 -> 32 on the raw cost (BN_0 affine + ReLU applied to the taps), output rows split-fp16 (scaled by sa);
+// 4 lanes per voxel, 8 output channels per lane; threads run over (b, y, d, x) with x fastest so the cost reads coalesce.
+__global__ void __launch_bounds__(256)
+    conv3d_first_ydx_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][32]*/, const float* __restrict__ bias,
+                            const float* __restrict__ affine, uint4* __restrict__ out, int D, int H, int W, long long total_vox) {
+  __shared__ __align__(16) float sW[27 * 32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[i] = __ldg(w + i);
+  __syncthreads();
+  const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+  const int sub = threadIdx.x & 3;
+  const int Wp = W + 2, Dp = D + 2;
+  const long long hw = (long long)H * W;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
+  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; vox < total_vox;
+       vox += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const int xp = (int)(vox % Wp);
+    long long t = vox / Wp;
+    const int dp = (int)(t % Dp);
+    t /= Dp;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    const int x = xp - 1, d = dp - 1;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bool border = x < 0 || x >= W || d < 0 || d >= D;
+    if (!border) {
+      const float* cb = cost + ((long long)b * D + d) * hw + (long long)y * W + x;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const bool okd = (unsigned)(d + kd - 1) < (unsigned)D;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const bool okh = okd && (unsigned)(y + kh - 1) < (unsigned)H;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const bool ok = okh && (unsigned)(x + kw - 1) < (unsigned)W;
+            float v = ok ? __ldg(cb + (kd - 1) * hw + (kh - 1) * W + (kw - 1)) : 0.f;
+            v = ok ? fmaxf(fmaf(v, s0, t0), 0.f) : 0.f;
+            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8 + 4);
+            acc[0] = fmaf(v, wa.x, acc[0]), acc[1] = fmaf(v, wa.y, acc[1]), acc[2] = fmaf(v, wa.z, acc[2]),
+            acc[3] = fmaf(v, wa.w, acc[3]), acc[4] = fmaf(v, wb.x, acc[4]), acc[5] = fmaf(v, wb.y, acc[5]),
+            acc[6] = fmaf(v, wb.z, acc[6]), acc[7] = fmaf(v, wb.w, acc[7]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + bv[j], 0.f) * kDwsepActScale;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const __half2 h = __floats2half2_rn(acc[2 * p], acc[2 * p + 1]);
+      const float2 f = __half22float2(h);
+      const __half2 l = __floats2half2_rn((acc[2 * p] - f.x) * 2048.f, (acc[2 * p + 1] - f.y) * 2048.f);
+      hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const long long row = (((long long)b * H + y) * Wp + xp) * Dp + dp;
+    out[row * 8 + sub] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out[row * 8 + 4 + sub] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// last conv 32 -> 1 from split-fp16 rows (+ skip), NCDHW fp32 output; 4 lanes per voxel, 8 input channels per lane
+__global__ void __launch_bounds__(256)
+    conv3d_last_ydx_kernel(const uint4* __restrict__ act, const float* __restrict__ w /*[32][27]*/, const float* __restrict__ skip,
+                           float* __restrict__ out, int D, int H, int W, long long total_vox) {
+  __shared__ __align__(16) float sW[27 * 32];  // [tap][ci], pre-divided by the activation scale
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[(i % 27) * 32 + i / 27] = __ldg(w + i) * (1.f / kDwsepActScale);
+  __syncthreads();
+  const int sub = threadIdx.x & 3;
+  const int Wp = W + 2, Dp = D + 2;
+  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; vox < total_vox;
+       vox += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const int x = (int)(vox % W);
+    long long t = vox / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int d = (int)(t % D);
+    const int b = (int)(t / D);
+    const long long row = (((long long)b * H + y) * Wp + (x + 1)) * Dp + (d + 1);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      if ((unsigned)(y + kh - 1) >= (unsigned)H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const long long r = row + ((long long)(kh - 1) * Wp + (kw - 1)) * Dp + (kd - 1);
+          const uint4 h = __ldg(act + r * 8 + sub), l = __ldg(act + r * 8 + 4 + sub);
+          const float* wt = sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8;
+          const float4 wa = *reinterpret_cast<const float4*>(wt), wb = *reinterpret_cast<const float4*>(wt + 4);
+          const uint32_t hw_[4] = {h.x, h.y, h.z, h.w}, lw_[4] = {l.x, l.y, l.z, l.w};
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw_[p]));
+            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw_[p]));
+            const float v0 = fmaf(fl.x, 1.f / 2048.f, fh.x), v1 = fmaf(fl.y, 1.f / 2048.f, fh.y);
+            acc0 = fmaf(v0, wv[2 * p], acc0), acc1 = fmaf(v1, wv[2 * p + 1], acc1);
+          }
+        }
+      }
+    }
+    float acc = acc0 + acc1;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0) out[vox] = acc + (skip ? __ldg(skip + vox) : 0.f);
+  }
+}
+
+size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W) {
+  const size_t rows = (size_t)B * H * (W + 2) * (D + 2);
+  return 2 * (rows * 128 + 1024);
+}
+
+// wtab[l]: per mid layer the Toeplitz operand table (5 tiles x 192 rows x 128 B, then scales[2]); bias_mid[l]: [32]
+int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
+                     const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
+                     int add_skip, cudaStream_t st) {
+  const int Wp = W + 2, Dp = D + 2;
+  const long long R = (long long)H * Wp * Dp;
+  if (R >= (1ll << 31) - 65536 || 128 + 2 * Dp > 256) return LWS_ERR_UNSUPPORTED;
+  const size_t half_ws = conv3d_f16_workspace_bytes(B, D, H, W) / 2;
+  float* bufA = (float*)ws;
+  float* bufB = (float*)((char*)ws + half_ws);
+  const long long nrows = (long long)B * R;
+  cudaError_t e;
+  {
+    const long long thr = nrows * 4;
+    const int blocks = (int)((thr + 255) / 256 < 148 * 16 ? (thr + 255) / 256 : 148 * 16);
+    conv3d_first_ydx_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W, nrows);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+  }
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int l = 0; l < layers; ++l) {
+    TzLayer L;
+    memset(&L, 0, sizeof(L));
+    L.src0 = L.src1 = cur, L.wtab = wtab[l], L.bias = bias_mid[l], L.out = nxt, L.B = B, L.R = (int)R;
+    L.n0 = Dp, L.p0 = 1, L.i0 = D, L.n1 = Wp, L.p1 = 1, L.i1 = W;
+    L.tz = 1, L.nstages = 3, L.nshift = 3, L.box_rows = 128 + 2 * Dp;
+    for (int kh = 0; kh < 3; ++kh) L.st_off[kh] = (kh - 1) * Wp * Dp - Dp, L.st_src[kh] = 0;  // box starts one x column early
+    for (int kw = 0; kw < 3; ++kw) L.shift_rows[kw] = kw * Dp;
+    L.out_split = 1, L.relu = 1;
+    int rc = launch_tz_gemm(L, st);
+    if (rc) return rc;
+    float* t = cur;
+    cur = nxt, nxt = t;
+  }
+  {
+    const long long vox = (long long)B * D * H * W;
+    const long long thr = vox * 4;
+    const int blocks = (int)((thr + 255) / 256 < 148 * 16 ? (thr + 255) / 256 : 148 * 16);
+    conv3d_last_ydx_kernel<<<blocks, 256, 0, st>>>((const uint4*)cur, w_last, add_skip ? cost : nullptr, out, D, H, W, vox);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+  }
+  return LWS_OK;
+}
+
+}  // namespace lws

@@ -13,6 +13,7 @@
 //            segment (2 LDS.128 + 2 LDS.32) and 3*Q weights (warp-uniform broadcast LDS.128) for 24*Q FFMA.
 //   lanes run over h first, rows are TW+4 floats apart (== 4 mod 32), so the 128-bit row loads are conflict-free.
 // These layers are compute-bound (54-216 flop/B): the bound is the FP32 FFMA rate, not HBM.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,8 +27,11 @@ size_t conv3d_tc_workspace_bytes(int B, int C, int D, int H, int W);
 int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,
                     const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last, float* out,
                     void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
-int conv3d_tc_layer(int C, const float* in_clp, const float* wtc, const float* bias, float* out_clp, int B, int D, int H,
-                    int W, cudaStream_t st);
+// conv3d_f16.cu: tcgen05 split-fp16 Toeplitz-N path for C = 32
+size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W);
+int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
+                     const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
+                     int add_skip, cudaStream_t st);
 constexpr int kTcLayerFloats = 9 * 192 * 32;  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
 
 struct Conv3dArgs {
@@ -338,11 +342,41 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
           w[((size_t)ci * 27 + t) * cout + co] = (float)((double)conv_w[i][((size_t)co * cin + ci) * 27 + t] * s);
     }
   }
-  if (has_tc_tables(C)) {
+  if (C == 32) {
+    // split-fp16 Toeplitz-N operand tables (conv3d_f16.cu), per 32 -> 32 layer: 9 blocks (kh, kw), two per 24 KB tile;
+    // tile row n = part*96 + kd*32 + co (part 0: hi = fp16(w * sw), part 1: lo = fp16((w * sw - hi) * 2^11)), 64 halves per
+    // row = [block 2i: ci 0..31 | block 2i+1: ci 0..31]; sw = the power of two that puts max|w| into [256, 512).  The
+    // epilogue scales 1/sw and 1/(sw * 2^11) follow the 5 tiles.
+    for (int l = 0; l < layers; ++l) {
+      const float* wf = packed + packed_offset(C, layers, l + 1, false);  // [ci][27][co]
+      float* tc = packed + packed_tc_offset(C, layers, l);
+      memset(tc, 0, kTcLayerFloats * sizeof(float));
+      float mx = 0.f;
+      for (int i = 0; i < 32 * 27 * 32; ++i) mx = fmaxf(mx, fabsf(wf[i]));
+      int e = 0;
+      if (mx > 0.f) frexpf(mx, &e);
+      const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+      __half* h = reinterpret_cast<__half*>(tc);
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          const int blk = kh * 3 + kw;
+          for (int kd = 0; kd < 3; ++kd)
+            for (int co = 0; co < 32; ++co)
+              for (int ci = 0; ci < 32; ++ci) {
+                const float w = wf[((size_t)ci * 27 + kd * 9 + kh * 3 + kw) * 32 + co] * sw;
+                const __half hi = __float2half_rn(w);
+                const size_t base = ((size_t)(blk >> 1) * 192) * 64 + (blk & 1) * 32 + ci;
+                h[base + (size_t)(kd * 32 + co) * 64] = hi;
+                h[base + (size_t)(96 + kd * 32 + co) * 64] = __float2half_rn((w - __half2float(hi)) * 2048.f);
+              }
+        }
+      tc[5 * 192 * 32] = 1.f / sw;
+      tc[5 * 192 * 32 + 1] = 1.f / (sw * 2048.f);
+    }
+  } else if (has_tc_tables(C)) {
     // 3xTF32 operand tables, [9 stages = (kd,kh)][3 shifts][64 rows][32]: rows 0..31 hold wh (tf32-truncated folded
-    // weights), rows 32..63 the remainders wl = w - wh.
-    //  C = 32: a GEMM row is one voxel, shift = kw: row n = cout, column k = cin.
-    //  C = 8 : a GEMM row is 4 consecutive voxels u = 0..3 (n = u_out*8 + cout, k = u_in*8 + cin).  Shift 1 (same row)
+    // weights), rows 32..63 the remainders wl = w - wh.  C = 8: a GEMM row is 4 consecutive voxels u = 0..3
+    // (n = u_out*8 + cout, k = u_in*8 + cin).  Shift 1 (same row)
     //          carries the taps with u_in - u_out = kw - 1 in {-1,0,1}; shift 0 (previous row) only its last voxel
     //          (u_in = 3 -> u_out = 0, kw = 0); shift 2 (next row) only its first voxel (u_in = 0 -> u_out = 3, kw = 2).
     auto split = [](float w, float* hi, float* lo) {
@@ -361,18 +395,13 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
           for (int co = 0; co < C; ++co)
             for (int ci = 0; ci < C; ++ci) {
               const float w = wf[((size_t)ci * 27 + stg * 3 + kw) * C + co];
-              if (C == 32) {
-                float* base = tc + (size_t)(stg * 3 + kw) * 64 * 32;
-                split(w, base + co * 32 + ci, base + (32 + co) * 32 + ci);
-              } else {
-                for (int uo = 0; uo < 4; ++uo) {
-                  const int ui = uo + kw - 1;  // input voxel relative to this row's first voxel
-                  int shift = 1, uin = ui;
-                  if (ui < 0) shift = 0, uin = 3;
-                  else if (ui > 3) shift = 2, uin = 0;
-                  float* base = tc + (size_t)(stg * 3 + shift) * 64 * 32;
-                  split(w, base + (uo * 8 + co) * 32 + uin * 8 + ci, base + (32 + uo * 8 + co) * 32 + uin * 8 + ci);
-                }
+              for (int uo = 0; uo < 4; ++uo) {
+                const int ui = uo + kw - 1;  // input voxel relative to this row's first voxel
+                int shift = 1, uin = ui;
+                if (ui < 0) shift = 0, uin = 3;
+                else if (ui > 3) shift = 2, uin = 0;
+                float* base = tc + (size_t)(stg * 3 + shift) * 64 * 32;
+                split(w, base + (uo * 8 + co) * 32 + uin * 8 + ci, base + (32 + uo * 8 + co) * 32 + uin * 8 + ci);
               }
             }
     }
@@ -384,7 +413,8 @@ extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, i
   (void)layers;
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
-  const size_t tc = lws::has_tc_tables(C) ? lws::conv3d_tc_workspace_bytes(B, C, D, H, W) : 0;
+  size_t tc = lws::has_tc_tables(C) ? lws::conv3d_tc_workspace_bytes(B, C, D, H, W) : 0;
+  if (C == 32 && lws::conv3d_f16_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_f16_workspace_bytes(B, D, H, W);
   return 2 * act > tc ? 2 * act : tc;
 }
 
@@ -410,6 +440,10 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
       wtc[l] = pk + packed_tc_offset(C, layers, l);
       bmid[l] = pk + packed_offset(C, layers, l + 1, true);
     }
+    if (C == 32 && 128 + 2 * (D + 2) <= 256)
+      return conv3d_stack_f16(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
+                              layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W, add_skip, st);
+    if (C == 32) return LWS_ERR_UNSUPPORTED;  // D > 62: use LWS_CONV3D_TC=0
     return conv3d_stack_tc(C, cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
                            wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
                            add_skip, st);
@@ -448,29 +482,4 @@ extern "C" int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folde
     case 32: return launch_conv3d<8, 32, 8, 2, 32, false, false>(a, B, st);
     default: return LWS_ERR_UNSUPPORTED;
   }
-}
-
-// ---- the tensor-core layer on its own ------------------------------------------------------------------------------------
-extern "C" size_t lws_conv3d_stack_tc_table_offset(int C, int layers, int mid_layer) {
-  if (!lws::has_tc_tables(C) || mid_layer < 0 || mid_layer >= layers) return 0;
-  return lws::packed_tc_offset(C, layers, mid_layer);
-}
-extern "C" size_t lws_conv3d_stack_bias_offset(int C, int layers, int conv) {
-  if (C <= 0 || conv < 0 || conv > layers) return 0;
-  return lws::packed_offset(C, layers, conv, true);
-}
-extern "C" size_t lws_conv3d_clp_floats(int B, int C, int D, int H, int W) {
-  if (!lws::has_tc_tables(C) || B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-  return lws::conv3d_tc_workspace_bytes(B, C, D, H, W) / 2 / sizeof(float);
-}
-extern "C" int lws_conv3d_tc_layer_f32(const float* in_clp, const float* tc_table, const float* bias, float* out_clp, int B,
-                                       int C, int D, int H, int W, lws_stream_t stream) {
-  using namespace lws;
-  LWS_CHECK_PTR(in_clp);
-  LWS_CHECK_PTR(tc_table);
-  LWS_CHECK_PTR(bias);
-  LWS_CHECK_PTR(out_clp);
-  if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return LWS_ERR_BAD_SHAPE;
-  if (((((uintptr_t)in_clp) | ((uintptr_t)out_clp)) & 127) || (((uintptr_t)tc_table) & 15)) return LWS_ERR_BAD_ALIGN;
-  return conv3d_tc_layer(C, in_clp, tc_table, bias, out_clp, B, D, H, W, (cudaStream_t)stream);
 }

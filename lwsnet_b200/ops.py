@@ -203,23 +203,6 @@ def conv3d_bnrelu_layer(x: torch.Tensor, w_folded: torch.Tensor, bias: torch.Ten
     return out
 
 
-def conv3d_tc_layer(in_clp: torch.Tensor, packed: torch.Tensor, C: int, layers: int, mid_layer: int, B: int, D: int, H: int,
-                    W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """One tcgen05 3xTF32 C->C layer on channels-last bordered (CLP) tensors; see include/lws.h."""
-    n = int(lib.lws_conv3d_clp_floats(B, C, D, H, W))
-    if in_clp.numel() != n:
-        raise ValueError(f"in_clp must hold {n} floats")
-    out = out if out is not None else torch.empty_like(in_clp)
-    tc = packed[int(lib.lws_conv3d_stack_tc_table_offset(C, layers, mid_layer)):]
-    bias = packed[int(lib.lws_conv3d_stack_bias_offset(C, layers, mid_layer + 1)):]
-    with torch.cuda.device(in_clp.device):
-        check(lib.lws_conv3d_tc_layer_f32(_ptr(in_clp, "in_clp"), ctypes.c_void_p(tc.data_ptr()),
-                                          ctypes.c_void_p(bias.data_ptr()), _ptr(out, "out"), B, C, D, H, W,
-                                          _stream(in_clp)), "lws_conv3d_tc_layer_f32")
-    LAUNCHES[0] += 1
-    return out
-
-
 # ------------------------------------------------------------------------------------------------ a6 / a7
 def softmax_regression(cost: torch.Tensor, start: float, step: float = 1.0) -> torch.Tensor:
     """disparity_regression(start, end)(softmax(-cost, axis=1)) (reference models/models.py:142,151-152,167-179)."""

@@ -19,8 +19,8 @@
 //   * the taps along the middle axis are row-shifted windows (UMMA descriptor offsets) of ONE TMA box per stage, the taps
 //     along the slowest axis are the stages: 3 TMA loads of 23 KB per 126 output voxels for the 3D stack;
 //   * all weights of the layer (27 x 32 x 32 hi + lo = 108 KB) stay resident in shared memory.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (2 accumulators x 192 columns),
-// warps 2-5 = epilogue (tcgen05.ld, Toeplitz row shifts by warp shuffles + a small shared-memory exchange at the warp
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (2 accumulators x 192 columns),
+// warps 2-9 = epilogue, two per TMEM lane quarter, 16 output channels each (tcgen05.ld, Toeplitz row shifts by warp shuffles + a small shared-memory exchange at the warp
 // boundaries, bias + ReLU, border zeroing, re-split into hi/lo, staged through shared memory into one TMA store).
 #include <cuda_fp16.h>
 #include <math.h>
@@ -28,13 +28,12 @@
 
 #include "lws_common.cuh"
 #include "tma_utils.cuh"
+#include "conv3d_f16.cuh"
 
 namespace lws {
 
-constexpr int TZ_THREADS = 192;
-constexpr int TZ_MAXST = 6;
+constexpr int TZ_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int TZ_BTILE = 192 * 128;  // one weight tile: 192 rows x [block 2i | block 2i+1] x 32 halves
-constexpr int TZ_NSLOT = 3;
 
 struct TzArgs {
   const float* bias;    // [32]
@@ -44,15 +43,35 @@ struct TzArgs {
   int out_split;        // 1: rows [32 hi | 32 lo] halves; 0: rows of 32 fp32
   int relu;
   int R;                // rows per batch element
-  int n0, p0, i0;       // fastest axis: length (padded), pad, interior length  -> rows outside the interior are written as 0
-  int n1, p1, i1;       // middle axis
-  int tiles_per_b, total_tiles;
-  int nstages, nshift, nbtiles;
+  FastDiv n0, n1;       // padded lengths of the fastest and the middle axis
+  int p0, i0, p1, i1;   // pad and interior length of each: rows outside the interior are written as 0
+  // strip schedule: the row space of one batch element is cut into super lines of `srow` rows (the distance between
+  // consecutive taps of the slowest axis); an item = (b, column tile ct of the super line, segment of <= seg_len consecutive
+  // super lines); tile n of an item outputs rows ct*OUTR + (n0 + n)*srow + [0, OUTR) and shares all but its last `G` stage
+  // boxes with tile n-1, so they stay in the shared-memory ring.  srow = R gives plain linear tiling (one tile per item).
+  int srow, strip_len, seg_len, total_items;
+  FastDiv ct_per_sl, segs;
+  int nstages, G, nshift, nbtiles, nslot;
   int slot_bytes, box_bytes;
   int st_off[TZ_MAXST];  // row offset of the stage's box relative to the tile's first GEMM row
   int st_src[TZ_MAXST];
   int shift_rows[3];     // row offset of window k inside the box
 };
+
+struct TzItem {
+  int b, orow0, ntiles;
+};
+template <int OUTR>
+__device__ __forceinline__ TzItem tz_decode(const TzArgs& a, int item) {
+  int t, seg, ct;
+  TzItem it;
+  fdivmod(item, a.segs, t, seg);
+  fdivmod(t, a.ct_per_sl, it.b, ct);
+  const int n0 = seg * a.seg_len;
+  it.ntiles = min(a.seg_len, a.strip_len - n0);
+  it.orow0 = ct * OUTR + n0 * a.srow;
+  return it;
+}
 
 __device__ __forceinline__ void tz_mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -75,7 +94,9 @@ __device__ __forceinline__ void tz_ld8(uint32_t taddr, float* v) {
 }
 
 // TZ = Toeplitz row shift (1: 3D stack along d; 8: dilated 2D conv along x).  Output rows per tile: 128 - 2*TZ.
-template <int TZ>
+// NST / NSH: stages per tile and row-shifted windows per stage (compile-time so the MMA issue loop is fully unrolled: the
+// single issuing thread must spend only a few uniform-datapath instructions per MMA or it, not the tensor pipe, is the limit).
+template <int TZ, int NST, int NSH>
 __global__ void __launch_bounds__(TZ_THREADS, 1)
     tz_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut, const TzArgs a) {
@@ -84,22 +105,22 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;                                   // [nbtiles][24576]
   uint8_t* sOut = sB + a.nbtiles * TZ_BTILE;             // [16384] staging tile
-  uint8_t* sA = sOut + 16384;                            // [NSLOT][slot_bytes]
-  uint8_t* tail = sA + TZ_NSLOT * a.slot_bytes;
+  uint8_t* sA = sOut + 16384;                            // [nslot][slot_bytes]
+  uint8_t* tail = sA + a.nslot * a.slot_bytes;
   float* xch = reinterpret_cast<float*>(tail);           // [4 quarters][3*TZ rows][32] boundary rows for the Toeplitz shifts
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4 * 3 * TZ * 32 * 4);
-  uint64_t* a_full = bars;                 // [NSLOT]
-  uint64_t* a_empty = a_full + TZ_NSLOT;   // [NSLOT]
-  uint64_t* b_full = a_empty + TZ_NSLOT;   // [1]
+  uint64_t* a_full = bars;                 // [8]
+  uint64_t* a_empty = a_full + 8;          // [8]
+  uint64_t* b_full = a_empty + 8;          // [1]
   uint64_t* t_full = b_full + 1;           // [2]
   uint64_t* t_empty = t_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < TZ_NSLOT; ++i) mbar_init(a_full + i, 1), mbar_init(a_empty + i, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(a_full + i, 1), mbar_init(a_empty + i, 1);
     mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
+    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 8);
     mbar_fence_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
@@ -114,28 +135,31 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const int nst = a.nstages;
+  constexpr int nst = NST;
+  const uint32_t nslot = (uint32_t)a.nslot;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one_sync()) {
       mbar_expect_tx(b_full, (uint32_t)a.nbtiles * TZ_BTILE);
       for (int i = 0; i < a.nbtiles; ++i) tma_load_2d(sB + i * TZ_BTILE, &mapB, b_full, 0, i * 192);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_b;
-        const int row0 = (tile - b * a.tiles_per_b) * OUTR - TZ;  // GEMM row 0 of the tile
-        for (int s = 0; s < nst; ++s, ++it) {
-          const uint32_t slot = it % TZ_NSLOT;
-          mbar_wait(a_empty + slot, ((it / TZ_NSLOT) & 1) ^ 1);
-          mbar_expect_tx(a_full + slot, (uint32_t)a.box_bytes);
-          const CUtensorMap* src = a.st_src[s] ? &mapA1 : &mapA0;
-          // 3D map {32 words, R, B}: rows outside [0, R) come back as zeros (the padding of the slowest axis)
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
-              "[%2];" ::"r"(smem_u32(sA + slot * a.slot_bytes)),
-              "l"(reinterpret_cast<uint64_t>(src)), "r"(smem_u32(a_full + slot)), "r"(0), "r"(row0 + a.st_off[s]), "r"(b)
-              : "memory");
+      uint32_t slot = 0, ph = 0;  // ring position and phase of the next entry
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const TzItem w = tz_decode<OUTR>(a, item);
+        for (int n = 0; n < w.ntiles; ++n) {
+          const int row0 = w.orow0 + n * a.srow - TZ;  // GEMM row 0 of the tile
+          for (int s = n == 0 ? 0 : nst - a.G; s < nst; ++s) {  // later tiles of a strip only load their newest stage group
+            mbar_wait(a_empty + slot, ph ^ 1);
+            mbar_expect_tx(a_full + slot, (uint32_t)a.box_bytes);
+            const CUtensorMap* src = a.st_src[s] ? &mapA1 : &mapA0;
+            // 3D map {32 words, R, B}: rows outside [0, R) come back as zeros (the padding of the slowest axis)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+                "[%2];" ::"r"(smem_u32(sA + slot * a.slot_bytes)),
+                "l"(reinterpret_cast<uint64_t>(src)), "r"(smem_u32(a_full + slot)), "r"(0), "r"(row0 + a.st_off[s]), "r"(w.b)
+                : "memory");
+            if (++slot == nslot) slot = 0, ph ^= 1;
+          }
         }
       }
     }
@@ -145,164 +169,184 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
     const uint32_t idesc96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
     const uint32_t b_lo = ((smem_u32(sB) & 0x3FFFF) >> 4) | (1u << 16);
-    const int nsh = a.nshift;
-    const uint32_t sh0 = (uint32_t)a.shift_rows[0] * 8, sh1 = (uint32_t)a.shift_rows[1] * 8, sh2 = (uint32_t)a.shift_rows[2] * 8;
+    const uint32_t shq[3] = {(uint32_t)a.shift_rows[0] * 8, (uint32_t)a.shift_rows[1] * 8, (uint32_t)a.shift_rows[2] * 8};
+    const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFF) >> 4) | (1u << 16), slot16 = (uint32_t)a.slot_bytes >> 4;
+    const int G = a.G;
     mbar_wait(b_full, 0);
-    uint32_t it = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t tb = ti & 1;
-      mbar_wait(t_empty + tb, ((ti >> 1) & 1) ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_main = tmem + tb * 256;
-      for (int s = 0; s < nst; ++s, ++it) {
-        const uint32_t slot = it % TZ_NSLOT;
-        mbar_wait(a_full + slot, (it / TZ_NSLOT) & 1);
+    uint32_t bslot = 0, bph = 0, ti = 0;  // ring position / phase of stage 0 of the current tile
+    auto advance = [&](uint32_t k) {
+      bslot += k;
+      if (bslot >= nslot) bslot -= nslot, bph ^= 1;
+    };
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const TzItem w = tz_decode<OUTR>(a, item);
+      for (int n = 0; n < w.ntiles; ++n, ++ti, advance(G)) {
+        const bool last = n == w.ntiles - 1;
+        const uint32_t tb = ti & 1;
+        mbar_wait(t_empty + tb, ((ti >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one_sync()) {
-          const uint32_t x_lo = ((smem_u32(sA + slot * a.slot_bytes) & 0x3FFFF) >> 4) | (1u << 16);
-          for (int k = 0; k < nsh; ++k) {
-            const int blk = s * nsh + k;
-            const uint32_t wa = x_lo + (k == 0 ? sh0 : (k == 1 ? sh1 : sh2));                   // window base (16-byte units)
-            const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE >> 4) + (blk & 1) * 4;  // weight block
-            const uint32_t first = (s | k) == 0 ? 0u : 1u;
-            tz_mma(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, first);
-            tz_mma(d_main, desc_hi | (uint64_t)(wa + 2), desc_hi | (uint64_t)(wb + 2), idesc192, 1u);
-            tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 4), desc_hi | (uint64_t)(wb + 0), idesc96, 1u);
-            tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wb + 2), idesc96, 1u);
+        const uint32_t d_main = tmem + tb * 256;
+        uint32_t slot = bslot, ph = bph;
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+          mbar_wait(a_full + slot, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one_sync()) {
+            const uint32_t x_lo = a_lo0 + slot * slot16;
+#pragma unroll
+            for (int k = 0; k < NSH; ++k) {
+              const int blk = s * NSH + k;
+              const uint32_t wa = x_lo + shq[k];                                                  // window base (16-byte units)
+              const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE >> 4) + (blk & 1) * 4;  // weight block
+              tz_mma(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, (s | k) == 0 ? 0u : 1u);
+              tz_mma(d_main, desc_hi | (uint64_t)(wa + 2), desc_hi | (uint64_t)(wb + 2), idesc192, 1u);
+              tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 4), desc_hi | (uint64_t)(wb + 0), idesc96, 1u);
+              tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wb + 2), idesc96, 1u);
+            }
+            if (s < G || last) tz_commit(a_empty + slot);  // the other boxes are stages s - G of the next tile of the strip
+            if (s == NST - 1) tz_commit(t_full + tb);
           }
-          tz_commit(a_empty + slot);
-          if (s == nst - 1) tz_commit(t_full + tb);
+          __syncwarp();
+          if (++slot == nslot) slot = 0, ph ^= 1;
         }
-        __syncwarp();
       }
+      advance(nst - G);  // the strip's last tile consumed all of its entries
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
     const int q = warp & 3;           // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;   // which 16 of the 32 output channels
     const int j = q * 32 + lane;      // GEMM row of the tile; this thread produces output row j + TZ -> staging row j
     const bool issuer = warp == 2 && lane == 0;
     const float c0 = __ldg(a.scales) * a.out_mul, c1 = __ldg(a.scales + 1) * a.out_mul;
     const float relu_lo = a.relu ? 0.f : -INFINITY;
     const bool has1 = lane + TZ < 32, has2 = lane + 2 * TZ < 32;
-    float bias[32];
+    float bias[16];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) bias[c] = __ldg(a.bias + c) * a.bias_mul;
-    float* xq = xch + q * (3 * TZ * 32);         // this quarter publishes: rows [0,TZ) E1 of lanes 0..TZ-1, [TZ,3TZ) E2 of lanes 0..2TZ-1
-    const float* xn = xch + ((q + 1) & 3) * (3 * TZ * 32);  // next quarter's rows
+    for (int c = 0; c < 16; ++c) bias[c] = __ldg(a.bias + hf * 16 + c) * a.bias_mul;
+    // quarter q publishes for quarter q-1: rows [0,TZ) = e1 of lanes 0..TZ-1, rows [TZ,3TZ) = e2 of lanes 0..2TZ-1
+    float* xq = xch + q * (3 * TZ * 32) + hf * 16;
+    const float* xn = xch + ((q + 1) & 3) * (3 * TZ * 32) + hf * 16;
     uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t tb = ti & 1;
-      const int b = tile / a.tiles_per_b;
-      const int orow0 = (tile - b * a.tiles_per_b) * OUTR;  // first output row of the tile
-      mbar_wait(t_full + tb, (ti >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tb * 256;
-      float out[32];
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const TzItem w = tz_decode<OUTR>(a, item);
+      for (int n = 0; n < w.ntiles; ++n, ++ti) {
+        const uint32_t tb = ti & 1;
+        const int orow0 = w.orow0 + n * a.srow;  // first output row of the tile
+        mbar_wait(t_full + tb, (ti >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tb * 256 + hf * 16;
+        float out[16];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {  // 8 output channels at a time
-        float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];
-        tz_ld8(taddr + cc * 8, m0);
-        tz_ld8(taddr + 32 + cc * 8, m1);
-        tz_ld8(taddr + 64 + cc * 8, m2);
-        tz_ld8(taddr + 96 + cc * 8, k0);
-        tz_ld8(taddr + 128 + cc * 8, k1);
-        tz_ld8(taddr + 160 + cc * 8, k2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // tap t of GEMM row j contributes to staging row j - t*TZ:
-        // staging row j = e0 of GEMM row j + e1 of GEMM row j + TZ + e2 of GEMM row j + 2 TZ
+        for (int cc = 0; cc < 2; ++cc) {  // 8 output channels at a time
+          float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];
+          tz_ld8(taddr + cc * 8, m0);
+          tz_ld8(taddr + 32 + cc * 8, m1);
+          tz_ld8(taddr + 64 + cc * 8, m2);
+          tz_ld8(taddr + 96 + cc * 8, k0);
+          tz_ld8(taddr + 128 + cc * 8, k1);
+          tz_ld8(taddr + 160 + cc * 8, k2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // tap t of GEMM row j contributes to staging row j - t*TZ:
+          // staging row j = e0 of GEMM row j + e1 of GEMM row j + TZ + e2 of GEMM row j + 2 TZ
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float e0 = fmaf(k0[c], c1, m0[c] * c0);
-          m1[c] = fmaf(k1[c], c1, m1[c] * c0);
-          m2[c] = fmaf(k2[c], c1, m2[c] * c0);
-          const float s1 = __shfl_down_sync(0xffffffffu, m1[c], TZ);
-          const float s2 = __shfl_down_sync(0xffffffffu, m2[c], (2 * TZ) & 31);
-          out[cc * 8 + c] = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
-        }
-        if (lane < 2 * TZ) {  // rows the previous quarter needs
-          float4* d2 = reinterpret_cast<float4*>(xq + (TZ + lane) * 32 + cc * 8);
-          d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
-          if (lane < TZ) {
-            float4* d1 = reinterpret_cast<float4*>(xq + lane * 32 + cc * 8);
-            d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
+          for (int c = 0; c < 8; ++c) {
+            const float e0 = fmaf(k0[c], c1, m0[c] * c0);
+            m1[c] = fmaf(k1[c], c1, m1[c] * c0);
+            m2[c] = fmaf(k2[c], c1, m2[c] * c0);
+            const float s1 = __shfl_down_sync(0xffffffffu, m1[c], TZ);
+            const float s2 = __shfl_down_sync(0xffffffffu, m2[c], (2 * TZ) & 31);
+            out[cc * 8 + c] = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
           }
+          if (lane < 2 * TZ) {  // rows the previous quarter needs
+            float4* d2 = reinterpret_cast<float4*>(xq + (TZ + lane) * 32 + cc * 8);
+            d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
+            if (lane < TZ) {
+              float4* d1 = reinterpret_cast<float4*>(xq + lane * 32 + cc * 8);
+              d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
+            }
+          }
+          __syncwarp();
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + tb);
-      // previous tile's TMA store must have finished reading the staging tile before anyone overwrites it
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      named_bar_sync(1, 128);
-      if (q < 3) {  // rows of the next quarter (the last quarter's missing rows belong to the next tile)
-        if (!has1) {
-          const float4* p1 = reinterpret_cast<const float4*>(xn + (lane + TZ - 32) * 32);
+        if (lane == 0) mbar_arrive(t_empty + tb);
+        // previous tile's TMA store must have finished reading the staging tile before anyone overwrites it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        named_bar_sync(1, 256);
+        if (q < 3) {  // rows of the next quarter (the last quarter's missing rows belong to the next tile)
+          if (!has1) {
+            const float4* p1 = reinterpret_cast<const float4*>(xn + (lane + TZ - 32) * 32);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = p1[c];
-            out[4 * c] += v.x, out[4 * c + 1] += v.y, out[4 * c + 2] += v.z, out[4 * c + 3] += v.w;
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = p1[c];
+              out[4 * c] += v.x, out[4 * c + 1] += v.y, out[4 * c + 2] += v.z, out[4 * c + 3] += v.w;
+            }
+          }
+          if (!has2) {
+            const float4* p2 = reinterpret_cast<const float4*>(xn + (TZ + lane + 2 * TZ - 32) * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = p2[c];
+              out[4 * c] += v.x, out[4 * c + 1] += v.y, out[4 * c + 2] += v.z, out[4 * c + 3] += v.w;
+            }
           }
         }
-        if (!has2) {
-          const float4* p2 = reinterpret_cast<const float4*>(xn + (TZ + lane + 2 * TZ - 32) * 32);
+        // bias, ReLU, border; output row index inside the batch element
+        const int r = orow0 + j;
+        int rq, c0i, c1i, rq2;
+        fdivmod(r, a.n0, rq, c0i);
+        fdivmod(rq, a.n1, rq2, c1i);
+        const bool border = c0i < a.p0 || c0i >= a.p0 + a.i0 || c1i < a.p1 || c1i >= a.p1 + a.i1;
+        const uint32_t so = smem_u32(sOut) + j * 128;
+        if (a.out_split) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = p2[c];
-            out[4 * c] += v.x, out[4 * c + 1] += v.y, out[4 * c + 2] += v.z, out[4 * c + 3] += v.w;
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c8 = hf * 2 + cc;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const int c = cc * 8 + 2 * p;
+              float v0 = fmaxf(out[c] + bias[c], relu_lo);
+              float v1 = fmaxf(out[c + 1] + bias[c + 1], relu_lo);
+              v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
+              const __half2 h = __floats2half2_rn(v0, v1);
+              const float2 f = __half22float2(h);
+              const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+              hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c8 ^ (j & 7)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                         "r"(hi[3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + (((c8 + 4) ^ (j & 7)) << 4)), "r"(lo[0]), "r"(lo[1]),
+                         "r"(lo[2]), "r"(lo[3])
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int cq = 0; cq < 4; ++cq) {
+            const int c4 = hf * 4 + cq;
+            float v[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const int c = cq * 4 + p;
+              const float t = fmaxf(out[c] + bias[c], relu_lo);
+              v[p] = border ? 0.f : t;
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c4 ^ (j & 7)) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                         "f"(v[3])
+                         : "memory");
           }
         }
-      }
-      // bias, ReLU, border; output row index inside the batch element
-      const int r = orow0 + j;
-      const int c0i = r % a.n0, c1i = (r / a.n0) % a.n1;
-      const bool border = c0i < a.p0 || c0i >= a.p0 + a.i0 || c1i < a.p1 || c1i >= a.p1 + a.i1;
-      const uint32_t so = smem_u32(sOut) + j * 128;
-      if (a.out_split) {
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int c = c8 * 8 + 2 * p;
-            float v0 = fmaxf(out[c] + bias[c], relu_lo);
-            float v1 = fmaxf(out[c + 1] + bias[c + 1], relu_lo);
-            v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
-            const __half2 h = __floats2half2_rn(v0, v1);
-            const float2 f = __half22float2(h);
-            const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
-            hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c8 ^ (j & 7)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
-                       "r"(hi[3])
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (issuer) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&mapOut)),
+                       "r"(smem_u32(sOut)), "r"(0), "r"(orow0), "r"(w.b)
                        : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + (((c8 + 4) ^ (j & 7)) << 4)), "r"(lo[0]), "r"(lo[1]),
-                       "r"(lo[2]), "r"(lo[3])
-                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-      } else {
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float v[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int c = c4 * 4 + p;
-            const float t = fmaxf(out[c] + bias[c], relu_lo);
-            v[p] = border ? 0.f : t;
-          }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c4 ^ (j & 7)) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                       "f"(v[3])
-                       : "memory");
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (issuer) {
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                         reinterpret_cast<uint64_t>(&mapOut)),
-                     "r"(smem_u32(sOut)), "r"(0), "r"(orow0), "r"(b)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -313,24 +357,9 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// ---- host: one Toeplitz-N GEMM layer -------------------------------------------------------------------------------------
-struct TzLayer {
-  const float* src0;    // rows [B][R][128 B]
-  const float* src1;    // second source (dense refinement conv) or src0
-  const float* wtab;    // device: [nbtiles][192][32 words] operand table, then scales[2]
-  const float* bias;
-  float* out;           // rows [B][R][128 B]
-  int B, R;
-  int n0, p0, i0, n1, p1, i1;
-  int tz;               // 1 or 8
-  int nstages, nshift;
-  int st_off[TZ_MAXST], st_src[TZ_MAXST], shift_rows[3];
-  int box_rows;         // rows per TMA box (<= 256)
-  int out_split, relu;
-};
-
-static size_t tz_smem_bytes(int nbtiles, int slot_bytes, int tz) {
-  return (size_t)nbtiles * TZ_BTILE + 16384 + (size_t)TZ_NSLOT * slot_bytes + 4 * 3 * tz * 32 * 4 + 256 + 1024;
+// ---- host: one Toeplitz-N GEMM layer (TzLayer: conv3d_f16.cuh) ------------------------------------------------------------
+static size_t tz_smem_bytes(int nbtiles, int nslot, int slot_bytes, int tz) {
+  return (size_t)nbtiles * TZ_BTILE + 16384 + (size_t)nslot * slot_bytes + 4 * 3 * tz * 32 * 4 + 256 + 1024;
 }
 
 int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
@@ -342,20 +371,36 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   a.nbtiles = (nblk + 1) / 2;
   a.box_bytes = L.box_rows * 128;
   a.slot_bytes = (a.box_bytes + 1023) / 1024 * 1024;
-  const size_t smem = tz_smem_bytes(a.nbtiles, a.slot_bytes, L.tz);
-  if (smem > 232448) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = L.tz == 1 ? cudaFuncSetAttribute(tz_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(tz_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   const int outr = 128 - 2 * L.tz;
+  a.nstages = L.nstages, a.nshift = L.nshift;
+  if (L.srow > 0) {  // strips along the slowest tap axis
+    a.G = L.G, a.srow = L.srow;
+    a.ct_per_sl = make_fastdiv((L.srow + outr - 1) / outr);
+    a.strip_len = (L.R + L.srow - 1) / L.srow;
+    a.seg_len = a.strip_len < 10 ? a.strip_len : 10;
+    a.segs = make_fastdiv((a.strip_len + a.seg_len - 1) / a.seg_len);
+  } else {
+    a.G = L.nstages, a.srow = L.R;
+    a.ct_per_sl = make_fastdiv((L.R + outr - 1) / outr);
+    a.strip_len = a.seg_len = 1;
+    a.segs = make_fastdiv(1);
+  }
+  a.total_items = L.B * a.ct_per_sl.d * a.segs.d;
+  // ring: one tile's stages plus as many more as fit (at most 8)
+  a.nslot = 8;
+  while (a.nslot > L.nstages && tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz) > 232448) --a.nslot;
+  const size_t smem = tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz);
+  if (smem > 232448 || a.nslot < L.nstages) return LWS_ERR_UNSUPPORTED;
+  const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1;
+  if (!is3d && !is2d) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = is3d ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(tz_gemm_kernel<8, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
   a.bias = L.bias, a.scales = L.wtab + (size_t)a.nbtiles * 192 * 32;
   a.out_split = L.out_split, a.relu = L.relu;
   a.out_mul = L.out_split ? 1.f : 1.f / kDwsepActScale;
   a.bias_mul = L.out_split ? kDwsepActScale : 1.f;
-  a.R = L.R, a.n0 = L.n0, a.p0 = L.p0, a.i0 = L.i0, a.n1 = L.n1, a.p1 = L.p1, a.i1 = L.i1;
-  a.tiles_per_b = (L.R + outr - 1) / outr;
-  a.total_tiles = L.B * a.tiles_per_b;
-  a.nstages = L.nstages, a.nshift = L.nshift;
+  a.R = L.R, a.n0 = make_fastdiv(L.n0), a.p0 = L.p0, a.i0 = L.i0, a.n1 = make_fastdiv(L.n1), a.p1 = L.p1, a.i1 = L.i1;
   for (int s = 0; s < L.nstages; ++s) a.st_off[s] = L.st_off[s], a.st_src[s] = L.st_src[s];
   for (int k = 0; k < 3; ++k) a.shift_rows[k] = k < L.nshift ? L.shift_rows[k] : 0;
   CUtensorMap mapA0, mapA1, mapB, mapOut;
@@ -371,9 +416,9 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   const uint32_t boxB[2] = {32, 192};
   rc = make_tensor_map_f32(&mapB, L.wtab, 2, dimsB, strB, boxB, true);
   if (rc) return rc;
-  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-  if (L.tz == 1) tz_gemm_kernel<1><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
-  else tz_gemm_kernel<8><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+  if (is3d) tz_gemm_kernel<1, 3, 3><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  else tz_gemm_kernel<8, 6, 1><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }

@@ -52,6 +52,7 @@ struct DsArgs {
   const float* bias;    // [32]
   float* out;           // CLP [B][Hp][Wp][32] (for the y-border zero fill; the interior goes through the TMA store map)
   int B, Hp, Wp, H, dil, relu;
+  int out_split;        // 1: write rows as [32 hi | 32 lo] halves of act * 2^-6 (operand format of conv3d_f16.cu) instead of fp32
   int nxt, segs, seg_len, total_items;
 };
 
@@ -260,8 +261,28 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
         if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DS_NOUT - 1) : "memory");
         named_bar_sync(1, 128);
         const uint32_t so = smem_u32(smem + DS_OFF_OUT + ob * DS_TILE) + p * 128;
+        if (a.out_split) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sts128(so + ((j ^ (p & 7)) << 4), make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]));
+          for (int c8 = 0; c8 < 4; ++c8) {
+            uint32_t hi[4], lw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float v0 = m[c8 * 8 + 2 * k] * DS_ACT_SCALE, v1 = m[c8 * 8 + 2 * k + 1] * DS_ACT_SCALE;
+              const __half2 h = __floats2half2_rn(v0, v1);
+              const float2 f = __half22float2(h);
+              hi[k] = h2_bits(h), lw[k] = h2_bits(__floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c8 ^ (p & 7)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                         "r"(hi[3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + (((c8 + 4) ^ (p & 7)) << 4)), "r"(lw[0]), "r"(lw[1]),
+                         "r"(lw[2]), "r"(lw[3])
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(so + ((j ^ (p & 7)) << 4), make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]));
+        }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
@@ -365,14 +386,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 
 // in/out: CLP [B][H + 2*RP][W + 2*RP][32]; dw [32][9]; pwh/scales: see DsArgs; dil in {1,2,4,8,16}
 int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
-                     int H, int W, int dil, int relu, cudaStream_t st) {
+                     int H, int W, int dil, int relu, int out_split, cudaStream_t st) {
   if (dil < 1 || dil > DS_RP || (32 % dil) != 0) return LWS_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(dwsep_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
   if (e != cudaSuccess) return (int)e;
   DsArgs a;
   memset(&a, 0, sizeof(a));
   a.dw = dw, a.pwh = (const __half*)pwh, a.scales = scales, a.bias = bias, a.out = out;
-  a.B = B, a.Hp = H + 2 * DS_RP, a.Wp = W + 2 * DS_RP, a.H = H, a.dil = dil, a.relu = relu;
+  a.B = B, a.Hp = H + 2 * DS_RP, a.Wp = W + 2 * DS_RP, a.H = H, a.dil = dil, a.relu = relu, a.out_split = out_split;
   a.nxt = (a.Wp + 127) / 128;
   const int rows_phase = (H + dil - 1) / dil;
   // segments of ~16 lines (two warm-up line loads each); at least ~4 items per SM so the static round-robin balances

@@ -26,6 +26,31 @@ constexpr float kDwsepActScale = 0.015625f;  // 2^-6
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return cdiv(a, b) * b; }
 
+// ---- division by a run-time constant without the ~100-cycle integer-divide sequence (dividend in [0, 2^31)) ----------
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+__host__ inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) {
+    f.mul = 0, f.shr = 0;
+    return f;
+  }
+  int lg = 0;
+  while ((1ll << lg) < d) ++lg;  // ceil(log2 d)
+  const unsigned p = 31 + lg;
+  f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+  f.shr = p - 32;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
+__device__ __forceinline__ void fdivmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fdiv(n, f);
+  r = n - q * f.d;
+}
+
 // ---- cp.async (LDGSTS) ------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

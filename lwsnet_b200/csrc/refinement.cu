@@ -317,17 +317,31 @@ extern "C" int lws_pack_refinement_weights(const float* const* t, int n_tensors,
     for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r1_pw[br][j], packed + L.r1_pwtc[br][j]);
   for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r2_pw[j], packed + L.r2_pwtc[j]);
   {
+    // dense 64 -> 32 conv as a split-fp16 Toeplitz-N operand table (conv3d_f16.cu): block = stage = kh*2 + source, two blocks
+    // per 24 KB tile; tile row n = part*96 + kw*32 + co, 64 halves per row = [block 2i | block 2i+1] x ci 0..31
     const float* wf = packed + L.r2_w;  // [64][9][32]
-    float* tc = packed + L.r2_wtc;      // stage = src*3 + kh; row (stage*3 + kw)*64 + n
-    for (int src = 0; src < 2; ++src)
-      for (int kh = 0; kh < 3; ++kh)
+    float* tc = packed + L.r2_wtc;
+    float mx = 0.f;
+    for (int i = 0; i < 64 * 9 * 32; ++i) mx = fmaxf(mx, fabsf(wf[i]));
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+    __half* h = reinterpret_cast<__half*>(tc);
+    for (int kh = 0; kh < 3; ++kh)
+      for (int src = 0; src < 2; ++src) {
+        const int blk = kh * 2 + src;
         for (int kw = 0; kw < 3; ++kw)
           for (int co = 0; co < 32; ++co)
             for (int k = 0; k < 32; ++k) {
-              const size_t row = (size_t)((src * 3 + kh) * 3 + kw) * 64;
-              split(wf[((size_t)(src * 32 + k) * 9 + kh * 3 + kw) * 32 + co], tc + (row + co) * 32 + k,
-                    tc + (row + 32 + co) * 32 + k);
+              const float w = wf[((size_t)(src * 32 + k) * 9 + kh * 3 + kw) * 32 + co] * sw;
+              const __half hi = __float2half_rn(w);
+              const size_t base = ((size_t)(blk >> 1) * 192) * 64 + (blk & 1) * 32 + k;
+              h[base + (size_t)(kw * 32 + co) * 64] = hi;
+              h[base + (size_t)(96 + kw * 32 + co) * 64] = __float2half_rn((w - __half2float(hi)) * 2048.f);
             }
+      }
+    tc[3 * 192 * 32] = 1.f / sw;
+    tc[3 * 192 * 32 + 1] = 1.f / (sw * 2048.f);
   }
   return LWS_OK;
 }

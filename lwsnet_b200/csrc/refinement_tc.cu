@@ -11,6 +11,7 @@
 
 #include "lws_common.cuh"
 #include "tma_utils.cuh"
+#include "conv3d_f16.cuh"
 
 namespace lws {
 
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256)
 
 // BN-ReLU-DW(dil)-PW block on CLP (dwsep_tc.cu)
 int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
-                     int H, int W, int dil, int relu, cudaStream_t st);
+                     int H, int W, int dil, int relu, int out_split, cudaStream_t st);
 
 // ---- host ------------------------------------------------------------------------------------------------------------------
 struct RefTcWeights {
@@ -147,24 +148,28 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
     for (int j = 0; j < 4; ++j) {
       float* dst = j < 3 ? nxt : (br == 0 ? catL : catD);
       if ((rc = launch_dwsep_f16(cur, dst, wt.dw[br][j], wt.pwtc[br][j], wt.pwtc[br][j] + 1024, wt.bias[br][j], B, H, W,
-                                 r1_dil[j], 1, st)))
+                                 r1_dil[j], 1, j == 3 /* the concat halves feed the dense conv: split-fp16 rows */, st)))
         return rc;
       float* t = cur;
       cur = nxt, nxt = t;
     }
   }
   {
-    int st_off[6], st_src[6];
-    for (int s = 0; s < 6; ++s) st_off[s] = (s % 3 - 1) * 8 * Wp - 8, st_src[s] = s / 3;
-    if ((rc = launch_tc_implicit_gemm(catL, catD, wt.dense_tc, wt.dense_bias, ping, B, (int)R, Hp, Wp, RP, H, W, 32, 6, st_off,
-                                      st_src, 8, 1, st)))
-      return rc;
+    // dense 64 -> 32, dilation 8: stages = (kh, source), kw folded into N (Toeplitz shift 8 pixels), strips down the image
+    TzLayer L;
+    memset(&L, 0, sizeof(L));
+    L.src0 = catL, L.src1 = catD, L.wtab = wt.dense_tc, L.bias = wt.dense_bias, L.out = ping, L.B = B, L.R = (int)R;
+    L.n0 = Wp, L.p0 = RP, L.i0 = W, L.n1 = Hp, L.p1 = RP, L.i1 = H;
+    L.tz = 8, L.nstages = 6, L.nshift = 1, L.box_rows = 128, L.G = 2, L.srow = 8 * Wp;
+    for (int s = 0; s < 6; ++s) L.st_off[s] = (s / 2 - 1) * 8 * Wp, L.st_src[s] = s & 1;
+    L.out_split = 0, L.relu = 1;
+    if ((rc = launch_tz_gemm(L, st))) return rc;
   }
   float* cur = ping;
   float* nxt = pong;
   for (int j = 0; j < 4; ++j) {
     if ((rc = launch_dwsep_f16(cur, nxt, wt.dw[2][j], wt.pwtc[2][j], wt.pwtc[2][j] + 1024, wt.bias[2][j], B, H, W, r2_dil[j],
-                               j < 3, st)))
+                               j < 3, 0, st)))
       return rc;
     float* t = cur;
     cur = nxt, nxt = t;

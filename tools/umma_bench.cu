@@ -60,6 +60,7 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 struct BenchCfg {
   int kind, N, layout, a_slots, nmma, two_acc;
+  int a_row_shift, b_half;  // A window shifted by rows (descriptor base not 1024-aligned); B block in the second 64 B of the rows
 };
 
 // ---- (a) issue-rate ---------------------------------------------------------------------------------------------
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(128) rate_kernel(BenchCfg c, long long* cycles
     const uint32_t idesc = (1u << 4) | ((uint32_t)c.kind << 7) | ((uint32_t)c.kind << 10) | ((uint32_t)(c.N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t lbo = c.layout == 0 ? 128 : 16, sbo = c.layout == 0 ? 256 : 1024;
     const uint64_t hi = make_desc(0, lbo, sbo, c.layout);
-    const uint32_t a_lo = (smem_u32(sA) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+    const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFF) >> 4) + c.a_row_shift * 8, b_lo = ((smem_u32(sB) & 0x3FFFF) >> 4) + c.b_half * 4;
     const uint32_t slot_step = c.a_slots > 1 ? (16384 >> 4) : 0;
     const uint32_t kstep = c.layout == 2 ? 2 : 0;
     long long t0 = 0;
@@ -258,7 +259,7 @@ int main() {
         for (int N : {16, 32, 48, 64, 96, 128, 192, 256})
           for (int slots : {1, 8}) {
             if (kind == 2 && layout == 0) continue;
-            BenchCfg c{kind, N, layout, slots, 2048, 1};
+            BenchCfg c{kind, N, layout, slots, 2048, 1, 0, 0};
             rate_kernel<<<grid, 128, 8 * 16384 + 32768 + 2048>>>(c, dcy);
             CK(cudaDeviceSynchronize());
             std::vector<long long> cy(grid);
@@ -269,6 +270,18 @@ int main() {
             printf("rate grid=%3d kind=%s layout=%s N=%3d a_slots=%d: %.1f cyc/MMA (ideal N/2=%d)\n", grid, kind == 2 ? "tf32" : "f16 ",
                    layout == 2 ? "SW128" : "NONE ", N, slots, (double)mx / c.nmma, N / 2);
           }
+  for (int N : {96, 192})
+    for (int shift : {0, 1, 26})
+      for (int bh : {0, 1}) {
+        BenchCfg c{0, N, 2, 4, 2048, 1, shift, bh};
+        rate_kernel<<<148, 128, 8 * 16384 + 32768 + 2048>>>(c, dcy);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> cy(148);
+        CK(cudaMemcpy(cy.data(), dcy, 148 * 8, cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (auto v : cy) mx = v > mx ? v : mx;
+        printf("rate2 f16 SW128 N=%3d a_row_shift=%2d b_half=%d: %.1f cyc/MMA\n", N, shift, bh, (double)mx / c.nmma);
+      }
   printf(fails ? "probe FAILED (%d)\n" : "probe OK\n", fails);
   return fails != 0;
 }

@@ -1,0 +1,461 @@
+// K3 (C = 8): the residual 3D-conv stacks of stages 2 and 3, post_3dconvs(4, 8) (reference models/submodules.py:190-221,
+// models/models.py:136-138), on tcgen05 with split-fp16 operands.  HBM/latency bound by nature (8 channels: 64 B of traffic and
+// 3456 flop per voxel and layer); the design minimises the number of MMAs, each of which costs ~40 + N/2 cycles.
+//
+// Layout: two planes per tensor, hi and lo, each  act[b][d+2][y+2][x+2][8] fp16  (one voxel = one 16-byte row; zero border in
+// all three axes; x*2^-6 = hi + lo*2^-11, see conv3d_f16.cu for the numerics).  With SWIZZLE_NONE K-major UMMA descriptors a
+// "core matrix" is 8 rows x 16 bytes stored contiguously, so a run of 128 consecutive voxels IS a 128 x 8 operand tile, and
+// the leading-dimension offset selects where the second K chunk comes from: K = 16 = [8 hi channels | 8 lo channels] with
+// LBO = distance between the hi and the lo box.  One tcgen05.mma (M=128, N=48, K=16) per (kd, kh) tap:
+//     B rows  0..23 = [wh(kw, co) | 0     ]  -> acc_main = xh*wh
+//     B rows 24..47 = [wl(kw, co) | wh    ]  -> acc_corr = xh*wl + xl*wh
+// and the three kw taps are Toeplitz column blocks: out[r] = E0[r-1] + E1[r] + E2[r+1], E = main/sw + corr/(sw*2^11).
+// 9 MMAs per 126 output voxels.  Operand boxes are plain 2 KB bulk copies (cp.async.bulk), one mbarrier per group of six
+// (3 kd x hi/lo) = one (y+kh) line position; a CTA walks down y so two of the three groups of a tile are already in the ring.
+// Warps: 0 = producer, 1 = MMA issuer, 2-5 / 6-9 = two epilogue groups that alternate tiles (accumulator ti & 1).
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include "lws_common.cuh"
+#include "tma_utils.cuh"
+
+namespace lws {
+
+constexpr int C8_THREADS = 320;
+constexpr int C8_NG = 8;                    // ring of line groups
+constexpr int C8_GBYTES = 6 * 2048;         // 3 kd x (hi, lo) x 128 voxels x 16 B
+constexpr int C8_BBYTES = 9 * 1536;         // 9 taps x 48 rows x 32 B
+constexpr int C8_OFF_RING = 14336;
+constexpr int C8_OFF_STAGE = C8_OFF_RING + C8_NG * C8_GBYTES;  // [2 groups][hi 2048 | lo 2048]
+constexpr int C8_OFF_XCH = C8_OFF_STAGE + 2 * 4096;            // [2 groups][4 quarters][3 rows][8] floats
+constexpr int C8_OFF_BAR = C8_OFF_XCH + 2 * 4 * 3 * 8 * 4;
+constexpr int C8_SMEM = C8_OFF_BAR + 256 + 128;
+
+struct C8Args {
+  const uint8_t* in_hi;   // plane base (voxel 0 of batch element 0); `slack` voxels before it are readable
+  const uint8_t* in_lo;
+  uint8_t* out_hi;
+  uint8_t* out_lo;
+  const uint8_t* wtab;    // device: 9 x 1536 B operand table, then scales[2] (float): 1/sw, 1/(sw * 2^11)
+  const float* bias;      // [8]
+  long long vox_b;        // voxels per batch element (Dp * Hp * Wp)
+  int Hp, Wp, H, W, D;    // padded / interior plane size, interior depth
+  FastDiv fWp, fHp;
+  int line0, strip_len;   // first computed line (= Hp: plane 1) and number of lines (D * Hp)
+  int seg_len, total_items;
+  FastDiv ct_per_line, segs;
+};
+
+struct C8Item {
+  int b, row0, ntiles;  // row0: first output voxel (inside the batch element) of tile 0; tile n is Wp voxels further
+};
+__device__ __forceinline__ C8Item c8_decode(const C8Args& a, int item) {
+  int t, seg, ct;
+  C8Item it;
+  fdivmod(item, a.segs, t, seg);
+  fdivmod(t, a.ct_per_line, it.b, ct);
+  const int n0 = seg * a.seg_len;
+  it.ntiles = min(a.seg_len, a.strip_len - n0);
+  it.row0 = (a.line0 + n0) * a.Wp + ct * 126;
+  return it;
+}
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst)),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void c8_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sB = smem;
+  uint8_t* sRing = smem + C8_OFF_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C8_OFF_BAR);
+  uint64_t* g_full = bars;              // [NG]
+  uint64_t* g_empty = g_full + C8_NG;   // [NG]
+  uint64_t* t_full = g_empty + C8_NG;   // [2]
+  uint64_t* t_empty = t_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < C8_NG; ++i) mbar_init(g_full + i, 1), mbar_init(g_empty + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < C8_BBYTES / 16; i += C8_THREADS)
+    reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.wtab) + i);
+  fence_proxy_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const long long plane = (long long)a.Hp * a.Wp;  // voxels per d plane
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    if (elect_one_sync()) {
+      uint32_t slot = 0, ph = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const C8Item w = c8_decode(a, item);
+        const long long base = (long long)w.b * a.vox_b + w.row0 - 1;  // GEMM row 0 of tile 0 (Toeplitz shift 1)
+        for (int n = 0; n < w.ntiles; ++n) {
+          for (int kh = n == 0 ? 0 : 2; kh < 3; ++kh) {  // later tiles of a strip only need the line below
+            mbar_wait(g_empty + slot, ph ^ 1);
+            mbar_expect_tx(g_full + slot, C8_GBYTES);
+            uint8_t* dst = sRing + slot * C8_GBYTES;
+            const long long v0 = base + (long long)(n + kh - 1) * a.Wp;
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+              const long long v = v0 + (kd - 1) * plane;
+              bulk_load(dst + kd * 4096, a.in_hi + v * 16, 2048, g_full + slot);
+              bulk_load(dst + kd * 4096 + 2048, a.in_lo + v * 16, 2048, g_full + slot);
+            }
+            if (++slot == C8_NG) slot = 0, ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = (1u << 4) | ((48u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128, N = 48
+    // SWIZZLE_NONE K-major: LBO = byte distance between the two K chunks, SBO = 128 B between 8-row groups
+    const uint64_t a_hi = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint64_t b_hi = ((uint64_t)(768 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t ring_lo = (smem_u32(sRing) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+    uint32_t bslot = 0, bph = 0, ti = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const C8Item w = c8_decode(a, item);
+      for (int n = 0; n < w.ntiles; ++n, ++ti) {
+        const bool last = n == w.ntiles - 1;
+        const uint32_t tb = ti & 1;
+        mbar_wait(t_empty + tb, ((ti >> 1) & 1) ^ 1);
+        uint32_t slot = bslot, ph = bph;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          if (n == 0 || kh == 2) mbar_wait(g_full + slot, ph);  // the other groups were waited for by the previous tile
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one_sync()) {
+            const uint32_t g_lo = ring_lo + slot * (C8_GBYTES >> 4);
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+              const uint64_t da = a_hi | (uint64_t)(g_lo + kd * (4096 >> 4));
+              const uint64_t db = b_hi | (uint64_t)(b_lo + (kd * 3 + kh) * (1536 >> 4));
+              const uint32_t acc = (kh | kd) == 0 ? 0u : 1u;
+              asm volatile(
+                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem + tb * 64),
+                  "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                  : "memory");
+            }
+            if (kh == 0 || last)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(g_empty + slot))
+                           : "memory");
+            if (kh == 2)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(t_full + tb))
+                           : "memory");
+          }
+          __syncwarp();
+          if (++slot == C8_NG) slot = 0, ph ^= 1;
+        }
+        if (++bslot == C8_NG) bslot = 0, bph ^= 1;
+      }
+      bslot += 2;  // the strip's last tile consumed its remaining two groups
+      if (bslot >= C8_NG) bslot -= C8_NG, bph ^= 1;
+    }
+  } else {
+    // ================================ epilogue: group g handles the tiles with ti & 1 == g ================================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int j = q * 32 + lane;       // GEMM row; this thread produces output voxel j (staging row j), valid for j < 126
+    const bool issuer = ((warp - 2) & 3) == 0 && lane == 0;
+    const float c0 = __ldg(reinterpret_cast<const float*>(a.wtab + C8_BBYTES));
+    const float c1 = __ldg(reinterpret_cast<const float*>(a.wtab + C8_BBYTES) + 1);
+    float bias[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bias[c] = __ldg(a.bias + c) * kDwsepActScale;
+    uint8_t* stage = smem + C8_OFF_STAGE + g * 4096;
+    float* xch = reinterpret_cast<float*>(smem + C8_OFF_XCH) + g * (4 * 3 * 8);
+    float* xq = xch + q * 24;                    // this quarter publishes e1 of lane 0, e2 of lanes 0 and 1
+    const float* xn = xch + ((q + 1) & 3) * 24;  // next quarter's
+    const int bar_id = 1 + g;
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const C8Item w = c8_decode(a, item);
+      for (int n = 0; n < w.ntiles; ++n, ++ti) {
+        if ((int)(ti & 1) != g) continue;
+        mbar_wait(t_full + g, (ti >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + g * 64;
+        float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];
+        c8_ld8(taddr, m0);
+        c8_ld8(taddr + 8, m1);
+        c8_ld8(taddr + 16, m2);
+        c8_ld8(taddr + 24, k0);
+        c8_ld8(taddr + 32, k1);
+        c8_ld8(taddr + 40, k2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + g);
+        float out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float e0 = fmaf(k0[c], c1, m0[c] * c0);
+          m1[c] = fmaf(k1[c], c1, m1[c] * c0);
+          m2[c] = fmaf(k2[c], c1, m2[c] * c0);
+          const float s1 = __shfl_down_sync(0xffffffffu, m1[c], 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, m2[c], 2);
+          out[c] = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
+        }
+        if (lane < 2) {
+          float4* d2 = reinterpret_cast<float4*>(xq + (1 + lane) * 8);
+          d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
+          if (lane == 0) {
+            float4* d1 = reinterpret_cast<float4*>(xq);
+            d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
+          }
+        }
+        // the bulk stores of this group's previous tile must have read the staging buffer
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        named_bar_sync(bar_id, 128);
+        if (q < 3 && lane >= 30) {
+          if (lane == 31) {
+            const float4* p1 = reinterpret_cast<const float4*>(xn);
+            const float4 u = p1[0], v = p1[1];
+            out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
+          }
+          const float4* p2 = reinterpret_cast<const float4*>(xn + (1 + lane - 30) * 8);
+          const float4 u = p2[0], v = p2[1];
+          out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
+        }
+        // voxel coordinates -> border
+        const int r = w.row0 + n * a.Wp + j;
+        int line, x, dpl, y;
+        fdivmod(r, a.fWp, line, x);
+        fdivmod(line, a.fHp, dpl, y);
+        const bool border = x < 1 || x > a.W || y < 1 || y > a.H || dpl < 1 || dpl > a.D;  // tiles may spill into the pad plane
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          float v0 = fmaxf(out[2 * p] + bias[2 * p], 0.f), v1 = fmaxf(out[2 * p + 1] + bias[2 * p + 1], 0.f);
+          v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
+          const __half2 h = __floats2half2_rn(v0, v1);
+          const float2 f = __half22float2(h);
+          const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+          hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        *reinterpret_cast<uint4*>(stage + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(stage + 2048 + j * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          const long long v = (long long)w.b * a.vox_b + w.row0 + (long long)n * a.Wp;
+          bulk_store(a.out_hi + v * 16, stage, 126 * 16);
+          bulk_store(a.out_lo + v * 16, stage + 2048, 126 * 16);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// ---- first conv 1 -> 8 on the raw cost (BN_0 affine + ReLU on the taps), writes every voxel of the padded hi/lo planes ----
+__global__ void __launch_bounds__(256)
+    conv3d_first_c8_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][8]*/, const float* __restrict__ bias,
+                           const float* __restrict__ affine, uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, int D, int H,
+                           int W, long long total_vox) {
+  __shared__ __align__(16) float sW[27 * 8];
+  for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sW[i] = __ldg(w + i);
+  __syncthreads();
+  const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+  const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+  const long long hw = (long long)H * W;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + j);
+  for (long long vox = (long long)blockIdx.x * blockDim.x + threadIdx.x; vox < total_vox; vox += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(vox % Wp) - 1;
+    long long t = vox / Wp;
+    const int y = (int)(t % Hp) - 1;
+    t /= Hp;
+    const int d = (int)(t % Dp) - 1;
+    const int b = (int)(t / Dp);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bool border = x < 0 || x >= W || y < 0 || y >= H || d < 0 || d >= D;
+    if (!border) {
+      const float* cb = cost + ((long long)b * D + d) * hw + (long long)y * W + x;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const bool okd = (unsigned)(d + kd - 1) < (unsigned)D;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const bool okh = okd && (unsigned)(y + kh - 1) < (unsigned)H;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const bool ok = okh && (unsigned)(x + kw - 1) < (unsigned)W;
+            float v = ok ? __ldg(cb + (kd - 1) * hw + (kh - 1) * W + (kw - 1)) : 0.f;
+            v = ok ? fmaxf(fmaf(v, s0, t0), 0.f) : 0.f;
+            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8 + 4);
+            acc[0] = fmaf(v, wa.x, acc[0]), acc[1] = fmaf(v, wa.y, acc[1]), acc[2] = fmaf(v, wa.z, acc[2]),
+            acc[3] = fmaf(v, wa.w, acc[3]), acc[4] = fmaf(v, wb.x, acc[4]), acc[5] = fmaf(v, wb.y, acc[5]),
+            acc[6] = fmaf(v, wb.z, acc[6]), acc[7] = fmaf(v, wb.w, acc[7]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + bv[j], 0.f) * kDwsepActScale;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const __half2 h = __floats2half2_rn(acc[2 * p], acc[2 * p + 1]);
+      const float2 f = __half22float2(h);
+      const __half2 l = __floats2half2_rn((acc[2 * p] - f.x) * 2048.f, (acc[2 * p + 1] - f.y) * 2048.f);
+      hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    out_hi[vox] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out_lo[vox] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ---- last conv 8 -> 1 from the hi/lo planes (+ skip), NCDHW fp32 output; one thread per voxel ------------------------------
+__global__ void __launch_bounds__(256)
+    conv3d_last_c8_kernel(const uint4* __restrict__ act_hi, const uint4* __restrict__ act_lo, const float* __restrict__ w /*[8][27]*/,
+                          const float* __restrict__ skip, float* __restrict__ out, int D, int H, int W, long long total_vox) {
+  __shared__ __align__(16) float sW[27 * 8];  // [tap][ci], pre-divided by the activation scale
+  for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sW[(i % 27) * 8 + i / 27] = __ldg(w + i) * (1.f / kDwsepActScale);
+  __syncthreads();
+  const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+  for (long long vox = (long long)blockIdx.x * blockDim.x + threadIdx.x; vox < total_vox; vox += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(vox % W);
+    long long t = vox / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int d = (int)(t % D);
+    const int b = (int)(t / D);
+    const long long row = (((long long)b * Dp + d + 1) * Hp + y + 1) * Wp + x + 1;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const long long r = row + ((long long)(kd - 1) * Hp + (kh - 1)) * Wp + (kw - 1);
+          const uint4 h = __ldg(act_hi + r), l = __ldg(act_lo + r);
+          const float* wt = sW + (kd * 9 + kh * 3 + kw) * 8;
+          const float4 wa = *reinterpret_cast<const float4*>(wt), wb = *reinterpret_cast<const float4*>(wt + 4);
+          const uint32_t hw_[4] = {h.x, h.y, h.z, h.w}, lw_[4] = {l.x, l.y, l.z, l.w};
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw_[p]));
+            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw_[p]));
+            acc0 = fmaf(fmaf(fl.x, 1.f / 2048.f, fh.x), wv[2 * p], acc0);
+            acc1 = fmaf(fmaf(fl.y, 1.f / 2048.f, fh.y), wv[2 * p + 1], acc1);
+          }
+        }
+    out[vox] = acc0 + acc1 + (skip ? __ldg(skip + vox) : 0.f);
+  }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------------------------
+static long long c8_plane_bytes(int B, int D, int H, int W) {
+  const long long vox = (long long)B * (D + 2) * (H + 2) * (W + 2);
+  const long long slack = (long long)(H + 2) * (W + 2) + (W + 2) + 256;  // one plane + one line + one tile before and after
+  return (vox + 2 * slack) * 16;
+}
+size_t conv3d_c8_workspace_bytes(int B, int D, int H, int W) { return (size_t)4 * ((c8_plane_bytes(B, D, H, W) + 255) / 256 * 256); }
+
+// wtab[l]: 9 x 1536 B operand table + scales[2]; bias_mid[l]: [8]
+int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
+                    const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
+                    int add_skip, cudaStream_t st) {
+  const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+  const long long vox_b = (long long)Dp * Hp * Wp;
+  if (vox_b * B >= (1ll << 31) - (1 << 20)) return LWS_ERR_BAD_SHAPE;
+  const long long pb = (c8_plane_bytes(B, D, H, W) + 255) / 256 * 256;
+  const long long slack = ((long long)Hp * Wp + Wp + 256) * 16;
+  uint8_t* base = (uint8_t*)ws;
+  uint8_t* plane[4];  // A.hi, A.lo, B.hi, B.lo (voxel 0)
+  for (int i = 0; i < 4; ++i) plane[i] = base + i * pb + slack;
+  cudaError_t e;
+  // the slack in front of / behind every plane and the d-padding planes of the second buffer pair are only ever read
+  for (int i = 0; i < 4; ++i) {
+    if ((e = cudaMemsetAsync(base + i * pb, 0, slack, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(plane[i] + vox_b * B * 16, 0, slack, st)) != cudaSuccess) return (int)e;
+  }
+  for (int i = 2; i < 4; ++i) {
+    const size_t pl = (size_t)Hp * Wp * 16;
+    if ((e = cudaMemset2DAsync(plane[i], vox_b * 16, 0, pl, B, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemset2DAsync(plane[i] + (size_t)(Dp - 1) * pl, vox_b * 16, 0, pl, B, st)) != cudaSuccess) return (int)e;
+  }
+  {
+    const long long nvox = (long long)B * vox_b;
+    const int blocks = (int)((nvox + 255) / 256 < 148 * 16 ? (nvox + 255) / 256 : 148 * 16);
+    conv3d_first_c8_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W, nvox);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+  }
+  e = cudaFuncSetAttribute(conv3d_c8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  int cur = 0;
+  for (int l = 0; l < layers; ++l) {
+    C8Args a;
+    memset(&a, 0, sizeof(a));
+    a.in_hi = plane[cur], a.in_lo = plane[cur + 1], a.out_hi = plane[2 - cur], a.out_lo = plane[3 - cur];
+    a.wtab = (const uint8_t*)wtab[l], a.bias = bias_mid[l];
+    a.vox_b = vox_b, a.Hp = Hp, a.Wp = Wp, a.H = H, a.W = W, a.D = D, a.fWp = make_fastdiv(Wp), a.fHp = make_fastdiv(Hp);
+    a.line0 = Hp, a.strip_len = D * Hp;
+    const int ct = (Wp + 125) / 126;
+    // segments: ~8 items per SM, at least 8 lines each (every segment reloads two lines)
+    int segs = (int)((148ll * 8 + (long long)B * ct - 1) / ((long long)B * ct));
+    if (segs < 1) segs = 1;
+    int seg_len = (a.strip_len + segs - 1) / segs;
+    if (seg_len < 8) seg_len = a.strip_len < 8 ? a.strip_len : 8;
+    segs = (a.strip_len + seg_len - 1) / seg_len;
+    a.seg_len = seg_len, a.segs = make_fastdiv(segs), a.ct_per_line = make_fastdiv(ct);
+    a.total_items = B * ct * segs;
+    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    conv3d_c8_kernel<<<grid, C8_THREADS, C8_SMEM, st>>>(a);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+    cur = 2 - cur;
+  }
+  {
+    const long long vox = (long long)B * D * H * W;
+    const int blocks = (int)((vox + 255) / 256 < 148 * 16 ? (vox + 255) / 256 : 148 * 16);
+    conv3d_last_c8_kernel<<<blocks, 256, 0, st>>>((const uint4*)plane[cur], (const uint4*)plane[cur + 1], w_last,
+                                                  add_skip ? cost : nullptr, out, D, H, W, vox);
+    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+  }
+  return LWS_OK;
+}
+
+}  // namespace lws

@@ -27,6 +27,11 @@ size_t conv3d_tc_workspace_bytes(int B, int C, int D, int H, int W);
 int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,
                     const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last, float* out,
                     void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
+// conv3d_c8.cu: tcgen05 split-fp16 path for C = 8
+size_t conv3d_c8_workspace_bytes(int B, int D, int H, int W);
+int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
+                    const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
+                    int add_skip, cudaStream_t st);
 // conv3d_f16.cu: tcgen05 split-fp16 Toeplitz-N path for C = 32
 size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W);
 int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
@@ -373,37 +378,37 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
       tc[5 * 192 * 32] = 1.f / sw;
       tc[5 * 192 * 32 + 1] = 1.f / (sw * 2048.f);
     }
-  } else if (has_tc_tables(C)) {
-    // 3xTF32 operand tables, [9 stages = (kd,kh)][3 shifts][64 rows][32]: rows 0..31 hold wh (tf32-truncated folded
-    // weights), rows 32..63 the remainders wl = w - wh.  C = 8: a GEMM row is 4 consecutive voxels u = 0..3
-    // (n = u_out*8 + cout, k = u_in*8 + cin).  Shift 1 (same row)
-    //          carries the taps with u_in - u_out = kw - 1 in {-1,0,1}; shift 0 (previous row) only its last voxel
-    //          (u_in = 3 -> u_out = 0, kw = 0); shift 2 (next row) only its first voxel (u_in = 0 -> u_out = 3, kw = 2).
-    auto split = [](float w, float* hi, float* lo) {
-      uint32_t u;
-      memcpy(&u, &w, 4);
-      u &= 0xFFFFE000u;
-      memcpy(hi, &u, 4);
-      *lo = w - *hi;
-    };
+  } else if (C == 8) {
+    // split-fp16 operand tables (conv3d_c8.cu), per 8 -> 8 layer: 9 taps t = kd*3 + kh of 1536 bytes each, SWIZZLE_NONE K-major:
+    // K chunk 0 (applied to the hi halves of the voxel) = 48 rows x 8 halves, K chunk 1 (applied to the lo halves) 768 bytes
+    // further; row n = part*24 + kw*8 + co: part 0 = [wh | 0], part 1 = [wl | wh]; wh = fp16(w * sw),
+    // wl = fp16((w * sw - wh) * 2^11), sw = the power of two that puts max|w| into [256, 512).  Scales 1/sw, 1/(sw*2^11) follow.
     for (int l = 0; l < layers; ++l) {
       const float* wf = packed + packed_offset(C, layers, l + 1, false);  // [ci][27][co]
       float* tc = packed + packed_tc_offset(C, layers, l);
       memset(tc, 0, kTcLayerFloats * sizeof(float));
-      for (int stg = 0; stg < 9; ++stg)
-        for (int kw = 0; kw < 3; ++kw)
-          for (int co = 0; co < C; ++co)
-            for (int ci = 0; ci < C; ++ci) {
-              const float w = wf[((size_t)ci * 27 + stg * 3 + kw) * C + co];
-              for (int uo = 0; uo < 4; ++uo) {
-                const int ui = uo + kw - 1;  // input voxel relative to this row's first voxel
-                int shift = 1, uin = ui;
-                if (ui < 0) shift = 0, uin = 3;
-                else if (ui > 3) shift = 2, uin = 0;
-                float* base = tc + (size_t)(stg * 3 + shift) * 64 * 32;
-                split(w, base + (uo * 8 + co) * 32 + uin * 8 + ci, base + (32 + uo * 8 + co) * 32 + uin * 8 + ci);
+      float mx = 0.f;
+      for (int i = 0; i < 8 * 27 * 8; ++i) mx = fmaxf(mx, fabsf(wf[i]));
+      int e = 0;
+      if (mx > 0.f) frexpf(mx, &e);
+      const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+      __half* h = reinterpret_cast<__half*>(tc);
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw)
+            for (int co = 0; co < 8; ++co)
+              for (int ci = 0; ci < 8; ++ci) {
+                const float w = wf[((size_t)ci * 27 + kd * 9 + kh * 3 + kw) * 8 + co] * sw;
+                const __half hi = __float2half_rn(w);
+                const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+                __half* t = h + (size_t)(kd * 3 + kh) * 768;  // 1536 bytes per tap
+                const int n0 = kw * 8 + co, n1 = 24 + kw * 8 + co;
+                t[n0 * 8 + ci] = hi;            // chunk 0, part 0
+                t[n1 * 8 + ci] = lo;            // chunk 0, part 1
+                t[384 + n1 * 8 + ci] = hi;      // chunk 1 (768 bytes further), part 1
               }
-            }
+      tc[9 * 384] = 1.f / sw;
+      tc[9 * 384 + 1] = 1.f / (sw * 2048.f);
     }
   }
   return LWS_OK;
@@ -415,6 +420,7 @@ extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, i
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
   size_t tc = lws::has_tc_tables(C) ? lws::conv3d_tc_workspace_bytes(B, C, D, H, W) : 0;
   if (C == 32 && lws::conv3d_f16_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_f16_workspace_bytes(B, D, H, W);
+  if (C == 8 && lws::conv3d_c8_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_c8_workspace_bytes(B, D, H, W);
   return 2 * act > tc ? 2 * act : tc;
 }
 
@@ -444,6 +450,9 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
       return conv3d_stack_f16(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
                               layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W, add_skip, st);
     if (C == 32) return LWS_ERR_UNSUPPORTED;  // D > 62: use LWS_CONV3D_TC=0
+    if (C == 8)
+      return conv3d_stack_c8(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
+                             layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W, add_skip, st);
     return conv3d_stack_tc(C, cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
                            wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
                            add_skip, st);

@@ -72,20 +72,23 @@ def test_pack_conv3d_stack_folds_bn():
         if i < layers + 1:
             assert np.allclose(packed[off:off + cout], t[i + 1], rtol=1e-6, atol=1e-7)
         off += (cout + 3) // 4 * 4
-    # C = 8 and C = 32 carry tensor-core operand tables behind the generic layout: [9 stages][3 shifts][64][32] per layer
+    # C = 8 and C = 32 carry split-fp16 tensor-core operand tables behind the generic layout (one 9*192*32-float slot per layer)
     assert packed.size == off + layers * 9 * 192 * 32
-    tc = packed[off:off + 9 * 192 * 32].reshape(9, 3, 64, 32)                  # first 8 -> 8 layer
+    slot = packed[off:off + 9 * 192 * 32]                                       # first 8 -> 8 layer
     wf = packed[4 + 216 + 8:4 + 216 + 8 + 8 * 27 * 8].reshape(8, 27, 8)         # its folded weights [ci][tap][co]
-    assert np.all((tc[:, :, :32].view(np.uint32) & 0x1FFF) == 0)               # hi rows are tf32-truncated
-    full = tc[:, :, :32] + tc[:, :, 32:]                                       # hi + lo == w, block structure for 4 voxels/row
-    for stg in (0, 4, 8):
-        for kw in range(3):
-            w = wf[:, stg * 3 + kw, :].T                                       # [co][ci]
-            for uo in range(4):
-                ui = uo + kw - 1
-                shift, uin = (0, 3) if ui < 0 else ((2, 0) if ui > 3 else (1, ui))
-                assert np.array_equal(full[stg, shift, uo * 8:uo * 8 + 8, uin * 8:uin * 8 + 8], w)
-    assert np.count_nonzero(full[:, 0, :, :24]) == 0 and np.count_nonzero(full[:, 2, :, 8:]) == 0  # side rows: one K step
+    tab = slot[:9 * 384].view(np.float16).reshape(9, 2, 48, 8).astype(np.float64)   # [tap kd*3+kh][K chunk][row][ci]
+    inv_sw, inv_sw_lo = float(slot[9 * 384]), float(slot[9 * 384 + 1])
+    sw = 1.0 / inv_sw
+    assert 256 <= np.abs(wf).max() * sw < 512 and inv_sw_lo == inv_sw / 2048
+    for kd in range(3):
+        for kh in range(3):
+            t = tab[kd * 3 + kh]
+            for kw in range(3):
+                w = wf[:, kd * 9 + kh * 3 + kw, :].T.astype(np.float64)       # [co][ci]
+                hi, lo = t[0, kw * 8:kw * 8 + 8], t[0, 24 + kw * 8:24 + kw * 8 + 8]
+                assert np.array_equal(t[1, 24 + kw * 8:24 + kw * 8 + 8], hi)   # corr rows: [wl | wh]
+                assert np.count_nonzero(t[1, kw * 8:kw * 8 + 8]) == 0          # main rows: [wh | 0]
+                assert np.abs((hi + lo / 2048) / sw - w).max() <= 2.0 ** -22 * np.abs(wf).max()
 
 
 def test_pack_refinement_folds_bn():

@@ -176,20 +176,31 @@ def kernel_probes(model, pk):
     o = torch.empty((B, 1, H_IMG, W_IMG), device=dev)
     us = time_rotating(lambda i: ops.scale_upsample_add(s[i][0], s[i][1], H_IMG, W_IMG, out=o), len(s))
     add("K5 scale_upsample_add [16,1,184,616]->[16,1,368,1232]", us, B * (184 * 616 + 2 * H_IMG * W_IMG) * 4)
-    # K3 dominant layers
-    for (C, D, h, w, b) in ((32, 24, 46, 154, 4), (8, 9, 184, 616, 4)):
-        xs = sets(3, (b, C, D, h, w), scale=1.0)
-        wt = torch.randn((C * 27 * C,), device=dev) * 0.05
-        bias = torch.zeros((C,), device=dev)
-        o3 = torch.empty((b, C, D, h, w), device=dev)
-        us = time_rotating(lambda i: ops.conv3d_bnrelu_layer(xs[i][0], wt, bias, out=o3), len(xs), iters=10, warm=3)
-        add(f"K3 conv3d_k3 {C}->{C} [{b},{C},{D},{h},{w}] (fp32 FFMA)", us, flops=2 * 27 * C * C * D * h * w * b)
-    # whole refinement (a8+a9), batch 2
+    # K3: the whole residual 3D stack per stage (first conv + 4 tensor-core layers + last conv = 6 launches)
+    for (C, D, h, w, b) in ((32, 24, 46, 154, 4), (8, 9, 92, 308, 4), (8, 9, 184, 616, 4)):
+        stack = model.volume_postprocess[{(32, 46): 0, (8, 92): 1, (8, 184): 2}[(C, h)]]
+        xs = [torch.rand((b, D, h, w), device=dev) * 20 for _ in range(3)]
+        us = time_rotating(lambda i: stack.run(xs[i], add_skip=True), len(xs), iters=10, warm=3)
+        flops = 2 * 27 * D * h * w * b * (C + 4 * C * C + C)
+        add(f"K3 conv3d stack C={C} [{b},{D},{h},{w}] (6 launches, split-fp16 tcgen05)", us, flops=flops)
+    # K6: one BN-ReLU-DW-PW block on its own (the step's dominant kernel, 12 launches per forward), then the whole refinement
+    rp = model._refinement_packed(dev)
+    Bk = 4
+    n = int(ops.lib.lws_refinement_clp_floats(Bk, H_IMG, W_IMG))
+    bufs = [torch.zeros(n, device=dev) for _ in range(3)]
+    for t in bufs:
+        t.view(Bk, H_IMG + 32, W_IMG + 32, 32)[:, 16:-16, 16:-16, :].uniform_(0.0, 3.0)
+    us = time_rotating(lambda i: ops.refinement_block_clp(bufs[i], rp, 2, 1, Bk, H_IMG, W_IMG, out=bufs[(i + 1) % 3]), 3, iters=12, warm=3)
+    add(f"K6 dwsep block dil 4 [{Bk},32,368,1232] channels-last (read + write every pixel once)", us,
+        bytes_=2 * Bk * 32 * H_IMG * W_IMG * 4, flops=2 * Bk * H_IMG * W_IMG * 32 * (9 + 32))
     left = [torch.randn((2, 3, H_IMG, W_IMG), device=dev) for _ in range(2)]
     p3 = [torch.rand((2, 1, H_IMG, W_IMG), device=dev) * 100 for _ in range(2)]
-    rp = model._refinement_packed(dev)
     us = time_rotating(lambda i: ops.refinement(left[i], p3[i], rp), 2, iters=6, warm=2)
     add("K6 refinement a8+a9 [2,*,368,1232] (16 launches)", us, flops=int(2 * 71232 * H_IMG * W_IMG))
+    # n1: feature pyramid, left and right stacked
+    imgs = [torch.randn((8, 3, H_IMG, W_IMG), device=dev) for _ in range(3)]
+    us = time_rotating(lambda i: model.feature_extraction(imgs[i]), 3, iters=6, warm=2)
+    add("FE feature pyramid [8,3,368,1232] (12 launches)", us, flops=int(8 * 2.27e9 / 2))
     return out
 
 
@@ -268,13 +279,14 @@ def run_ours(args, rank, world, local_rank):
     kernels, roofline = [], None
     if not args.skip_probes:
         kernels = kernel_probes(model, pk)
-        dom = max((k for k in kernels if k["kernel"].startswith("K3 conv3d_k3 32")), key=lambda k: k["us"])
-        roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": pk["tensor"],
-                    "unit": "TFLOP/s", "frac": round(dom["tflops"] / pk["tensor"], 4), "traffic": None,
-                    "peak_source": pk["source"] + " bf16 burst",
-                    "note": "dominant kernel by time (4 launches per pair, 37.6 of 91.6 GFLOP); fp32 FFMA on the CUDA "
-                            "cores this round, so the fraction of the tensor roofline is small by construction; "
-                            "see the `kernels` table for the HBM-bound kernels"}
+        dom = next(k for k in kernels if k["kernel"].startswith("K6 dwsep block"))
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full (profiles/r01_ncu_*dwsep*)
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": round(dom["gbs"] / pk["hbm"], 4), "traffic": 474624512,
+                    "peak_source": pk["source"] + " copy bandwidth",
+                    "note": "dominant kernel by time (12 launches per forward, ~27% of the step); timed alone with CUDA events on "
+                            "the launching stream over 3 rotating 259 MB tensors (> L2); algorithmic bytes = interior pixels x 32 "
+                            "channels x 4 B, read once + written once; the conv stacks are tensor-core kernels, see `kernels`"}
 
     # ---- CPU baseline beside it (N=1 only): the oracle port on the host cores, bounded sample -----------------------
     cpu = None
@@ -301,7 +313,8 @@ def run_ours(args, rank, world, local_rank):
                    "batch_per_gpu": BATCH, "micro_batch": args.micro_batch, "maxdisplist": [24, 5, 5],
                    "weights": "random init (KaimingNormal, seed 0)", "cuda_graphs": not args.no_graphs,
                    "l2": "inputs (697 MB per step) and per-step activations exceed the 126 MB L2",
-                   "feature_extractor": "torch/cuDNN (off the north-star hot path, SURVEY.md 8(f))",
+                   "numerics": "fp32 storage at the ABI; conv stacks and pointwise convs on tcgen05 with split-fp16 operands "
+                               "(x = hi + lo*2^-11, 3 exact products, fp32 accumulation)",
                    "tflops_equiv": round(value * GFLOP_PER_PAIR / 1e3, 2)},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(left_h.nbytes + right_h.nbytes),
                 "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
@@ -322,7 +335,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=2)
+    ap.add_argument("--micro-batch", type=int, default=4)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--skip-probes", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

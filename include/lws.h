@@ -121,6 +121,14 @@ LWS_API size_t lws_refinement_workspace_bytes(int B, int H, int W);
 LWS_API int lws_refinement_f32(const float* left, const float* pred3, const float* packed_weights, float* pred4, void* ws,
                        size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
 
+/* One BN-ReLU-DW3x3(dil)-PW1x1 block of the refinement (models/submodules.py:236-261) on its own, on the channels-last bordered
+ * tensors the refinement uses internally: act[b][H+32][W+32][32] fp32, 16-pixel zero border (lws_refinement_clp_floats elements).
+ * branch 0/1/2 = refinement1_left / refinement1_disp / refinement2, block 0..3 selects the block's weights and dilation from
+ * the packed blob.  The refinement's dominant kernel: for per-block tests and for timing it against the HBM roofline. */
+LWS_API size_t lws_refinement_clp_floats(int B, int H, int W);
+LWS_API int lws_refinement_block_clp_f32(const float* in_clp, float* out_clp, const float* packed_weights, int branch, int block,
+                                         int B, int H, int W, lws_stream_t stream);
+
 /* ---- n1 (SURVEY.md 8(f) "next"): feature_extraction  (models/submodules.py:5-188) ----------------------------
  * img [B,3,H,W] -> f8 [B,16,H/8,W/8], f4 [B,16,H/4,W/4], f2 [B,8,H/2,W/2]; H, W multiples of 8.  12 launches, fp32.
  * HOST pack: tensors = for each of the 12 convs in execution order (dres0.0, dres0.2, dres1.0, dres1.2, dres2.conv1..4,

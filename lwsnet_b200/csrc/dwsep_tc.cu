@@ -12,8 +12,9 @@
 //     accumulated onto the hi*wl columns, both carry the 2^-11 weight); products of 11-bit significands are exact in the
 //     fp32 accumulator, so the result has the accuracy of an fp32 FMA chain (the dropped lo*lo term is 2^-22 relative).
 //     One tcgen05.mma costs ~40 + N/2 cycles with both operands in shared memory (tools/umma_bench.cu), hence few, wide MMAs.
-//   * 4 epilogue warps: tcgen05.ld, rescale + bias + ReLU, zero the x border, stage the 128 x 128 B tile in shared memory and
-//     TMA-store it (clipped at the line end by the tensor map).
+//   * 4 epilogue warps: tcgen05.ld, rescale + bias + ReLU, zero the x border; every warp stages its own 32 x 128 B quarter in
+//     shared memory and TMA-stores it (clipped at the line end by the tensor map), so the tile's critical path has no
+//     cross-warp barrier.
 // The y-border lines of the output are zero-filled by all threads at kernel start.
 #include <cuda_fp16.h>
 #include <math.h>
@@ -229,7 +230,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     // ================================ epilogue (warps 8..11) ================================
     const int quarter = warp & 3;
     const int p = quarter * 32 + lane;  // pixel of the tile = TMEM lane
-    const bool issuer = warp == DS_EPI_WARP0 && lane == 0;
     float bias[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias[c] = __ldg(a.bias + c);
@@ -257,9 +257,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
           const float v = fmaxf(fmaf(c[j], c1, fmaf(m[j], c0, bias[j])), lo);
           m[j] = border ? 0.f : v;
         }
-        // staging tile `ob` was last read by the TMA store issued DS_NOUT tiles ago
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DS_NOUT - 1) : "memory");
-        named_bar_sync(1, 128);
+        // every epilogue warp stages and stores its own 32 pixels (no cross-warp barrier on the tile's critical path);
+        // staging quarter `ob` was last read by the TMA store this warp issued DS_NOUT tiles ago
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DS_NOUT - 1) : "memory");
+        __syncwarp();
         const uint32_t so = smem_u32(smem + DS_OFF_OUT + ob * DS_TILE) + p * 128;
         if (a.out_split) {
 #pragma unroll
@@ -284,18 +285,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
           for (int j = 0; j < 8; ++j) sts128(so + ((j ^ (p & 7)) << 4), make_float4(m[4 * j], m[4 * j + 1], m[4 * j + 2], m[4 * j + 3]));
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (issuer) {
+        __syncwarp();
+        if (lane == 0) {
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&map_out)),
-                       "r"(smem_u32(smem + DS_OFF_OUT + ob * DS_TILE)), "r"(0), "r"(w.x0),
+                       "r"(smem_u32(smem + DS_OFF_OUT + ob * DS_TILE + quarter * 4096)), "r"(0), "r"(w.x0 + quarter * 32),
                        "r"(w.b * a.Hp + DS_RP + w.yi0 + i * dil)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ================================ depthwise warps (0..7) ================================
     const int q = tid & 7;    // channel quad
@@ -404,7 +405,7 @@ int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* p
   const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
   CUtensorMap map_in, map_out;
   const uint64_t dims[3] = {32, (uint64_t)a.Wp, (uint64_t)B * a.Hp}, strides[2] = {128, (uint64_t)a.Wp * 128};
-  const uint32_t box_in[3] = {32, (uint32_t)(128 + 2 * dil), 1}, box_out[3] = {32, 128, 1};
+  const uint32_t box_in[3] = {32, (uint32_t)(128 + 2 * dil), 1}, box_out[3] = {32, 32, 1};  // one TMA store per epilogue warp
   int rc = make_tensor_map_f32(&map_in, in, 3, dims, strides, box_in, false);
   if (rc) return rc;
   rc = make_tensor_map_f32(&map_out, out, 3, dims, strides, box_out, true);

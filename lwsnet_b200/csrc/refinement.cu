@@ -353,6 +353,31 @@ extern "C" size_t lws_refinement_workspace_bytes(int B, int H, int W) {
   return ffma > tc ? ffma : tc;
 }
 
+namespace lws {
+int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
+                     int H, int W, int dil, int relu, int out_split, cudaStream_t st);
+}
+extern "C" size_t lws_refinement_clp_floats(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * (H + 32) * (W + 32) * 32;
+}
+extern "C" int lws_refinement_block_clp_f32(const float* in_clp, float* out_clp, const float* pk, int branch, int block, int B,
+                                            int H, int W, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(in_clp);
+  LWS_CHECK_PTR(out_clp);
+  LWS_CHECK_PTR(pk);
+  if (B <= 0 || H <= 0 || W <= 0 || branch < 0 || branch > 2 || block < 0 || block > 3) return LWS_ERR_BAD_SHAPE;
+  if ((((uintptr_t)in_clp) | ((uintptr_t)out_clp) | ((uintptr_t)pk)) & 15) return LWS_ERR_BAD_ALIGN;
+  const RefLayout L = ref_layout();
+  static const int r1_dil[4] = {2, 4, 8, 16}, r2_dil[4] = {8, 4, 2, 1};
+  const float* dw = pk + (branch < 2 ? L.r1_dw[branch][block] : L.r2_dw[block]);
+  const float* tc = pk + (branch < 2 ? L.r1_pwtc[branch][block] : L.r2_pwtc[block]);
+  const float* bias = pk + (branch < 2 ? L.r1_b[branch][block] : L.r2_bb[block]);
+  const int dil = branch < 2 ? r1_dil[block] : r2_dil[block];
+  return launch_dwsep_f16(in_clp, out_clp, dw, tc, tc + 1024, bias, B, H, W, dil, branch < 2 || block < 3, 0, (cudaStream_t)stream);
+}
+
 extern "C" int lws_refinement_f32(const float* left, const float* pred3, const float* pk, float* pred4, void* ws,
                                   size_t ws_bytes, int B, int H, int W, lws_stream_t stream) {
   using namespace lws;

@@ -261,6 +261,21 @@ def refinement(left: torch.Tensor, pred3: torch.Tensor, packed: torch.Tensor,
     return pred4
 
 
+def refinement_block_clp(in_clp: torch.Tensor, packed: torch.Tensor, branch: int, block: int, B: int, H: int, W: int,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One BN-ReLU-DW(dil)-PW block (reference models/submodules.py:236-261) on the refinement's internal channels-last
+    bordered layout [B, H+32, W+32, 32]; branch 0/1/2 = refinement1_left / refinement1_disp / refinement2, block 0..3."""
+    n = int(lib.lws_refinement_clp_floats(B, H, W))
+    if in_clp.numel() != n:
+        raise ValueError(f"in_clp must hold {n} floats")
+    out = out if out is not None else torch.empty_like(in_clp)
+    with torch.cuda.device(in_clp.device):
+        check(lib.lws_refinement_block_clp_f32(_ptr(in_clp, "in_clp"), _ptr(out, "out_clp"), _ptr(packed, "packed"), branch,
+                                               block, B, H, W, _stream(in_clp)), "lws_refinement_block_clp_f32")
+    LAUNCHES[0] += 1
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ n1 feature pyramid
 def pack_feature_extraction(tensors: Sequence[torch.Tensor], eps: float) -> torch.Tensor:
     """Fold the BNs of feature_extraction (host); tensor order: include/lws.h."""

@@ -283,6 +283,34 @@ def test_refinement_golden(refine_path):
     _check_refine(out, ref, None, refine_path)
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 40, 150), (2, 24, 30), (1, 368, 1232)])
+def test_refinement_block_clp_vs_fp64(B, H, W):
+    """One BN-ReLU-DW(dil 2)-PW block (block 1 of refinement1_left) through its own C-ABI entry, on the internal channels-last
+    bordered layout, against fp64 torch convs on the same folded weights: |d| <= 2e-5 * (1 + |y|) (fp32 depthwise FMA chain,
+    then the split-fp16 tensor-core pointwise: 22-bit operands, exact products, fp32 accumulation), border pixels exactly 0."""
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    import torch.nn.functional as F
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=True))
+    packed = model._refinement_packed(torch.device("cuda"))
+    pk = packed.cpu()
+    dw = pk[896:896 + 288].reshape(32, 1, 3, 3).double()                       # block 1 of R1_left: depthwise [32][9]
+    pw = pk[896 + 288:896 + 288 + 1024].reshape(32, 32).double()               # folded pointwise [ci][co]
+    bias = pk[896 + 288 + 1024:896 + 288 + 1024 + 32].double()
+    x = rnd(51, B, 32, H, W, scale=3.0).abs()                                  # post-ReLU activations
+    clp = torch.zeros(B, H + 32, W + 32, 32)
+    clp[:, 16:16 + H, 16:16 + W, :] = x.permute(0, 2, 3, 1)
+    out = ops().refinement_block_clp(clp.cuda().reshape(-1), packed, 0, 0, B, H, W).cpu().reshape(B, H + 32, W + 32, 32)
+    d = F.conv2d(x.double(), dw, padding=2, dilation=2, groups=32)
+    ref = torch.relu(torch.einsum("bihw,io->bohw", d, pw) + bias[None, :, None, None])
+    got = out[:, 16:16 + H, 16:16 + W, :].permute(0, 3, 1, 2).double()
+    err = (got - ref).abs()
+    assert (err <= 2e-5 * (1 + ref.abs())).all(), f"max err {err.max().item():.3e}"
+    border = out.clone()
+    border[:, 16:16 + H, 16:16 + W, :] = 0
+    assert border.abs().max().item() == 0.0
+
+
 # ------------------------------------------------------------------------------------------------ n1 feature pyramid
 @pytest.mark.parametrize("B,H,W,random_bn", [(1, 64, 128, True), (2, 40, 72, True), (1, 368, 1232, False), (1, 24, 40, True)])
 def test_feature_extraction_vs_fp64_oracle(B, H, W, random_bn):

@@ -37,6 +37,8 @@ constexpr int TZ_BTILE = 192 * 128;  // one weight tile: 192 rows x [block 2i | 
 
 struct TzArgs {
   const float* bias;    // [32]
+  const float* skip;    // LAST: raw cost [B,D,H,W] or null
+  float* out_f32;       // LAST: [B,D,H,W]
   const float* scales;  // [2] device: 1/sw, 1/(sw * 2^11)
   float out_mul;        // epilogue multiplier on top of scales: 1 for split-fp16 output (values stay scaled by sa), 1/sa for fp32
   float bias_mul;       // sa for split-fp16 output, 1 for fp32
@@ -96,7 +98,10 @@ __device__ __forceinline__ void tz_ld8(uint32_t taddr, float* v) {
 // TZ = Toeplitz row shift (1: 3D stack along d; 8: dilated 2D conv along x).  Output rows per tile: 128 - 2*TZ.
 // NST / NSH: stages per tile and row-shifted windows per stage (compile-time so the MMA issue loop is fully unrolled: the
 // single issuing thread must spend only a few uniform-datapath instructions per MMA or it, not the tensor pipe, is the limit).
-template <int TZ, int NST, int NSH>
+// LAST: the C -> 1 convolution that closes the stack.  Same pipeline with N = 16 per MMA: the weight block of a (stage,
+// window) is 16 rows x [B1 | B2] with B1 = rows {t: wh_t, 8+t: wl_t} for the xh operand and B2 = rows {8+t: wh_t} for the xl
+// operand, so acc[:, t] = main and acc[:, 8+t] = corr of Toeplitz tap t; the epilogue writes fp32 NCDHW (+ skip).
+template <int TZ, int NST, int NSH, bool LAST>
 __global__ void __launch_bounds__(TZ_THREADS, 1)
     tz_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut, const TzArgs a) {
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(a_full + i, 1), mbar_init(a_empty + i, 1);
     mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 8);
+    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, LAST ? 4 : 8);
     mbar_fence_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
@@ -141,8 +146,13 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one_sync()) {
-      mbar_expect_tx(b_full, (uint32_t)a.nbtiles * TZ_BTILE);
-      for (int i = 0; i < a.nbtiles; ++i) tma_load_2d(sB + i * TZ_BTILE, &mapB, b_full, 0, i * 192);
+      if (LAST) {  // one box: NST*NSH blocks x 16 rows
+        mbar_expect_tx(b_full, (uint32_t)(NST * NSH) * 2048);
+        tma_load_2d(sB, &mapB, b_full, 0, 0);
+      } else {
+        mbar_expect_tx(b_full, (uint32_t)a.nbtiles * TZ_BTILE);
+        for (int i = 0; i < a.nbtiles; ++i) tma_load_2d(sB + i * TZ_BTILE, &mapB, b_full, 0, i * 192);
+      }
       uint32_t slot = 0, ph = 0;  // ring position and phase of the next entry
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         const TzItem w = tz_decode<OUTR>(a, item);
@@ -167,6 +177,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
     // ================================ MMA issuer ================================
     const uint32_t idesc192 = (1u << 4) | ((192u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128
     const uint32_t idesc96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
     const uint32_t b_lo = ((smem_u32(sB) & 0x3FFFF) >> 4) | (1u << 16);
     const uint32_t shq[3] = {(uint32_t)a.shift_rows[0] * 8, (uint32_t)a.shift_rows[1] * 8, (uint32_t)a.shift_rows[2] * 8};
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         const uint32_t tb = ti & 1;
         mbar_wait(t_empty + tb, ((ti >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_main = tmem + tb * 256;
+        const uint32_t d_main = tmem + tb * (LAST ? 32 : 256);
         uint32_t slot = bslot, ph = bph;
 #pragma unroll
         for (int s = 0; s < NST; ++s) {
@@ -197,11 +208,18 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
             for (int k = 0; k < NSH; ++k) {
               const int blk = s * NSH + k;
               const uint32_t wa = x_lo + shq[k];                                                  // window base (16-byte units)
-              const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE >> 4) + (blk & 1) * 4;  // weight block
-              tz_mma(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, (s | k) == 0 ? 0u : 1u);
-              tz_mma(d_main, desc_hi | (uint64_t)(wa + 2), desc_hi | (uint64_t)(wb + 2), idesc192, 1u);
-              tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 4), desc_hi | (uint64_t)(wb + 0), idesc96, 1u);
-              tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wb + 2), idesc96, 1u);
+              if (LAST) {
+                const uint32_t wb = b_lo + (uint32_t)blk * (2048 >> 4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)  // xh k-steps against B1, xl k-steps against B2, all into the same 16 columns
+                  tz_mma(d_main, desc_hi | (uint64_t)(wa + 2 * u), desc_hi | (uint64_t)(wb + 2 * u), idesc16, (s | k | u) == 0 ? 0u : 1u);
+              } else {
+                const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE >> 4) + (blk & 1) * 4;  // weight block
+                tz_mma(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, (s | k) == 0 ? 0u : 1u);
+                tz_mma(d_main, desc_hi | (uint64_t)(wa + 2), desc_hi | (uint64_t)(wb + 2), idesc192, 1u);
+                tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 4), desc_hi | (uint64_t)(wb + 0), idesc96, 1u);
+                tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wb + 2), idesc96, 1u);
+              }
             }
             if (s < G || last) tz_commit(a_empty + slot);  // the other boxes are stages s - G of the next tile of the strip
             if (s == NST - 1) tz_commit(t_full + tb);
@@ -211,6 +229,54 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         }
       }
       advance(nst - G);  // the strip's last tile consumed all of its entries
+    }
+  } else if (LAST) {
+    // ================================ epilogue of the C -> 1 layer (warps 2..5) ================================
+    if (warp < 6) {
+      const int q = warp & 3;
+      const int j = q * 32 + lane;  // GEMM row; produces output row j (relative to the tile's first output row), valid for j < OUTR
+      const float c0 = __ldg(a.scales) * a.out_mul, c1 = __ldg(a.scales + 1) * a.out_mul;
+      const bool has1 = lane + TZ < 32, has2 = lane + 2 * TZ < 32;
+      const int Hdim = a.R / (a.n0.d * a.n1.d);  // interior length of the slowest axis
+      uint32_t ti = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const TzItem w = tz_decode<OUTR>(a, item);
+        for (int n = 0; n < w.ntiles; ++n, ++ti) {
+          const uint32_t tb = ti & 1;
+          const int orow0 = w.orow0 + n * a.srow;
+          mbar_wait(t_full + tb, (ti >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          float m[8], k[8];
+          tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + tb * 32, m);
+          tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + tb * 32 + 8, k);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + tb);
+          const float e0 = fmaf(k[0], c1, m[0] * c0), e1 = fmaf(k[1], c1, m[1] * c0), e2 = fmaf(k[2], c1, m[2] * c0);
+          const float s1 = __shfl_down_sync(0xffffffffu, e1, TZ), s2 = __shfl_down_sync(0xffffffffu, e2, (2 * TZ) & 31);
+          float v = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
+          float* xq = xch + tb * (4 * 3 * TZ) + q * (3 * TZ);  // double-buffered by tile parity
+          if (lane < TZ) xq[lane] = e1;
+          if (lane < 2 * TZ) xq[TZ + lane] = e2;
+          named_bar_sync(1, 128);
+          if (q < 3) {
+            const float* xn = xch + tb * (4 * 3 * TZ) + (q + 1) * (3 * TZ);
+            if (!has1) v += xn[lane + TZ - 32];
+            if (!has2) v += xn[TZ + lane + 2 * TZ - 32];
+          }
+          const int r = orow0 + j;
+          int rq, c0i, c1i, c2i;
+          fdivmod(r, a.n0, rq, c0i);
+          fdivmod(rq, a.n1, c2i, c1i);
+          const bool ok = j < OUTR && c0i >= a.p0 && c0i < a.p0 + a.i0 && c1i >= a.p1 && c1i < a.p1 + a.i1 && c2i < Hdim;
+          if (ok) {
+            // NCDHW index for rows ordered (slowest = y, middle = x, fastest = d)
+            const long long o = (((long long)w.b * a.i0 + (c0i - a.p0)) * Hdim + c2i) * a.i1 + (c1i - a.p1);
+            a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
+          }
+        }
+      }
     }
   } else {
     // ================================ epilogue (warps 2..9) ================================
@@ -368,7 +434,8 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   TzArgs a;
   memset(&a, 0, sizeof(a));
   const int nblk = L.nstages * L.nshift;
-  a.nbtiles = (nblk + 1) / 2;
+  a.nbtiles = L.last ? 1 : (nblk + 1) / 2;
+  if (L.last && nblk * 2048 > TZ_BTILE) return LWS_ERR_UNSUPPORTED;
   a.box_bytes = L.box_rows * 128;
   a.slot_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   const int outr = 128 - 2 * L.tz;
@@ -391,12 +458,14 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   while (a.nslot > L.nstages && tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz) > 232448) --a.nslot;
   const size_t smem = tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz);
   if (smem > 232448 || a.nslot < L.nstages) return LWS_ERR_UNSUPPORTED;
-  const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1;
+  const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1 && !L.last;
   if (!is3d && !is2d) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = is3d ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                       : cudaFuncSetAttribute(tz_gemm_kernel<8, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = is2d      ? cudaFuncSetAttribute(tz_gemm_kernel<8, 6, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : L.last  ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  a.bias = L.bias, a.scales = L.wtab + (size_t)a.nbtiles * 192 * 32;
+  a.bias = L.bias, a.scales = L.wtab + (L.last ? (size_t)nblk * 16 * 32 : (size_t)a.nbtiles * 192 * 32);
+  a.skip = L.skip, a.out_f32 = L.out_f32;
   a.out_split = L.out_split, a.relu = L.relu;
   a.out_mul = L.out_split ? 1.f : 1.f / kDwsepActScale;
   a.bias_mul = L.out_split ? kDwsepActScale : 1.f;
@@ -410,15 +479,16 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tensor_map_f32(&mapA1, L.src1, 3, dimsA, strA, boxA, true);
   if (rc) return rc;
-  rc = make_tensor_map_f32(&mapOut, L.out, 3, dimsA, strA, boxO, true);
+  rc = make_tensor_map_f32(&mapOut, L.last ? L.src0 : L.out, 3, dimsA, strA, boxO, true);  // unused by the C -> 1 layer
   if (rc) return rc;
-  const uint64_t dimsB[2] = {32, (uint64_t)a.nbtiles * 192}, strB[1] = {128};
-  const uint32_t boxB[2] = {32, 192};
+  const uint64_t dimsB[2] = {32, L.last ? (uint64_t)nblk * 16 : (uint64_t)a.nbtiles * 192}, strB[1] = {128};
+  const uint32_t boxB[2] = {32, L.last ? (uint32_t)nblk * 16 : 192u};
   rc = make_tensor_map_f32(&mapB, L.wtab, 2, dimsB, strB, boxB, true);
   if (rc) return rc;
   const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-  if (is3d) tz_gemm_kernel<1, 3, 3><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
-  else tz_gemm_kernel<8, 6, 1><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  if (is2d) tz_gemm_kernel<8, 6, 1, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  else if (L.last) tz_gemm_kernel<1, 3, 3, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  else tz_gemm_kernel<1, 3, 3, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }
@@ -490,64 +560,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// last conv 32 -> 1 from split-fp16 rows (+ skip), NCDHW fp32 output; 4 lanes per voxel, 8 input channels per lane
-__global__ void __launch_bounds__(256)
-    conv3d_last_ydx_kernel(const uint4* __restrict__ act, const float* __restrict__ w /*[32][27]*/, const float* __restrict__ skip,
-                           float* __restrict__ out, int D, int H, int W, long long total_vox) {
-  __shared__ __align__(16) float sW[27 * 32];  // [tap][ci], pre-divided by the activation scale
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[(i % 27) * 32 + i / 27] = __ldg(w + i) * (1.f / kDwsepActScale);
-  __syncthreads();
-  const int sub = threadIdx.x & 3;
-  const int Wp = W + 2, Dp = D + 2;
-  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; vox < total_vox;
-       vox += ((long long)gridDim.x * blockDim.x) >> 2) {
-    const int x = (int)(vox % W);
-    long long t = vox / W;
-    const int y = (int)(t % H);
-    t /= H;
-    const int d = (int)(t % D);
-    const int b = (int)(t / D);
-    const long long row = (((long long)b * H + y) * Wp + (x + 1)) * Dp + (d + 1);
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      if ((unsigned)(y + kh - 1) >= (unsigned)H) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
-          const long long r = row + ((long long)(kh - 1) * Wp + (kw - 1)) * Dp + (kd - 1);
-          const uint4 h = __ldg(act + r * 8 + sub), l = __ldg(act + r * 8 + 4 + sub);
-          const float* wt = sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8;
-          const float4 wa = *reinterpret_cast<const float4*>(wt), wb = *reinterpret_cast<const float4*>(wt + 4);
-          const uint32_t hw_[4] = {h.x, h.y, h.z, h.w}, lw_[4] = {l.x, l.y, l.z, l.w};
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw_[p]));
-            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw_[p]));
-            const float v0 = fmaf(fl.x, 1.f / 2048.f, fh.x), v1 = fmaf(fl.y, 1.f / 2048.f, fh.y);
-            acc0 = fmaf(v0, wv[2 * p], acc0), acc1 = fmaf(v1, wv[2 * p + 1], acc1);
-          }
-        }
-      }
-    }
-    float acc = acc0 + acc1;
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (sub == 0) out[vox] = acc + (skip ? __ldg(skip + vox) : 0.f);
-  }
-}
-
 size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W) {
   const size_t rows = (size_t)B * H * (W + 2) * (D + 2);
   return 2 * (rows * 128 + 1024);
 }
 
-// wtab[l]: per mid layer the Toeplitz operand table (5 tiles x 192 rows x 128 B, then scales[2]); bias_mid[l]: [32]
+// wtab[l]: per mid layer the Toeplitz operand table (5 tiles x 192 rows x 128 B, then scales[2]); bias_mid[l]: [32];
+// w_last_tab: operand table of the closing 32 -> 1 conv (9 blocks x 16 rows x 128 B, then scales[2])
 int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
-                     const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
-                     int add_skip, cudaStream_t st) {
+                     const float* const* bias_mid, int layers, const float* w_last_tab, float* out, void* ws, int B, int D, int H,
+                     int W, int add_skip, cudaStream_t st) {
   const int Wp = W + 2, Dp = D + 2;
   const long long R = (long long)H * Wp * Dp;
   if (R >= (1ll << 31) - 65536 || 128 + 2 * Dp > 256) return LWS_ERR_UNSUPPORTED;
@@ -579,11 +601,16 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
     cur = nxt, nxt = t;
   }
   {
-    const long long vox = (long long)B * D * H * W;
-    const long long thr = vox * 4;
-    const int blocks = (int)((thr + 255) / 256 < 148 * 16 ? (thr + 255) / 256 : 148 * 16);
-    conv3d_last_ydx_kernel<<<blocks, 256, 0, st>>>((const uint4*)cur, w_last, add_skip ? cost : nullptr, out, D, H, W, vox);
-    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+    TzLayer L;
+    memset(&L, 0, sizeof(L));
+    L.src0 = L.src1 = cur, L.wtab = w_last_tab, L.B = B, L.R = (int)R;
+    L.n0 = Dp, L.p0 = 1, L.i0 = D, L.n1 = Wp, L.p1 = 1, L.i1 = W;
+    L.tz = 1, L.nstages = 3, L.nshift = 3, L.box_rows = 128 + 2 * Dp;
+    for (int kh = 0; kh < 3; ++kh) L.st_off[kh] = (kh - 1) * Wp * Dp - Dp, L.st_src[kh] = 0;
+    for (int kw = 0; kw < 3; ++kw) L.shift_rows[kw] = kw * Dp;
+    L.last = 1, L.skip = add_skip ? cost : nullptr, L.out_f32 = out;
+    int rc = launch_tz_gemm(L, st);
+    if (rc) return rc;
   }
   return LWS_OK;
 }

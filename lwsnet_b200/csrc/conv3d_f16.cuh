@@ -22,6 +22,10 @@ struct TzLayer {
   int srow;             // rows between consecutive taps of the slowest axis if the stages are ordered [tap][G sources] and
                         // st_off[tap*G + g] = (tap - 1) * srow + const (strip schedule with ring reuse); 0 = linear tiling
   int G;
+  int last;             // 1: the closing C -> 1 layer: wtab = [nstages*nshift blocks][16 rows][32 words] + scales[2], fp32 NCDHW
+                        //    output out_f32 (+ skip) instead of rows
+  const float* skip;
+  float* out_f32;
 };
 
 int launch_tz_gemm(const TzLayer& L, cudaStream_t st);

@@ -37,7 +37,8 @@ size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W);
 int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
                      const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
                      int add_skip, cudaStream_t st);
-constexpr int kTcLayerFloats = 9 * 192 * 32;  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
+constexpr int kTcLayerFloats = 9 * 192 * 32;
+constexpr int kTcLastOff = 32768;  // C = 32: table of the closing 32 -> 1 conv inside the first mid layer's slot  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
 
 struct Conv3dArgs {
   const float* in;      // [B,Cin,D,H,W]  post-activation (or raw cost when FIRST)
@@ -378,6 +379,32 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
       tc[5 * 192 * 32] = 1.f / sw;
       tc[5 * 192 * 32 + 1] = 1.f / (sw * 2048.f);
     }
+    if (layers > 0) {
+      // closing 32 -> 1 conv as a Toeplitz-N layer with N = 16, kept behind the first mid layer's table (float offset
+      // kTcLastOff of its slot): block (kh, kw) = 16 rows x 64 halves [B1 | B2]; B1 row kd = wh, row 8+kd = wl (applied to
+      // the hi halves of a voxel), B2 row 8+kd = wh (applied to the lo halves); scales follow the 9 blocks.
+      const float* wl_ = packed + packed_offset(C, layers, layers + 1, false);  // [ci][27][1]
+      float* tc = packed + packed_tc_offset(C, layers, 0) + kTcLastOff;
+      float mx = 0.f;
+      for (int i = 0; i < 32 * 27; ++i) mx = fmaxf(mx, fabsf(wl_[i]));
+      int e = 0;
+      if (mx > 0.f) frexpf(mx, &e);
+      const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+      __half* h = reinterpret_cast<__half*>(tc);
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          for (int kd = 0; kd < 3; ++kd)
+            for (int ci = 0; ci < 32; ++ci) {
+              const float w = wl_[ci * 27 + kd * 9 + kh * 3 + kw] * sw;
+              const __half hi = __float2half_rn(w);
+              __half* blk = h + (size_t)(kh * 3 + kw) * 16 * 64;
+              blk[kd * 64 + ci] = hi;
+              blk[(8 + kd) * 64 + ci] = __float2half_rn((w - __half2float(hi)) * 2048.f);
+              blk[(8 + kd) * 64 + 32 + ci] = hi;
+            }
+      tc[9 * 16 * 32] = 1.f / sw;
+      tc[9 * 16 * 32 + 1] = 1.f / (sw * 2048.f);
+    }
   } else if (C == 8) {
     // split-fp16 operand tables (conv3d_c8.cu), per 8 -> 8 layer: 9 taps t = kd*3 + kh of 1536 bytes each, SWIZZLE_NONE K-major:
     // K chunk 0 (applied to the hi halves of the voxel) = 48 rows x 8 halves, K chunk 1 (applied to the lo halves) 768 bytes
@@ -437,7 +464,8 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
   if (ws_bytes < lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers)) return LWS_ERR_WORKSPACE_TOO_SMALL;
   if ((((uintptr_t)ws) | ((uintptr_t)packed_weights)) & 15) return LWS_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc_path(C)) {
+  // C = 32: the tensor-core path needs 128 + 2 (D + 2) <= 256 box rows and at least one mid layer; otherwise the FFMA kernels run
+  if (use_tc_path(C) && !(C == 32 && (128 + 2 * (D + 2) > 256 || layers == 0))) {
     const float* pk = packed_weights;
     const float* wtc[16];
     const float* bmid[16];
@@ -446,10 +474,9 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
       wtc[l] = pk + packed_tc_offset(C, layers, l);
       bmid[l] = pk + packed_offset(C, layers, l + 1, true);
     }
-    if (C == 32 && 128 + 2 * (D + 2) <= 256)
+    if (C == 32)
       return conv3d_stack_f16(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
-                              layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W, add_skip, st);
-    if (C == 32) return LWS_ERR_UNSUPPORTED;  // D > 62: use LWS_CONV3D_TC=0
+                              layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
     if (C == 8)
       return conv3d_stack_c8(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
                              layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W, add_skip, st);

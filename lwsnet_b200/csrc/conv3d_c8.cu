@@ -39,6 +39,8 @@ struct C8Args {
   uint8_t* out_lo;
   const uint8_t* wtab;    // device: 9 x 1536 B operand table, then scales[2] (float): 1/sw, 1/(sw * 2^11)
   const float* bias;      // [8]
+  const float* skip;      // LAST: raw cost [B,D,H,W] or null
+  float* out_f32;         // LAST: [B,D,H,W]
   long long vox_b;        // voxels per batch element (Dp * Hp * Wp)
   int Hp, Wp, H, W, D;    // padded / interior plane size, interior depth
   FastDiv fWp, fHp;
@@ -81,6 +83,8 @@ __device__ __forceinline__ void c8_ld8(uint32_t taddr, float* v) {
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// LAST: the closing 8 -> 1 conv: N = 16 (row kw = [wh | 0], row 8 + kw = [wl | wh]), fp32 NCDHW output (+ skip).
+template <bool LAST>
 __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < C8_BBYTES / 16; i += C8_THREADS)
+  for (int i = tid; i < (LAST ? 9 * 512 : C8_BBYTES) / 16; i += C8_THREADS)
     reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.wtab) + i);
   fence_proxy_async_smem();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -137,10 +141,11 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    const uint32_t idesc = (1u << 4) | ((48u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128, N = 48
+    constexpr uint32_t NN = LAST ? 16 : 48;
+    const uint32_t idesc = (1u << 4) | ((NN >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128, N = 48 / 16
     // SWIZZLE_NONE K-major: LBO = byte distance between the two K chunks, SBO = 128 B between 8-row groups
     const uint64_t a_hi = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-    const uint64_t b_hi = ((uint64_t)(768 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint64_t b_hi = ((uint64_t)((NN * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint32_t ring_lo = (smem_u32(sRing) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
     uint32_t bslot = 0, bph = 0, ti = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
               const uint64_t da = a_hi | (uint64_t)(g_lo + kd * (4096 >> 4));
-              const uint64_t db = b_hi | (uint64_t)(b_lo + (kd * 3 + kh) * (1536 >> 4));
+              const uint64_t db = b_hi | (uint64_t)(b_lo + (kd * 3 + kh) * ((NN * 32) >> 4));
               const uint32_t acc = (kh | kd) == 0 ? 0u : 1u;
               asm volatile(
                   "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -188,8 +193,8 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     const int q = warp & 3;            // TMEM lane quarter
     const int j = q * 32 + lane;       // GEMM row; this thread produces output voxel j (staging row j), valid for j < 126
     const bool issuer = ((warp - 2) & 3) == 0 && lane == 0;
-    const float c0 = __ldg(reinterpret_cast<const float*>(a.wtab + C8_BBYTES));
-    const float c1 = __ldg(reinterpret_cast<const float*>(a.wtab + C8_BBYTES) + 1);
+    const float* scl = reinterpret_cast<const float*>(a.wtab + (LAST ? 9 * 512 : C8_BBYTES));
+    const float c0 = __ldg(scl) * (LAST ? 1.f / kDwsepActScale : 1.f), c1 = __ldg(scl + 1) * (LAST ? 1.f / kDwsepActScale : 1.f);
     float bias[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) bias[c] = __ldg(a.bias + c) * kDwsepActScale;
@@ -206,6 +211,35 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
         mbar_wait(t_full + g, (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + g * 64;
+        if (LAST) {
+          float m[8], k[8];
+          c8_ld8(taddr, m);
+          c8_ld8(taddr + 8, k);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + g);
+          const float e0 = fmaf(k[0], c1, m[0] * c0), e1 = fmaf(k[1], c1, m[1] * c0), e2 = fmaf(k[2], c1, m[2] * c0);
+          const float s1 = __shfl_down_sync(0xffffffffu, e1, 1), s2 = __shfl_down_sync(0xffffffffu, e2, 2);
+          float v = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
+          float* xp = xch + ((ti >> 1) & 1) * 12;  // this group's exchange rows, double-buffered by its tile parity
+          if (lane == 0) xp[q * 3] = e1;
+          if (lane < 2) xp[q * 3 + 1 + lane] = e2;
+          named_bar_sync(bar_id, 128);
+          if (q < 3 && lane >= 30) {
+            if (lane == 31) v += xp[(q + 1) * 3];
+            v += xp[(q + 1) * 3 + 1 + lane - 30];
+          }
+          const int r = w.row0 + n * a.Wp + j;
+          int line, x, dpl, y;
+          fdivmod(r, a.fWp, line, x);
+          fdivmod(line, a.fHp, dpl, y);
+          if (j < 126 && x >= 1 && x <= a.W && y >= 1 && y <= a.H && dpl >= 1 && dpl <= a.D) {
+            const long long o = (((long long)w.b * a.D + (dpl - 1)) * a.H + (y - 1)) * a.W + (x - 1);
+            a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
+          }
+          continue;
+        }
         float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];
         c8_ld8(taddr, m0);
         c8_ld8(taddr + 8, m1);
@@ -346,47 +380,6 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---- last conv 8 -> 1 from the hi/lo planes (+ skip), NCDHW fp32 output; one thread per voxel ------------------------------
-__global__ void __launch_bounds__(256)
-    conv3d_last_c8_kernel(const uint4* __restrict__ act_hi, const uint4* __restrict__ act_lo, const float* __restrict__ w /*[8][27]*/,
-                          const float* __restrict__ skip, float* __restrict__ out, int D, int H, int W, long long total_vox) {
-  __shared__ __align__(16) float sW[27 * 8];  // [tap][ci], pre-divided by the activation scale
-  for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sW[(i % 27) * 8 + i / 27] = __ldg(w + i) * (1.f / kDwsepActScale);
-  __syncthreads();
-  const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
-  for (long long vox = (long long)blockIdx.x * blockDim.x + threadIdx.x; vox < total_vox; vox += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(vox % W);
-    long long t = vox / W;
-    const int y = (int)(t % H);
-    t /= H;
-    const int d = (int)(t % D);
-    const int b = (int)(t / D);
-    const long long row = (((long long)b * Dp + d + 1) * Hp + y + 1) * Wp + x + 1;
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const long long r = row + ((long long)(kd - 1) * Hp + (kh - 1)) * Wp + (kw - 1);
-          const uint4 h = __ldg(act_hi + r), l = __ldg(act_lo + r);
-          const float* wt = sW + (kd * 9 + kh * 3 + kw) * 8;
-          const float4 wa = *reinterpret_cast<const float4*>(wt), wb = *reinterpret_cast<const float4*>(wt + 4);
-          const uint32_t hw_[4] = {h.x, h.y, h.z, h.w}, lw_[4] = {l.x, l.y, l.z, l.w};
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw_[p]));
-            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw_[p]));
-            acc0 = fmaf(fmaf(fl.x, 1.f / 2048.f, fh.x), wv[2 * p], acc0);
-            acc1 = fmaf(fmaf(fl.y, 1.f / 2048.f, fh.y), wv[2 * p + 1], acc1);
-          }
-        }
-    out[vox] = acc0 + acc1 + (skip ? __ldg(skip + vox) : 0.f);
-  }
-}
-
 // ---- host -------------------------------------------------------------------------------------------------------------------
 static long long c8_plane_bytes(int B, int D, int H, int W) {
   const long long vox = (long long)B * (D + 2) * (H + 2) * (W + 2);
@@ -395,10 +388,10 @@ static long long c8_plane_bytes(int B, int D, int H, int W) {
 }
 size_t conv3d_c8_workspace_bytes(int B, int D, int H, int W) { return (size_t)4 * ((c8_plane_bytes(B, D, H, W) + 255) / 256 * 256); }
 
-// wtab[l]: 9 x 1536 B operand table + scales[2]; bias_mid[l]: [8]
+// wtab[l]: 9 x 1536 B operand table + scales[2]; bias_mid[l]: [8]; w_last_tab: 9 x 512 B table of the closing conv + scales[2]
 int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
-                    const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
-                    int add_skip, cudaStream_t st) {
+                    const float* const* bias_mid, int layers, const float* w_last_tab, float* out, void* ws, int B, int D, int H,
+                    int W, int add_skip, cudaStream_t st) {
   const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
   const long long vox_b = (long long)Dp * Hp * Wp;
   if (vox_b * B >= (1ll << 31) - (1 << 20)) return LWS_ERR_BAD_SHAPE;
@@ -424,14 +417,18 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     conv3d_first_c8_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W, nvox);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
-  e = cudaFuncSetAttribute(conv3d_c8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
+  e = cudaFuncSetAttribute(conv3d_c8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(conv3d_c8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
   if (e != cudaSuccess) return (int)e;
   int cur = 0;
-  for (int l = 0; l < layers; ++l) {
+  for (int l = 0; l <= layers; ++l) {  // l == layers: the closing 8 -> 1 conv
     C8Args a;
     memset(&a, 0, sizeof(a));
+    const bool last = l == layers;
     a.in_hi = plane[cur], a.in_lo = plane[cur + 1], a.out_hi = plane[2 - cur], a.out_lo = plane[3 - cur];
-    a.wtab = (const uint8_t*)wtab[l], a.bias = bias_mid[l];
+    a.wtab = (const uint8_t*)(last ? w_last_tab : wtab[l]), a.bias = last ? bias_mid[0] : bias_mid[l];
+    a.skip = add_skip ? cost : nullptr, a.out_f32 = out;
     a.vox_b = vox_b, a.Hp = Hp, a.Wp = Wp, a.H = H, a.W = W, a.D = D, a.fWp = make_fastdiv(Wp), a.fHp = make_fastdiv(Hp);
     a.line0 = Hp, a.strip_len = D * Hp;
     const int ct = (Wp + 125) / 126;
@@ -444,16 +441,10 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     a.seg_len = seg_len, a.segs = make_fastdiv(segs), a.ct_per_line = make_fastdiv(ct);
     a.total_items = B * ct * segs;
     const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-    conv3d_c8_kernel<<<grid, C8_THREADS, C8_SMEM, st>>>(a);
+    if (last) conv3d_c8_kernel<true><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
+    else conv3d_c8_kernel<false><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
     cur = 2 - cur;
-  }
-  {
-    const long long vox = (long long)B * D * H * W;
-    const int blocks = (int)((vox + 255) / 256 < 148 * 16 ? (vox + 255) / 256 : 148 * 16);
-    conv3d_last_c8_kernel<<<blocks, 256, 0, st>>>((const uint4*)plane[cur], (const uint4*)plane[cur + 1], w_last,
-                                                  add_skip ? cost : nullptr, out, D, H, W, vox);
-    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   return LWS_OK;
 }

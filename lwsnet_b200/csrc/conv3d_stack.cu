@@ -437,6 +437,31 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
       tc[9 * 384] = 1.f / sw;
       tc[9 * 384 + 1] = 1.f / (sw * 2048.f);
     }
+    if (layers > 0) {
+      // closing 8 -> 1 conv with N = 16, behind the first mid layer's table (float offset kTcLastOff): per tap (kd, kh) 512
+      // bytes = K chunk 0 [16 rows x 8 halves] then K chunk 1; row kw = [wh | 0], row 8 + kw = [wl | wh]; scales follow
+      const float* wl_ = packed + packed_offset(C, layers, layers + 1, false);  // [ci][27][1]
+      float* tc = packed + packed_tc_offset(C, layers, 0) + kTcLastOff;
+      float mx = 0.f;
+      for (int i = 0; i < 8 * 27; ++i) mx = fmaxf(mx, fabsf(wl_[i]));
+      int e = 0;
+      if (mx > 0.f) frexpf(mx, &e);
+      const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+      __half* h = reinterpret_cast<__half*>(tc);
+      for (int kd = 0; kd < 3; ++kd)
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw)
+            for (int ci = 0; ci < 8; ++ci) {
+              const float w = wl_[ci * 27 + kd * 9 + kh * 3 + kw] * sw;
+              const __half hi = __float2half_rn(w);
+              __half* t = h + (size_t)(kd * 3 + kh) * 256;  // 512 bytes per tap
+              t[kw * 8 + ci] = hi;
+              t[(8 + kw) * 8 + ci] = __float2half_rn((w - __half2float(hi)) * 2048.f);
+              t[128 + (8 + kw) * 8 + ci] = hi;
+            }
+      tc[9 * 128] = 1.f / sw;
+      tc[9 * 128 + 1] = 1.f / (sw * 2048.f);
+    }
   }
   return LWS_OK;
 }
@@ -464,8 +489,8 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
   if (ws_bytes < lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers)) return LWS_ERR_WORKSPACE_TOO_SMALL;
   if ((((uintptr_t)ws) | ((uintptr_t)packed_weights)) & 15) return LWS_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
-  // C = 32: the tensor-core path needs 128 + 2 (D + 2) <= 256 box rows and at least one mid layer; otherwise the FFMA kernels run
-  if (use_tc_path(C) && !(C == 32 && (128 + 2 * (D + 2) > 256 || layers == 0))) {
+  // the tensor-core paths need at least one mid layer, C = 32 also 128 + 2 (D + 2) <= 256 box rows; otherwise the FFMA kernels run
+  if (use_tc_path(C) && !(C == 32 && 128 + 2 * (D + 2) > 256) && layers > 0) {
     const float* pk = packed_weights;
     const float* wtc[16];
     const float* bmid[16];
@@ -479,7 +504,7 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
                               layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
     if (C == 8)
       return conv3d_stack_c8(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
-                             layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W, add_skip, st);
+                             layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
     return conv3d_stack_tc(C, cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
                            wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
                            add_skip, st);

@@ -12,7 +12,8 @@
 // and the three kw taps are Toeplitz column blocks: out[r] = E0[r-1] + E1[r] + E2[r+1], E = main/sw + corr/(sw*2^11).
 // 9 MMAs per 126 output voxels.  Operand boxes are plain 2 KB bulk copies (cp.async.bulk), one mbarrier per group of six
 // (3 kd x hi/lo) = one (y+kh) line position; a CTA walks down y so two of the three groups of a tile are already in the ring.
-// Warps: 0 = producer, 1 = MMA issuer, 2-5 / 6-9 = two epilogue groups that alternate tiles (accumulator ti & 1).
+// Warps: 0 = producer, 1 = MMA issuer, 2.. = four epilogue groups of four warps that take tiles round robin (accumulator
+// ti % 4): the epilogue of a tile is a ~1500-cycle dependent chain, a tile's MMAs only ~500 cycles.
 #include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
@@ -22,14 +23,15 @@
 
 namespace lws {
 
-constexpr int C8_THREADS = 320;
+constexpr int C8_NGRP = 4;                  // epilogue groups = TMEM accumulators; group g handles the tiles with ti % NGRP == g
+constexpr int C8_THREADS = 64 + C8_NGRP * 128;
 constexpr int C8_NG = 8;                    // ring of line groups
 constexpr int C8_GBYTES = 6 * 2048;         // 3 kd x (hi, lo) x 128 voxels x 16 B
 constexpr int C8_BBYTES = 9 * 1536;         // 9 taps x 48 rows x 32 B
 constexpr int C8_OFF_RING = 14336;
-constexpr int C8_OFF_STAGE = C8_OFF_RING + C8_NG * C8_GBYTES;  // [2 groups][hi 2048 | lo 2048]
-constexpr int C8_OFF_XCH = C8_OFF_STAGE + 2 * 4096;            // [2 groups][4 quarters][3 rows][8] floats
-constexpr int C8_OFF_BAR = C8_OFF_XCH + 2 * 4 * 3 * 8 * 4;
+constexpr int C8_OFF_STAGE = C8_OFF_RING + C8_NG * C8_GBYTES;  // [NGRP groups][hi 2048 | lo 2048]
+constexpr int C8_OFF_XCH = C8_OFF_STAGE + C8_NGRP * 4096;      // [NGRP groups][4 quarters][3 rows][8] floats
+constexpr int C8_OFF_BAR = C8_OFF_XCH + C8_NGRP * 4 * 3 * 8 * 4;
 constexpr int C8_SMEM = C8_OFF_BAR + 256 + 128;
 
 struct C8Args {
@@ -92,18 +94,18 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C8_OFF_BAR);
   uint64_t* g_full = bars;              // [NG]
   uint64_t* g_empty = g_full + C8_NG;   // [NG]
-  uint64_t* t_full = g_empty + C8_NG;   // [2]
-  uint64_t* t_empty = t_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = g_empty + C8_NG;       // [NGRP]
+  uint64_t* t_empty = t_full + C8_NGRP;     // [NGRP]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + C8_NGRP);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < C8_NG; ++i) mbar_init(g_full + i, 1), mbar_init(g_empty + i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
+    for (int i = 0; i < C8_NGRP; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C8_NGRP * 64));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < (LAST ? 9 * 512 : C8_BBYTES) / 16; i += C8_THREADS)
@@ -113,29 +115,28 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  const long long plane = (long long)a.Hp * a.Wp;  // voxels per d plane
 
   if (warp == 0) {
     // ================================ producer ================================
-    if (elect_one_sync()) {
-      uint32_t slot = 0, ph = 0;
-      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const C8Item w = c8_decode(a, item);
-        const long long base = (long long)w.b * a.vox_b + w.row0 - 1;  // GEMM row 0 of tile 0 (Toeplitz shift 1)
-        for (int n = 0; n < w.ntiles; ++n) {
-          for (int kh = n == 0 ? 0 : 2; kh < 3; ++kh) {  // later tiles of a strip only need the line below
-            mbar_wait(g_empty + slot, ph ^ 1);
-            mbar_expect_tx(g_full + slot, C8_GBYTES);
-            uint8_t* dst = sRing + slot * C8_GBYTES;
-            const long long v0 = base + (long long)(n + kh - 1) * a.Wp;
-#pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-              const long long v = v0 + (kd - 1) * plane;
-              bulk_load(dst + kd * 4096, a.in_hi + v * 16, 2048, g_full + slot);
-              bulk_load(dst + kd * 4096 + 2048, a.in_lo + v * 16, 2048, g_full + slot);
-            }
-            if (++slot == C8_NG) slot = 0, ph ^= 1;
+    // lanes 0..5 each issue one of the six 2 KB bulk copies of a group (kd = lane / 2, hi / lo = lane % 2).  (A 4D TMA tensor
+    // box with a 16-byte inner extent moves the same 12 KB in one operation but runs ~1.5x slower.)
+    const int kd = (lane >> 1) % 3, part = lane & 1;
+    const uint8_t* src_plane = part ? a.in_lo : a.in_hi;
+    const long long plane = (long long)a.Hp * a.Wp;  // voxels per d plane
+    uint32_t slot = 0, ph = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const C8Item w = c8_decode(a, item);
+      const long long base = (long long)w.b * a.vox_b + w.row0 - 1;  // GEMM row 0 of tile 0 (Toeplitz shift 1)
+      for (int n = 0; n < w.ntiles; ++n) {
+        for (int kh = n == 0 ? 0 : 2; kh < 3; ++kh) {  // later tiles of a strip only need the line below
+          mbar_wait(g_empty + slot, ph ^ 1);
+          if (lane == 0) mbar_expect_tx(g_full + slot, C8_GBYTES);
+          __syncwarp();
+          if (lane < 6) {
+            const long long v = base + (long long)(n + kh - 1) * a.Wp + (kd - 1) * plane;
+            bulk_load(sRing + slot * C8_GBYTES + kd * 4096 + part * 2048, src_plane + v * 16, 2048, g_full + slot);
           }
+          if (++slot == C8_NG) slot = 0, ph ^= 1;
         }
       }
     }
@@ -147,19 +148,21 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     const uint64_t a_hi = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint64_t b_hi = ((uint64_t)((NN * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint32_t ring_lo = (smem_u32(sRing) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
-    uint32_t bslot = 0, bph = 0, ti = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const C8Item w = c8_decode(a, item);
-      for (int n = 0; n < w.ntiles; ++n, ++ti) {
-        const bool last = n == w.ntiles - 1;
-        const uint32_t tb = ti & 1;
-        mbar_wait(t_empty + tb, ((ti >> 1) & 1) ^ 1);
-        uint32_t slot = bslot, ph = bph;
+    // the whole schedule runs inside one elected lane: a tile is only nine MMAs (~500 cycles of tensor time), so per-tile
+    // elect / reconverge / __syncwarp overhead in the issuing warp would be the kernel's critical path
+    if (elect_one_sync()) {
+      uint32_t bslot = 0, bph = 0, ti = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const C8Item w = c8_decode(a, item);
+        for (int n = 0; n < w.ntiles; ++n, ++ti) {
+          const bool last = n == w.ntiles - 1;
+          const uint32_t tb = ti % C8_NGRP;
+          mbar_wait(t_empty + tb, ((ti / C8_NGRP) & 1) ^ 1);
+          uint32_t slot = bslot, ph = bph;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          if (n == 0 || kh == 2) mbar_wait(g_full + slot, ph);  // the other groups were waited for by the previous tile
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (elect_one_sync()) {
+          for (int kh = 0; kh < 3; ++kh) {
+            if (n == 0 || kh == 2) mbar_wait(g_full + slot, ph);  // the other groups were waited for by the previous tile
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t g_lo = ring_lo + slot * (C8_GBYTES >> 4);
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
@@ -178,15 +181,15 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
             if (kh == 2)
               asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(t_full + tb))
                            : "memory");
+            if (++slot == C8_NG) slot = 0, ph ^= 1;
           }
-          __syncwarp();
-          if (++slot == C8_NG) slot = 0, ph ^= 1;
+          if (++bslot == C8_NG) bslot = 0, bph ^= 1;
         }
-        if (++bslot == C8_NG) bslot = 0, bph ^= 1;
+        bslot += 2;  // the strip's last tile consumed its remaining two groups
+        if (bslot >= C8_NG) bslot -= C8_NG, bph ^= 1;
       }
-      bslot += 2;  // the strip's last tile consumed its remaining two groups
-      if (bslot >= C8_NG) bslot -= C8_NG, bph ^= 1;
     }
+    __syncwarp();
   } else {
     // ================================ epilogue: group g handles the tiles with ti & 1 == g ================================
     const int g = (warp - 2) >> 2;
@@ -207,8 +210,8 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const C8Item w = c8_decode(a, item);
       for (int n = 0; n < w.ntiles; ++n, ++ti) {
-        if ((int)(ti & 1) != g) continue;
-        mbar_wait(t_full + g, (ti >> 1) & 1);
+        if ((int)(ti % C8_NGRP) != g) continue;
+        mbar_wait(t_full + g, (ti / C8_NGRP) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + g * 64;
         if (LAST) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
           const float e0 = fmaf(k[0], c1, m[0] * c0), e1 = fmaf(k[1], c1, m[1] * c0), e2 = fmaf(k[2], c1, m[2] * c0);
           const float s1 = __shfl_down_sync(0xffffffffu, e1, 1), s2 = __shfl_down_sync(0xffffffffu, e2, 2);
           float v = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
-          float* xp = xch + ((ti >> 1) & 1) * 12;  // this group's exchange rows, double-buffered by its tile parity
+          float* xp = xch + ((ti / C8_NGRP) & 1) * 12;  // this group's exchange rows, double-buffered by its tile parity
           if (lane == 0) xp[q * 3] = e1;
           if (lane < 2) xp[q * 3 + 1 + lane] = e2;
           named_bar_sync(bar_id, 128);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C8_NGRP * 64));
 }
 
 // ---- first conv 1 -> 8 on the raw cost (BN_0 affine + ReLU on the taps), writes every voxel of the padded hi/lo planes ----

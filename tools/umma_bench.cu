@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) rate_kernel(BenchCfg c, long long* cycles
         for (int u = 0; u < 8; ++u) {
           const uint64_t da = hi | (uint64_t)(a_lo + u * slot_step + (u & 3) * kstep);
           const uint64_t db = hi | (uint64_t)(b_lo + (u & 3) * kstep);
-          const uint32_t d = tmem + (c.two_acc ? (u & 1) * 256 : 0);
+          const uint32_t d = tmem + (c.two_acc >= 2 ? (u & (c.two_acc - 1)) * 64 : (c.two_acc ? (u & 1) * 256 : 0));
           if (c.kind == 2) mma<2>(d, da, db, idesc, 1);
           else mma<0>(d, da, db, idesc, 1);
         }
@@ -282,6 +282,18 @@ int main() {
         for (auto v : cy) mx = v > mx ? v : mx;
         printf("rate2 f16 SW128 N=%3d a_row_shift=%2d b_half=%d: %.1f cyc/MMA\n", N, shift, bh, (double)mx / c.nmma);
       }
+  // accumulate-chain latency: back-to-back MMAs into the SAME accumulator vs 2 / 4 / 8 independent accumulators
+  for (int N : {16, 48, 64})
+    for (int nacc : {0, 2, 4, 8}) {
+      BenchCfg c{0, N, 0, 4, 2048, nacc, 0, 0};
+      rate_kernel<<<148, 128, 8 * 16384 + 32768 + 2048>>>(c, dcy);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> cy(148);
+      CK(cudaMemcpy(cy.data(), dcy, 148 * 8, cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (auto v : cy) mx = v > mx ? v : mx;
+      printf("rate3 f16 NONE N=%3d accumulators=%d: %.1f cyc/MMA\n", N, nacc ? nacc : 1, (double)mx / c.nmma);
+    }
   printf(fails ? "probe FAILED (%d)\n" : "probe OK\n", fails);
   return fails != 0;
 }

@@ -39,6 +39,7 @@ struct TzArgs {
   const float* bias;    // [32]
   const float* skip;    // LAST: raw cost [B,D,H,W] or null
   float* out_f32;       // LAST: [B,D,H,W]
+  int out_mode;         // LAST: 0 = rows ordered (y, x, d) -> NCDHW; 1 = rows ordered (y, x) -> NCHW
   const float* scales;  // [2] device: 1/sw, 1/(sw * 2^11)
   float out_mul;        // epilogue multiplier on top of scales: 1 for split-fp16 output (values stay scaled by sa), 1/sa for fp32
   float bias_mul;       // sa for split-fp16 output, 1 for fp32
@@ -272,7 +273,8 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
           const bool ok = j < OUTR && c0i >= a.p0 && c0i < a.p0 + a.i0 && c1i >= a.p1 && c1i < a.p1 + a.i1 && c2i < Hdim;
           if (ok) {
             // NCDHW index for rows ordered (slowest = y, middle = x, fastest = d)
-            const long long o = (((long long)w.b * a.i0 + (c0i - a.p0)) * Hdim + c2i) * a.i1 + (c1i - a.p1);
+            const long long o = a.out_mode ? ((long long)w.b * a.i1 + (c1i - a.p1)) * a.i0 + (c0i - a.p0)
+                                           : (((long long)w.b * a.i0 + (c0i - a.p0)) * Hdim + c2i) * a.i1 + (c1i - a.p1);
             a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
           }
         }
@@ -459,13 +461,15 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   const size_t smem = tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz);
   if (smem > 232448 || a.nslot < L.nstages) return LWS_ERR_UNSUPPORTED;
   const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1 && !L.last;
-  if (!is3d && !is2d) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = is2d      ? cudaFuncSetAttribute(tz_gemm_kernel<8, 6, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+  const bool is2dlast = L.tz == 1 && L.nstages == 3 && L.nshift == 1 && L.last;
+  if (!is3d && !is2d && !is2dlast) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = is2dlast  ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : is2d    ? cudaFuncSetAttribute(tz_gemm_kernel<8, 6, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                   : L.last  ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   a.bias = L.bias, a.scales = L.wtab + (L.last ? (size_t)nblk * 16 * 32 : (size_t)a.nbtiles * 192 * 32);
-  a.skip = L.skip, a.out_f32 = L.out_f32;
+  a.skip = L.skip, a.out_f32 = L.out_f32, a.out_mode = L.out_mode;
   a.out_split = L.out_split, a.relu = L.relu;
   a.out_mul = L.out_split ? 1.f : 1.f / kDwsepActScale;
   a.bias_mul = L.out_split ? kDwsepActScale : 1.f;
@@ -486,7 +490,8 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   rc = make_tensor_map_f32(&mapB, L.wtab, 2, dimsB, strB, boxB, true);
   if (rc) return rc;
   const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-  if (is2d) tz_gemm_kernel<8, 6, 1, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  if (is2dlast) tz_gemm_kernel<1, 3, 1, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
+  else if (is2d) tz_gemm_kernel<8, 6, 1, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   else if (L.last) tz_gemm_kernel<1, 3, 3, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   else tz_gemm_kernel<1, 3, 3, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   e = cudaPeekAtLastError();

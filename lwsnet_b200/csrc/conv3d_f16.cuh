@@ -26,6 +26,7 @@ struct TzLayer {
                         //    output out_f32 (+ skip) instead of rows
   const float* skip;
   float* out_f32;
+  int out_mode;         // last: 0 = rows (y, x, d) -> NCDHW, 1 = rows (y, x) -> NCHW
 };
 
 int launch_tz_gemm(const TzLayer& L, cudaStream_t st);

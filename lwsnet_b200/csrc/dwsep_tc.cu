@@ -52,6 +52,8 @@ struct DsArgs {
   const float* scales;  // [2]: c0 = 1 / (DS_ACT_SCALE * sw), c1 = c0 * 2^-11
   const float* bias;    // [32]
   float* out;           // CLP [B][Hp][Wp][32] (for the y-border zero fill; the interior goes through the TMA store map)
+  const float* img;     // CIN > 0 (first conv of a refinement branch): NCHW fp32 input [B][CIN][H][W]
+  int W;
   int B, Hp, Wp, H, dil, relu;
   int out_split;        // 1: write rows as [32 hi | 32 lo] halves of act * 2^-6 (operand format of conv3d_f16.cu) instead of fp32
   int nxt, segs, seg_len, total_items;
@@ -107,6 +109,11 @@ __device__ __forceinline__ DsItem ds_decode(const DsArgs& a, int item) {
   return it;
 }
 
+// CIN = 0: the depthwise-separable block described above.  CIN = 3 / 1: the dense 3x3 first conv of a refinement branch
+// (reference models/submodules.py:284-300: conv CIN -> 32 on the NCHW image / disparity), same back end with an im2col front end:
+// the eight front-end warps gather the CIN*9 taps of a pixel straight from the NCHW input (coalesced along x), split them into
+// hi/lo halves and write the A row [K = ci*9 + tap, zero padded to 32]; the 32 x 32 "pointwise" operand is the folded conv weight.
+template <int CIN>
 __global__ void __launch_bounds__(DS_THREADS, 1)
     dwsep_f16_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, const DsArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -142,7 +149,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     *reinterpret_cast<uint4*>(smem + DS_OFF_B + n * 128 + ((c ^ (n & 7)) << 4)) =
         __ldg(reinterpret_cast<const uint4*>(a.pwh + n * 32 + c * 8));
   }
-  for (int idx = tid; idx < 9 * 32; idx += DS_THREADS) sW[idx] = __ldg(a.dw + (idx & 31) * 9 + (idx >> 5)) * DS_ACT_SCALE;
+  if (CIN == 0)
+    for (int idx = tid; idx < 9 * 32; idx += DS_THREADS) sW[idx] = __ldg(a.dw + (idx & 31) * 9 + (idx >> 5)) * DS_ACT_SCALE;
   // zero the y-border lines of the output
   {
     const long long line4 = (long long)a.Wp * 8;  // float4 per line
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 
   if (warp == DS_PROD_WARP) {
     // ================================ TMA producer ================================
-    if (elect_one_sync()) {
+    if (CIN == 0 && elect_one_sync()) {
       uint32_t it = 0;
       const uint32_t bytes = (uint32_t)(128 + 2 * dil) * 128;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
@@ -297,6 +305,71 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (CIN > 0) {
+    // ================================ im2col warps (0..7) ================================
+    const int h = warp & 1;                  // which 16 of the 32 K slots (warp-uniform)
+    const int p = (warp >> 1) * 32 + lane;   // pixel of the tile
+    const uint32_t a_base = smem_u32(smem + DS_OFF_A);
+    const uint32_t row = (uint32_t)p * 128;
+    const long long hw = (long long)a.H * a.W;
+    uint32_t t = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const DsItem w = ds_decode(a, item);
+      const int x = w.x0 + p - DS_RP;  // image column of this pixel
+      for (int i = 0; i < w.nrows; ++i, ++t) {
+        const int y = w.yi0 + i;
+        const float* src = a.img + (long long)w.b * CIN * hw + (long long)y * a.W + x;
+        // every step touches one new image line (y + 1); a line comes from DRAM (~1.5 us under load, several steps), so pull the
+        // line four steps ahead into L1 now
+        if (h == 0 && y + 5 < a.H && (unsigned)x < (unsigned)a.W) {
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + ci * hw + 5 * a.W));
+        }
+        float v[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          // K slot k = ci*9 + ky*3 + kx; both halves are unrolled and the warp-uniform h selects one
+          const int k0 = kk, k1 = 16 + kk;
+          float r = 0.f;
+          if (h == 0) {
+            if (k0 < CIN * 9) {
+              const int ci = k0 / 9, ky = (k0 % 9) / 3, kx = k0 % 3;
+              const bool ok = (unsigned)(y + ky - 1) < (unsigned)a.H && (unsigned)(x + kx - 1) < (unsigned)a.W;
+              r = ok ? __ldg(src + ci * hw + (ky - 1) * a.W + (kx - 1)) : 0.f;
+            }
+          } else {
+            if (k1 < CIN * 9) {
+              const int ci = k1 / 9, ky = (k1 % 9) / 3, kx = k1 % 3;
+              const bool ok = (unsigned)(y + ky - 1) < (unsigned)a.H && (unsigned)(x + kx - 1) < (unsigned)a.W;
+              r = ok ? __ldg(src + ci * hw + (ky - 1) * a.W + (kx - 1)) : 0.f;
+            }
+          }
+          v[kk] = r * DS_ACT_SCALE;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const __half2 hh = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+          const float2 f = __half22float2(hh);
+          hi[k] = h2_bits(hh), lo[k] = h2_bits(__floats2half2_rn((v[2 * k] - f.x) * 2048.f, (v[2 * k + 1] - f.y) * 2048.f));
+        }
+        const uint32_t ab = t % DS_NA;
+        mbar_wait(a_empty + ab, ((t / DS_NA) & 1) ^ 1);
+        const uint32_t dst = a_base + ab * DS_TILE + row;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {  // hi chunks 2h, 2h+1; lo chunks 4+2h, 4+2h+1
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((2 * h + c) ^ (p & 7)) << 4)), "r"(hi[4 * c]), "r"(hi[4 * c + 1]),
+                       "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((4 + 2 * h + c) ^ (p & 7)) << 4)), "r"(lo[4 * c]),
+                       "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + ab);
+      }
+    }
   } else {
     // ================================ depthwise warps (0..7) ================================
     const int q = tid & 7;    // channel quad
@@ -389,7 +462,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
                      int H, int W, int dil, int relu, int out_split, cudaStream_t st) {
   if (dil < 1 || dil > DS_RP || (32 % dil) != 0) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(dwsep_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(dwsep_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
   if (e != cudaSuccess) return (int)e;
   DsArgs a;
   memset(&a, 0, sizeof(a));
@@ -410,7 +483,37 @@ int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* p
   if (rc) return rc;
   rc = make_tensor_map_f32(&map_out, out, 3, dims, strides, box_out, true);
   if (rc) return rc;
-  dwsep_f16_kernel<<<grid, DS_THREADS, DS_SMEM, st>>>(map_in, map_out, a);
+  dwsep_f16_kernel<0><<<grid, DS_THREADS, DS_SMEM, st>>>(map_in, map_out, a);
+  e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
+// first conv of a refinement branch: img NCHW [B][CIN][H][W] fp32 -> CLP [B][H+32][W+32][32] fp32 = ReLU(conv3x3 + bias)
+// (bias = the folded BatchNorm of the following block); wtab: [64][32] halves (row co / 32 + co = hi / lo of w[k][co] * sw, K slot
+// k = ci*9 + tap, zero padded), scales as for the pointwise tables
+int launch_conv0_f16(const float* img, float* out, const void* wtab, const float* scales, const float* bias, int B, int CIN, int H,
+                     int W, cudaStream_t st) {
+  if (CIN != 1 && CIN != 3) return LWS_ERR_UNSUPPORTED;
+  cudaError_t e = CIN == 3 ? cudaFuncSetAttribute(dwsep_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM)
+                           : cudaFuncSetAttribute(dwsep_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  DsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dw = bias /*unused*/, a.pwh = (const __half*)wtab, a.scales = scales, a.bias = bias, a.out = out, a.img = img, a.W = W;
+  a.B = B, a.Hp = H + 2 * DS_RP, a.Wp = W + 2 * DS_RP, a.H = H, a.dil = 1, a.relu = 1, a.out_split = 0;
+  a.nxt = (a.Wp + 127) / 128;
+  a.seg_len = H < 16 ? H : 16;
+  a.segs = (H + a.seg_len - 1) / a.seg_len;
+  a.seg_len = (H + a.segs - 1) / a.segs;
+  a.total_items = B * a.nxt * a.segs;
+  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+  CUtensorMap map_out;
+  const uint64_t dims[3] = {32, (uint64_t)a.Wp, (uint64_t)B * a.Hp}, strides[2] = {128, (uint64_t)a.Wp * 128};
+  const uint32_t box_out[3] = {32, 32, 1};
+  int rc = make_tensor_map_f32(&map_out, out, 3, dims, strides, box_out, true);
+  if (rc) return rc;
+  if (CIN == 3) dwsep_f16_kernel<3><<<grid, DS_THREADS, DS_SMEM, st>>>(map_out, map_out, a);
+  else dwsep_f16_kernel<1><<<grid, DS_THREADS, DS_SMEM, st>>>(map_out, map_out, a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }

@@ -22,6 +22,8 @@ struct RefTcWeights {
   const float *w0[2], *b0[2];
   const float *dw[3][4], *pwtc[3][4], *bias[3][4];
   const float *dense_tc, *dense_bias, *last_w;
+  const float* w0tc[2];
+  const float* last_tc;
 };
 size_t refinement_tc_workspace_bytes(int B, int H, int W);
 int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt, float* pred4, void* ws, int B, int H,
@@ -191,6 +193,8 @@ struct RefLayout {
   size_t last_w;                        // [32][9][1]
   // tensor-core operand tables (refinement_tc.cu): pointwise [64][32] per block, dense conv [6*192][32]
   size_t r1_pwtc[2][4], r2_pwtc[4], r2_wtc;
+  size_t last_tc;                       // closing 32 -> 1 conv as an N = 16 Toeplitz operand table (3 blocks x 16 rows x 128 B + scales)
+  size_t r1_w0tc[2];                    // first convs as [64][32] split-fp16 operand tables (+ scales), dwsep_tc.cu
   size_t total;
 };
 static RefLayout ref_layout() {
@@ -214,6 +218,8 @@ static RefLayout ref_layout() {
     for (int j = 0; j < 4; ++j) L.r1_pwtc[br][j] = take(64 * 32);
   for (int j = 0; j < 4; ++j) L.r2_pwtc[j] = take(64 * 32);
   L.r2_wtc = take(6 * 192 * 32);
+  for (int br = 0; br < 2; ++br) L.r1_w0tc[br] = take(64 * 32);
+  L.last_tc = take(3 * 16 * 32 + 4);
   L.total = off;
   return L;
 }
@@ -313,6 +319,39 @@ extern "C" int lws_pack_refinement_weights(const float* const* t, int n_tensors,
     slot[1024] = 1.f / (kDwsepActScale * sw);
     slot[1025] = slot[1024] / 2048.f;
   };
+  {
+    // closing 32 -> 1 conv (conv3d_f16.cu, LAST layer): block kh = 16 rows x 64 halves [B1 | B2]; B1 row kw = wh, row 8 + kw = wl
+    // (applied to the hi halves of a pixel), B2 row 8 + kw = wh (applied to the lo halves); scales follow the 3 blocks
+    const float* wl_ = packed + L.last_w;  // [32][9]
+    float* tc = packed + L.last_tc;
+    float mx = 0.f;
+    for (int i = 0; i < 32 * 9; ++i) mx = fmaxf(mx, fabsf(wl_[i]));
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    const float sw = mx > 0.f ? ldexpf(1.f, 9 - e) : 1.f;
+    __half* h = reinterpret_cast<__half*>(tc);
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int ci = 0; ci < 32; ++ci) {
+          const float w = wl_[ci * 9 + kh * 3 + kw] * sw;
+          const __half hi = __float2half_rn(w);
+          __half* blk = h + (size_t)kh * 16 * 64;
+          blk[kw * 64 + ci] = hi;
+          blk[(8 + kw) * 64 + ci] = __float2half_rn((w - __half2float(hi)) * 2048.f);
+          blk[(8 + kw) * 64 + 32 + ci] = hi;
+        }
+    tc[3 * 16 * 32] = 1.f / sw;
+    tc[3 * 16 * 32 + 1] = 1.f / (sw * 2048.f);
+  }
+  for (int br = 0; br < 2; ++br) {
+    // first conv [CIN][9][32] -> [K = ci*9 + tap (zero padded to 32)][co]: the same table format as a pointwise conv
+    float kxc[32 * 32];
+    memset(kxc, 0, sizeof(kxc));
+    const int nk = (br == 0 ? 3 : 1) * 9;
+    for (int k = 0; k < nk; ++k)
+      for (int co = 0; co < 32; ++co) kxc[k * 32 + co] = packed[L.r1_w0[br] + (size_t)k * 32 + co];
+    pack_pwtc(kxc, packed + L.r1_w0tc[br]);
+  }
   for (int br = 0; br < 2; ++br)
     for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r1_pw[br][j], packed + L.r1_pwtc[br][j]);
   for (int j = 0; j < 4; ++j) pack_pwtc(packed + L.r2_pw[j], packed + L.r2_pwtc[j]);
@@ -402,6 +441,7 @@ extern "C" int lws_refinement_f32(const float* left, const float* pred3, const f
       }
       for (int j = 0; j < 4; ++j) wt.dw[2][j] = pk + L.r2_dw[j], wt.pwtc[2][j] = pk + L.r2_pwtc[j], wt.bias[2][j] = pk + L.r2_bb[j];
       wt.dense_tc = pk + L.r2_wtc, wt.dense_bias = pk + L.r2_b, wt.last_w = pk + L.last_w;
+      wt.w0tc[0] = pk + L.r1_w0tc[0], wt.w0tc[1] = pk + L.r1_w0tc[1], wt.last_tc = pk + L.last_tc;
       return refinement_tc(left, pred3, wt, pred4, ws, B, H, W, st);
     }
   }

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(256)
 }
 
 // BN-ReLU-DW(dil)-PW block on CLP (dwsep_tc.cu)
+int launch_conv0_f16(const float* img, float* out, const void* wtab, const float* scales, const float* bias, int B, int CIN, int H,
+                     int W, cudaStream_t st);
 int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
                      int H, int W, int dil, int relu, int out_split, cudaStream_t st);
 
@@ -117,6 +119,8 @@ struct RefTcWeights {
   const float *w0[2], *b0[2];              // first convs
   const float *dw[3][4], *pwtc[3][4], *bias[3][4];  // [left, disp, r2][block]
   const float *dense_tc, *dense_bias, *last_w;
+  const float* w0tc[2];
+  const float* last_tc;
 };
 
 size_t refinement_tc_workspace_bytes(int B, int H, int W) {
@@ -140,9 +144,8 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
   int rc;
   cudaError_t e;
   for (int br = 0; br < 2; ++br) {
-    if (br == 0) ref_conv0_clp_kernel<3><<<cblocks, 256, 0, st>>>(left, wt.w0[0], wt.b0[0], ping, H, W, rows);
-    else ref_conv0_clp_kernel<1><<<cblocks, 256, 0, st>>>(pred3, wt.w0[1], wt.b0[1], ping, H, W, rows);
-    if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+    if ((rc = launch_conv0_f16(br == 0 ? left : pred3, ping, wt.w0tc[br], wt.w0tc[br] + 1024, wt.b0[br], B, br == 0 ? 3 : 1, H, W, st)))
+      return rc;
     float* cur = ping;
     float* nxt = pong;
     for (int j = 0; j < 4; ++j) {
@@ -169,15 +172,22 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
   float* nxt = pong;
   for (int j = 0; j < 4; ++j) {
     if ((rc = launch_dwsep_f16(cur, nxt, wt.dw[2][j], wt.pwtc[2][j], wt.pwtc[2][j] + 1024, wt.bias[2][j], B, H, W, r2_dil[j],
-                               j < 3, 0, st)))
+                               j < 3, j == 3 /* the last block feeds the closing conv: split-fp16 rows */, st)))
       return rc;
     float* t = cur;
     cur = nxt, nxt = t;
   }
-  const long long px = (long long)B * H * W;
-  const int lblocks = (int)((px * 4 + 255) / 256 < 148 * 16 ? (px * 4 + 255) / 256 : 148 * 16);
-  ref_last_clp_kernel<<<lblocks, 256, 0, st>>>(cur, wt.last_w, pred3, pred4, H, W, px);
-  if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
+  {
+    // closing 32 -> 1 conv + skip (pred4 = pred3 + r): stages = kh, kw folded into N = 16, strips down the image
+    TzLayer L;
+    memset(&L, 0, sizeof(L));
+    L.src0 = L.src1 = cur, L.wtab = wt.last_tc, L.B = B, L.R = (int)R;
+    L.n0 = Wp, L.p0 = RP, L.i0 = W, L.n1 = Hp, L.p1 = RP, L.i1 = H;
+    L.tz = 1, L.nstages = 3, L.nshift = 1, L.box_rows = 128, L.G = 1, L.srow = Wp;
+    for (int s = 0; s < 3; ++s) L.st_off[s] = (s - 1) * Wp, L.st_src[s] = 0;
+    L.last = 1, L.skip = pred3, L.out_f32 = pred4, L.out_mode = 1;
+    if ((rc = launch_tz_gemm(L, st))) return rc;
+  }
   return LWS_OK;
 }
 

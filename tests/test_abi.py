@@ -102,7 +102,7 @@ def test_pack_refinement_folds_bn():
     r2.load_state_dict(m.refinement2.state_dict())
     packed = ops.pack_refinement(refinement_tensor_list(r1l, r1d, r2), BN_EPS).numpy()
     from lwsnet_b200._lib import lib
-    assert packed.size == lib.lws_refinement_packed_floats() == 36096 + 12 * 2048 + 6 * 192 * 32
+    assert packed.size == lib.lws_refinement_packed_floats() == 36096 + 12 * 2048 + 6 * 192 * 32 + 2 * 2048 + 1540
     # first section: conv0 of R1_left [3][9][32] scaled by block-1 BN; then its bias
     bn = m.refinement1_left[1][0]
     s = (bn.weight.double() / torch.sqrt(bn._variance.double() + BN_EPS)).detach().numpy()

@@ -22,11 +22,6 @@
 
 namespace lws {
 
-// conv3d_tc.cu: tcgen05 3xTF32 path for C = 32
-size_t conv3d_tc_workspace_bytes(int B, int C, int D, int H, int W);
-int conv3d_stack_tc(int C, const float* cost, const float* affine, const float* w_first, const float* b_first,
-                    const float* const* wtc, const float* const* bias_mid, int layers, const float* w_last, float* out,
-                    void* ws, int B, int D, int H, int W, int add_skip, cudaStream_t st);
 // conv3d_c8.cu: tcgen05 split-fp16 path for C = 8
 size_t conv3d_c8_workspace_bytes(int B, int D, int H, int W);
 int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
@@ -470,7 +465,7 @@ extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, i
   (void)layers;
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
-  size_t tc = lws::has_tc_tables(C) ? lws::conv3d_tc_workspace_bytes(B, C, D, H, W) : 0;
+  size_t tc = 0;
   if (C == 32 && lws::conv3d_f16_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_f16_workspace_bytes(B, D, H, W);
   if (C == 8 && lws::conv3d_c8_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_c8_workspace_bytes(B, D, H, W);
   return 2 * act > tc ? 2 * act : tc;
@@ -505,9 +500,7 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
     if (C == 8)
       return conv3d_stack_c8(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
                              layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
-    return conv3d_stack_tc(C, cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
-                           wtc, bmid, layers, pk + packed_offset(C, layers, layers + 1, false), out, ws, B, D, H, W,
-                           add_skip, st);
+    return LWS_ERR_UNSUPPORTED;
   }
   const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
   float* bufA = (float*)ws;

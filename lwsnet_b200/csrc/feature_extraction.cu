@@ -124,7 +124,187 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
   }
 }
 
+
+// ---- fast path 1: stride-1 3x3 conv with dilation DIL (pad = DIL), Wi % 4 == 0 ---------------------------------------------
+// A thread owns 4 consecutive output pixels x all COUT.  Per (ci, ky) it issues three aligned, fully coalesced float4 loads
+// [x0-4, x0+8) that cover all three kx taps of its four pixels for DIL in {1, 2, 4} (the generic kernel issues 12 predicated
+// scalar loads for the same data and is LSU bound).
+template <int COUT, int DIL>
+__global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
+  extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
+  for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
+  __syncthreads();
+  const int wq = a.Wo >> 2;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= wq * a.Ho) return;
+  const int yo = item / wq;
+  const int b = blockIdx.y;
+  const int x0 = (item - yo * wq) * 4;
+  const long long hw = (long long)a.Hi * a.Wi;
+  const float* in_b = a.in + (long long)b * a.Cin * hw;
+  const bool okL = x0 >= 4, okR = x0 + 8 <= a.Wi;
+
+  float acc[4][COUT];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < COUT; ++q) acc[p][q] = 0.f;
+
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float* plane = in_b + ci * hw;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yi = yo + (ky - 1) * DIL;
+      if ((unsigned)yi >= (unsigned)a.Hi) continue;
+      const float4* row = reinterpret_cast<const float4*>(plane + (long long)yi * a.Wi + x0);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 L = okL ? __ldg(row - 1) : z, M = __ldg(row), R = okR ? __ldg(row + 1) : z;
+      const float win[12] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w, R.x, R.y, R.z, R.w};
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT;
+#pragma unroll
+        for (int q = 0; q < COUT; q += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = win[4 + p + (kx - 1) * DIL];
+            acc[p][q] = fmaf(v, w4.x, acc[p][q]);
+            acc[p][q + 1] = fmaf(v, w4.y, acc[p][q + 1]);
+            acc[p][q + 2] = fmaf(v, w4.z, acc[p][q + 2]);
+            acc[p][q + 3] = fmaf(v, w4.w, acc[p][q + 3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < COUT; ++q) {
+    const float bias = __ldg(a.bias + q);
+    const long long o = ((long long)b * COUT + q) * hw + (long long)yo * a.Wo + x0;
+    float r[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
+    if (a.res) {
+      const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
+      r[0] += rv.x, r[1] += rv.y, r[2] += rv.z, r[3] += rv.w;
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) r[p] = fmaxf(r[p], 0.f);
+    }
+    *reinterpret_cast<float4*>(a.out + o) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ---- fast path 2: 3x3 stride-2 transposed conv (pad 1, output_padding 1 -> exact 2x upsampling), Wi % 2 == 0 ------------------
+// yo = 2*yi - 1 + ky: an even output row sees only (yi = yo/2, ky = 1), an odd one (yi = (yo-1)/2, ky = 2) and (yi = (yo+1)/2,
+// ky = 0); same along x.  A thread owns the 2 x 4 outputs (rows 2i, 2i+1; columns 4j .. 4j+3) of 8 output channels: 6 input
+// values and 18 FMA per (ci, co) instead of the generic kernel's 72 predicated taps.
+template <int COUT>
+__global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
+  extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
+  for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
+  __syncthreads();
+  constexpr int NG = COUT / 8;  // groups of 8 output channels
+  const int wq = a.Wi >> 1;     // column quads per row pair (Wo / 4)
+  int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= wq * a.Hi * NG) return;
+  const int cg = item % NG;
+  item /= NG;
+  const int i = item / wq, j = item - i * wq;
+  const int b = blockIdx.y;
+  const long long ihw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
+  const float* in_b = a.in + (long long)b * a.Cin * ihw + (long long)i * a.Wi + 2 * j;
+  const bool r1 = i + 1 < a.Hi, c2 = 2 * j + 2 < a.Wi;
+
+  float acc[2][4][8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[r][p][q] = 0.f;
+
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float* p0 = in_b + ci * ihw;
+    const float2 a01 = __ldg(reinterpret_cast<const float2*>(p0));
+    const float a02 = c2 ? __ldg(p0 + 2) : 0.f;
+    float2 b01 = make_float2(0.f, 0.f);
+    float b02 = 0.f;
+    if (r1) {
+      b01 = __ldg(reinterpret_cast<const float2*>(p0 + a.Wi));
+      b02 = c2 ? __ldg(p0 + a.Wi + 2) : 0.f;
+    }
+    const float in0[3] = {a01.x, a01.y, a02}, in1[3] = {b01.x, b01.y, b02};
+    const float* wc = sW + ci * 9 * COUT + cg * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q += 4) {
+      float4 w[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(wc + k * COUT + q);
+      // x pattern for output columns 4j + {0,1,2,3}: (kx=1,c=0) | (kx=2,c=0)+(kx=0,c=1) | (kx=1,c=1) | (kx=2,c=1)+(kx=0,c=2)
+#define LWS_ROW(ACC, IN, KY)                                                                                            \
+  {                                                                                                                     \
+    const float4 k0 = w[(KY) * 3], k1 = w[(KY) * 3 + 1], k2 = w[(KY) * 3 + 2];                                           \
+    ACC[0][q] = fmaf(IN[0], k1.x, ACC[0][q]), ACC[0][q + 1] = fmaf(IN[0], k1.y, ACC[0][q + 1]);                          \
+    ACC[0][q + 2] = fmaf(IN[0], k1.z, ACC[0][q + 2]), ACC[0][q + 3] = fmaf(IN[0], k1.w, ACC[0][q + 3]);                  \
+    ACC[1][q] = fmaf(IN[0], k2.x, fmaf(IN[1], k0.x, ACC[1][q])), ACC[1][q + 1] = fmaf(IN[0], k2.y, fmaf(IN[1], k0.y, ACC[1][q + 1])); \
+    ACC[1][q + 2] = fmaf(IN[0], k2.z, fmaf(IN[1], k0.z, ACC[1][q + 2])), ACC[1][q + 3] = fmaf(IN[0], k2.w, fmaf(IN[1], k0.w, ACC[1][q + 3])); \
+    ACC[2][q] = fmaf(IN[1], k1.x, ACC[2][q]), ACC[2][q + 1] = fmaf(IN[1], k1.y, ACC[2][q + 1]);                          \
+    ACC[2][q + 2] = fmaf(IN[1], k1.z, ACC[2][q + 2]), ACC[2][q + 3] = fmaf(IN[1], k1.w, ACC[2][q + 3]);                  \
+    ACC[3][q] = fmaf(IN[1], k2.x, fmaf(IN[2], k0.x, ACC[3][q])), ACC[3][q + 1] = fmaf(IN[1], k2.y, fmaf(IN[2], k0.y, ACC[3][q + 1])); \
+    ACC[3][q + 2] = fmaf(IN[1], k2.z, fmaf(IN[2], k0.z, ACC[3][q + 2])), ACC[3][q + 3] = fmaf(IN[1], k2.w, fmaf(IN[2], k0.w, ACC[3][q + 3])); \
+  }
+      LWS_ROW(acc[0], in0, 1)  // even output row: ky = 1 on input row i
+      LWS_ROW(acc[1], in0, 2)  // odd output row: ky = 2 on input row i ...
+      LWS_ROW(acc[1], in1, 0)  // ... and ky = 0 on input row i + 1
+#undef LWS_ROW
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int co = cg * 8 + q;
+    const float bias = __ldg(a.bias + co);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long o = ((long long)b * COUT + co) * ohw + (long long)(2 * i + r) * a.Wo + 4 * j;
+      float v[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v[p] = acc[r][p][q] + bias;
+      if (a.res) {
+        const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
+        v[0] += rv.x, v[1] += rv.y, v[2] += rv.z, v[3] += rv.w;
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[p] = fmaxf(v[p], 0.f);
+      }
+      *reinterpret_cast<float4*>(a.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
 static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
+  const size_t smem_w = (size_t)a.Cin * 9 * cout * sizeof(float);
+  if (!a.transposed && a.stride == 1 && (a.Wi & 3) == 0 && a.pad == a.dil && (a.dil == 1 || a.dil == 2 || a.dil == 4) &&
+      (cout == 8 || cout == 16 || cout == 4)) {
+    dim3 g(cdiv((a.Wo >> 2) * a.Ho, 128), B);
+#define LWS_S1(CO, DL) fe_conv_s1_kernel<CO, DL><<<g, 128, smem_w, st>>>(a)
+    if (cout == 4) { if (a.dil == 1) LWS_S1(4, 1); else if (a.dil == 2) LWS_S1(4, 2); else LWS_S1(4, 4); }
+    else if (cout == 8) { if (a.dil == 1) LWS_S1(8, 1); else if (a.dil == 2) LWS_S1(8, 2); else LWS_S1(8, 4); }
+    else { if (a.dil == 1) LWS_S1(16, 1); else if (a.dil == 2) LWS_S1(16, 2); else LWS_S1(16, 4); }
+#undef LWS_S1
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? LWS_OK : (int)e;
+  }
+  if (a.transposed && a.stride == 2 && a.pad == 1 && (a.Wi & 1) == 0 && a.Ho == 2 * a.Hi && a.Wo == 2 * a.Wi && (cout == 8 || cout == 16)) {
+    dim3 g(cdiv((a.Wi >> 1) * a.Hi * (cout / 8), 128), B);
+    if (cout == 8) fe_deconv_kernel<8><<<g, 128, smem_w, st>>>(a);
+    else fe_deconv_kernel<16><<<g, 128, smem_w, st>>>(a);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? LWS_OK : (int)e;
+  }
   dim3 grid(cdiv(cdiv(a.Wo, 4) * a.Ho, 128), B);
   const size_t smem = (size_t)a.Cin * 9 * cout * sizeof(float);
   switch (cout) {

@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
 }
 
 
-// ---- fast path 1: stride-1 3x3 conv with dilation DIL (pad = DIL), Wi % 4 == 0 ---------------------------------------------
+// ---- fast path 1: 3x3 conv with dilation DIL (pad = DIL), stride 1 or (DIL = 1) stride 2, Wi % 4 == 0 ---------------------------------------------
 // A thread owns 4 consecutive output pixels x all COUT.  Per (ci, ky) it issues three aligned, fully coalesced float4 loads
 // [x0-4, x0+8) that cover all three kx taps of its four pixels for DIL in {1, 2, 4} (the generic kernel issues 12 predicated
 // scalar loads for the same data and is LSU bound).
-template <int COUT, int DIL>
+template <int COUT, int DIL, int STRIDE>
 __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
   extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
   for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
@@ -140,9 +140,10 @@ __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
   const int yo = item / wq;
   const int b = blockIdx.y;
   const int x0 = (item - yo * wq) * 4;
-  const long long hw = (long long)a.Hi * a.Wi;
+  const long long hw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
   const float* in_b = a.in + (long long)b * a.Cin * hw;
-  const bool okL = x0 >= 4, okR = x0 + 8 <= a.Wi;
+  const int xi0 = x0 * STRIDE;  // first input column of the aligned 12-wide window is xi0 - 4
+  const bool okL = xi0 >= 4, okM = xi0 + 4 <= a.Wi, okR = xi0 + 8 <= a.Wi;
 
   float acc[4][COUT];
 #pragma unroll
@@ -154,11 +155,11 @@ __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
     const float* plane = in_b + ci * hw;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int yi = yo + (ky - 1) * DIL;
+      const int yi = yo * STRIDE + (ky - 1) * DIL;
       if ((unsigned)yi >= (unsigned)a.Hi) continue;
-      const float4* row = reinterpret_cast<const float4*>(plane + (long long)yi * a.Wi + x0);
+      const float4* row = reinterpret_cast<const float4*>(plane + (long long)yi * a.Wi + xi0);
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 L = okL ? __ldg(row - 1) : z, M = __ldg(row), R = okR ? __ldg(row + 1) : z;
+      const float4 L = okL ? __ldg(row - 1) : z, M = okM ? __ldg(row) : z, R = okR ? __ldg(row + 1) : z;
       const float win[12] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w, R.x, R.y, R.z, R.w};
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
           const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const float v = win[4 + p + (kx - 1) * DIL];
+            const float v = win[4 + p * STRIDE + (kx - 1) * DIL];
             acc[p][q] = fmaf(v, w4.x, acc[p][q]);
             acc[p][q + 1] = fmaf(v, w4.y, acc[p][q + 1]);
             acc[p][q + 2] = fmaf(v, w4.z, acc[p][q + 2]);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
 #pragma unroll
   for (int q = 0; q < COUT; ++q) {
     const float bias = __ldg(a.bias + q);
-    const long long o = ((long long)b * COUT + q) * hw + (long long)yo * a.Wo + x0;
+    const long long o = ((long long)b * COUT + q) * ohw + (long long)yo * a.Wo + x0;
     float r[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
@@ -290,11 +291,17 @@ static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
   if (!a.transposed && a.stride == 1 && (a.Wi & 3) == 0 && a.pad == a.dil && (a.dil == 1 || a.dil == 2 || a.dil == 4) &&
       (cout == 8 || cout == 16 || cout == 4)) {
     dim3 g(cdiv((a.Wo >> 2) * a.Ho, 128), B);
-#define LWS_S1(CO, DL) fe_conv_s1_kernel<CO, DL><<<g, 128, smem_w, st>>>(a)
+#define LWS_S1(CO, DL) fe_conv_s1_kernel<CO, DL, 1><<<g, 128, smem_w, st>>>(a)
     if (cout == 4) { if (a.dil == 1) LWS_S1(4, 1); else if (a.dil == 2) LWS_S1(4, 2); else LWS_S1(4, 4); }
     else if (cout == 8) { if (a.dil == 1) LWS_S1(8, 1); else if (a.dil == 2) LWS_S1(8, 2); else LWS_S1(8, 4); }
     else { if (a.dil == 1) LWS_S1(16, 1); else if (a.dil == 2) LWS_S1(16, 2); else LWS_S1(16, 4); }
 #undef LWS_S1
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? LWS_OK : (int)e;
+  }
+  if (!a.transposed && a.stride == 2 && a.dil == 1 && a.pad == 1 && (a.Wi & 3) == 0 && (a.Wo & 3) == 0 && cout == 16) {
+    dim3 g(cdiv((a.Wo >> 2) * a.Ho, 128), B);
+    fe_conv_s1_kernel<16, 1, 2><<<g, 128, smem_w, st>>>(a);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? LWS_OK : (int)e;
   }

@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--skip-probes", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

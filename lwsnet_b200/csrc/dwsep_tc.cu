@@ -56,7 +56,8 @@ struct DsArgs {
   int W;
   int B, Hp, Wp, H, dil, relu;
   int out_split;        // 1: write rows as [32 hi | 32 lo] halves of act * 2^-6 (operand format of conv3d_f16.cu) instead of fp32
-  int nxt, segs, seg_len, total_items;
+  int nxt, rows_phase;     // x tiles per line; lines per row phase (max over phases)
+  long long total_rows;     // B * nxt * dil * rows_phase tile-rows, split evenly (contiguously) over the CTAs
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -87,27 +88,40 @@ __device__ __forceinline__ void ds_ld32(uint32_t taddr, float* v) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-// Work item = (b, x tile, row phase py, segment): image lines yi = py + i*dil, i in [seg*seg_len, (seg+1)*seg_len) clipped to
-// the phase.  All warp roles walk the same static schedule.
+// Schedule: a strip = (b, x tile, row phase py) = the image lines yi = py + i*dil, i in [0, rows_phase), of one 128-pixel
+// column tile.  All B * nxt * dil * rows_phase tile-rows are numbered strip-major and every CTA takes one contiguous range of
+// them, so the load is balanced to within one tile-row and a CTA pays the two warm-up line loads only once per (partial) strip.
+// All warp roles walk the same static schedule through DsSched.
 struct DsItem {
   int b, x0, yi0, nrows;
 };
-__device__ __forceinline__ DsItem ds_decode(const DsArgs& a, int item) {
-  int t = item;
-  const int seg = t % a.segs;
-  t /= a.segs;
-  const int py = t % a.dil;
-  t /= a.dil;
-  const int xt = t % a.nxt;
-  DsItem it;
-  it.b = t / a.nxt;
-  it.x0 = xt * 128;
-  const int rows_phase = py < a.H ? (a.H - py + a.dil - 1) / a.dil : 0;
-  const int i0 = seg * a.seg_len;
-  it.nrows = max(0, min(a.seg_len, rows_phase - i0));
-  it.yi0 = py + i0 * a.dil;
-  return it;
-}
+struct DsSched {
+  long long g, g1;
+  __device__ __forceinline__ DsSched(const DsArgs& a) {
+    g = a.total_rows * blockIdx.x / gridDim.x;
+    g1 = a.total_rows * (blockIdx.x + 1) / gridDim.x;
+  }
+  // next (partial) strip of this CTA; false when the range is exhausted
+  __device__ __forceinline__ bool next(const DsArgs& a, DsItem& it) {
+    while (g < g1) {
+      const long long strip = g / a.rows_phase;
+      const int i0 = (int)(g - strip * a.rows_phase);
+      const int n = (int)min((long long)(a.rows_phase - i0), g1 - g);
+      g += n;
+      int t = (int)strip;
+      const int py = t % a.dil;
+      t /= a.dil;
+      const int xt = t % a.nxt;
+      it.b = t / a.nxt;
+      it.x0 = xt * 128;
+      const int rows_here = py < a.H ? (a.H - py + a.dil - 1) / a.dil : 0;  // this phase may be one line shorter
+      it.nrows = min(n, rows_here - i0);
+      it.yi0 = py + i0 * a.dil;
+      if (it.nrows > 0) return true;
+    }
+    return false;
+  }
+};
 
 // CIN = 0: the depthwise-separable block described above.  CIN = 3 / 1: the dense 3x3 first conv of a refinement branch
 // (reference models/submodules.py:284-300: conv CIN -> 32 on the NCHW image / disparity), same back end with an im2col front end:
@@ -174,9 +188,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     if (CIN == 0 && elect_one_sync()) {
       uint32_t it = 0;
       const uint32_t bytes = (uint32_t)(128 + 2 * dil) * 128;
-      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const DsItem w = ds_decode(a, item);
-        if (w.nrows == 0) continue;
+      DsSched sched(a);
+        DsItem w;
+        while (sched.next(a, w)) {
         const int line0 = w.b * a.Hp + DS_RP + w.yi0 - dil;  // first line needed: y - dil
         for (int k = 0; k < w.nrows + 2; ++k, ++it) {
           const uint32_t slot = it % DS_NIN;
@@ -199,8 +213,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
     const uint32_t b_lo = ((smem_u32(smem + DS_OFF_B) & 0x3FFFF) >> 4) | (1u << 16);
     uint32_t t = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const DsItem w = ds_decode(a, item);
+    DsSched sched(a);
+      DsItem w;
+      while (sched.next(a, w)) {
       for (int i = 0; i < w.nrows; ++i, ++t) {
         const uint32_t ab = t % DS_NA, tb = t % DS_NT;
         mbar_wait(t_empty + tb, ((t / DS_NT) & 1) ^ 1);
@@ -244,8 +259,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     const float c0 = __ldg(a.scales), c1 = __ldg(a.scales + 1);
     const float lo = a.relu ? 0.f : -INFINITY;
     uint32_t t = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const DsItem w = ds_decode(a, item);
+    DsSched sched(a);
+      DsItem w;
+      while (sched.next(a, w)) {
       const int xpix = w.x0 + p;
       const bool border = xpix < DS_RP || xpix >= a.Wp - DS_RP;
       for (int i = 0; i < w.nrows; ++i, ++t) {
@@ -313,8 +329,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     const uint32_t row = (uint32_t)p * 128;
     const long long hw = (long long)a.H * a.W;
     uint32_t t = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const DsItem w = ds_decode(a, item);
+    DsSched sched(a);
+      DsItem w;
+      while (sched.next(a, w)) {
       const int x = w.x0 + p - DS_RP;  // image column of this pixel
       for (int i = 0; i < w.nrows; ++i, ++t) {
         const int y = w.yi0 + i;
@@ -388,9 +405,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     }
     uint32_t it = 0, t = 0;
     float4 win[3][6];
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const DsItem w = ds_decode(a, item);
-      if (w.nrows == 0) continue;
+    DsSched sched(a);
+      DsItem w;
+      while (sched.next(a, w)) {
       int npend = 0;  // ring slots read but not yet released (released once their values have been consumed)
       auto load_line = [&](float4(&dst)[6]) {
         const uint32_t slot = it % DS_NIN;
@@ -469,13 +486,9 @@ int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* p
   a.dw = dw, a.pwh = (const __half*)pwh, a.scales = scales, a.bias = bias, a.out = out;
   a.B = B, a.Hp = H + 2 * DS_RP, a.Wp = W + 2 * DS_RP, a.H = H, a.dil = dil, a.relu = relu, a.out_split = out_split;
   a.nxt = (a.Wp + 127) / 128;
-  const int rows_phase = (H + dil - 1) / dil;
-  // segments of ~16 lines (two warm-up line loads each); at least ~4 items per SM so the static round-robin balances
-  a.seg_len = rows_phase < 16 ? rows_phase : 16;
-  a.segs = (rows_phase + a.seg_len - 1) / a.seg_len;
-  a.seg_len = (rows_phase + a.segs - 1) / a.segs;
-  a.total_items = B * a.nxt * dil * a.segs;
-  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+  a.rows_phase = (H + dil - 1) / dil;
+  a.total_rows = (long long)B * a.nxt * dil * a.rows_phase;
+  const int grid = a.total_rows < kNumSMs ? (int)a.total_rows : kNumSMs;
   CUtensorMap map_in, map_out;
   const uint64_t dims[3] = {32, (uint64_t)a.Wp, (uint64_t)B * a.Hp}, strides[2] = {128, (uint64_t)a.Wp * 128};
   const uint32_t box_in[3] = {32, (uint32_t)(128 + 2 * dil), 1}, box_out[3] = {32, 32, 1};  // one TMA store per epilogue warp
@@ -502,11 +515,9 @@ int launch_conv0_f16(const float* img, float* out, const void* wtab, const float
   a.dw = bias /*unused*/, a.pwh = (const __half*)wtab, a.scales = scales, a.bias = bias, a.out = out, a.img = img, a.W = W;
   a.B = B, a.Hp = H + 2 * DS_RP, a.Wp = W + 2 * DS_RP, a.H = H, a.dil = 1, a.relu = 1, a.out_split = 0;
   a.nxt = (a.Wp + 127) / 128;
-  a.seg_len = H < 16 ? H : 16;
-  a.segs = (H + a.seg_len - 1) / a.seg_len;
-  a.seg_len = (H + a.segs - 1) / a.segs;
-  a.total_items = B * a.nxt * a.segs;
-  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+  a.rows_phase = H;
+  a.total_rows = (long long)B * a.nxt * H;
+  const int grid = a.total_rows < kNumSMs ? (int)a.total_rows : kNumSMs;
   CUtensorMap map_out;
   const uint64_t dims[3] = {32, (uint64_t)a.Wp, (uint64_t)B * a.Hp}, strides[2] = {128, (uint64_t)a.Wp * 128};
   const uint32_t box_out[3] = {32, 32, 1};

@@ -47,23 +47,32 @@ struct C8Args {
   int Hp, Wp, H, W, D;    // padded / interior plane size, interior depth
   FastDiv fWp, fHp;
   int line0, strip_len;   // first computed line (= Hp: plane 1) and number of lines (D * Hp)
-  int seg_len, total_items;
-  FastDiv ct_per_line, segs;
+  int total_tiles;        // B * ct_per_line * strip_len, split evenly (contiguously) over the CTAs
+  FastDiv ct_per_line;
 };
 
 struct C8Item {
   int b, row0, ntiles;  // row0: first output voxel (inside the batch element) of tile 0; tile n is Wp voxels further
 };
-__device__ __forceinline__ C8Item c8_decode(const C8Args& a, int item) {
-  int t, seg, ct;
-  C8Item it;
-  fdivmod(item, a.segs, t, seg);
-  fdivmod(t, a.ct_per_line, it.b, ct);
-  const int n0 = seg * a.seg_len;
-  it.ntiles = min(a.seg_len, a.strip_len - n0);
-  it.row0 = (a.line0 + n0) * a.Wp + ct * 126;
-  return it;
-}
+// Schedule: a strip = (b, column tile ct) walked down all strip_len lines; the B * ct * strip_len tiles are numbered strip-major
+// and every CTA takes one contiguous range (balanced to one tile; two warm-up line groups per partial strip only).
+struct C8Sched {
+  int g, g1;
+  __device__ __forceinline__ C8Sched(const C8Args& a) {
+    g = (int)((long long)a.total_tiles * blockIdx.x / gridDim.x);
+    g1 = (int)((long long)a.total_tiles * (blockIdx.x + 1) / gridDim.x);
+  }
+  __device__ __forceinline__ bool next(const C8Args& a, C8Item& it) {
+    if (g >= g1) return false;
+    const int strip = g / a.strip_len, n0 = g - strip * a.strip_len;
+    int ct;
+    fdivmod(strip, a.ct_per_line, it.b, ct);
+    it.ntiles = min(a.strip_len - n0, g1 - g);
+    it.row0 = (a.line0 + n0) * a.Wp + ct * 126;
+    g += it.ntiles;
+    return true;
+  }
+};
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -124,8 +133,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     const uint8_t* src_plane = part ? a.in_lo : a.in_hi;
     const long long plane = (long long)a.Hp * a.Wp;  // voxels per d plane
     uint32_t slot = 0, ph = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const C8Item w = c8_decode(a, item);
+    C8Sched sched(a);
+      C8Item w;
+      while (sched.next(a, w)) {
       const long long base = (long long)w.b * a.vox_b + w.row0 - 1;  // GEMM row 0 of tile 0 (Toeplitz shift 1)
       for (int n = 0; n < w.ntiles; ++n) {
         for (int kh = n == 0 ? 0 : 2; kh < 3; ++kh) {  // later tiles of a strip only need the line below
@@ -152,8 +162,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     // elect / reconverge / __syncwarp overhead in the issuing warp would be the kernel's critical path
     if (elect_one_sync()) {
       uint32_t bslot = 0, bph = 0, ti = 0;
-      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const C8Item w = c8_decode(a, item);
+      C8Sched sched(a);
+        C8Item w;
+        while (sched.next(a, w)) {
         for (int n = 0; n < w.ntiles; ++n, ++ti) {
           const bool last = n == w.ntiles - 1;
           const uint32_t tb = ti % C8_NGRP;
@@ -207,8 +218,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
     const float* xn = xch + ((q + 1) & 3) * 24;  // next quarter's
     const int bar_id = 1 + g;
     uint32_t ti = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const C8Item w = c8_decode(a, item);
+    C8Sched sched(a);
+      C8Item w;
+      while (sched.next(a, w)) {
       for (int n = 0; n < w.ntiles; ++n, ++ti) {
         if ((int)(ti % C8_NGRP) != g) continue;
         mbar_wait(t_full + g, (ti / C8_NGRP) & 1);
@@ -435,15 +447,9 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     a.vox_b = vox_b, a.Hp = Hp, a.Wp = Wp, a.H = H, a.W = W, a.D = D, a.fWp = make_fastdiv(Wp), a.fHp = make_fastdiv(Hp);
     a.line0 = Hp, a.strip_len = D * Hp;
     const int ct = (Wp + 125) / 126;
-    // segments: ~8 items per SM, at least 8 lines each (every segment reloads two lines)
-    int segs = (int)((148ll * 8 + (long long)B * ct - 1) / ((long long)B * ct));
-    if (segs < 1) segs = 1;
-    int seg_len = (a.strip_len + segs - 1) / segs;
-    if (seg_len < 8) seg_len = a.strip_len < 8 ? a.strip_len : 8;
-    segs = (a.strip_len + seg_len - 1) / seg_len;
-    a.seg_len = seg_len, a.segs = make_fastdiv(segs), a.ct_per_line = make_fastdiv(ct);
-    a.total_items = B * ct * segs;
-    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    a.ct_per_line = make_fastdiv(ct);
+    a.total_tiles = B * ct * a.strip_len;
+    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
     if (last) conv3d_c8_kernel<true><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
     else conv3d_c8_kernel<false><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;

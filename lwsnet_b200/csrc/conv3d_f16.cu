@@ -49,11 +49,11 @@ struct TzArgs {
   FastDiv n0, n1;       // padded lengths of the fastest and the middle axis
   int p0, i0, p1, i1;   // pad and interior length of each: rows outside the interior are written as 0
   // strip schedule: the row space of one batch element is cut into super lines of `srow` rows (the distance between
-  // consecutive taps of the slowest axis); an item = (b, column tile ct of the super line, segment of <= seg_len consecutive
-  // super lines); tile n of an item outputs rows ct*OUTR + (n0 + n)*srow + [0, OUTR) and shares all but its last `G` stage
-  // boxes with tile n-1, so they stay in the shared-memory ring.  srow = R gives plain linear tiling (one tile per item).
-  int srow, strip_len, seg_len, total_items;
-  FastDiv ct_per_sl, segs;
+  // consecutive taps of the slowest axis); a strip = (b, column tile ct of the super line) walked down the super lines; tile n of
+  // a strip outputs rows ct*OUTR + n*srow + [0, OUTR) and shares all but its last `G` stage boxes with tile n-1, so they stay
+  // in the shared-memory ring.  srow = R gives plain linear tiling (strips of one tile).
+  int srow, strip_len, total_tiles;  // total_tiles = B * ct_per_sl * strip_len, split evenly (contiguously) over the CTAs
+  FastDiv ct_per_sl;
   int nstages, G, nshift, nbtiles, nslot;
   int slot_bytes, box_bytes;
   int st_off[TZ_MAXST];  // row offset of the stage's box relative to the tile's first GEMM row
@@ -64,17 +64,31 @@ struct TzArgs {
 struct TzItem {
   int b, orow0, ntiles;
 };
+// A strip = (b, column tile ct) walked down all strip_len super lines; tiles are numbered strip-major and every CTA takes one
+// contiguous range (balanced to one tile; a CTA reloads the shared stage boxes only at the start of a (partial) strip).
 template <int OUTR>
-__device__ __forceinline__ TzItem tz_decode(const TzArgs& a, int item) {
-  int t, seg, ct;
-  TzItem it;
-  fdivmod(item, a.segs, t, seg);
-  fdivmod(t, a.ct_per_sl, it.b, ct);
-  const int n0 = seg * a.seg_len;
-  it.ntiles = min(a.seg_len, a.strip_len - n0);
-  it.orow0 = ct * OUTR + n0 * a.srow;
-  return it;
-}
+struct TzSched {
+  int g, g1, step;
+  __device__ __forceinline__ TzSched(const TzArgs& a) {
+    if (a.strip_len == 1) {  // linear tiling: interleave the tiles over the CTAs (neighbouring tiles run concurrently: L2 reuse)
+      g = blockIdx.x, g1 = a.total_tiles, step = gridDim.x;
+    } else {
+      g = (int)((long long)a.total_tiles * blockIdx.x / gridDim.x);
+      g1 = (int)((long long)a.total_tiles * (blockIdx.x + 1) / gridDim.x);
+      step = 0;
+    }
+  }
+  __device__ __forceinline__ bool next(const TzArgs& a, TzItem& it) {
+    if (g >= g1) return false;
+    const int strip = g / a.strip_len, n0 = g - strip * a.strip_len;
+    int ct;
+    fdivmod(strip, a.ct_per_sl, it.b, ct);
+    it.ntiles = step ? 1 : min(a.strip_len - n0, g1 - g);
+    it.orow0 = ct * OUTR + n0 * a.srow;
+    g += step ? step : it.ntiles;
+    return true;
+  }
+};
 
 __device__ __forceinline__ void tz_mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -155,8 +169,9 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         for (int i = 0; i < a.nbtiles; ++i) tma_load_2d(sB + i * TZ_BTILE, &mapB, b_full, 0, i * 192);
       }
       uint32_t slot = 0, ph = 0;  // ring position and phase of the next entry
-      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const TzItem w = tz_decode<OUTR>(a, item);
+      TzSched<OUTR> sched(a);
+        TzItem w;
+        while (sched.next(a, w)) {
         for (int n = 0; n < w.ntiles; ++n) {
           const int row0 = w.orow0 + n * a.srow - TZ;  // GEMM row 0 of the tile
           for (int s = n == 0 ? 0 : nst - a.G; s < nst; ++s) {  // later tiles of a strip only load their newest stage group
@@ -190,8 +205,9 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
       bslot += k;
       if (bslot >= nslot) bslot -= nslot, bph ^= 1;
     };
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const TzItem w = tz_decode<OUTR>(a, item);
+    TzSched<OUTR> sched(a);
+      TzItem w;
+      while (sched.next(a, w)) {
       for (int n = 0; n < w.ntiles; ++n, ++ti, advance(G)) {
         const bool last = n == w.ntiles - 1;
         const uint32_t tb = ti & 1;
@@ -240,8 +256,9 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
       const bool has1 = lane + TZ < 32, has2 = lane + 2 * TZ < 32;
       const int Hdim = a.R / (a.n0.d * a.n1.d);  // interior length of the slowest axis
       uint32_t ti = 0;
-      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const TzItem w = tz_decode<OUTR>(a, item);
+      TzSched<OUTR> sched(a);
+        TzItem w;
+        while (sched.next(a, w)) {
         for (int n = 0; n < w.ntiles; ++n, ++ti) {
           const uint32_t tb = ti & 1;
           const int orow0 = w.orow0 + n * a.srow;
@@ -296,8 +313,9 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
     float* xq = xch + q * (3 * TZ * 32) + hf * 16;
     const float* xn = xch + ((q + 1) & 3) * (3 * TZ * 32) + hf * 16;
     uint32_t ti = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const TzItem w = tz_decode<OUTR>(a, item);
+    TzSched<OUTR> sched(a);
+      TzItem w;
+      while (sched.next(a, w)) {
       for (int n = 0; n < w.ntiles; ++n, ++ti) {
         const uint32_t tb = ti & 1;
         const int orow0 = w.orow0 + n * a.srow;  // first output row of the tile
@@ -446,15 +464,12 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
     a.G = L.G, a.srow = L.srow;
     a.ct_per_sl = make_fastdiv((L.srow + outr - 1) / outr);
     a.strip_len = (L.R + L.srow - 1) / L.srow;
-    a.seg_len = a.strip_len < 10 ? a.strip_len : 10;
-    a.segs = make_fastdiv((a.strip_len + a.seg_len - 1) / a.seg_len);
   } else {
     a.G = L.nstages, a.srow = L.R;
     a.ct_per_sl = make_fastdiv((L.R + outr - 1) / outr);
-    a.strip_len = a.seg_len = 1;
-    a.segs = make_fastdiv(1);
+    a.strip_len = 1;
   }
-  a.total_items = L.B * a.ct_per_sl.d * a.segs.d;
+  a.total_tiles = L.B * a.ct_per_sl.d * a.strip_len;
   // ring: one tile's stages plus as many more as fit (at most 8)
   a.nslot = 8;
   while (a.nslot > L.nstages && tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz) > 232448) --a.nslot;
@@ -489,7 +504,7 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   const uint32_t boxB[2] = {32, L.last ? (uint32_t)nblk * 16 : 192u};
   rc = make_tensor_map_f32(&mapB, L.wtab, 2, dimsB, strB, boxB, true);
   if (rc) return rc;
-  const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
   if (is2dlast) tz_gemm_kernel<1, 3, 1, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   else if (is2d) tz_gemm_kernel<8, 6, 1, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   else if (L.last) tz_gemm_kernel<1, 3, 3, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);

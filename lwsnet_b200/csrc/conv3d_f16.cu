@@ -248,52 +248,57 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
       advance(nst - G);  // the strip's last tile consumed all of its entries
     }
   } else if (LAST) {
-    // ================================ epilogue of the C -> 1 layer (warps 2..5) ================================
-    if (warp < 6) {
+    // ================================ epilogue of the C -> 1 layer ================================
+    // two groups of four warps (2..5, 6..9) take alternate tiles (group = accumulator = ti & 1): a tile's epilogue is a long
+    // dependent chain (TMEM load, shuffles, skip load, scattered store) while its MMAs take only ~600 cycles
+    {
+      const int grp = (warp - 2) >> 2;
       const int q = warp & 3;
       const int j = q * 32 + lane;  // GEMM row; produces output row j (relative to the tile's first output row), valid for j < OUTR
       const float c0 = __ldg(a.scales) * a.out_mul, c1 = __ldg(a.scales + 1) * a.out_mul;
       const bool has1 = lane + TZ < 32, has2 = lane + 2 * TZ < 32;
       const int Hdim = a.R / (a.n0.d * a.n1.d);  // interior length of the slowest axis
+      float* xg = xch + grp * (4 * 3 * TZ);
       uint32_t ti = 0;
       TzSched<OUTR> sched(a);
-        TzItem w;
-        while (sched.next(a, w)) {
+      TzItem w;
+      while (sched.next(a, w)) {
         for (int n = 0; n < w.ntiles; ++n, ++ti) {
-          const uint32_t tb = ti & 1;
+          if ((int)(ti & 1) != grp) continue;
           const int orow0 = w.orow0 + n * a.srow;
-          mbar_wait(t_full + tb, (ti >> 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          float m[8], k[8];
-          tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + tb * 32, m);
-          tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + tb * 32 + 8, k);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + tb);
-          const float e0 = fmaf(k[0], c1, m[0] * c0), e1 = fmaf(k[1], c1, m[1] * c0), e2 = fmaf(k[2], c1, m[2] * c0);
-          const float s1 = __shfl_down_sync(0xffffffffu, e1, TZ), s2 = __shfl_down_sync(0xffffffffu, e2, (2 * TZ) & 31);
-          float v = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
-          float* xq = xch + tb * (4 * 3 * TZ) + q * (3 * TZ);  // double-buffered by tile parity
-          if (lane < TZ) xq[lane] = e1;
-          if (lane < 2 * TZ) xq[TZ + lane] = e2;
-          named_bar_sync(1, 128);
-          if (q < 3) {
-            const float* xn = xch + tb * (4 * 3 * TZ) + (q + 1) * (3 * TZ);
-            if (!has1) v += xn[lane + TZ - 32];
-            if (!has2) v += xn[TZ + lane + 2 * TZ - 32];
-          }
+          // output coordinates and the skip value do not depend on the accumulator: fetch them before waiting for it
           const int r = orow0 + j;
           int rq, c0i, c1i, c2i;
           fdivmod(r, a.n0, rq, c0i);
           fdivmod(rq, a.n1, c2i, c1i);
           const bool ok = j < OUTR && c0i >= a.p0 && c0i < a.p0 + a.i0 && c1i >= a.p1 && c1i < a.p1 + a.i1 && c2i < Hdim;
-          if (ok) {
-            // NCDHW index for rows ordered (slowest = y, middle = x, fastest = d)
-            const long long o = a.out_mode ? ((long long)w.b * a.i1 + (c1i - a.p1)) * a.i0 + (c0i - a.p0)
-                                           : (((long long)w.b * a.i0 + (c0i - a.p0)) * Hdim + c2i) * a.i1 + (c1i - a.p1);
-            a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
+          // NCDHW index for rows ordered (slowest = y, middle = x, fastest = d); NCHW for rows ordered (y, x)
+          const long long o = a.out_mode ? ((long long)w.b * a.i1 + (c1i - a.p1)) * a.i0 + (c0i - a.p0)
+                                         : (((long long)w.b * a.i0 + (c0i - a.p0)) * Hdim + c2i) * a.i1 + (c1i - a.p1);
+          const float sk = (ok && a.skip) ? __ldg(a.skip + o) : 0.f;
+          mbar_wait(t_full + grp, (ti >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          float m[8], k[8];
+          tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + grp * 32, m);
+          tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + grp * 32 + 8, k);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + grp);
+          const float e0 = fmaf(k[0], c1, m[0] * c0), e1 = fmaf(k[1], c1, m[1] * c0), e2 = fmaf(k[2], c1, m[2] * c0);
+          const float s1 = __shfl_down_sync(0xffffffffu, e1, TZ), s2 = __shfl_down_sync(0xffffffffu, e2, (2 * TZ) & 31);
+          float v = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
+          float* xq = xg + q * (3 * TZ);
+          named_bar_sync(1 + grp, 128);  // the group's previous tile has been read by everyone
+          if (lane < TZ) xq[lane] = e1;
+          if (lane < 2 * TZ) xq[TZ + lane] = e2;
+          named_bar_sync(1 + grp, 128);
+          if (q < 3) {
+            const float* xn = xg + (q + 1) * (3 * TZ);
+            if (!has1) v += xn[lane + TZ - 32];
+            if (!has2) v += xn[TZ + lane + 2 * TZ - 32];
           }
+          if (ok) a.out_f32[o] = v + sk;
         }
       }
     }

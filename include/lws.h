@@ -140,6 +140,16 @@ LWS_API size_t lws_feature_extraction_workspace_bytes(int B, int H, int W);
 LWS_API int lws_feature_extraction_f32(const float* img, const float* packed_weights, float* f8, float* f4, float* f2,
                                        void* ws, size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
 
+/* ---- n2 (SURVEY.md 8(f) "next"): the steps either side of the model in the reference's inference loop ----------------
+ * lws_preprocess_bgr_u8  (inference.py:93-103): img [B,h,w,3] uint8 HWC BGR (cv2.imread) -> bottom-right crop th x tw, BGR->RGB,
+ *   ToTensor + Normalize -> out [B,3,th,tw] fp32.  lut [3][256] (device, RGB order) holds ((v/255) - mean[c]) / std[c] evaluated by
+ *   the host in fp32 exactly as the reference does, so the output is bit-identical to the CPU preprocessing.
+ * lws_disparity_to_u8    (inference.py:114-115): gray[i] = (uint8)disp[i] (numpy astype: truncate, wrap modulo 256) and/or
+ *   bgr[i] = COLORMAP_JET[gray[i]] (cv2.applyColorMap; convertScaleAbs(alpha=1, beta=0) is the identity on uint8). */
+LWS_API int lws_preprocess_bgr_u8(const uint8_t* img, const float* lut, float* out, int B, int h, int w, int th, int tw,
+                                  lws_stream_t stream);
+LWS_API int lws_disparity_to_u8(const float* disp, uint8_t* gray_or_null, uint8_t* bgr_or_null, long long n, lws_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LWS_B200_LIB", os.path.join(_HERE, "lib", "liblws_b200.so"))
@@ -41,6 +41,8 @@ SIGNATURES = {
     "lws_refinement_clp_floats": (c_size_t, [c_int, c_int, c_int]),
     "lws_refinement_block_clp_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_refinement_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "lws_preprocess_bgr_u8": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "lws_disparity_to_u8": (c_int, [_fp, _fp, _fp, c_longlong, c_void_p]),
     "lws_feature_extraction_packed_floats": (c_size_t, []),
     "lws_pack_feature_extraction_weights": (c_int, [_pp, c_int, c_float, _fp]),
     "lws_feature_extraction_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

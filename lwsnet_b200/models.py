@@ -34,6 +34,20 @@ class LWSNet(nn.Module):
         self._ref_key = None
         self.eval()  # inference only: BatchNorm always uses its running statistics
 
+    # -- Paddle Layer API used by the reference's scripts (inference.py:45, train.py:84-85) ------------------------
+    def set_state_dict(self, state_dict, use_structured_name=True):
+        """``model.set_state_dict(paddle.load(path))``: accepts {key: ndarray | tensor | (name, ndarray)} with the Paddle key
+        grammar; unlike Paddle, a key or shape mismatch raises instead of warning."""
+        from .checkpoint import convert_state
+        return self.load_state_dict(convert_state(state_dict, self.state_dict()), strict=True)
+
+    set_dict = set_state_dict  # Paddle 2.0 alias
+
+    def load_pdparams(self, path):
+        """Restore a reference ``.pdparams`` checkpoint (restricted unpickler, no Paddle needed)."""
+        from .checkpoint import load_pdparams
+        return self.set_state_dict(load_pdparams(path))
+
     # -- reference models/models.py:28-55 ------------------------------------------------------------------------
     def warp(self, x, disp):
         """x [B,C,H,W] (right features), disp [B,1,H,W] -> x sampled at (x - disp, y), bilinear, zero padding."""

@@ -304,3 +304,63 @@ def feature_extraction(img: torch.Tensor, packed: torch.Tensor):
                                              _stream(img)), "lws_feature_extraction_f32")
     LAUNCHES[0] += 12
     return [f8, f4, f2]
+
+
+# ------------------------------------------------------------------------------------------------ n2 pre / post
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # reference dataloader/dataloader.py:10-11, used by inference.py:80-82
+IMAGENET_STD = (0.229, 0.224, 0.225)
+_luts: dict = {}
+
+
+def normalize_lut(device: torch.device) -> torch.Tensor:
+    """[3,256] fp32 table (RGB order) of Normalize(ToTensor(v)) = ((v / 255) - mean[c]) / std[c], evaluated in fp32 with the
+    reference's own operation order (inference.py:80-82,102-103), so the device preprocessing is bit-identical to the host's."""
+    key = device.index
+    t = _luts.get(key)
+    if t is None:
+        v = torch.arange(256, dtype=torch.float32) / 255.0
+        mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1)
+        std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1)
+        t = ((v.view(1, 256) - mean) / std).contiguous().to(device)
+        _luts[key] = t
+    return t
+
+
+def preprocess_bgr_u8(img: torch.Tensor, th: int = 368, tw: int = 1232, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """inference.py:93-103 on the device: img [B,h,w,3] uint8 HWC BGR (cv2.imread layout) -> bottom-right th x tw crop,
+    BGR->RGB, ToTensor, Normalize -> [B,3,th,tw] fp32.  Raises ValueError when the image is smaller than the crop (the
+    reference skips such images, inference.py:96-97)."""
+    if img.dim() != 4 or img.shape[-1] != 3:
+        raise ValueError(f"img must be [B,h,w,3] uint8 HWC, got {tuple(img.shape)}")
+    B, h, w, _ = img.shape
+    if h < th or w < tw:
+        raise ValueError(f"image {h}x{w} is smaller than the crop {th}x{tw}")
+    res = out if out is not None else torch.empty((B, 3, th, tw), dtype=torch.float32, device=img.device)
+    if tuple(res.shape) != (B, 3, th, tw):
+        raise ValueError("out must be [B,3,th,tw]")
+    if B == 0:
+        return res
+    with torch.cuda.device(img.device):
+        check(lib.lws_preprocess_bgr_u8(_ptr(img, "img", torch.uint8), _ptr(normalize_lut(img.device), "lut"), _ptr(res, "out"),
+                                        B, h, w, th, tw, _stream(img)), "lws_preprocess_bgr_u8")
+    LAUNCHES[0] += 1
+    return res
+
+
+def disparity_to_u8(disp: torch.Tensor, gray: bool = True, color: bool = True, out_gray: Optional[torch.Tensor] = None,
+                    out_color: Optional[torch.Tensor] = None):
+    """inference.py:114-115 on the device: gray = disp.astype(uint8) (truncate, wrap modulo 256), color = cv2.applyColorMap(
+    convertScaleAbs(gray, alpha=1, beta=0), COLORMAP_JET) as [..., 3] BGR.  Returns (gray or None, color or None)."""
+    disp = _f32c(disp)
+    if not (gray or color):
+        raise ValueError("ask for gray and/or color")
+    g = (out_gray if out_gray is not None else torch.empty(disp.shape, dtype=torch.uint8, device=disp.device)) if gray else None
+    c = (out_color if out_color is not None else torch.empty(tuple(disp.shape) + (3,), dtype=torch.uint8, device=disp.device)) \
+        if color else None
+    if disp.numel() == 0:
+        return g, c
+    with torch.cuda.device(disp.device):
+        check(lib.lws_disparity_to_u8(_ptr(disp, "disp"), _ptr(g, "gray", torch.uint8), _ptr(c, "color", torch.uint8),
+                                      disp.numel(), _stream(disp)), "lws_disparity_to_u8")
+    LAUNCHES[0] += 1
+    return g, c

@@ -150,3 +150,79 @@ class StereoEngine:
         cur.wait_stream(self._d2h)
         cur.wait_stream(self._h2d)
         return out
+
+    # ------------------------------------------------------------------------------------------ host-resident, uint8 I/O
+    @torch.no_grad()
+    def infer_host_u8(self, left: torch.Tensor, right: torch.Tensor, th: int = 368, tw: int = 1232,
+                      out_gray: Optional[torch.Tensor] = None, out_color: Optional[torch.Tensor] = None,
+                      color: bool = False):
+        """The reference's whole inference loop body (inference.py:90-115) with only uint8 crossing PCIe.
+
+        left/right: CPU uint8 [B,h,w,3] HWC BGR images as cv2.imread returns them (pinned for async copies).  Crop, BGR->RGB,
+        ToTensor and Normalize run on the device (ops.preprocess_bgr_u8), the four stage disparities are cast to uint8 on the
+        device (ops.disparity_to_u8) and, when ``color``, JET colour-mapped.  Returns (gray [B,4,th,tw] uint8 CPU,
+        color [B,4,th,tw,3] uint8 CPU or None).  H2D / compute / D2H of neighbouring micro-batches overlap as in infer_host.
+        """
+        B, h, w, _ = left.shape
+        dev = self.device
+        if out_gray is None:
+            out_gray = torch.empty((B, 4, th, tw), dtype=torch.uint8, pin_memory=True)
+        if color and out_color is None:
+            out_color = torch.empty((B, 4, th, tw, 3), dtype=torch.uint8, pin_memory=True)
+        cur = torch.cuda.current_stream(dev)
+        chunks = micro_batches(B, self.mb)
+        slots = []
+        for slot in range(2):
+            key = ("u8", h, w, th, tw, color, slot)
+            io = self._graphs.get(key)
+            if io is None:
+                io = (torch.empty((self.mb, h, w, 3), dtype=torch.uint8, device=dev),
+                      torch.empty((self.mb, h, w, 3), dtype=torch.uint8, device=dev),
+                      torch.empty((self.mb, 4, th, tw), dtype=torch.uint8, device=dev),
+                      torch.empty((self.mb, 4, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
+                self._graphs[key] = io
+            if self.use_graphs:
+                fwd = self._graph_for(self.mb, th, tw, slot)
+            else:
+                fwd = (None, torch.empty((self.mb, 3, th, tw), device=dev), torch.empty((self.mb, 3, th, tw), device=dev),
+                       torch.empty((self.mb, 4, th, tw), device=dev))
+            slots.append((io, fwd))
+        in_ready = [torch.cuda.Event() for _ in chunks]
+        done = [torch.cuda.Event() for _ in chunks]
+        out_free = [None, None]
+        in_free = [None, None]
+        self._h2d.wait_stream(cur)
+        self._d2h.wait_stream(cur)
+        for i, (lo, hi) in enumerate(chunks):
+            slot = i & 1
+            (ul, ur, ug, uc), (graph, gl, gr, go) = slots[slot]
+            n = hi - lo
+            with torch.cuda.stream(self._h2d):
+                if in_free[slot] is not None:
+                    self._h2d.wait_event(in_free[slot])
+                ul[:n].copy_(left[lo:hi], non_blocking=True)
+                ur[:n].copy_(right[lo:hi], non_blocking=True)
+                in_ready[i].record(self._h2d)
+            cur.wait_event(in_ready[i])
+            if out_free[slot] is not None:
+                cur.wait_event(out_free[slot])
+            ops.preprocess_bgr_u8(ul[:n], th, tw, out=gl[:n])
+            ops.preprocess_bgr_u8(ur[:n], th, tw, out=gr[:n])
+            if graph is not None and n == self.mb:
+                self._replay(graph)
+            else:
+                self._forward_into(gl[:n], gr[:n], go[:n])
+            ops.disparity_to_u8(go[:n], gray=True, color=color, out_gray=ug[:n], out_color=uc[:n] if color else None)
+            done[i].record(cur)
+            in_free[slot] = done[i]
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(done[i])
+                out_gray[lo:hi].copy_(ug[:n], non_blocking=True)
+                if color:
+                    out_color[lo:hi].copy_(uc[:n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._d2h)
+                out_free[slot] = ev
+        cur.wait_stream(self._d2h)
+        cur.wait_stream(self._h2d)
+        return out_gray, out_color

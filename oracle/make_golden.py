@@ -100,5 +100,13 @@ def main():
     print(f"wrote {sorted(os.listdir(OUT))} ({total / 1e6:.2f} MB) to {OUT}")
 
 
+def make_jet_lut():
+    """cv2.COLORMAP_JET as a 256 x 3 BGR table (inference.py:115 applyColorMap): the fixture the n2 output kernel is checked against."""
+    import cv2
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET).reshape(256, 3)
+    np.save(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "jet_lut_bgr.npy"), lut)
+
+
 if __name__ == "__main__":
     main()
+    make_jet_lut()

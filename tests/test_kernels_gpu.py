@@ -338,3 +338,33 @@ def test_cpu_tensors_are_refused():
     from lwsnet_b200._lib import LwsError
     with pytest.raises(LwsError):
         ops().cost_volume_l1(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8), 4)
+
+
+# ------------------------------------------------------------------------------------------------ n2 pre / post (bit-exact)
+@pytest.mark.parametrize("B,h,w,th,tw", [(2, 375, 1242, 368, 1232), (1, 20, 33, 16, 24), (3, 16, 24, 16, 24)])
+def test_preprocess_u8_bit_exact(B, h, w, th, tw):
+    """inference.py:93-103 (crop, BGR->RGB, ToTensor, Normalize): byte-identical to the CPU oracle."""
+    from oracle import lwsnet_torch as O
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (B, h, w, 3), dtype=np.uint8)
+    ref = torch.cat([O.preprocess_bgr_uint8(img[b], th, tw) for b in range(B)])
+    out = ops().preprocess_bgr_u8(cu(img), th, tw)
+    assert torch.equal(out.cpu(), ref)
+    with pytest.raises(ValueError):  # the reference skips images smaller than the crop (inference.py:96-97)
+        ops().preprocess_bgr_u8(cu(img), h + 1, tw)
+
+
+def test_disparity_to_u8_and_jet_bit_exact():
+    """inference.py:114-115: astype(uint8) + applyColorMap(JET), against numpy and the committed cv2 LUT fixture."""
+    import os
+    from util import GOLDEN
+    lut = np.load(os.path.join(GOLDEN, "jet_lut_bgr.npy"))
+    g = torch.Generator().manual_seed(11)
+    disp = torch.rand(2, 4, 37, 129, generator=g) * 300.0 - 20.0  # includes negatives and > 255 (wrap modulo 256)
+    disp[0, 0, 0, :6] = torch.tensor([0.0, 0.999, 1.0, 255.0, 255.999, 256.0])
+    gray, color = ops().disparity_to_u8(disp.cuda())
+    ref = disp.numpy().astype(np.int64).astype(np.uint8)  # C cast: truncate toward zero, then wrap
+    assert np.array_equal(gray.cpu().numpy(), ref)
+    assert np.array_equal(color.cpu().numpy(), lut[ref])
+    g2, c2 = ops().disparity_to_u8(disp.cuda(), gray=True, color=False)
+    assert c2 is None and np.array_equal(g2.cpu().numpy(), ref)

@@ -4,6 +4,9 @@ Free-running max error <= 1e-3 px is below the fp32 noise floor of the reference
 (SURVEY.md S4), so the end-to-end criterion is: error against the fp64 oracle <= 2x the fp32 oracle's own error
 against the fp64 oracle (+1e-4 absolute slack) on max / p99.9 / mean, per stage.
 """
+import os
+
+import numpy as np
 import pytest
 import torch
 
@@ -126,3 +129,25 @@ def test_cpu_input_raises(models):
     O, o32, o64, prod = models
     with pytest.raises(LwsError):
         prod(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128))
+
+
+def test_infer_host_u8_matches_fp32_path(models):
+    """n2: uint8 images in, uint8 disparities out == preprocess on the host + fp32 engine + astype(uint8) on the host."""
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200.runner import StereoEngine
+    _, o32, o64, m = models
+    rng = np.random.default_rng(5)
+    B, h, w, th, tw = 3, 70, 140, 64, 128
+    base = rng.integers(0, 256, (B, h, w + 8, 3), dtype=np.uint8)
+    left, right = np.ascontiguousarray(base[:, :, 8:]), np.ascontiguousarray(base[:, :, :-8])  # 8 px of true disparity
+    eng = StereoEngine(m, micro_batch=2)
+    gray, color = eng.infer_host_u8(torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory(), th, tw, color=True)
+    torch.cuda.synchronize()
+    lf = torch.cat([O.preprocess_bgr_uint8(left[b], th, tw) for b in range(B)])
+    rf = torch.cat([O.preprocess_bgr_uint8(right[b], th, tw) for b in range(B)])
+    ref = eng.infer_host(lf.pin_memory(), rf.pin_memory())
+    torch.cuda.synchronize()
+    ref_u8 = ref.numpy().astype(np.int64).astype(np.uint8)
+    assert np.array_equal(gray.numpy(), ref_u8)
+    lut = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jet_lut_bgr.npy"))
+    assert np.array_equal(color.numpy(), lut[ref_u8])

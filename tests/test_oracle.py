@@ -103,3 +103,19 @@ def test_preprocess_matches_reference_crop():
     assert tuple(t.shape) == (1, 3, 368, 1232)
     r = img[374, 1241, 2] / 255.0
     assert abs(t[0, 0, -1, -1].item() - (r - 0.485) / 0.229) < 1e-6
+
+
+def test_jet_fixture_matches_opencv_definition():
+    """tests/golden/jet_lut_bgr.npy (made by oracle/make_golden.py:make_jet_lut with cv2.applyColorMap, inference.py:115):
+    the known anchor colours of COLORMAP_JET, and agreement with cv2 itself when it is importable."""
+    import os
+    lut = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jet_lut_bgr.npy"))
+    assert lut.shape == (256, 3) and lut.dtype == np.uint8
+    assert tuple(lut[0]) == (128, 0, 0) and tuple(lut[255]) == (0, 0, 128)      # dark blue -> dark red (BGR)
+    assert tuple(lut[96]) == (255, 255, 0) or lut[96][1] == 255                    # cyan band
+    try:
+        import cv2
+    except ImportError:
+        return
+    ref = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET).reshape(256, 3)
+    assert np.array_equal(lut, ref)

@@ -119,29 +119,43 @@ def run_reference(args, rank, world):
 
 # --------------------------------------------------------------------------------------------- kernel probes
 def time_rotating(fn, nsets, iters=20, warm=5):
-    """Average device time (us) of fn(i % nsets) with CUDA events on the current stream; buffer sets rotate so inputs
-    are not L2 resident."""
+    """Average DEVICE time (us) of one fn(i) call.  One rotation fn(0..nsets-1) is captured into a CUDA graph and the graph is
+    replayed between two CUDA events on the launching stream, so the figure is the kernels' own back-to-back duration and not the
+    host's per-call overhead (ctypes + allocation, ~20 us, which would swamp the few-microsecond streaming kernels); the buffer
+    sets rotate so inputs are never L2 resident."""
     import torch
-    for i in range(warm):
-        fn(i % nsets)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(max(warm, 1)):
+            fn(i % nsets)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(nsets):
+            fn(i)
+    reps = max(2, -(-iters // nsets))
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i % nsets)
+    for _ in range(reps):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return 1e3 * e0.elapsed_time(e1) / iters
+    us = 1e3 * e0.elapsed_time(e1) / (reps * nsets)
+    del g
+    return us
 
 
-def kernel_probes(model, pk):
+def kernel_probes(model, pk, B=16):
     """Per-kernel achieved HBM GB/s (streaming kernels) / TFLOP/s (conv kernels), each timed alone on KITTI shapes at
-    batch 16 with >= 3 rotating buffer sets (> 126 MB in total, so nothing is L2 resident)."""
+    batch B with >= 3 rotating buffer sets (> 126 MB in total, so nothing is L2 resident)."""
     import torch
     from lwsnet_b200 import ops
     dev = torch.device("cuda")
     out = []
-    B = 16
 
     def sets(n, *shapes, scale=2.0):
         return [[torch.randn(s, device=dev) * scale for s in shapes] for _ in range(n)]
@@ -156,26 +170,29 @@ def kernel_probes(model, pk):
 
     # K1 stage-1 volume: (2*C + D) * h*w*4 bytes
     h, w, C, D = 46, 154, 16, 24
-    s = sets(12, (B, C, h, w), (B, C, h, w))
+
+    def nsets(bytes_per_set):  # enough rotating sets that a launch never finds its inputs in the 126 MB L2
+        return int(min(64, max(3, -(-300e6 // bytes_per_set))))
+
+    s = sets(nsets(B * (2 * C + D) * h * w * 4), (B, C, h, w), (B, C, h, w))
     us = time_rotating(lambda i: ops.cost_volume_l1(s[i][0], s[i][1], D), len(s))
-    add("K1 cost_volume_l1 [16,16,46,154] D=24", us, B * (2 * C + D) * h * w * 4)
+    add(f"K1 cost_volume_l1 [{B},16,46,154] D=24", us, B * (2 * C + D) * h * w * 4)
     # K2 stages 2 and 3
     for (h, w, C) in ((92, 308, 16), (184, 616, 8)):
-        s = sets(6, (B, C, h, w), (B, C, h, w))
+        s = sets(nsets(B * (2 * C + 10) * h * w * 4), (B, C, h, w), (B, C, h, w))
         d = [torch.rand((B, 1, h, w), device=dev) * 20 for _ in s]
         us = time_rotating(lambda i: ops.warp_residual_volume_l1(s[i][0], s[i][1], d[i], 5), len(s))
-        add(f"K2 warp_residual_volume_l1 [16,{C},{h},{w}] m=5", us, B * (2 * C + 1 + 9) * h * w * 4)
+        add(f"K2 warp_residual_volume_l1 [{B},{C},{h},{w}] m=5", us, B * (2 * C + 1 + 9) * h * w * 4)
     # K4
     for (D, h, w) in ((24, 46, 154), (9, 92, 308), (9, 184, 616)):
-        n = 12 if h < 100 else 4
-        s = sets(n, (B, D, h, w), scale=8.0)
+        s = sets(nsets(B * (D + 1) * h * w * 4), (B, D, h, w), scale=8.0)
         us = time_rotating(lambda i: ops.softmax_regression(s[i][0], 0.0), len(s))
-        add(f"K4 softmax_regression [16,{D},{h},{w}]", us, B * (D + 1) * h * w * 4)
+        add(f"K4 softmax_regression [{B},{D},{h},{w}]", us, B * (D + 1) * h * w * 4)
     # K5
-    s = sets(4, (B, 1, 184, 616), (B, 1, H_IMG, W_IMG))
+    s = sets(nsets(B * (184 * 616 + H_IMG * W_IMG) * 4), (B, 1, 184, 616), (B, 1, H_IMG, W_IMG))
     o = torch.empty((B, 1, H_IMG, W_IMG), device=dev)
     us = time_rotating(lambda i: ops.scale_upsample_add(s[i][0], s[i][1], H_IMG, W_IMG, out=o), len(s))
-    add("K5 scale_upsample_add [16,1,184,616]->[16,1,368,1232]", us, B * (184 * 616 + 2 * H_IMG * W_IMG) * 4)
+    add(f"K5 scale_upsample_add [{B},1,184,616]->[{B},1,368,1232]", us, B * (184 * 616 + 2 * H_IMG * W_IMG) * 4)
     # K3: the whole residual 3D stack per stage (first conv + 4 tensor-core layers + last conv = 6 launches)
     for (C, D, h, w, b) in ((32, 24, 46, 154, 4), (8, 9, 92, 308, 4), (8, 9, 184, 616, 4)):
         stack = model.volume_postprocess[{(32, 46): 0, (8, 92): 1, (8, 184): 2}[(C, h)]]
@@ -235,6 +252,10 @@ def run_ours(args, rank, world, local_rank):
     model.load_state_dict(oracle_model.state_dict(), strict=True)
     model = model.to(dev)
     engine = StereoEngine(model, micro_batch=args.micro_batch, device=dev, use_graphs=not args.no_graphs)
+    if args.probes_only:  # developer mode: the per-kernel probes alone
+        for rec in kernel_probes(model, pk, args.probe_batch):
+            print(json.dumps(rec))
+        return
 
     # synthetic batch: 8 distinct pairs tiled to 64 (content does not change the work); rank-dependent seed
     base_l, base_r = O.synthetic_pair(8, H_IMG, W_IMG, seed=1234 + 8 * rank)
@@ -289,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the kernels (rank 0, timed alone) ----------------------------------------------------------------
     kernels, roofline = [], None
     if not args.skip_probes:
-        kernels = kernel_probes(model, pk)
+        kernels = kernel_probes(model, pk, args.probe_batch)
         dom = next(k for k in kernels if k["kernel"].startswith("K6 dwsep block"))
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full (profiles/r01_ncu_*dwsep*)
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": pk["hbm"], "unit": "GB/s",
@@ -350,6 +371,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--skip-probes", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--probes-only", action="store_true")
+    ap.add_argument("--probe-batch", type=int, default=16, help="pairs per launch in the streaming-kernel probes")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

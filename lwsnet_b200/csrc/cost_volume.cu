@@ -39,13 +39,13 @@ __global__ void cost_volume_l1_generic_kernel(const float* __restrict__ L, const
 }
 
 template <int DT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128, 3)
     cost_volume_l1_tile_kernel(const float* __restrict__ L, const float* __restrict__ R, float* __restrict__ cost,
-                               int C, int H, int W, int D, int n_xtiles, int txq, int nr, int ck, int n_dtiles) {
+                               int C, int H, int W, int D, int n_xtiles, int txq, int nr, int ck, int n_dtiles, int vec2) {
   extern __shared__ __align__(16) float smem[];
   const int tx = txq * 4;
   const int pitchR = tx + DT;
-  const int stage_floats = ck * nr * (tx + pitchR);
+  const int stage_floats = ck * nr * (tx + pitchR);  // one stage when ck == C
   const int xtile = blockIdx.x % n_xtiles;
   const int rowgroup = blockIdx.x / n_xtiles;
   const int b = blockIdx.y / n_dtiles;
@@ -70,18 +70,19 @@ __global__ void __launch_bounds__(256, 1)
       const int ri = which ? item - nrows : item;
       const int cl = ri / rows_here, r = ri - cl * rows_here;
       const float* grow = (which ? Rb : Lb) + (long long)(c0 + cl) * cs + (long long)(y_begin + r) * W;
-      if (!which) {
-        float* srow = sL + (cl * nr + r) * tx;
-        for (int i = lane; i < tx; i += 32) {
-          int x = x_begin + i;
-          if (x < W) cp_async_4(srow + i, grow + x);
-          else srow[i] = 0.f;
+      // sR[i] = R[xs + i]; xs, x_begin and (with vec2) W and the row starts are even, so an element pair is wholly in or out
+      float* srow = which ? sR + (cl * nr + r) * pitchR : sL + (cl * nr + r) * tx;
+      const int xs = which ? x_begin - d0 - DT : x_begin;
+      const int n = which ? pitchR : tx;
+      if (vec2) {
+        for (int i = 2 * lane; i < n; i += 64) {
+          const int x = xs + i;
+          if (x >= 0 && x < W) cp_async_8(srow + i, grow + x);
+          else *reinterpret_cast<float2*>(srow + i) = make_float2(0.f, 0.f);
         }
       } else {
-        float* srow = sR + (cl * nr + r) * pitchR;
-        const int xs = x_begin - d0 - DT;  // sR[i] = R[xs + i]
-        for (int i = lane; i < pitchR; i += 32) {
-          int x = xs + i;
+        for (int i = lane; i < n; i += 32) {
+          const int x = xs + i;
           if (x >= 0 && x < W) cp_async_4(srow + i, grow + x);
           else srow[i] = 0.f;
         }
@@ -154,25 +155,47 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
-template <int DT>
-static int launch_tile(const float* L, const float* R, float* cost, int B, int C, int H, int W, int D,
-                       cudaStream_t st) {
+struct TileCfg {
+  int threads, txq, n_xtiles, nr, ck, n_dtiles;
+  size_t smem;
+  long long blocks;
+};
+
+// One block = nr row segments x DT disparities.  All C channels are staged in one shot when they fit (a single HBM round trip
+// per block; the stage-1 volume of a few pairs is latency-, not bandwidth-limited), otherwise 4-channel chunks double-buffered.
+static TileCfg tile_cfg(int B, int C, int H, int W, int D, int DT, int threads) {
+  TileCfg t;
   const int W4 = cdiv(W, 4);
-  const int txq = W4 < 256 ? W4 : 256;
-  const int n_xtiles = cdiv(W4, txq);
-  int nr = 256 / txq;
-  if (nr < 1) nr = 1;
-  if (nr > H) nr = H;
-  const int ck = (C % 4 == 0) ? 4 : (C % 2 == 0 ? 2 : 1);
-  const int n_dtiles = cdiv(D, DT);
-  const int tx = txq * 4;
-  const size_t smem = (size_t)2 * ck * nr * (tx + tx + DT) * sizeof(float);
-  if (smem > 200 * 1024) return LWS_ERR_UNSUPPORTED;
+  t.threads = threads;
+  t.txq = W4 < threads ? W4 : threads;
+  t.n_xtiles = cdiv(W4, t.txq);
+  t.nr = threads / t.txq;
+  t.nr = t.nr < 1 ? 1 : (t.nr > H ? H : t.nr);
+  t.n_dtiles = cdiv(D, DT);
+  const int tx = t.txq * 4;
+  const size_t one = (size_t)C * t.nr * (tx + tx + DT) * sizeof(float);
+  if (one <= 72 * 1024) {
+    t.ck = C, t.smem = one;
+  } else {
+    t.ck = (C % 4 == 0) ? 4 : (C % 2 == 0 ? 2 : 1);
+    t.smem = (size_t)2 * t.ck * t.nr * (tx + tx + DT) * sizeof(float);
+  }
+  t.blocks = (long long)t.n_xtiles * cdiv(H, t.nr) * B * t.n_dtiles;
+  return t;
+}
+
+template <int DT>
+static int launch_tile(const float* L, const float* R, float* cost, int B, int C, int H, int W, int D, const TileCfg& t,
+                       cudaStream_t st) {
+  if (t.smem > 200 * 1024) return LWS_ERR_UNSUPPORTED;
   auto kern = cost_volume_l1_tile_kernel<DT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  dim3 grid(n_xtiles * cdiv(H, nr), B * n_dtiles);
-  kern<<<grid, 256, smem, st>>>(L, R, cost, C, H, W, D, n_xtiles, txq, nr, ck, n_dtiles);
+  if (t.smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int vec2 = (W % 2 == 0) && ((((uintptr_t)L) | ((uintptr_t)R)) & 7) == 0;
+  dim3 grid(t.n_xtiles * cdiv(H, t.nr), B * t.n_dtiles);
+  kern<<<grid, t.threads, t.smem, st>>>(L, R, cost, C, H, W, D, t.n_xtiles, t.txq, t.nr, t.ck, t.n_dtiles, vec2);
   LWS_RETURN_LAUNCH_STATUS();
 }
 
@@ -190,11 +213,21 @@ extern "C" int lws_cost_volume_l1_f32(const float* L, const float* R, float* cos
   const int D = maxdisp / stride;
   const bool aligned = (((uintptr_t)cost) & 15) == 0;
   if (stride == 1 && aligned && B * (long long)cdiv(D, 8) < 65535) {
-    int rc;
-    if (D % 24 == 0) rc = launch_tile<24>(L, R, cost, B, C, H, W, D, st);
-    else if (D % 16 == 0) rc = launch_tile<16>(L, R, cost, B, C, H, W, D, st);
-    else if (D % 12 == 0) rc = launch_tile<12>(L, R, cost, B, C, H, W, D, st);
-    else rc = launch_tile<8>(L, R, cost, B, C, H, W, D, st);
+    // Widest disparity tile (fewest re-reads of the staged rows, from L2) that still puts >= 3 blocks on every SM; the
+    // stage-1 volume of a few pairs is only a few hundred row segments, so small batches trade tile width for blocks.
+    int rc = LWS_ERR_UNSUPPORTED;
+    const long long want = 3 * kNumSMs;
+    const int dts[4] = {24, 16, 12, 8};
+    int pick = 8, threads = 128;
+    bool found = false;
+    for (int i = 0; i < 4 && !found; ++i)
+      if ((D % dts[i] == 0 || dts[i] == 8) && tile_cfg(B, C, H, W, D, dts[i], 128).blocks >= want) pick = dts[i], found = true;
+    if (!found && tile_cfg(B, C, H, W, D, 8, 128).blocks < 2 * kNumSMs) threads = 64;
+    const TileCfg t = tile_cfg(B, C, H, W, D, pick, threads);
+    if (pick == 24) rc = launch_tile<24>(L, R, cost, B, C, H, W, D, t, st);
+    else if (pick == 16) rc = launch_tile<16>(L, R, cost, B, C, H, W, D, t, st);
+    else if (pick == 12) rc = launch_tile<12>(L, R, cost, B, C, H, W, D, t, st);
+    else rc = launch_tile<8>(L, R, cost, B, C, H, W, D, t, st);
     if (rc != LWS_ERR_UNSUPPORTED) return rc;
   }
   const long long total = (long long)B * D * H * W;

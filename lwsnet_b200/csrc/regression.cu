@@ -7,9 +7,11 @@
 
 namespace lws {
 
-// One thread owns VEC horizontally adjacent pixels and walks the D planes in chunks of 8 with a chunked online
-// softmax (one rescale per chunk, so ~1.125 exp per element instead of 2 for the classic online form).
-template <int VEC>
+// One thread owns VEC horizontally adjacent pixels and walks the D planes in chunks of CH with a chunked online
+// softmax (one rescale per chunk, so ~(1 + 1/CH) exp per element instead of 2 for the classic online form).  CH is matched to D
+// (9 planes of a residual volume = one chunk, 24 planes of the stage-1 volume = two chunks of 12): on B200 the 16/clk/SM
+// MUFU.EX2 rate is within 2x of what the HBM stream asks for, so masked-out lanes of a partial chunk are not free.
+template <int VEC, int CH>
 __global__ void __launch_bounds__(256)
     softmax_regression_kernel(const float* __restrict__ cost, float* __restrict__ low, int D, long long hw,
                               long long n_items_per_b, float start, float step) {
@@ -22,10 +24,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int v = 0; v < VEC; ++v) m[v] = -INFINITY, s[v] = 0.f, ws[v] = 0.f;
 
-  for (int d0 = 0; d0 < D; d0 += 8) {
-    float z[8][VEC];
+  for (int d0 = 0; d0 < D; d0 += CH) {
+    float z[CH][VEC];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < CH; ++j) {
       if (d0 + j < D) {
         if constexpr (VEC == 4) {
           float4 t = __ldcs(reinterpret_cast<const float4*>(p + (long long)(d0 + j) * hw));
@@ -43,12 +45,12 @@ __global__ void __launch_bounds__(256)
     for (int v = 0; v < VEC; ++v) {
       float cm = z[0][v];
 #pragma unroll
-      for (int j = 1; j < 8; ++j) cm = fmaxf(cm, z[j][v]);
+      for (int j = 1; j < CH; ++j) cm = fmaxf(cm, z[j][v]);
       const float nm = fmaxf(m[v], cm);
       const float r = exp2f((m[v] - nm) * kLog2e);  // exp2f(-inf) = 0 on the first chunk
       float cs = 0.f, cws = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CH; ++j) {
         const float e = exp2f((z[j][v] - nm) * kLog2e);
         cs += e;
         cws += e * (start + step * (float)(d0 + j));
@@ -137,11 +139,15 @@ extern "C" int lws_softmax_regression_f32(const float* cost, float* low, int B, 
   const bool vec = (hw % 4 == 0) && ((((uintptr_t)cost) | ((uintptr_t)low)) & 15) == 0;
   if (vec) {
     const long long n = hw / 4;
-    dim3 grid((unsigned)((n + 255) / 256), B);
-    softmax_regression_kernel<4><<<grid, 256, 0, st>>>(cost, low, D, hw, n, start, step);
+    // small volumes: narrower blocks so that every SM gets work
+    const int threads = ((n + 255) / 256) * B >= 2 * kNumSMs ? 256 : 64;
+    dim3 grid((unsigned)((n + threads - 1) / threads), B);
+    if (D % 9 == 0) softmax_regression_kernel<4, 9><<<grid, threads, 0, st>>>(cost, low, D, hw, n, start, step);
+    else if (D % 12 == 0) softmax_regression_kernel<4, 12><<<grid, threads, 0, st>>>(cost, low, D, hw, n, start, step);
+    else softmax_regression_kernel<4, 8><<<grid, threads, 0, st>>>(cost, low, D, hw, n, start, step);
   } else {
     dim3 grid((unsigned)((hw + 255) / 256), B);
-    softmax_regression_kernel<1><<<grid, 256, 0, st>>>(cost, low, D, hw, hw, start, step);
+    softmax_regression_kernel<1, 8><<<grid, 256, 0, st>>>(cost, low, D, hw, hw, start, step);
   }
   LWS_RETURN_LAUNCH_STATUS();
 }

@@ -136,6 +136,104 @@ __global__ void __launch_bounds__(128)
   for (int k = 0; k < K; ++k) o[k * hw] = acc[k];
 }
 
+// ---- a4, staged: one block per (pair, row) ----------------------------------------------------------------------
+// The per-pixel window loads of the kernel above are gathers whose start depends on the pixel's own disparity; straight from
+// global memory every warp-wide load touches up to 32 different 128-byte lines and the kernel is bound by L1 wavefronts, not by
+// HBM.  Here the block first stages the (vertically blended) right-feature row of all C channels into shared memory as C/4
+// planes of float4 = 4 channels of one pixel ([q][x][4], 2 zero pixels left / 3 right = the clamp range of make_tap), so a
+// thread's 10-pixel window of 4 channels is 10 consecutive float4: 10*C/4 LDS.128 per pixel instead of 10*C (or 20*C) scattered
+// LDG.32, and neighbouring pixels with neighbouring disparities read neighbouring 16-byte words (no bank conflicts; chaotic
+// disparities cost ~2.4x in conflicts).  Global traffic is the algorithmic minimum: L, R (each row read once, twice for the rows
+// whose fp32 coordinate round trip lands on y - eps) and disp read once, the volume written once.
+// |l - (a*w0 + b*w1)| is evaluated as |fma(-b, w1, fma(-a, w0, l))|: 3 instructions per (shift, channel), 2 roundings.
+template <int C, int K>
+__global__ void __launch_bounds__(256)
+    warp_residual_volume_row_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ disp,
+                                    float* __restrict__ cost, int H, int W, int m, float fstride, WarpAxis ax, WarpAxis ay) {
+  extern __shared__ __align__(16) float4 s_row[];  // [C/4][W + 5], pixel -2 first
+  constexpr int PADL = 2, PADR = 3, Q = C / 4;
+  const int pitch = W + PADL + PADR;
+  const int py = blockIdx.x;
+  const int b = blockIdx.y;
+  const long long hw = (long long)H * W;
+  const Tap ty = make_tap(warp_coord_nodisp((float)py, ay), H);
+  const bool r0 = ty.i0 >= 0 && ty.i0 < H && ty.w0 != 0.f;
+  const bool r1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < H && ty.w1 != 0.f;
+  const float* Rb = R + (long long)b * C * hw + (long long)ty.i0 * W;
+
+  for (int i = threadIdx.x; i < (PADL + PADR) * Q; i += blockDim.x) {
+    const int q = i / (PADL + PADR), j = i - q * (PADL + PADR);
+    s_row[q * pitch + (j < PADL ? j : W + j)] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int p = threadIdx.x; p < W; p += blockDim.x) {
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = r0 ? ty.w0 * __ldg(Rb + c * hw + p) : 0.f;
+    if (r1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] += ty.w1 * __ldg(Rb + c * hw + W + p);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) s_row[q * pitch + p + PADL] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  __syncthreads();
+
+  for (int px = threadIdx.x; px < W; px += blockDim.x) {
+    const long long pix = (long long)py * W + px;
+    const float d = __ldg(disp + (long long)b * hw + pix);
+    const float* Lp = L + (long long)b * C * hw + pix;
+    float l[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) l[c] = __ldg(Lp + c * hw);
+
+    int xi[K];
+    float wx0[K], wx1[K];
+    bool run = true;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float shift = __fmul_rn((float)(k - (m - 1)), fstride);  // batch_shift * stride (models.py:90-92)
+      const Tap t = make_tap(warp_coord((float)px, __fsub_rn(d, shift), ax), W);
+      xi[k] = t.i0, wx0[k] = -t.w0, wx1[k] = -t.w1;
+      run = run && (t.i0 == xi[0] + k);
+    }
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    if (run) {
+      const float4* win0 = s_row + xi[0] + PADL;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        float4 win[K + 1];
+#pragma unroll
+        for (int j = 0; j <= K; ++j) win[j] = win0[q * pitch + j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          acc[k] += fabsf(fmaf(win[k + 1].x, wx1[k], fmaf(win[k].x, wx0[k], l[4 * q + 0])));
+          acc[k] += fabsf(fmaf(win[k + 1].y, wx1[k], fmaf(win[k].y, wx0[k], l[4 * q + 1])));
+          acc[k] += fabsf(fmaf(win[k + 1].z, wx1[k], fmaf(win[k].z, wx0[k], l[4 * q + 2])));
+          acc[k] += fabsf(fmaf(win[k + 1].w, wx1[k], fmaf(win[k].w, wx0[k], l[4 * q + 3])));
+        }
+      }
+    } else {  // taps within 1 ulp of an integer coordinate: per-shift gather keeps the indices bit-exact
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float4 a = s_row[q * pitch + xi[k] + PADL];
+          const float4 bb = s_row[q * pitch + xi[k] + 1 + PADL];
+          acc[k] += fabsf(fmaf(bb.x, wx1[k], fmaf(a.x, wx0[k], l[4 * q + 0])));
+          acc[k] += fabsf(fmaf(bb.y, wx1[k], fmaf(a.y, wx0[k], l[4 * q + 1])));
+          acc[k] += fabsf(fmaf(bb.z, wx1[k], fmaf(a.z, wx0[k], l[4 * q + 2])));
+          acc[k] += fabsf(fmaf(bb.w, wx1[k], fmaf(a.w, wx0[k], l[4 * q + 3])));
+        }
+      }
+    }
+    float* o = cost + (long long)b * K * hw + pix;
+#pragma unroll
+    for (int k = 0; k < K; ++k) __stcs(o + k * hw, acc[k]);
+  }
+}
+
 // any m: one thread per (pixel, shift)
 __global__ void __launch_bounds__(256)
     warp_residual_volume_generic_kernel(const float* __restrict__ L, const float* __restrict__ R,
@@ -207,7 +305,22 @@ extern "C" int lws_warp_residual_volume_l1_f32(const float* L, const float* R, c
   if ((long long)B * (2 * m - 1) > 65535) return LWS_ERR_BAD_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   const WarpAxis ax = make_warp_axis(W), ay = make_warp_axis(H);
-  if (m == 5) {
+  const size_t row_smem = (size_t)(W + 5) * C * sizeof(float);
+  if (m == 5 && (C == 8 || C == 16) && row_smem <= 96 * 1024 && B <= 65535) {
+    // threads: the row in as few equal passes as possible (W = 616 -> 3 x 224, W = 308 -> 2 x 160)
+    const int passes = cdiv(W, 256);
+    const int threads = round_up(cdiv(W, passes), 32);
+    dim3 grid(H, B);
+    if (C == 8) {
+      if (row_smem > 48 * 1024)
+        cudaFuncSetAttribute(warp_residual_volume_row_kernel<8, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      warp_residual_volume_row_kernel<8, 9><<<grid, threads, row_smem, st>>>(L, R, disp, cost, H, W, m, (float)stride, ax, ay);
+    } else {
+      if (row_smem > 48 * 1024)
+        cudaFuncSetAttribute(warp_residual_volume_row_kernel<16, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      warp_residual_volume_row_kernel<16, 9><<<grid, threads, row_smem, st>>>(L, R, disp, cost, H, W, m, (float)stride, ax, ay);
+    }
+  } else if (m == 5) {
     dim3 grid(cdiv(W, 128), H, B);
     warp_residual_volume_kernel<9><<<grid, 128, 0, st>>>(L, R, disp, cost, C, H, W, m, (float)stride, ax, ay);
   } else {

@@ -153,3 +153,12 @@ def test_pack_feature_extraction_folds_bn():
     assert np.all(packed[-8:] == 0)
     assert lib.lws_feature_extraction_workspace_bytes(1, 368, 1232) > 0
     assert lib.lws_feature_extraction_workspace_bytes(1, 370, 1232) == 0  # H, W must be multiples of 8
+
+
+def test_jet_table_in_kernel_source_equals_cv2_fixture():
+    """The __constant__ COLORMAP_JET table compiled into prepost.cu is the committed cv2 fixture, entry for entry."""
+    src = open(os.path.join(ROOT, "lwsnet_b200", "csrc", "prepost.cu")).read()
+    body = src[src.index("kJetBgr[256][3] = {"):]
+    body = body[:body.index("};")]
+    table = np.array([[int(v) for v in m] for m in re.findall(r"\{(\d+),(\d+),(\d+)\}", body)], np.uint8)
+    assert np.array_equal(table, np.load(os.path.join(ROOT, "tests", "golden", "jet_lut_bgr.npy")))

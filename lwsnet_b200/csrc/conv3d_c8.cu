@@ -334,64 +334,92 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
 }
 
 // ---- first conv 1 -> 8 on the raw cost (BN_0 affine + ReLU on the taps), writes every voxel of the padded hi/lo planes ----
-__global__ void __launch_bounds__(256)
+// One thread = 4 voxels that are neighbours in y (same padded x): the 27-tap window of the four voxels is 6 rows x 3 x 3, so the
+// cost loads (coalesced along x) and the broadcast weight loads from shared memory are shared 4 ways (54 + 54 per 864 FFMAs) and the
+// 16-byte voxel stores of a warp are contiguous.  Grid = (pair x padded plane, 4-row group, 128-voxel x segment): no index division.
+__global__ void __launch_bounds__(128, 5)
     conv3d_first_c8_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][8]*/, const float* __restrict__ bias,
                            const float* __restrict__ affine, uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, int D, int H,
-                           int W, long long total_vox) {
+                           int W) {
   __shared__ __align__(16) float sW[27 * 8];
   for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sW[i] = __ldg(w + i);
   __syncthreads();
-  const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
   const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+  const int xp = blockIdx.z * 128 + threadIdx.x;
+  if (xp >= Wp) return;
+  const int b = blockIdx.x / Dp, dp = blockIdx.x - b * Dp;
+  const int yp0 = blockIdx.y * 4;
+  const int x = xp - 1, d = dp - 1;
   const long long hw = (long long)H * W;
-  float bv[8];
+  const long long vox0 = (((long long)b * Dp + dp) * Hp + yp0) * Wp + xp;
+  const bool zero_all = d < 0 || d >= D || x < 0 || x >= W;
+  float acc[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + j);
-  for (long long vox = (long long)blockIdx.x * blockDim.x + threadIdx.x; vox < total_vox; vox += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(vox % Wp) - 1;
-    long long t = vox / Wp;
-    const int y = (int)(t % Hp) - 1;
-    t /= Hp;
-    const int d = (int)(t % Dp) - 1;
-    const int b = (int)(t / Dp);
-    float acc[8];
+  for (int v = 0; v < 4; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const bool border = x < 0 || x >= W || y < 0 || y >= H || d < 0 || d >= D;
-    if (!border) {
-      const float* cb = cost + ((long long)b * D + d) * hw + (long long)y * W + x;
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  if (!zero_all) {
+    const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+    const float* cb = cost + (long long)b * D * hw;  // 32-bit offsets inside one pair's volume (host checks D*H*W < 2^31)
+    const int ihw = H * W;
+    int offr[6];
+    bool okr[6];
 #pragma unroll
-      for (int kd = 0; kd < 3; ++kd) {
-        const bool okd = (unsigned)(d + kd - 1) < (unsigned)D;
+    for (int r = 0; r < 6; ++r) {
+      const int yy = yp0 + r - 2;  // input row of (voxel vy, tap kh) with vy + kh = r
+      okr[r] = (unsigned)yy < (unsigned)H;
+      offr[r] = d * ihw + yy * W + x;
+    }
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const bool okd = (unsigned)(d + kd - 1) < (unsigned)D;  // block-uniform
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const bool okx = okd && (unsigned)(x + kw - 1) < (unsigned)W;
+        const int tap = (kd - 1) * ihw + (kw - 1);
+        float v[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const bool ok = okx && okr[r];
+          const float c = ok ? __ldg(cb + (offr[r] + tap)) : 0.f;
+          v[r] = ok ? fmaxf(fmaf(c, s0, t0), 0.f) : 0.f;
+        }
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          const bool okh = okd && (unsigned)(y + kh - 1) < (unsigned)H;
+          const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8 + 4);
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const bool ok = okh && (unsigned)(x + kw - 1) < (unsigned)W;
-            float v = ok ? __ldg(cb + (kd - 1) * hw + (kh - 1) * W + (kw - 1)) : 0.f;
-            v = ok ? fmaxf(fmaf(v, s0, t0), 0.f) : 0.f;
-            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8 + 4);
-            acc[0] = fmaf(v, wa.x, acc[0]), acc[1] = fmaf(v, wa.y, acc[1]), acc[2] = fmaf(v, wa.z, acc[2]),
-            acc[3] = fmaf(v, wa.w, acc[3]), acc[4] = fmaf(v, wb.x, acc[4]), acc[5] = fmaf(v, wb.y, acc[5]),
-            acc[6] = fmaf(v, wb.z, acc[6]), acc[7] = fmaf(v, wb.w, acc[7]);
+          for (int vy = 0; vy < 4; ++vy) {
+            const float t = v[vy + kh];
+            acc[vy][0] = fmaf(t, wa.x, acc[vy][0]), acc[vy][1] = fmaf(t, wa.y, acc[vy][1]);
+            acc[vy][2] = fmaf(t, wa.z, acc[vy][2]), acc[vy][3] = fmaf(t, wa.w, acc[vy][3]);
+            acc[vy][4] = fmaf(t, wb.x, acc[vy][4]), acc[vy][5] = fmaf(t, wb.y, acc[vy][5]);
+            acc[vy][6] = fmaf(t, wb.z, acc[vy][6]), acc[vy][7] = fmaf(t, wb.w, acc[vy][7]);
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + bv[j], 0.f) * kDwsepActScale;
     }
+  }
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + j);
+#pragma unroll
+  for (int vy = 0; vy < 4; ++vy) {
+    const int yp = yp0 + vy;
+    if (yp >= Hp) break;
+    const bool border = zero_all || yp == 0 || yp == Hp - 1;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const __half2 h = __floats2half2_rn(acc[2 * p], acc[2 * p + 1]);
+      const float a0 = border ? 0.f : fmaxf(acc[vy][2 * p] + bv[2 * p], 0.f) * kDwsepActScale;
+      const float a1 = border ? 0.f : fmaxf(acc[vy][2 * p + 1] + bv[2 * p + 1], 0.f) * kDwsepActScale;
+      const __half2 h = __floats2half2_rn(a0, a1);
       const float2 f = __half22float2(h);
-      const __half2 l = __floats2half2_rn((acc[2 * p] - f.x) * 2048.f, (acc[2 * p + 1] - f.y) * 2048.f);
+      const __half2 l = __floats2half2_rn((a0 - f.x) * 2048.f, (a1 - f.y) * 2048.f);
       hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    out_hi[vox] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    out_lo[vox] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    out_hi[vox0 + (long long)vy * Wp] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out_lo[vox0 + (long long)vy * Wp] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -409,7 +437,7 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
                     int W, int add_skip, cudaStream_t st) {
   const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
   const long long vox_b = (long long)Dp * Hp * Wp;
-  if (vox_b * B >= (1ll << 31) - (1 << 20)) return LWS_ERR_BAD_SHAPE;
+  if (vox_b * B >= (1ll << 31) - (1 << 20) || (long long)D * H * W >= (1ll << 31)) return LWS_ERR_BAD_SHAPE;
   const long long pb = (c8_plane_bytes(B, D, H, W) + 255) / 256 * 256;
   const long long slack = ((long long)Hp * Wp + Wp + 256) * 16;
   uint8_t* base = (uint8_t*)ws;
@@ -427,9 +455,9 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     if ((e = cudaMemset2DAsync(plane[i] + (size_t)(Dp - 1) * pl, vox_b * 16, 0, pl, B, st)) != cudaSuccess) return (int)e;
   }
   {
-    const long long nvox = (long long)B * vox_b;
-    const int blocks = (int)((nvox + 255) / 256 < 148 * 16 ? (nvox + 255) / 256 : 148 * 16);
-    conv3d_first_c8_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W, nvox);
+    if ((Hp + 3) / 4 > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
+    dim3 grid(B * Dp, (Hp + 3) / 4, (Wp + 127) / 128);
+    conv3d_first_c8_kernel<<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   e = cudaFuncSetAttribute(conv3d_c8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);

@@ -519,69 +519,95 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
 }
 
 // ---- 3D stack, C = 32: rows ordered (y, x, d) with x and d padded by one zero voxel each side -------------------------------
-// first conv 1 -> 32 on the raw cost (BN_0 affine + ReLU applied to the taps), output rows split-fp16 (scaled by sa);
-// 4 lanes per voxel, 8 output channels per lane; threads run over (b, y, d, x) with x fastest so the cost reads coalesce.
+// first conv 1 -> 32 on the raw cost (BN_0 affine + ReLU applied to the taps), output rows split-fp16 (scaled by sa).
+// 4 lanes per voxel group (8 output channels each); a group owns 4 voxels that are neighbours in d (consecutive output rows), so
+// its 27-tap window is 6 planes x 3 x 3: cost loads and weight loads are shared 4 ways (54 + 54 per 864 FFMAs per lane).  Groups
+// run over (d-group, x) with x fastest so the cost reads of a warp coalesce; grid = (group chunk, y, pair).
 __global__ void __launch_bounds__(256)
     conv3d_first_ydx_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][32]*/, const float* __restrict__ bias,
-                            const float* __restrict__ affine, uint4* __restrict__ out, int D, int H, int W, long long total_vox) {
+                            const float* __restrict__ affine, uint4* __restrict__ out, int D, int H, int W, FastDiv fWp) {
   __shared__ __align__(16) float sW[27 * 32];
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sW[i] = __ldg(w + i);
   __syncthreads();
-  const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
   const int sub = threadIdx.x & 3;
   const int Wp = W + 2, Dp = D + 2;
+  const int ngd = (Dp + 3) >> 2;
+  const int gid = blockIdx.x * 64 + (threadIdx.x >> 2);
+  if (gid >= Wp * ngd) return;
+  int dpg, xp;
+  fdivmod(gid, fWp, dpg, xp);
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = xp - 1, dp0 = dpg * 4;
   const long long hw = (long long)H * W;
-  float bv[8];
+  float acc[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
-  for (long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; vox < total_vox;
-       vox += ((long long)gridDim.x * blockDim.x) >> 2) {
-    const int xp = (int)(vox % Wp);
-    long long t = vox / Wp;
-    const int dp = (int)(t % Dp);
-    t /= Dp;
-    const int y = (int)(t % H);
-    const int b = (int)(t / H);
-    const int x = xp - 1, d = dp - 1;
-    float acc[8];
+  for (int v = 0; v < 4; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const bool border = x < 0 || x >= W || d < 0 || d >= D;
-    if (!border) {
-      const float* cb = cost + ((long long)b * D + d) * hw + (long long)y * W + x;
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  const bool xborder = x < 0 || x >= W;
+  if (!xborder) {
+    const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+    const float* cb = cost + (long long)b * D * hw;  // 32-bit offsets inside one pair's volume (host checks D*H*W < 2^31)
+    const int ihw = H * W;
+    const float* pr[6];
+    bool okr[6];
 #pragma unroll
-      for (int kd = 0; kd < 3; ++kd) {
-        const bool okd = (unsigned)(d + kd - 1) < (unsigned)D;
+    for (int r = 0; r < 6; ++r) {
+      const int dd = dp0 + r - 2;  // input plane of (voxel vd, tap kd) with vd + kd = r  (d = dp - 1)
+      okr[r] = (unsigned)dd < (unsigned)D;
+      pr[r] = cb + (dd * ihw + y * W + x);
+    }
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const bool okh = okd && (unsigned)(y + kh - 1) < (unsigned)H;
+    for (int kh = 0; kh < 3; ++kh) {
+      const bool oky = (unsigned)(y + kh - 1) < (unsigned)H;  // block-uniform
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const bool ok = okh && (unsigned)(x + kw - 1) < (unsigned)W;
-            float v = ok ? __ldg(cb + (kd - 1) * hw + (kh - 1) * W + (kw - 1)) : 0.f;
-            v = ok ? fmaxf(fmaf(v, s0, t0), 0.f) : 0.f;
-            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8 + 4);
-            acc[0] = fmaf(v, wa.x, acc[0]), acc[1] = fmaf(v, wa.y, acc[1]), acc[2] = fmaf(v, wa.z, acc[2]),
-            acc[3] = fmaf(v, wa.w, acc[3]), acc[4] = fmaf(v, wb.x, acc[4]), acc[5] = fmaf(v, wb.y, acc[5]),
-            acc[6] = fmaf(v, wb.z, acc[6]), acc[7] = fmaf(v, wb.w, acc[7]);
+      for (int kw = 0; kw < 3; ++kw) {
+        const bool okx = oky && (unsigned)(x + kw - 1) < (unsigned)W;
+        const int tap = (kh - 1) * W + (kw - 1);
+        float v[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const bool ok = okx && okr[r];
+          const float c = ok ? __ldg(pr[r] + tap) : 0.f;
+          v[r] = ok ? fmaxf(fmaf(c, s0, t0), 0.f) : 0.f;
+        }
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8 + 4);
+#pragma unroll
+          for (int vd = 0; vd < 4; ++vd) {
+            const float t = v[vd + kd];
+            acc[vd][0] = fmaf(t, wa.x, acc[vd][0]), acc[vd][1] = fmaf(t, wa.y, acc[vd][1]);
+            acc[vd][2] = fmaf(t, wa.z, acc[vd][2]), acc[vd][3] = fmaf(t, wa.w, acc[vd][3]);
+            acc[vd][4] = fmaf(t, wb.x, acc[vd][4]), acc[vd][5] = fmaf(t, wb.y, acc[vd][5]);
+            acc[vd][6] = fmaf(t, wb.z, acc[vd][6]), acc[vd][7] = fmaf(t, wb.w, acc[vd][7]);
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + bv[j], 0.f) * kDwsepActScale;
     }
+  }
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
+  const long long row0 = (((long long)b * H + y) * Wp + xp) * Dp + dp0;
+#pragma unroll
+  for (int vd = 0; vd < 4; ++vd) {
+    const int dp = dp0 + vd;
+    if (dp >= Dp) break;
+    const bool border = xborder || dp == 0 || dp == Dp - 1;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const __half2 h = __floats2half2_rn(acc[2 * p], acc[2 * p + 1]);
+      const float a0 = border ? 0.f : fmaxf(acc[vd][2 * p] + bv[2 * p], 0.f) * kDwsepActScale;
+      const float a1 = border ? 0.f : fmaxf(acc[vd][2 * p + 1] + bv[2 * p + 1], 0.f) * kDwsepActScale;
+      const __half2 h = __floats2half2_rn(a0, a1);
       const float2 f = __half22float2(h);
-      const __half2 l = __floats2half2_rn((acc[2 * p] - f.x) * 2048.f, (acc[2 * p + 1] - f.y) * 2048.f);
+      const __half2 l = __floats2half2_rn((a0 - f.x) * 2048.f, (a1 - f.y) * 2048.f);
       hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    const long long row = (((long long)b * H + y) * Wp + xp) * Dp + dp;
-    out[row * 8 + sub] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    out[row * 8 + 4 + sub] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    out[(row0 + vd) * 8 + sub] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out[(row0 + vd) * 8 + 4 + sub] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -597,16 +623,17 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
                      int W, int add_skip, cudaStream_t st) {
   const int Wp = W + 2, Dp = D + 2;
   const long long R = (long long)H * Wp * Dp;
-  if (R >= (1ll << 31) - 65536 || 128 + 2 * Dp > 256) return LWS_ERR_UNSUPPORTED;
+  if (R >= (1ll << 31) - 65536 || 128 + 2 * Dp > 256 || (long long)D * H * W >= (1ll << 31)) return LWS_ERR_UNSUPPORTED;
   const size_t half_ws = conv3d_f16_workspace_bytes(B, D, H, W) / 2;
   float* bufA = (float*)ws;
   float* bufB = (float*)((char*)ws + half_ws);
   const long long nrows = (long long)B * R;
   cudaError_t e;
   {
-    const long long thr = nrows * 4;
-    const int blocks = (int)((thr + 255) / 256 < 148 * 16 ? (thr + 255) / 256 : 148 * 16);
-    conv3d_first_ydx_kernel<<<blocks, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W, nrows);
+    if (H > 65535 || B > 65535) return LWS_ERR_BAD_SHAPE;
+    const int groups = Wp * ((Dp + 3) / 4);
+    dim3 grid((groups + 63) / 64, H, B);
+    conv3d_first_ydx_kernel<<<grid, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W, make_fastdiv(Wp));
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   float* cur = bufA;

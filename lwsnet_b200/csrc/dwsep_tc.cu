@@ -333,19 +333,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
       DsItem w;
       while (sched.next(a, w)) {
       const int x = w.x0 + p - DS_RP;  // image column of this pixel
-      for (int i = 0; i < w.nrows; ++i, ++t) {
-        const int y = w.yi0 + i;
-        const float* src = a.img + (long long)w.b * CIN * hw + (long long)y * a.W + x;
-        // every step touches one new image line (y + 1); a line comes from DRAM (~1.5 us under load, several steps), so pull the
-        // line four steps ahead into L1 now
-        if (h == 0 && y + 5 < a.H && (unsigned)x < (unsigned)a.W) {
-#pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + ci * hw + 5 * a.W));
-        }
-        float v[16];
+      const float* src0 = a.img + (long long)w.b * CIN * hw + x;
+      // the 16 K slots (k = ci*9 + ky*3 + kx) of this warp's half for image line y; both halves are unrolled and the
+      // warp-uniform h selects one
+      auto load_taps = [&](int y, float (&v)[16]) {
+        const float* src = src0 + (long long)y * a.W;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-          // K slot k = ci*9 + ky*3 + kx; both halves are unrolled and the warp-uniform h selects one
           const int k0 = kk, k1 = 16 + kk;
           float r = 0.f;
           if (h == 0) {
@@ -361,8 +355,23 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
               r = ok ? __ldg(src + ci * hw + (ky - 1) * a.W + (kx - 1)) : 0.f;
             }
           }
-          v[kk] = r * DS_ACT_SCALE;
+          v[kk] = r;
         }
+      };
+      float v[16], vn[16];
+      load_taps(w.yi0, v);
+      for (int i = 0; i < w.nrows; ++i, ++t) {
+        const int y = w.yi0 + i;
+        // every step touches one new image line (y + 1); a line comes from DRAM (~1.5 us under load, several steps), so pull the
+        // line a few steps ahead into L1 now, and issue the next step's tap loads before converting this step's (the loads are
+        // L1 / L2 hits whose latency then overlaps the conversion and the wait for a free A tile)
+        if (h == 0 && y + 5 < a.H && (unsigned)x < (unsigned)a.W) {
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) asm volatile("prefetch.global.L1 [%0];" ::"l"(src0 + (long long)(y + 5) * a.W + ci * hw));
+        }
+        if (i + 1 < w.nrows) load_taps(y + 1, vn);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) v[kk] *= DS_ACT_SCALE;
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -385,6 +394,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + ab);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) v[kk] = vn[kk];
       }
     }
   } else {

@@ -21,7 +21,9 @@ struct FeConvArgs {
   int stride, dil, pad, transposed, relu;
 };
 
-template <int COUT>
+// CT = output channels per thread: the 1/8-resolution layers of a few pairs are only ~14k output pixels per image, so they are
+// spread over COUT / CT times more threads (blockIdx.z = channel group) instead of leaving most SMs idle.
+template <int COUT, int CT>
 __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
   extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
   for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
@@ -33,15 +35,16 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
   const int yo = item / wq;
   const int b = blockIdx.y;
   const int x0 = (item - yo * wq) * 4;
+  const int c0 = blockIdx.z * CT;
   const long long in_hw = (long long)a.Hi * a.Wi;
   const long long out_hw = (long long)a.Ho * a.Wo;
   const float* in_b = a.in + (long long)b * a.Cin * in_hw;
 
-  float acc[4][COUT];
+  float acc[4][CT];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int q = 0; q < COUT; ++q) acc[p][q] = 0.f;
+    for (int q = 0; q < CT; ++q) acc[p][q] = 0.f;
 
   // input coordinates of the 3 taps per axis (-1 = contributes nothing)
   int yi[3], xi[3][4];
@@ -78,9 +81,9 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
         float v[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) v[p] = xi[kx][p] >= 0 ? __ldg(row + xi[kx][p]) : 0.f;
-        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT;
+        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT + c0;
 #pragma unroll
-        for (int q = 0; q < COUT; q += 4) {
+        for (int q = 0; q < CT; q += 4) {
           const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
@@ -96,9 +99,9 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
 
   const bool vec = ((a.Wo & 3) == 0);
 #pragma unroll
-  for (int q = 0; q < COUT; ++q) {
-    const float bias = __ldg(a.bias + q);
-    const long long o = ((long long)b * COUT + q) * out_hw + (long long)yo * a.Wo + x0;
+  for (int q = 0; q < CT; ++q) {
+    const float bias = __ldg(a.bias + c0 + q);
+    const long long o = ((long long)b * COUT + c0 + q) * out_hw + (long long)yo * a.Wo + x0;
     float r[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
@@ -314,10 +317,17 @@ static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
   }
   dim3 grid(cdiv(cdiv(a.Wo, 4) * a.Ho, 128), B);
   const size_t smem = (size_t)a.Cin * 9 * cout * sizeof(float);
+  const bool split = (long long)grid.x * B < 4 * kNumSMs;  // too few blocks for the machine: 4 output channels per thread
   switch (cout) {
-    case 4: fe_conv_kernel<4><<<grid, 128, smem, st>>>(a); break;
-    case 8: fe_conv_kernel<8><<<grid, 128, smem, st>>>(a); break;
-    case 16: fe_conv_kernel<16><<<grid, 128, smem, st>>>(a); break;
+    case 4: fe_conv_kernel<4, 4><<<grid, 128, smem, st>>>(a); break;
+    case 8:
+      if (split) grid.z = 2, fe_conv_kernel<8, 4><<<grid, 128, smem, st>>>(a);
+      else fe_conv_kernel<8, 8><<<grid, 128, smem, st>>>(a);
+      break;
+    case 16:
+      if (split) grid.z = 4, fe_conv_kernel<16, 4><<<grid, 128, smem, st>>>(a);
+      else fe_conv_kernel<16, 16><<<grid, 128, smem, st>>>(a);
+      break;
     default: return LWS_ERR_UNSUPPORTED;
   }
   cudaError_t e = cudaPeekAtLastError();

@@ -251,7 +251,8 @@ def run_ours(args, rank, world, local_rank):
     model = LWSNet(O.default_args())
     model.load_state_dict(oracle_model.state_dict(), strict=True)
     model = model.to(dev)
-    engine = StereoEngine(model, micro_batch=args.micro_batch, device=dev, use_graphs=not args.no_graphs)
+    engine = StereoEngine(model, micro_batch=args.micro_batch, device=dev, use_graphs=not args.no_graphs,
+                          host_edge=args.host_edge if args.host_edge > 0 else None)
     if args.probes_only:  # developer mode: the per-kernel probes alone
         for rec in kernel_probes(model, pk, args.probe_batch):
             print(json.dumps(rec))
@@ -342,7 +343,8 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": "configs[2]: full 4-stage LWSNet inference (volume build + warp + residual volumes + 3D stacks "
                                "+ regression + colour-guidance refinement), KITTI 1232x368, batch 64 per GPU",
-                   "batch_per_gpu": BATCH, "micro_batch": args.micro_batch, "maxdisplist": [24, 5, 5],
+                   "batch_per_gpu": BATCH, "micro_batch": args.micro_batch,
+                   "e2e_chunks": [hi - lo for lo, hi in engine._host_chunks(BATCH)], "maxdisplist": [24, 5, 5],
                    "weights": "random init (KaimingNormal, seed 0)", "cuda_graphs": not args.no_graphs,
                    "l2": "inputs (697 MB per step) and per-step activations exceed the 126 MB L2",
                    "numerics": "fp32 storage at the ABI; conv stacks and pointwise convs on tcgen05 with split-fp16 operands "
@@ -367,7 +369,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--micro-batch", type=int, default=24, help="pairs per forward (one CUDA-graph replay)")
+    ap.add_argument("--host-edge", type=int, default=8,
+                    help="e2e: pairs in the first / last chunk of the host-resident schedule (0 = all chunks are --micro-batch)")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--skip-probes", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

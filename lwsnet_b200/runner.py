@@ -29,6 +29,24 @@ def micro_batches(n: int, mb: int) -> List[Tuple[int, int]]:
     return [(i, min(i + mb, n)) for i in range(0, n, mb)]
 
 
+def ramp_batches(n: int, mb: int, edge: int) -> List[Tuple[int, int]]:
+    """Host-resident schedule: a short first and last chunk (`edge` pairs) around `mb`-pair chunks.  The first chunk's H2D and the
+    last chunk's D2H are the only copies that cannot overlap compute, so they are kept small while the bulk of the batch runs at
+    the larger, more efficient micro-batch."""
+    if mb <= 0 or edge <= 0:
+        raise ValueError("micro-batch sizes must be positive")
+    edge = min(edge, mb)
+    if n <= 2 * edge:
+        return micro_batches(n, edge)
+    out, lo = [(0, edge)], edge
+    while n - lo > edge:
+        hi = lo + min(mb, n - lo - edge)
+        out.append((lo, hi))
+        lo = hi
+    out.append((lo, n))
+    return out
+
+
 class StereoEngine:
     """Runs ``model`` (lwsnet_b200.LWSNet on one CUDA device) over batches.
 
@@ -37,9 +55,11 @@ class StereoEngine:
                   i+1 and D2H of micro-batch i-1 overlap the compute of micro-batch i (three streams, two buffer sets).
     """
 
-    def __init__(self, model, micro_batch: int = 2, device: Optional[torch.device] = None, use_graphs: bool = True):
+    def __init__(self, model, micro_batch: int = 2, device: Optional[torch.device] = None, use_graphs: bool = True,
+                 host_edge: Optional[int] = None):
         self.model = model
         self.mb = micro_batch
+        self.host_edge = host_edge  # infer_host: size of the first / last chunk (None: all chunks are micro_batch pairs)
         self.device = device or next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("StereoEngine needs a CUDA device: lwsnet_b200 has no CPU path")
@@ -100,6 +120,22 @@ class StereoEngine:
         return out
 
     # ------------------------------------------------------------------------------------------ host-resident
+    def _host_chunks(self, B):
+        return ramp_batches(B, self.mb, self.host_edge) if self.host_edge else micro_batches(B, self.mb)
+
+    def _host_slot(self, n, H, W, slot):
+        """(graph | None, left, right, out) device buffers for an n-pair chunk in pipeline slot 0/1."""
+        if self.use_graphs:
+            return self._graph_for(n, H, W, slot)
+        key = ("eager", n, H, W, slot)
+        buf = self._graphs.get(key)
+        if buf is None:
+            dev = self.device
+            buf = (None, torch.empty((n, 3, H, W), device=dev), torch.empty((n, 3, H, W), device=dev),
+                   torch.empty((n, 4, H, W), device=dev))
+            self._graphs[key] = buf
+        return buf
+
     @torch.no_grad()
     def infer_host(self, left: torch.Tensor, right: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """left/right: CPU tensors [B,3,H,W] (pinned for async copies).  Returns a CPU tensor [B,4,H,W]."""
@@ -108,45 +144,38 @@ class StereoEngine:
         if out is None:
             out = torch.empty((B, 4, H, W), pin_memory=True)
         cur = torch.cuda.current_stream(dev)
-        chunks = micro_batches(B, self.mb)
-        slots = []
-        for slot in range(2):
-            if self.use_graphs:
-                slots.append(self._graph_for(self.mb, H, W, slot))
-            else:
-                slots.append((None, torch.empty((self.mb, 3, H, W), device=dev), torch.empty((self.mb, 3, H, W), device=dev),
-                              torch.empty((self.mb, 4, H, W), device=dev)))
+        chunks = self._host_chunks(B)
+        bufs = [self._host_slot(hi - lo, H, W, i & 1) for i, (lo, hi) in enumerate(chunks)]  # before the timed copies start
         in_ready = [torch.cuda.Event() for _ in chunks]
         done = [torch.cuda.Event() for _ in chunks]
-        out_free = [None, None]   # event: D2H that last read slot's output buffer finished
-        in_free = [None, None]    # event: compute that last read slot's input buffers finished
+        out_free = {}  # buffer set -> event: the D2H that last read its output buffer finished
+        in_free = {}   # buffer set -> event: the compute that last read its input buffers finished
         self._h2d.wait_stream(cur)
         self._d2h.wait_stream(cur)
         for i, (lo, hi) in enumerate(chunks):
-            slot = i & 1
-            graph, gl, gr, go = slots[slot]
-            n = hi - lo
+            graph, gl, gr, go = bufs[i]
+            key = id(gl)
             with torch.cuda.stream(self._h2d):
-                if in_free[slot] is not None:
-                    self._h2d.wait_event(in_free[slot])
-                gl[:n].copy_(left[lo:hi], non_blocking=True)
-                gr[:n].copy_(right[lo:hi], non_blocking=True)
+                if key in in_free:
+                    self._h2d.wait_event(in_free[key])
+                gl.copy_(left[lo:hi], non_blocking=True)
+                gr.copy_(right[lo:hi], non_blocking=True)
                 in_ready[i].record(self._h2d)
             cur.wait_event(in_ready[i])
-            if out_free[slot] is not None:
-                cur.wait_event(out_free[slot])
-            if graph is not None and n == self.mb:
+            if key in out_free:
+                cur.wait_event(out_free[key])
+            if graph is not None:
                 self._replay(graph)
             else:
-                self._forward_into(gl[:n], gr[:n], go[:n])
+                self._forward_into(gl, gr, go)
             done[i].record(cur)
-            in_free[slot] = done[i]
+            in_free[key] = done[i]
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done[i])
-                out[lo:hi].copy_(go[:n], non_blocking=True)
+                out[lo:hi].copy_(go, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._d2h)
-                out_free[slot] = ev
+                out_free[key] = ev
         cur.wait_stream(self._d2h)
         cur.wait_stream(self._h2d)
         return out
@@ -170,59 +199,53 @@ class StereoEngine:
         if color and out_color is None:
             out_color = torch.empty((B, 4, th, tw, 3), dtype=torch.uint8, pin_memory=True)
         cur = torch.cuda.current_stream(dev)
-        chunks = micro_batches(B, self.mb)
-        slots = []
-        for slot in range(2):
-            key = ("u8", h, w, th, tw, color, slot)
+        chunks = self._host_chunks(B)
+        bufs = []
+        for i, (lo, hi) in enumerate(chunks):
+            n, slot = hi - lo, i & 1
+            key = ("u8", n, h, w, th, tw, color, slot)
             io = self._graphs.get(key)
             if io is None:
-                io = (torch.empty((self.mb, h, w, 3), dtype=torch.uint8, device=dev),
-                      torch.empty((self.mb, h, w, 3), dtype=torch.uint8, device=dev),
-                      torch.empty((self.mb, 4, th, tw), dtype=torch.uint8, device=dev),
-                      torch.empty((self.mb, 4, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
+                io = (torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
+                      torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
+                      torch.empty((n, 4, th, tw), dtype=torch.uint8, device=dev),
+                      torch.empty((n, 4, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
                 self._graphs[key] = io
-            if self.use_graphs:
-                fwd = self._graph_for(self.mb, th, tw, slot)
-            else:
-                fwd = (None, torch.empty((self.mb, 3, th, tw), device=dev), torch.empty((self.mb, 3, th, tw), device=dev),
-                       torch.empty((self.mb, 4, th, tw), device=dev))
-            slots.append((io, fwd))
+            bufs.append((io, self._host_slot(n, th, tw, slot)))
         in_ready = [torch.cuda.Event() for _ in chunks]
         done = [torch.cuda.Event() for _ in chunks]
-        out_free = [None, None]
-        in_free = [None, None]
+        out_free, in_free = {}, {}
         self._h2d.wait_stream(cur)
         self._d2h.wait_stream(cur)
         for i, (lo, hi) in enumerate(chunks):
-            slot = i & 1
-            (ul, ur, ug, uc), (graph, gl, gr, go) = slots[slot]
-            n = hi - lo
+            (ul, ur, ug, uc), (graph, gl, gr, go) = bufs[i]
+            key = id(ul)
             with torch.cuda.stream(self._h2d):
-                if in_free[slot] is not None:
-                    self._h2d.wait_event(in_free[slot])
-                ul[:n].copy_(left[lo:hi], non_blocking=True)
-                ur[:n].copy_(right[lo:hi], non_blocking=True)
+                if key in in_free:
+                    self._h2d.wait_event(in_free[key])
+                ul.copy_(left[lo:hi], non_blocking=True)
+                ur.copy_(right[lo:hi], non_blocking=True)
                 in_ready[i].record(self._h2d)
             cur.wait_event(in_ready[i])
-            if out_free[slot] is not None:
-                cur.wait_event(out_free[slot])
-            ops.preprocess_bgr_u8(ul[:n], th, tw, out=gl[:n])
-            ops.preprocess_bgr_u8(ur[:n], th, tw, out=gr[:n])
-            if graph is not None and n == self.mb:
+            if key in out_free:
+                cur.wait_event(out_free[key])
+            ops.preprocess_bgr_u8(ul, th, tw, out=gl)
+            ops.preprocess_bgr_u8(ur, th, tw, out=gr)
+            if graph is not None:
                 self._replay(graph)
             else:
-                self._forward_into(gl[:n], gr[:n], go[:n])
-            ops.disparity_to_u8(go[:n], gray=True, color=color, out_gray=ug[:n], out_color=uc[:n] if color else None)
+                self._forward_into(gl, gr, go)
+            ops.disparity_to_u8(go, gray=True, color=color, out_gray=ug, out_color=uc if color else None)
             done[i].record(cur)
-            in_free[slot] = done[i]
+            in_free[key] = done[i]
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done[i])
-                out_gray[lo:hi].copy_(ug[:n], non_blocking=True)
+                out_gray[lo:hi].copy_(ug, non_blocking=True)
                 if color:
-                    out_color[lo:hi].copy_(uc[:n], non_blocking=True)
+                    out_color[lo:hi].copy_(uc, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._d2h)
-                out_free[slot] = ev
+                out_free[key] = ev
         cur.wait_stream(self._d2h)
         cur.wait_stream(self._h2d)
         return out_gray, out_color

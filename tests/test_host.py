@@ -85,6 +85,13 @@ def test_shard_range_and_micro_batches():
             assert max(sizes) - min(sizes) <= 1
     assert shard_range(256, 3, 8) == (96, 128)
     assert micro_batches(5, 2) == [(0, 2), (2, 4), (4, 5)]
+    from lwsnet_b200.runner import ramp_batches
+    assert ramp_batches(64, 32, 8) == [(0, 8), (8, 40), (40, 56), (56, 64)]
+    assert ramp_batches(10, 24, 8) == [(0, 8), (8, 10)] and ramp_batches(3, 2, 2) == [(0, 2), (2, 3)]
+    for n, mb, e in ((64, 24, 8), (17, 8, 8), (1, 4, 2), (100, 7, 3)):
+        ch = ramp_batches(n, mb, e)
+        assert ch[0][0] == 0 and ch[-1][1] == n and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all(0 < hi - lo <= mb for lo, hi in ch)
     with pytest.raises(ValueError):
         shard_range(8, 2, 2)
 

@@ -140,7 +140,7 @@ def test_infer_host_u8_matches_fp32_path(models):
     B, h, w, th, tw = 3, 70, 140, 64, 128
     base = rng.integers(0, 256, (B, h, w + 8, 3), dtype=np.uint8)
     left, right = np.ascontiguousarray(base[:, :, 8:]), np.ascontiguousarray(base[:, :, :-8])  # 8 px of true disparity
-    eng = StereoEngine(m, micro_batch=2)
+    eng = StereoEngine(m, micro_batch=2, host_edge=1)
     gray, color = eng.infer_host_u8(torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory(), th, tw, color=True)
     torch.cuda.synchronize()
     lf = torch.cat([O.preprocess_bgr_uint8(left[b], th, tw) for b in range(B)])
@@ -151,3 +151,61 @@ def test_infer_host_u8_matches_fp32_path(models):
     assert np.array_equal(gray.numpy(), ref_u8)
     lut = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jet_lut_bgr.npy"))
     assert np.array_equal(color.numpy(), lut[ref_u8])
+
+
+@pytest.mark.parametrize("name,H,W,maxdisplist", [
+    ("configs[3] SceneFlow 960x544", 544, 960, (24, 5, 5)),
+    ("configs[4] 1920 wide, maxdisp 384 (D = 48 at 1/8), quarter height", 272, 1920, (48, 5, 5)),
+])
+def test_other_baseline_configs_teacher_forced(name, H, W, maxdisplist):
+    """BASELINE.json configs[3] / configs[4] shapes (the parity-test cases next to the benchmarked configs[2]): every stage, fed
+    the fp64 oracle's features and previous prediction, against the fp64 oracle; same bars as test_stages_teacher_forced.
+    configs[4] keeps its full width and its D = 48 stage-1 volume but a quarter of its 1088 rows so that the CPU oracle
+    finishes in seconds (no kernel's tiling depends on the image height beyond the row count)."""
+    from oracle import lwsnet_torch as O
+    args = O.default_args(maxdisplist=maxdisplist)
+    o32 = O.build_oracle(seed=0, args=args, random_bn=True)
+    o64 = O.build_oracle(seed=0, args=args, random_bn=True, dtype=torch.float64)
+    prod = product_from_oracle(o32, args)
+    left, right = O.synthetic_pair(1, H, W, seed=13, max_disp=min(150.0, W / 8))
+    with torch.no_grad():
+        pred64, tr = o64.forward_trace(left.double(), right.double())
+        pred32, _ = o32.forward_trace(left, right)
+    for s in range(3):
+        fl, fr = tr[f"feat_l{s}"].float().cuda(), tr[f"feat_r{s}"].float().cuda()
+        prev = pred64[s - 1].float().cuda() if s > 0 else None
+        out = prod._stage(s, fl, fr, prev, H, W)
+        e, floor = err_stats(out.cpu(), pred64[s]), err_stats(pred32[s], pred64[s])
+        print(f"{name} stage {s + 1} teacher-forced: {e} | fp32-oracle floor (free-running): {floor}")
+        k = 4 if s == 0 else 2
+        assert e["mean"] <= k * floor["mean"] + 1e-4 and e["mean"] <= 1e-3, (name, s, e, floor)
+        assert e["max"] <= k * floor["max"] + 5e-3, (name, s, e, floor)
+        assert e["frac_le_1e3"] >= 0.95, (name, s, e)
+    out4 = prod._refine(left.cuda(), pred64[2].float().cuda())
+    e = err_stats(out4.cpu(), pred64[3])
+    assert e["mean"] <= 1e-3 * (1 + pred64[3].abs().mean().item()), (name, e)
+    # the feature pyramid at this shape
+    feats = prod.feature_extraction(left.cuda())
+    for s in range(3):
+        ref = tr[f"feat_l{s}"]
+        d = (feats[s].cpu().double() - ref).abs()
+        assert (d <= 1e-4 * (1 + ref.abs()) + 2e-6 * ref.abs().max()).all(), (name, s, d.max().item())
+
+
+def test_engine_schedules_agree_bitwise(models):
+    """StereoEngine: device-resident micro-batches, the ramped host-resident schedule (short first / last chunk) and the eager
+    (no CUDA graph) path give identical bits (no kernel's arithmetic depends on the batch size or on graph capture)."""
+    from lwsnet_b200.runner import StereoEngine
+    O, o32, o64, prod = models
+    left, right = O.synthetic_pair(7, 64, 128, seed=31, max_disp=20.0)
+    ref = torch.cat([torch.cat(prod(left[i:i + 1].cuda(), right[i:i + 1].cuda()), dim=1) for i in range(7)]).cpu()
+    eng = StereoEngine(prod, micro_batch=3, host_edge=1)
+    assert [hi - lo for lo, hi in eng._host_chunks(7)] == [1, 3, 2, 1]
+    out_h = eng.infer_host(left.pin_memory(), right.pin_memory())
+    out_d = eng.infer_device(left.cuda(), right.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(out_h, ref) and torch.equal(out_d.cpu(), ref)
+    eager = StereoEngine(prod, micro_batch=4, use_graphs=False)
+    out_e = eager.infer_host(left.pin_memory(), right.pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(out_e, ref)

@@ -1,4 +1,4 @@
-tools/gpu_quick.sh q28 "conv3d or stack or stage"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:dwsep_f16_kernel -c 1 -o gpurun_out/dw3_q28 python tools/profile_step.py --batch 4 --iters 1 > gpurun_out/dw3_q28.log 2>&1
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'fe_conv_kernel|fe_deconv_kernel|fe_conv_s1_kernel' -c 12 -o gpurun_out/fe_q28 python tools/profile_step.py --batch 4 --iters 1 > gpurun_out/fe_q28.log 2>&1
-tail -1 gpurun_out/fe_q28.log
+python -m pytest tests -m gpu -x -q -k "engine or u8 or shard" 2>&1 | tail -3
+for cfg in "32 8" "24 8" "32 4" "16 8"; do set -- $cfg; python bench.py --steps 4 --warmup 3 --micro-batch $1 --host-edge $2 --skip-probes --skip-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('mb', d['config']['micro_batch'], d['config']['e2e_chunks'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1))"; done

@@ -201,6 +201,123 @@ __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
   }
 }
 
+// ---- fast path 1b: the same window scheme, software pipelined --------------------------------------------------------------------
+// The layers of the pyramid are small (a 1/8-resolution map of a few pairs is ~100k pixels), so a kernel whose threads wait for
+// their loads once per input channel is latency bound however many FLOPs the machine has.  Here a thread owns 4 consecutive output
+// pixels x CT output channels (blockIdx.z = channel group, so the small layers still fill the SMs), the three window rows of input
+// channel ci+1 are loaded into a second register set while channel ci is being multiplied (ping-pong, Cin even), and rows whose
+// pitch is only 8-byte aligned (W = 154 at 1/8 of KITTI) use 64-bit loads / stores instead of falling back to scalar taps.
+template <int COUT, int CT, int DIL, int STRIDE, bool V4>
+__global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
+  extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
+  for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
+  __syncthreads();
+  constexpr int G = V4 ? 4 : 2, NG = 12 / G;
+  const int wq = (a.Wo + 3) >> 2;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= wq * a.Ho) return;
+  const int yo = item / wq;
+  const int b = blockIdx.y, c0 = blockIdx.z * CT;
+  const int x0 = (item - yo * wq) * 4;
+  const long long hw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
+  const int xi0 = x0 * STRIDE;  // the aligned 12-wide window starts at input column xi0 - 4
+  const float* in_b = a.in + (long long)b * a.Cin * hw + (xi0 - 4);
+  bool okc[NG], oky[3];
+  int rowoff[3];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) okc[g] = xi0 - 4 + g * G >= 0 && xi0 - 4 + g * G + G <= a.Wi;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yi = yo * STRIDE + (ky - 1) * DIL;
+    oky[ky] = (unsigned)yi < (unsigned)a.Hi;
+    rowoff[ky] = yi * a.Wi;
+  }
+  auto load = [&](int ci, float (&w)[3][12]) {
+    const float* plane = in_b + ci * hw;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if constexpr (V4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (oky[ky] && okc[g]) v = __ldg(reinterpret_cast<const float4*>(plane + rowoff[ky]) + g);
+          w[ky][4 * g] = v.x, w[ky][4 * g + 1] = v.y, w[ky][4 * g + 2] = v.z, w[ky][4 * g + 3] = v.w;
+        } else {
+          float2 v = make_float2(0.f, 0.f);
+          if (oky[ky] && okc[g]) v = __ldg(reinterpret_cast<const float2*>(plane + rowoff[ky]) + g);
+          w[ky][2 * g] = v.x, w[ky][2 * g + 1] = v.y;
+        }
+      }
+    }
+  };
+  float acc[4][CT];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < CT; ++q) acc[p][q] = 0.f;
+  auto mac = [&](int ci, const float (&w)[3][12]) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT + c0;
+#pragma unroll
+        for (int q = 0; q < CT; q += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = w[ky][4 + p * STRIDE + (kx - 1) * DIL];
+            acc[p][q] = fmaf(v, w4.x, acc[p][q]);
+            acc[p][q + 1] = fmaf(v, w4.y, acc[p][q + 1]);
+            acc[p][q + 2] = fmaf(v, w4.z, acc[p][q + 2]);
+            acc[p][q + 3] = fmaf(v, w4.w, acc[p][q + 3]);
+          }
+        }
+      }
+    }
+  };
+  float wa[3][12], wb[3][12];
+  load(0, wa);
+  for (int ci = 0; ci < a.Cin; ci += 2) {  // Cin is even (host-checked)
+    load(ci + 1, wb);
+    mac(ci, wa);
+    if (ci + 2 < a.Cin) load(ci + 2, wa);
+    mac(ci + 1, wb);
+  }
+#pragma unroll
+  for (int q = 0; q < CT; ++q) {
+    const float bias = __ldg(a.bias + c0 + q);
+    const long long o = ((long long)b * COUT + c0 + q) * ohw + (long long)yo * a.Wo + x0;
+    float r[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
+    if constexpr (V4) {
+      if (a.res) {
+        const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
+        r[0] += rv.x, r[1] += rv.y, r[2] += rv.z, r[3] += rv.w;
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) r[p] = fmaxf(r[p], 0.f);
+      }
+      *reinterpret_cast<float4*>(a.out + o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (x0 + 2 * h < a.Wo) {  // Wo is even: a pixel pair is wholly in or out
+          float u0 = r[2 * h], u1 = r[2 * h + 1];
+          if (a.res) {
+            const float2 rv = *reinterpret_cast<const float2*>(a.res + o + 2 * h);
+            u0 += rv.x, u1 += rv.y;
+          }
+          if (a.relu) u0 = fmaxf(u0, 0.f), u1 = fmaxf(u1, 0.f);
+          *reinterpret_cast<float2*>(a.out + o + 2 * h) = make_float2(u0, u1);
+        }
+      }
+    }
+  }
+}
+
 // ---- fast path 2: 3x3 stride-2 transposed conv (pad 1, output_padding 1 -> exact 2x upsampling), Wi % 2 == 0 ------------------
 // yo = 2*yi - 1 + ky: an even output row sees only (yi = yo/2, ky = 1), an odd one (yi = (yo-1)/2, ky = 2) and (yi = (yo+1)/2,
 // ky = 0); same along x.  A thread owns the 2 x 4 outputs (rows 2i, 2i+1; columns 4j .. 4j+3) of 8 output channels: 6 input
@@ -289,25 +406,27 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
   }
 }
 
+template <int COUT, int CT, int DIL, int STRIDE>
+static int launch_pipe(const FeConvArgs& a, int B, size_t smem_w, cudaStream_t st) {
+  dim3 g(cdiv(cdiv(a.Wo, 4) * a.Ho, 128), B, COUT / CT);
+  if ((a.Wi & 3) == 0 && (a.Wo & 3) == 0) fe_conv_pipe_kernel<COUT, CT, DIL, STRIDE, true><<<g, 128, smem_w, st>>>(a);
+  else fe_conv_pipe_kernel<COUT, CT, DIL, STRIDE, false><<<g, 128, smem_w, st>>>(a);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
 static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
   const size_t smem_w = (size_t)a.Cin * 9 * cout * sizeof(float);
-  if (!a.transposed && a.stride == 1 && (a.Wi & 3) == 0 && a.pad == a.dil && (a.dil == 1 || a.dil == 2 || a.dil == 4) &&
-      (cout == 8 || cout == 16 || cout == 4)) {
-    dim3 g(cdiv((a.Wo >> 2) * a.Ho, 128), B);
-#define LWS_S1(CO, DL) fe_conv_s1_kernel<CO, DL, 1><<<g, 128, smem_w, st>>>(a)
-    if (cout == 4) { if (a.dil == 1) LWS_S1(4, 1); else if (a.dil == 2) LWS_S1(4, 2); else LWS_S1(4, 4); }
-    else if (cout == 8) { if (a.dil == 1) LWS_S1(8, 1); else if (a.dil == 2) LWS_S1(8, 2); else LWS_S1(8, 4); }
-    else { if (a.dil == 1) LWS_S1(16, 1); else if (a.dil == 2) LWS_S1(16, 2); else LWS_S1(16, 4); }
-#undef LWS_S1
-    cudaError_t e = cudaPeekAtLastError();
-    return e == cudaSuccess ? LWS_OK : (int)e;
+  const bool even = (a.Wi & 1) == 0 && (a.Wo & 1) == 0 && (a.Cin & 1) == 0 && a.pad == a.dil && !a.transposed &&
+                    (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.res) & 15) == 0;
+  if (even && a.stride == 1 && a.Wo == a.Wi) {
+    if (cout == 16 && a.dil == 1) return launch_pipe<16, 8, 1, 1>(a, B, smem_w, st);
+    if (cout == 8 && a.dil == 1) return launch_pipe<8, 8, 1, 1>(a, B, smem_w, st);
+    if (cout == 8 && a.dil == 2) return launch_pipe<8, 8, 2, 1>(a, B, smem_w, st);
+    if (cout == 8 && a.dil == 4) return launch_pipe<8, 8, 4, 1>(a, B, smem_w, st);
+    if (cout == 4 && a.dil == 2) return launch_pipe<4, 4, 2, 1>(a, B, smem_w, st);
   }
-  if (!a.transposed && a.stride == 2 && a.dil == 1 && a.pad == 1 && (a.Wi & 3) == 0 && (a.Wo & 3) == 0 && cout == 16) {
-    dim3 g(cdiv((a.Wo >> 2) * a.Ho, 128), B);
-    fe_conv_s1_kernel<16, 1, 2><<<g, 128, smem_w, st>>>(a);
-    cudaError_t e = cudaPeekAtLastError();
-    return e == cudaSuccess ? LWS_OK : (int)e;
-  }
+  if (even && a.stride == 2 && a.dil == 1 && a.Wi == 2 * a.Wo && cout == 16) return launch_pipe<16, 8, 1, 2>(a, B, smem_w, st);
   if (a.transposed && a.stride == 2 && a.pad == 1 && (a.Wi & 1) == 0 && a.Ho == 2 * a.Hi && a.Wo == 2 * a.Wi && (cout == 8 || cout == 16)) {
     dim3 g(cdiv((a.Wi >> 1) * a.Hi * (cout / 8), 128), B);
     if (cout == 8) fe_deconv_kernel<8><<<g, 128, smem_w, st>>>(a);

@@ -1,4 +1,3 @@
-python -m pytest tests -m gpu -x -q -k "engine or u8 or shard" 2>&1 | tail -3
-for cfg in "32 8" "24 8" "32 4" "16 8"; do set -- $cfg; python bench.py --steps 4 --warmup 3 --micro-batch $1 --host-edge $2 --skip-probes --skip-cpu 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('mb', d['config']['micro_batch'], d['config']['e2e_chunks'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1))"; done
+python -m pytest tests -m gpu -x -q -k "feature or fe_ or other_baseline or end_to_end or shard" 2>&1 | tail -3
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_q31_b8.csv python tools/profile_step.py --batch 8 --iters 1 > gpurun_out/prof_q31.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_q31_b8.csv > gpurun_out/launches_q31_b8.txt; head -1 gpurun_out/launches_q31_b8.txt; grep "fe_" gpurun_out/launches_q31_b8.txt

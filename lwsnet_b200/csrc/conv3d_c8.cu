@@ -16,6 +16,7 @@
 // ti % 4): the epilogue of a tile is a ~1500-cycle dependent chain, a tile's MMAs only ~500 cycles.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "lws_common.cuh"
@@ -333,6 +334,327 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C8_NGRP * 64));
 }
 
+// ================================================================================================================================
+// Plane-group version: one step = the tiles (dp0 + i, y, ct), i < L <= 3, of THREE neighbouring d planes at once.
+// The kernel above reads every input line three times (as kd = 0, 1, 2 of three different output planes: 12 KB of shared-memory
+// fills and 9 MMAs per 4 KB of output, ~6 TB/s of L2 -> SM traffic) and is bound by that.  Here a line group is the same line of
+// the L + 2 planes dp0 - 1 .. dp0 + L (10 bulk copies per step = 1.67 per output tile instead of 6), and the kd taps are folded
+// into N next to kw: with the operand table of a kh tap stored as [W(kd=2); W(kd=1); W(kd=0)] (3 x 48 rows), input plane
+// t = -1 .. L feeds the accumulators i = max(0, t-1) .. min(L-1, t+1), which are neighbouring column blocks of TMEM, through ONE
+// MMA whose B operand is a row sub-range of that table:  N = 48, 96, 144, 96, 48 for L = 3  ->  15 MMAs / 1248 issue cycles per
+// three tiles instead of 27 / 1728.  The plane that feeds all L accumulators goes first with accumulate = 0.
+// Tiles are numbered k = 3 * step + i and handled round robin by the four epilogue groups; TMEM holds two steps (2 x 192 columns).
+constexpr int CP_L = 3;
+constexpr int CP_NG = 6;                      // ring of line groups
+constexpr int CP_GBYTES = (CP_L + 2) * 4096;  // (L + 2) planes x (hi, lo) x 128 voxels x 16 B
+constexpr int CP_OFF_RING = 14336;
+constexpr int CP_OFF_STAGE = CP_OFF_RING + CP_NG * CP_GBYTES;
+constexpr int CP_OFF_XCH = CP_OFF_STAGE + C8_NGRP * 4096;
+constexpr int CP_OFF_BAR = CP_OFF_XCH + C8_NGRP * 4 * 3 * 8 * 4;
+constexpr int CP_SMEM = CP_OFF_BAR + 256 + 128;
+constexpr int CP_TCOLS = 192;                 // TMEM columns per step buffer
+
+struct CPArgs {
+  C8Args c;       // tensors, sizes, fast divisors (line0 / strip_len / total_tiles / ct_per_line unused)
+  int ct, ndg;    // column tiles per line, d groups
+  int total_steps;
+  FastDiv fndg, fct;
+};
+struct CPItem {
+  int b, L, row0, nsteps;  // row0: first output voxel (inside the batch element) of accumulator 0 of step 0
+};
+// strip = (b, column tile, d group) walked down the Hp lines of its planes; all strips' steps are numbered strip-major and every
+// CTA takes one contiguous range
+struct CPSched {
+  int g, g1;
+  __device__ __forceinline__ CPSched(const CPArgs& a) {
+    g = (int)((long long)a.total_steps * blockIdx.x / gridDim.x);
+    g1 = (int)((long long)a.total_steps * (blockIdx.x + 1) / gridDim.x);
+  }
+  __device__ __forceinline__ bool next(const CPArgs& a, CPItem& it) {
+    if (g >= g1) return false;
+    int strip, y0, t, dg, cti;
+    fdivmod(g, a.c.fHp, strip, y0);
+    fdivmod(strip, a.fndg, t, dg);
+    fdivmod(t, a.fct, it.b, cti);
+    it.nsteps = min(a.c.Hp - y0, g1 - g);
+    it.L = min(CP_L, a.c.D - CP_L * dg);
+    it.row0 = ((1 + CP_L * dg) * a.c.Hp + y0) * a.c.Wp + cti * 126;
+    g += it.nsteps;
+    return true;
+  }
+};
+
+// MMAs of one line group (one kh) for L accumulators; INIT: the first one overwrites
+template <int L, uint32_t NB>
+__device__ __forceinline__ void cp_issue_group(uint32_t tmem_buf, uint32_t g_lo, uint32_t b_kh, uint64_t a_hi, uint64_t b_hi, bool init) {
+  constexpr int t_init = L == 3 ? 1 : 0;
+#pragma unroll
+  for (int o = 0; o < L + 2; ++o) {
+    // issue order: the plane that covers every accumulator first
+    const int t = o == 0 ? t_init : (o - 2 < t_init ? o - 2 : o - 1);  // o = 0 -> t_init; then -1 .. L without t_init
+    const int i_min = t - 1 > 0 ? t - 1 : 0, i_max = t + 1 < L - 1 ? t + 1 : L - 1;
+    const uint32_t N = NB * (uint32_t)(i_max - i_min + 1);
+    const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t da = a_hi | (uint64_t)(g_lo + (uint32_t)(t + 1) * (4096 >> 4));
+    const uint64_t db = b_hi | (uint64_t)(b_kh + (uint32_t)(1 - t + i_min) * NB);  // row start (16-byte units)
+    const uint32_t acc = (init && o == 0) ? 0u : 1u;
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_buf + (uint32_t)i_min * NB),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs pa) {
+  const C8Args& a = pa.c;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sB = smem;
+  uint8_t* sRing = smem + CP_OFF_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CP_OFF_BAR);
+  uint64_t* g_full = bars;              // [NG]
+  uint64_t* g_empty = g_full + CP_NG;   // [NG]
+  uint64_t* t_full = g_empty + CP_NG;   // [2]
+  uint64_t* t_empty = t_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  constexpr uint32_t NB = LAST ? 16 : 48;  // accumulator columns per output tile = B rows per kd
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < CP_NG; ++i) mbar_init(g_full + i, 1), mbar_init(g_empty + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, CP_L * 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // operand table: global block (kd*3 + kh) = [chunk 0: NB rows x 16 B][chunk 1]  ->  per kh: [chunk][(2 - kd) * NB + row]
+  for (int u = tid; u < 9 * (int)NB * 2; u += C8_THREADS) {
+    const int blk = u / ((int)NB * 2), rem = u - blk * (int)NB * 2;
+    const int c = rem / (int)NB, r = rem - c * (int)NB;
+    const int kd = blk / 3, kh = blk - kd * 3;
+    reinterpret_cast<uint4*>(sB)[kh * 3 * (int)NB * 2 + c * 3 * (int)NB + (2 - kd) * (int)NB + r] =
+        __ldg(reinterpret_cast<const uint4*>(a.wtab) + u);
+  }
+  fence_proxy_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int plane = a.Hp * a.Wp;  // voxels per d plane
+
+  if (warp == 0) {
+    // ================================ producer: lanes 0 .. 2(L+2)-1 issue one 2 KB bulk copy each ================================
+    const int pl = lane >> 1, part = lane & 1;
+    const uint8_t* src_plane = part ? a.in_lo : a.in_hi;
+    uint32_t slot = 0, ph = 0;
+    CPSched sched(pa);
+    CPItem w;
+    while (sched.next(pa, w)) {
+      const long long base = (long long)w.b * a.vox_b + w.row0 - 1 + (long long)(pl - 1) * plane;  // GEMM row 0 (Toeplitz shift 1)
+      for (int n = 0; n < w.nsteps; ++n) {
+        for (int kh = n == 0 ? 0 : 2; kh < 3; ++kh) {  // later steps of a strip only need the line below
+          mbar_wait(g_empty + slot, ph ^ 1);
+          if (lane == 0) mbar_expect_tx(g_full + slot, (uint32_t)(w.L + 2) * 4096);
+          __syncwarp();
+          if (lane < 2 * (w.L + 2))
+            bulk_load(sRing + slot * CP_GBYTES + pl * 4096 + part * 2048, src_plane + (base + (long long)(n + kh - 1) * a.Wp) * 16, 2048,
+                      g_full + slot);
+          if (++slot == CP_NG) slot = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (whole schedule inside one elected lane) ================================
+    const uint64_t a_hi = ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint64_t b_hi = ((uint64_t)((3 * NB * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t ring_lo = (smem_u32(sRing) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+    if (elect_one_sync()) {
+      uint32_t bslot = 0, bph = 0, st = 0;
+      CPSched sched(pa);
+      CPItem w;
+      while (sched.next(pa, w)) {
+        for (int n = 0; n < w.nsteps; ++n, ++st) {
+          const bool last = n == w.nsteps - 1;
+          const uint32_t tb = st & 1;
+          mbar_wait(t_empty + tb, ((st >> 1) & 1) ^ 1);
+          uint32_t slot = bslot, ph = bph;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            if (n == 0 || kh == 2) mbar_wait(g_full + slot, ph);  // the other groups were waited for by the previous step
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t g_lo = ring_lo + slot * (CP_GBYTES >> 4);
+            const uint32_t b_kh = b_lo + (uint32_t)kh * ((3 * NB * 32) >> 4);
+            const uint32_t tbuf = tmem + tb * CP_TCOLS;
+            if (w.L == 3) cp_issue_group<3, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
+            else if (w.L == 2) cp_issue_group<2, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
+            else cp_issue_group<1, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
+            if (kh == 0 || last)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(g_empty + slot))
+                           : "memory");
+            if (kh == 2)
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(t_full + tb))
+                           : "memory");
+            if (++slot == CP_NG) slot = 0, ph ^= 1;
+          }
+          if (++bslot == CP_NG) bslot = 0, bph ^= 1;
+        }
+        bslot += 2;  // the strip's last step consumed its remaining two groups
+        if (bslot >= CP_NG) bslot -= CP_NG, bph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue: group g handles the tiles k = 3 * step + i with k % 4 == g ================================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int j = q * 32 + lane;       // GEMM row; this thread produces output voxel j (staging row j), valid for j < 126
+    const bool issuer = ((warp - 2) & 3) == 0 && lane == 0;
+    const float* scl = reinterpret_cast<const float*>(a.wtab + (LAST ? 9 * 512 : C8_BBYTES));
+    const float c0 = __ldg(scl) * (LAST ? 1.f / kDwsepActScale : 1.f), c1 = __ldg(scl + 1) * (LAST ? 1.f / kDwsepActScale : 1.f);
+    float bias[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bias[c] = __ldg(a.bias + c) * kDwsepActScale;
+    uint8_t* stage = smem + CP_OFF_STAGE + g * 4096;
+    float* xch = reinterpret_cast<float*>(smem + CP_OFF_XCH) + g * (4 * 3 * 8);
+    float* xq = xch + q * 24;                    // this quarter publishes e1 of lane 0, e2 of lanes 0 and 1
+    const float* xn = xch + ((q + 1) & 3) * 24;  // next quarter's
+    const int bar_id = 1 + g;
+    uint32_t st = 0, mine = 0;  // step counter; tiles this group has handled (double-buffers the LAST exchange rows)
+    CPSched sched(pa);
+    CPItem w;
+    while (sched.next(pa, w)) {
+      for (int n = 0; n < w.nsteps; ++n, ++st) {
+#pragma unroll 1
+        for (int i = 0; i < CP_L; ++i) {
+          if ((int)((st * CP_L + i) & 3) != g) continue;
+          const uint32_t tb = st & 1;
+          mbar_wait(t_full + tb, (st >> 1) & 1);
+          if (i >= w.L) {  // no such plane in this d group: only release the buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + tb);
+            continue;
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tb * CP_TCOLS + (uint32_t)i * NB;
+          const int r = w.row0 + n * a.Wp + i * plane + j;  // output voxel (inside the batch element) of this thread
+          if (LAST) {
+            float m[8], k[8];
+            c8_ld8(taddr, m);
+            c8_ld8(taddr + 8, k);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + tb);
+            const float e0 = fmaf(k[0], c1, m[0] * c0), e1 = fmaf(k[1], c1, m[1] * c0), e2 = fmaf(k[2], c1, m[2] * c0);
+            const float s1 = __shfl_down_sync(0xffffffffu, e1, 1), s2 = __shfl_down_sync(0xffffffffu, e2, 2);
+            float v = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
+            float* xp = xch + (mine & 1) * 12;  // this group's exchange rows, double-buffered by its tile parity
+            ++mine;
+            if (lane == 0) xp[q * 3] = e1;
+            if (lane < 2) xp[q * 3 + 1 + lane] = e2;
+            named_bar_sync(bar_id, 128);
+            if (q < 3 && lane >= 30) {
+              if (lane == 31) v += xp[(q + 1) * 3];
+              v += xp[(q + 1) * 3 + 1 + lane - 30];
+            }
+            int line, x, dpl, y;
+            fdivmod(r, a.fWp, line, x);
+            fdivmod(line, a.fHp, dpl, y);
+            // a tile that runs past the end of its plane would produce voxels of the next plane, which that plane's own tile
+            // accumulates in a different kd order (other accumulator index): leave them to their owner so results are unique
+            const int dp_tile = fdiv(fdiv(r - j, a.fWp), a.fHp);
+            if (j < 126 && x >= 1 && x <= a.W && y >= 1 && y <= a.H && dpl == dp_tile && dpl <= a.D) {
+              const long long o = (((long long)w.b * a.D + (dpl - 1)) * a.H + (y - 1)) * a.W + (x - 1);
+              a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
+            }
+            continue;
+          }
+          float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];
+          c8_ld8(taddr, m0);
+          c8_ld8(taddr + 8, m1);
+          c8_ld8(taddr + 16, m2);
+          c8_ld8(taddr + 24, k0);
+          c8_ld8(taddr + 32, k1);
+          c8_ld8(taddr + 40, k2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + tb);
+          float out[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float e0 = fmaf(k0[c], c1, m0[c] * c0);
+            m1[c] = fmaf(k1[c], c1, m1[c] * c0);
+            m2[c] = fmaf(k2[c], c1, m2[c] * c0);
+            const float s1 = __shfl_down_sync(0xffffffffu, m1[c], 1);
+            const float s2 = __shfl_down_sync(0xffffffffu, m2[c], 2);
+            out[c] = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
+          }
+          if (lane < 2) {
+            float4* d2 = reinterpret_cast<float4*>(xq + (1 + lane) * 8);
+            d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
+            if (lane == 0) {
+              float4* d1 = reinterpret_cast<float4*>(xq);
+              d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
+            }
+          }
+          // the bulk stores of this group's previous tile must have read the staging buffer
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          named_bar_sync(bar_id, 128);
+          if (q < 3 && lane >= 30) {
+            if (lane == 31) {
+              const float4* p1 = reinterpret_cast<const float4*>(xn);
+              const float4 u = p1[0], v = p1[1];
+              out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
+            }
+            const float4* p2 = reinterpret_cast<const float4*>(xn + (1 + lane - 30) * 8);
+            const float4 u = p2[0], v = p2[1];
+            out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
+          }
+          int line, x, dpl, y;
+          fdivmod(r, a.fWp, line, x);
+          fdivmod(line, a.fHp, dpl, y);
+          const bool border = x < 1 || x > a.W || y < 1 || y > a.H || dpl < 1 || dpl > a.D;
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            float v0 = fmaxf(out[2 * p] + bias[2 * p], 0.f), v1 = fmaxf(out[2 * p + 1] + bias[2 * p + 1], 0.f);
+            v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+            hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          *reinterpret_cast<uint4*>(stage + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(stage + 2048 + j * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            const int r0 = r - j;  // the tile's first voxel
+            const long long v = (long long)w.b * a.vox_b + r0;
+            // stop at the end of the tile's own plane: the voxels beyond belong to the next plane's tile, which accumulates its
+            // kd taps in a different order (other accumulator index) -- one writer per voxel keeps the result unique
+            const int dp_tile = fdiv(fdiv(r0, a.fWp), a.fHp);
+            const uint32_t nv = (uint32_t)min(126, (dp_tile + 1) * plane - r0);
+            bulk_store(a.out_hi + v * 16, stage, nv * 16);
+            bulk_store(a.out_lo + v * 16, stage + 2048, nv * 16);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // ---- first conv 1 -> 8 on the raw cost (BN_0 affine + ReLU on the taps), writes every voxel of the padded hi/lo planes ----
 // One thread = 4 voxels that are neighbours in y (same padded x): the 27-tap window of the four voxels is 6 rows x 3 x 3, so the
 // cost loads (coalesced along x) and the broadcast weight loads from shared memory are shared 4 ways (54 + 54 per 864 FFMAs) and the
@@ -460,6 +782,12 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     conv3d_first_c8_kernel<<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
+  const char* v1 = getenv("LWS_C8_V1");  // developer switch: the one-plane-per-tile kernel
+  const bool plane_groups = !(v1 && v1[0] == '1') && (long long)B * ((Wp + 125) / 126) * ((D + CP_L - 1) / CP_L) * Hp < (1ll << 31);
+  e = cudaFuncSetAttribute(conv3d_c8p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(conv3d_c8p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
+  if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(conv3d_c8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(conv3d_c8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
@@ -477,9 +805,20 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     const int ct = (Wp + 125) / 126;
     a.ct_per_line = make_fastdiv(ct);
     a.total_tiles = B * ct * a.strip_len;
-    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    if (last) conv3d_c8_kernel<true><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
-    else conv3d_c8_kernel<false><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
+    if (plane_groups) {
+      CPArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      pa.c = a, pa.ct = ct, pa.ndg = (D + CP_L - 1) / CP_L;
+      pa.total_steps = B * ct * pa.ndg * Hp;
+      pa.fndg = make_fastdiv(pa.ndg), pa.fct = make_fastdiv(ct);
+      const int grid = pa.total_steps < kNumSMs ? pa.total_steps : kNumSMs;
+      if (last) conv3d_c8p_kernel<true><<<grid, C8_THREADS, CP_SMEM, st>>>(pa);
+      else conv3d_c8p_kernel<false><<<grid, C8_THREADS, CP_SMEM, st>>>(pa);
+    } else {
+      const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+      if (last) conv3d_c8_kernel<true><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
+      else conv3d_c8_kernel<false><<<grid, C8_THREADS, C8_SMEM, st>>>(a);
+    }
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
     cur = 2 - cur;
   }

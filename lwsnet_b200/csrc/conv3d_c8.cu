@@ -363,6 +363,7 @@ struct CPArgs {
 };
 struct CPItem {
   int b, L, row0, nsteps;  // row0: first output voxel (inside the batch element) of accumulator 0 of step 0
+  int dp0, y0, x0;         // its plane, line and column
 };
 // Work order: (b, column tile) -> chunks of `ch` lines -> d group -> line; every CTA takes one contiguous range of it (a range
 // start or a new (chunk, d group) costs two warm-up line groups).  Neighbouring d groups share two of their five input planes.
@@ -387,7 +388,8 @@ struct CPSched {
     const int y0 = yc * a.ch + yy;
     it.nsteps = min(chl - yy, g1 - g);
     it.L = min(CP_L, a.c.D - CP_L * dg);
-    it.row0 = ((1 + CP_L * dg) * a.c.Hp + y0) * a.c.Wp + cti * 126;
+    it.dp0 = 1 + CP_L * dg, it.y0 = y0, it.x0 = cti * 126;
+    it.row0 = (it.dp0 * a.c.Hp + y0) * a.c.Wp + it.x0;
     g += it.nsteps;
     return true;
   }
@@ -535,6 +537,11 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
     CPSched sched(pa);
     CPItem w;
     while (sched.next(pa, w)) {
+      // this thread's voxel column and line offset are the same for every step of the item (a tile may wrap over line ends)
+      int xj, carry;
+      fdivmod(w.x0 + j, a.fWp, carry, xj);
+      const bool xborder = xj < 1 || xj > a.W || j >= 126;
+      const int yj = w.y0 + carry;  // line of this thread's voxel at step 0; >= Hp: next plane (never stored from here)
       for (int n = 0; n < w.nsteps; ++n, ++st) {
 #pragma unroll 1
         for (int i = 0; i < CP_L; ++i) {
@@ -569,14 +576,11 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
               if (lane == 31) v += xp[(q + 1) * 3];
               v += xp[(q + 1) * 3 + 1 + lane - 30];
             }
-            int line, x, dpl, y;
-            fdivmod(r, a.fWp, line, x);
-            fdivmod(line, a.fHp, dpl, y);
-            // a tile that runs past the end of its plane would produce voxels of the next plane, which that plane's own tile
-            // accumulates in a different kd order (other accumulator index): leave them to their owner so results are unique
-            const int dp_tile = fdiv(fdiv(r - j, a.fWp), a.fHp);
-            if (j < 126 && x >= 1 && x <= a.W && y >= 1 && y <= a.H && dpl == dp_tile && dpl <= a.D) {
-              const long long o = (((long long)w.b * a.D + (dpl - 1)) * a.H + (y - 1)) * a.W + (x - 1);
+            // a tile that runs past the end of its plane (y > H) would produce voxels of the next plane, which that plane's own
+            // tile accumulates in a different kd order (other accumulator index): leave them to their owner so results are unique
+            const int y = yj + n;
+            if (!xborder && y >= 1 && y <= a.H) {
+              const long long o = (((long long)w.b * a.D + (w.dp0 + i - 1)) * a.H + (y - 1)) * a.W + (xj - 1);
               a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
             }
             continue;
@@ -592,12 +596,14 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty + tb);
+          // E = c0 * (main + corr * 2^-11) with c0 a power of two: the scale commutes with every rounding below, so it is applied
+          // once, together with the bias, after the shifted sum (bit-identical to scaling each E)
           float out[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float e0 = fmaf(k0[c], c1, m0[c] * c0);
-            m1[c] = fmaf(k1[c], c1, m1[c] * c0);
-            m2[c] = fmaf(k2[c], c1, m2[c] * c0);
+            const float e0 = fmaf(k0[c], 0x1p-11f, m0[c]);
+            m1[c] = fmaf(k1[c], 0x1p-11f, m1[c]);
+            m2[c] = fmaf(k2[c], 0x1p-11f, m2[c]);
             const float s1 = __shfl_down_sync(0xffffffffu, m1[c], 1);
             const float s2 = __shfl_down_sync(0xffffffffu, m2[c], 2);
             out[c] = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
@@ -623,14 +629,11 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
             const float4 u = p2[0], v = p2[1];
             out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
           }
-          int line, x, dpl, y;
-          fdivmod(r, a.fWp, line, x);
-          fdivmod(line, a.fHp, dpl, y);
-          const bool border = x < 1 || x > a.W || y < 1 || y > a.H || dpl < 1 || dpl > a.D;
+          const bool border = xborder || yj + n < 1 || yj + n > a.H;  // beyond the plane end: not stored from this tile anyway
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            float v0 = fmaxf(out[2 * p] + bias[2 * p], 0.f), v1 = fmaxf(out[2 * p + 1] + bias[2 * p + 1], 0.f);
+            float v0 = fmaxf(fmaf(out[2 * p], c0, bias[2 * p]), 0.f), v1 = fmaxf(fmaf(out[2 * p + 1], c0, bias[2 * p + 1]), 0.f);
             v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
             const __half2 h = __floats2half2_rn(v0, v1);
             const float2 f = __half22float2(h);
@@ -646,8 +649,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
             const long long v = (long long)w.b * a.vox_b + r0;
             // stop at the end of the tile's own plane: the voxels beyond belong to the next plane's tile, which accumulates its
             // kd taps in a different order (other accumulator index) -- one writer per voxel keeps the result unique
-            const int dp_tile = fdiv(fdiv(r0, a.fWp), a.fHp);
-            const uint32_t nv = (uint32_t)min(126, (dp_tile + 1) * plane - r0);
+            const uint32_t nv = (uint32_t)min(126, (w.dp0 + i + 1) * plane - r0);
             bulk_store(a.out_hi + v * 16, stage, nv * 16);
             bulk_store(a.out_lo + v * 16, stage + 2048, nv * 16);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -1,4 +1,4 @@
-for ch in 4 8 12 16 1000; do
-LWS_C8_CH=$ch ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none --profile-from-start off -k regex:conv3d_c8p_kernel -s 5 -c 1 --csv --log-file gpurun_out/c8p_q36_$ch.csv python tools/profile_step.py --batch 8 --iters 1 > /dev/null 2>&1
-echo "CH $ch: $(grep -o '"gpu__time_duration.sum","ns","[0-9,]*"\|"dram__bytes_read.sum","byte","[0-9,]*"\|"dram__bytes_read.sum","Mbyte","[0-9.]*"' gpurun_out/c8p_q36_$ch.csv | tr '\n' ' ')"
-done
+python tools/_dbg.py | tail -5
+timeout 300 python -m pytest tests -m gpu -x -q -k "conv3d_stack or shard or stage or other_baseline" 2>&1 | tail -2
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_q37_b8.csv python tools/profile_step.py --batch 8 --iters 1 > gpurun_out/prof_q37.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_q37_b8.csv > gpurun_out/launches_q37_b8.txt; head -10 gpurun_out/launches_q37_b8.txt

@@ -8,5 +8,5 @@ tail -3 gpurun_out/pytest_$tag.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$tag.log 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
 cat gpurun_out/bench_$tag.log | cut -c1-600
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$tag.csv \
-    python tools/profile_step.py --batch 4 --iters 1 > gpurun_out/prof_$tag.log 2>&1
+    python tools/profile_step.py --batch 8 --iters 1 > gpurun_out/prof_$tag.log 2>&1
 python tools/launch_summary.py gpurun_out/launches_$tag.csv

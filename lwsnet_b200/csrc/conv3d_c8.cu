@@ -666,10 +666,11 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
 }
 
 // ---- first conv 1 -> 8 on the raw cost (BN_0 affine + ReLU on the taps), writes every voxel of the padded hi/lo planes ----
-// One thread = 4 voxels that are neighbours in y (same padded x): the 27-tap window of the four voxels is 6 rows x 3 x 3, so the
-// cost loads (coalesced along x) and the broadcast weight loads from shared memory are shared 4 ways (54 + 54 per 864 FFMAs) and the
-// 16-byte voxel stores of a warp are contiguous.  Grid = (pair x padded plane, 4-row group, 128-voxel x segment): no index division.
-__global__ void __launch_bounds__(128, 5)
+// One thread = NV voxels that are neighbours in y (same padded x): the 27-tap window of the NV voxels is (NV + 2) rows x 3 x 3, so
+// the cost loads (coalesced along x) and the broadcast weight loads from shared memory are shared NV ways (NV = 8: 90 + 54 per 1728
+// FFMAs) and the 16-byte voxel stores of a warp are contiguous.  Grid = (pair x padded plane, NV-row group, 128-voxel x segment).
+template <int NV>
+__global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
     conv3d_first_c8_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][8]*/, const float* __restrict__ bias,
                            const float* __restrict__ affine, uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, int D, int H,
                            int W) {
@@ -680,24 +681,24 @@ __global__ void __launch_bounds__(128, 5)
   const int xp = blockIdx.z * 128 + threadIdx.x;
   if (xp >= Wp) return;
   const int b = blockIdx.x / Dp, dp = blockIdx.x - b * Dp;
-  const int yp0 = blockIdx.y * 4;
+  const int yp0 = blockIdx.y * NV;
   const int x = xp - 1, d = dp - 1;
   const long long hw = (long long)H * W;
   const long long vox0 = (((long long)b * Dp + dp) * Hp + yp0) * Wp + xp;
   const bool zero_all = d < 0 || d >= D || x < 0 || x >= W;
-  float acc[4][8];
+  float acc[NV][8];
 #pragma unroll
-  for (int v = 0; v < 4; ++v)
+  for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
   if (!zero_all) {
     const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
     const float* cb = cost + (long long)b * D * hw;  // 32-bit offsets inside one pair's volume (host checks D*H*W < 2^31)
     const int ihw = H * W;
-    int offr[6];
-    bool okr[6];
+    int offr[NV + 2];
+    bool okr[NV + 2];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
+    for (int r = 0; r < NV + 2; ++r) {
       const int yy = yp0 + r - 2;  // input row of (voxel vy, tap kh) with vy + kh = r
       okr[r] = (unsigned)yy < (unsigned)H;
       offr[r] = d * ihw + yy * W + x;
@@ -709,9 +710,9 @@ __global__ void __launch_bounds__(128, 5)
       for (int kw = 0; kw < 3; ++kw) {
         const bool okx = okd && (unsigned)(x + kw - 1) < (unsigned)W;
         const int tap = (kd - 1) * ihw + (kw - 1);
-        float v[6];
+        float v[NV + 2];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
+        for (int r = 0; r < NV + 2; ++r) {
           const bool ok = okx && okr[r];
           const float c = ok ? __ldg(cb + (offr[r] + tap)) : 0.f;
           v[r] = ok ? fmaxf(fmaf(c, s0, t0), 0.f) : 0.f;
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(128, 5)
           const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8);
           const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8 + 4);
 #pragma unroll
-          for (int vy = 0; vy < 4; ++vy) {
+          for (int vy = 0; vy < NV; ++vy) {
             const float t = v[vy + kh];
             acc[vy][0] = fmaf(t, wa.x, acc[vy][0]), acc[vy][1] = fmaf(t, wa.y, acc[vy][1]);
             acc[vy][2] = fmaf(t, wa.z, acc[vy][2]), acc[vy][3] = fmaf(t, wa.w, acc[vy][3]);
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(128, 5)
 #pragma unroll
   for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + j);
 #pragma unroll
-  for (int vy = 0; vy < 4; ++vy) {
+  for (int vy = 0; vy < NV; ++vy) {
     const int yp = yp0 + vy;
     if (yp >= Hp) break;
     const bool border = zero_all || yp == 0 || yp == Hp - 1;
@@ -787,9 +788,10 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     if ((e = cudaMemset2DAsync(plane[i] + (size_t)(Dp - 1) * pl, vox_b * 16, 0, pl, B, st)) != cudaSuccess) return (int)e;
   }
   {
-    if ((Hp + 3) / 4 > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
-    dim3 grid(B * Dp, (Hp + 3) / 4, (Wp + 127) / 128);
-    conv3d_first_c8_kernel<<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
+    constexpr int NV = 4;  // NV = 8 (168 registers, 2-3 blocks / SM) measured slower
+    if ((Hp + NV - 1) / NV > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
+    dim3 grid(B * Dp, (Hp + NV - 1) / NV, (Wp + 127) / 128);
+    conv3d_first_c8_kernel<NV><<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   const char* v1 = getenv("LWS_C8_V1");  // developer switch: the one-plane-per-tile kernel

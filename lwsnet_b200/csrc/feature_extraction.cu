@@ -205,14 +205,15 @@ __global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
 // The layers of the pyramid are small (a 1/8-resolution map of a few pairs is ~100k pixels), so a kernel whose threads wait for
 // their loads once per input channel is latency bound however many FLOPs the machine has.  Here a thread owns 4 consecutive output
 // pixels x CT output channels (blockIdx.z = channel group, so the small layers still fill the SMs), the three window rows of input
-// channel ci+1 are loaded into a second register set while channel ci is being multiplied (ping-pong, Cin even), and rows whose
+// channel ci+1 are loaded into a second register set while channel ci is being multiplied (ping-pong), and rows whose
 // pitch is only 8-byte aligned (W = 154 at 1/8 of KITTI) use 64-bit loads / stores instead of falling back to scalar taps.
-template <int COUT, int CT, int DIL, int STRIDE, bool V4>
+template <int COUT, int CT, int DIL, int STRIDE, bool V4, int WIN = 12, bool ODD = false>
 __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
   extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
   for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
   __syncthreads();
-  constexpr int G = V4 ? 4 : 2, NG = 12 / G;
+  static_assert(4 + 3 * STRIDE + DIL < WIN, "window too narrow for this stride / dilation");
+  constexpr int G = V4 ? 4 : 2, NG = WIN / G;
   const int wq = (a.Wo + 3) >> 2;
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= wq * a.Ho) return;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
   const int b = blockIdx.y, c0 = blockIdx.z * CT;
   const int x0 = (item - yo * wq) * 4;
   const long long hw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
-  const int xi0 = x0 * STRIDE;  // the aligned 12-wide window starts at input column xi0 - 4
+  const int xi0 = x0 * STRIDE;  // the aligned WIN-wide window starts at input column xi0 - 4
   const float* in_b = a.in + (long long)b * a.Cin * hw + (xi0 - 4);
   bool okc[NG], oky[3];
   int rowoff[3];
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
     oky[ky] = (unsigned)yi < (unsigned)a.Hi;
     rowoff[ky] = yi * a.Wi;
   }
-  auto load = [&](int ci, float (&w)[3][12]) {
+  auto load = [&](int ci, float (&w)[3][WIN]) {
     const float* plane = in_b + ci * hw;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int q = 0; q < CT; ++q) acc[p][q] = 0.f;
-  auto mac = [&](int ci, const float (&w)[3][12]) {
+  auto mac = [&](int ci, const float (&w)[3][WIN]) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -276,13 +277,22 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
       }
     }
   };
-  float wa[3][12], wb[3][12];
+  float wa[3][WIN], wb[3][WIN];
   load(0, wa);
-  for (int ci = 0; ci < a.Cin; ci += 2) {  // Cin is even (host-checked)
-    load(ci + 1, wb);
-    mac(ci, wa);
-    if (ci + 2 < a.Cin) load(ci + 2, wa);
-    mac(ci + 1, wb);
+  if constexpr (ODD) {  // odd channel count (the RGB input layer)
+    for (int ci = 0; ci < a.Cin; ci += 2) {
+      if (ci + 1 < a.Cin) load(ci + 1, wb);
+      mac(ci, wa);
+      if (ci + 2 < a.Cin) load(ci + 2, wa);
+      if (ci + 1 < a.Cin) mac(ci + 1, wb);
+    }
+  } else {
+    for (int ci = 0; ci < a.Cin; ci += 2) {
+      load(ci + 1, wb);
+      mac(ci, wa);
+      if (ci + 2 < a.Cin) load(ci + 2, wa);
+      mac(ci + 1, wb);
+    }
   }
 #pragma unroll
   for (int q = 0; q < CT; ++q) {
@@ -347,17 +357,22 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[r][p][q] = 0.f;
 
-  for (int ci = 0; ci < a.Cin; ++ci) {
+  // the six input values of channel ci + 1 are loaded while channel ci is multiplied (ping-pong register sets)
+  auto load6 = [&](int ci, float (&v0)[3], float (&v1)[3]) {
     const float* p0 = in_b + ci * ihw;
     const float2 a01 = __ldg(reinterpret_cast<const float2*>(p0));
-    const float a02 = c2 ? __ldg(p0 + 2) : 0.f;
-    float2 b01 = make_float2(0.f, 0.f);
-    float b02 = 0.f;
+    v0[0] = a01.x, v0[1] = a01.y, v0[2] = c2 ? __ldg(p0 + 2) : 0.f;
+    v1[0] = v1[1] = v1[2] = 0.f;
     if (r1) {
-      b01 = __ldg(reinterpret_cast<const float2*>(p0 + a.Wi));
-      b02 = c2 ? __ldg(p0 + a.Wi + 2) : 0.f;
+      const float2 b01 = __ldg(reinterpret_cast<const float2*>(p0 + a.Wi));
+      v1[0] = b01.x, v1[1] = b01.y, v1[2] = c2 ? __ldg(p0 + a.Wi + 2) : 0.f;
     }
-    const float in0[3] = {a01.x, a01.y, a02}, in1[3] = {b01.x, b01.y, b02};
+  };
+  float nx0[3], nx1[3];
+  load6(0, nx0, nx1);
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float in0[3] = {nx0[0], nx0[1], nx0[2]}, in1[3] = {nx1[0], nx1[1], nx1[2]};
+    if (ci + 1 < a.Cin) load6(ci + 1, nx0, nx1);
     const float* wc = sW + ci * 9 * COUT + cg * 8;
 #pragma unroll
     for (int q = 0; q < 8; q += 4) {
@@ -406,27 +421,30 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
   }
 }
 
-template <int COUT, int CT, int DIL, int STRIDE>
+template <int COUT, int CT, int DIL, int STRIDE, int WIN = 12, bool ODD = false>
 static int launch_pipe(const FeConvArgs& a, int B, size_t smem_w, cudaStream_t st) {
+  if (!ODD && (a.Cin & 1)) return LWS_ERR_UNSUPPORTED;
   dim3 g(cdiv(cdiv(a.Wo, 4) * a.Ho, 128), B, COUT / CT);
-  if ((a.Wi & 3) == 0 && (a.Wo & 3) == 0) fe_conv_pipe_kernel<COUT, CT, DIL, STRIDE, true><<<g, 128, smem_w, st>>>(a);
-  else fe_conv_pipe_kernel<COUT, CT, DIL, STRIDE, false><<<g, 128, smem_w, st>>>(a);
+  if ((a.Wi & 3) == 0 && (a.Wo & 3) == 0) fe_conv_pipe_kernel<COUT, CT, DIL, STRIDE, true, WIN, ODD><<<g, 128, smem_w, st>>>(a);
+  else fe_conv_pipe_kernel<COUT, CT, DIL, STRIDE, false, WIN, ODD><<<g, 128, smem_w, st>>>(a);
   cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }
 
 static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
   const size_t smem_w = (size_t)a.Cin * 9 * cout * sizeof(float);
-  const bool even = (a.Wi & 1) == 0 && (a.Wo & 1) == 0 && (a.Cin & 1) == 0 && a.pad == a.dil && !a.transposed &&
+  const bool cin_even = (a.Cin & 1) == 0;
+  const bool even = (a.Wi & 1) == 0 && (a.Wo & 1) == 0 && a.pad == a.dil && !a.transposed &&
                     (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.res) & 15) == 0;
-  if (even && a.stride == 1 && a.Wo == a.Wi) {
+  if (even && cin_even && a.stride == 1 && a.Wo == a.Wi) {
     if (cout == 16 && a.dil == 1) return launch_pipe<16, 8, 1, 1>(a, B, smem_w, st);
     if (cout == 8 && a.dil == 1) return launch_pipe<8, 8, 1, 1>(a, B, smem_w, st);
     if (cout == 8 && a.dil == 2) return launch_pipe<8, 8, 2, 1>(a, B, smem_w, st);
     if (cout == 8 && a.dil == 4) return launch_pipe<8, 8, 4, 1>(a, B, smem_w, st);
     if (cout == 4 && a.dil == 2) return launch_pipe<4, 4, 2, 1>(a, B, smem_w, st);
   }
-  if (even && a.stride == 2 && a.dil == 1 && a.Wi == 2 * a.Wo && cout == 16) return launch_pipe<16, 8, 1, 2>(a, B, smem_w, st);
+  if (even && cin_even && a.stride == 2 && a.dil == 1 && a.Wi == 2 * a.Wo && cout == 16) return launch_pipe<16, 8, 1, 2>(a, B, smem_w, st);
+  if (even && a.stride == 2 && a.dil == 2 && a.Wi == 2 * a.Wo && cout == 4) return launch_pipe<4, 4, 2, 2, 16, true>(a, B, smem_w, st);
   if (a.transposed && a.stride == 2 && a.pad == 1 && (a.Wi & 1) == 0 && a.Ho == 2 * a.Hi && a.Wo == 2 * a.Wi && (cout == 8 || cout == 16)) {
     dim3 g(cdiv((a.Wi >> 1) * a.Hi * (cout / 8), 128), B);
     if (cout == 8) fe_deconv_kernel<8><<<g, 128, smem_w, st>>>(a);

@@ -44,6 +44,9 @@ constexpr int DS_OFF_IN = DS_OFF_B + 8192;
 constexpr int DS_OFF_W = DS_OFF_IN + DS_NIN * DS_INBYTES;   // depthwise weights [9][32] fp32
 constexpr int DS_OFF_BAR = DS_OFF_W + 9 * 32 * 4;
 constexpr int DS_SMEM = DS_OFF_BAR + 256 + 1024 /*align slack*/;
+// the im2col modes (CIN > 0) have no input ring: their shared memory ends 100 KB earlier, which the SM gives to L1 -- the front end's
+// tap loads are L1 hits only if the few image lines in flight stay resident
+constexpr int DS_SMEM_IM2COL = DS_SMEM - DS_NIN * DS_INBYTES;
 constexpr float DS_ACT_SCALE = kDwsepActScale;
 
 struct DsArgs {
@@ -132,7 +135,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     dwsep_f16_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, const DsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DS_OFF_BAR);
+  constexpr int OFF_W = CIN > 0 ? DS_OFF_IN : DS_OFF_W, OFF_BAR = OFF_W + 9 * 32 * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* in_full = bars;                 // [NIN]
   uint64_t* in_empty = in_full + DS_NIN;    // [NIN]
   uint64_t* a_full = in_empty + DS_NIN;     // [NA]
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
   uint64_t* t_full = a_empty + DS_NA;       // [NT]
   uint64_t* t_empty = t_full + DS_NT;       // [NT]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + DS_NT);
-  float* sW = reinterpret_cast<float*>(smem + DS_OFF_W);
+  float* sW = reinterpret_cast<float*>(smem + OFF_W);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dil = a.dil;
@@ -328,50 +332,63 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     const uint32_t a_base = smem_u32(smem + DS_OFF_A);
     const uint32_t row = (uint32_t)p * 128;
     const long long hw = (long long)a.H * a.W;
-    uint32_t t = 0;
+    uint32_t t_ = 0;
     DsSched sched(a);
       DsItem w;
       while (sched.next(a, w)) {
       const int x = w.x0 + p - DS_RP;  // image column of this pixel
       const float* src0 = a.img + (long long)w.b * CIN * hw + x;
-      // the 16 K slots (k = ci*9 + ky*3 + kx) of this warp's half for image line y; both halves are unrolled and the
-      // warp-uniform h selects one
-      auto load_taps = [&](int y, float (&v)[16]) {
-        const float* src = src0 + (long long)y * a.W;
+      // K slots are ordered by tap column c = ci*3 + kx with the three ky taps of a column adjacent (slot = 3c + ky for c < 5,
+      // 16 + 3(c-5) + ky otherwise; slot 15 is padding), so each half warp owns whole columns and a step down the image is a
+      // register shift: only the new bottom row (5 / 4 values per thread instead of 16) is loaded, and it is loaded PF steps
+      // ahead through a register FIFO -- a new image line comes from DRAM (~1.5 us under load), longer than one step.
+      constexpr int PF = 3, NCOL = CIN * 3;
+      auto load_row = [&](int yrow, float (&r)[5]) {
+        const bool oky = (unsigned)yrow < (unsigned)a.H;
+        const float* src = src0 + (long long)yrow * a.W;
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const int k0 = kk, k1 = 16 + kk;
-          float r = 0.f;
+        for (int lc = 0; lc < 5; ++lc) {
+          // both halves are unrolled and the warp-uniform h selects one
+          const int c0 = lc, c1 = 5 + lc;
+          float v0 = 0.f, v1 = 0.f;
           if (h == 0) {
-            if (k0 < CIN * 9) {
-              const int ci = k0 / 9, ky = (k0 % 9) / 3, kx = k0 % 3;
-              const bool ok = (unsigned)(y + ky - 1) < (unsigned)a.H && (unsigned)(x + kx - 1) < (unsigned)a.W;
-              r = ok ? __ldg(src + ci * hw + (ky - 1) * a.W + (kx - 1)) : 0.f;
+            if (c0 < NCOL) {
+              const int ci = c0 / 3, kx = c0 % 3;
+              if (oky && (unsigned)(x + kx - 1) < (unsigned)a.W) v0 = __ldg(src + ci * hw + (kx - 1));
             }
           } else {
-            if (k1 < CIN * 9) {
-              const int ci = k1 / 9, ky = (k1 % 9) / 3, kx = k1 % 3;
-              const bool ok = (unsigned)(y + ky - 1) < (unsigned)a.H && (unsigned)(x + kx - 1) < (unsigned)a.W;
-              r = ok ? __ldg(src + ci * hw + (ky - 1) * a.W + (kx - 1)) : 0.f;
+            if (c1 < NCOL) {
+              const int ci = c1 / 3, kx = c1 % 3;
+              if (oky && (unsigned)(x + kx - 1) < (unsigned)a.W) v1 = __ldg(src + ci * hw + (kx - 1));
             }
           }
-          v[kk] = r;
+          r[lc] = h == 0 ? v0 : v1;
         }
       };
-      float v[16], vn[16];
-      load_taps(w.yi0, v);
-      for (int i = 0; i < w.nrows; ++i, ++t) {
+      float t[16], fifo[PF][5];
+      {
+        float r0[5], r1[5];
+        load_row(w.yi0 - 1, r0);
+        load_row(w.yi0, r1);
+#pragma unroll
+        for (int lc = 0; lc < 5; ++lc) t[3 * lc] = 0.f, t[3 * lc + 1] = r0[lc], t[3 * lc + 2] = r1[lc];
+        t[15] = 0.f;
+#pragma unroll
+        for (int f = 0; f < PF; ++f) load_row(w.yi0 + 1 + f, fifo[f]);
+      }
+      for (int i = 0; i < w.nrows; ++i, ++t_) {
         const int y = w.yi0 + i;
-        // every step touches one new image line (y + 1); a line comes from DRAM (~1.5 us under load, several steps), so pull the
-        // line a few steps ahead into L1 now, and issue the next step's tap loads before converting this step's (the loads are
-        // L1 / L2 hits whose latency then overlaps the conversion and the wait for a free A tile)
-        if (h == 0 && y + 5 < a.H && (unsigned)x < (unsigned)a.W) {
+        // slide the window one image line down and refill the FIFO PF lines ahead
 #pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) asm volatile("prefetch.global.L1 [%0];" ::"l"(src0 + (long long)(y + 5) * a.W + ci * hw));
-        }
-        if (i + 1 < w.nrows) load_taps(y + 1, vn);
+        for (int lc = 0; lc < 5; ++lc) t[3 * lc] = t[3 * lc + 1], t[3 * lc + 1] = t[3 * lc + 2], t[3 * lc + 2] = fifo[0][lc];
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) v[kk] *= DS_ACT_SCALE;
+        for (int f = 0; f + 1 < PF; ++f)
+#pragma unroll
+          for (int lc = 0; lc < 5; ++lc) fifo[f][lc] = fifo[f + 1][lc];
+        load_row(y + 1 + PF, fifo[PF - 1]);
+        float v[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) v[kk] = t[kk] * DS_ACT_SCALE;
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -379,8 +396,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
           const float2 f = __half22float2(hh);
           hi[k] = h2_bits(hh), lo[k] = h2_bits(__floats2half2_rn((v[2 * k] - f.x) * 2048.f, (v[2 * k + 1] - f.y) * 2048.f));
         }
-        const uint32_t ab = t % DS_NA;
-        mbar_wait(a_empty + ab, ((t / DS_NA) & 1) ^ 1);
+        const uint32_t ab = t_ % DS_NA;
+        mbar_wait(a_empty + ab, ((t_ / DS_NA) & 1) ^ 1);
         const uint32_t dst = a_base + ab * DS_TILE + row;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // hi chunks 2h, 2h+1; lo chunks 4+2h, 4+2h+1
@@ -394,8 +411,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + ab);
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) v[kk] = vn[kk];
       }
     }
   } else {
@@ -518,8 +533,8 @@ int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* p
 int launch_conv0_f16(const float* img, float* out, const void* wtab, const float* scales, const float* bias, int B, int CIN, int H,
                      int W, cudaStream_t st) {
   if (CIN != 1 && CIN != 3) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = CIN == 3 ? cudaFuncSetAttribute(dwsep_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM)
-                           : cudaFuncSetAttribute(dwsep_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
+  cudaError_t e = CIN == 3 ? cudaFuncSetAttribute(dwsep_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_IM2COL)
+                           : cudaFuncSetAttribute(dwsep_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_IM2COL);
   if (e != cudaSuccess) return (int)e;
   DsArgs a;
   memset(&a, 0, sizeof(a));
@@ -534,8 +549,8 @@ int launch_conv0_f16(const float* img, float* out, const void* wtab, const float
   const uint32_t box_out[3] = {32, 32, 1};
   int rc = make_tensor_map_f32(&map_out, out, 3, dims, strides, box_out, true);
   if (rc) return rc;
-  if (CIN == 3) dwsep_f16_kernel<3><<<grid, DS_THREADS, DS_SMEM, st>>>(map_out, map_out, a);
-  else dwsep_f16_kernel<1><<<grid, DS_THREADS, DS_SMEM, st>>>(map_out, map_out, a);
+  if (CIN == 3) dwsep_f16_kernel<3><<<grid, DS_THREADS, DS_SMEM_IM2COL, st>>>(map_out, map_out, a);
+  else dwsep_f16_kernel<1><<<grid, DS_THREADS, DS_SMEM_IM2COL, st>>>(map_out, map_out, a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }

@@ -344,12 +344,18 @@ extern "C" int lws_pack_refinement_weights(const float* const* t, int n_tensors,
     tc[3 * 16 * 32 + 1] = 1.f / (sw * 2048.f);
   }
   for (int br = 0; br < 2; ++br) {
-    // first conv [CIN][9][32] -> [K = ci*9 + tap (zero padded to 32)][co]: the same table format as a pointwise conv
+    // first conv [CIN][9][32] -> [K slot (zero padded to 32)][co]: the same table format as a pointwise conv.  Slots are ordered
+    // by tap column c = ci*3 + kx with the three ky taps adjacent (slot = 3c + ky for c < 5, 16 + 3(c-5) + ky otherwise, slot 15
+    // unused): the layout the im2col front end of dwsep_tc.cu slides down the image in registers
     float kxc[32 * 32];
     memset(kxc, 0, sizeof(kxc));
-    const int nk = (br == 0 ? 3 : 1) * 9;
-    for (int k = 0; k < nk; ++k)
-      for (int co = 0; co < 32; ++co) kxc[k * 32 + co] = packed[L.r1_w0[br] + (size_t)k * 32 + co];
+    const int cin0 = br == 0 ? 3 : 1;
+    for (int ci = 0; ci < cin0; ++ci)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int c = ci * 3 + kx, slot = c < 5 ? 3 * c + ky : 16 + 3 * (c - 5) + ky;
+          for (int co = 0; co < 32; ++co) kxc[slot * 32 + co] = packed[L.r1_w0[br] + (size_t)(ci * 9 + ky * 3 + kx) * 32 + co];
+        }
     pack_pwtc(kxc, packed + L.r1_w0tc[br]);
   }
   for (int br = 0; br < 2; ++br)

@@ -202,9 +202,9 @@ def kernel_probes(model, pk, B=16):
         add(f"K3 conv3d stack C={C} [{b},{D},{h},{w}] (6 launches, split-fp16 tcgen05)", us, flops=flops)
     # K6: one BN-ReLU-DW-PW block on its own (the step's dominant kernel, 12 launches per forward), then the whole refinement
     rp = model._refinement_packed(dev)
-    Bk = 4
+    Bk = 8
     n = int(ops.lib.lws_refinement_clp_floats(Bk, H_IMG, W_IMG))
-    bufs = [torch.zeros(n, device=dev) for _ in range(3)]
+    bufs = [torch.zeros(n, device=dev) for _ in range(3)]  # 3 x 518 MB
     for t in bufs:
         t.view(Bk, H_IMG + 32, W_IMG + 32, 32)[:, 16:-16, 16:-16, :].uniform_(0.0, 3.0)
     us = time_rotating(lambda i: ops.refinement_block_clp(bufs[i], rp, 2, 1, Bk, H_IMG, W_IMG, out=bufs[(i + 1) % 3]), 3, iters=12, warm=3)
@@ -315,11 +315,13 @@ def run_ours(args, rank, world, local_rank):
         dom = next(k for k in kernels if k["kernel"].startswith("K6 dwsep block"))
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full (profiles/r01_ncu_*dwsep*)
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": round(dom["gbs"] / pk["hbm"], 4), "traffic": 474624512,
+                    "frac": round(dom["gbs"] / pk["hbm"], 4), "traffic": 987819520,
                     "peak_source": pk["source"] + " copy bandwidth",
-                    "note": "dominant kernel by time (12 launches per forward, ~27% of the step); timed alone with CUDA events on "
-                            "the launching stream over 3 rotating 259 MB tensors (> L2); algorithmic bytes = interior pixels x 32 "
-                            "channels x 4 B, read once + written once; the conv stacks are tensor-core kernels, see `kernels`"}
+                    "note": "dominant kernel by time (12 launches per forward, ~34% of the step); timed alone (CUDA-graph replay "
+                            "between CUDA events) over 3 rotating 518 MB tensors (> L2) at 8 pairs per launch; algorithmic bytes = "
+                            "interior pixels x 32 channels x 4 B, read once + written once; traffic = ncu dram read + write of one "
+                            "launch at the same shape (profiles/r01_ncu_full_dwsep_f16_q42_8pairs.txt); the conv stacks are "
+                            "tensor-core kernels, see `kernels`"}
 
     # ---- CPU baseline beside it (N=1 only): the oracle port on the host cores, bounded sample -----------------------
     cpu = None

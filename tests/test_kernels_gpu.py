@@ -368,3 +368,26 @@ def test_disparity_to_u8_and_jet_bit_exact():
     assert np.array_equal(color.cpu().numpy(), lut[ref])
     g2, c2 = ops().disparity_to_u8(disp.cuda(), gray=True, color=False)
     assert c2 is None and np.array_equal(g2.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("D,H,W", [(9, 16, 32), (9, 32, 64), (4, 6, 9), (7, 10, 20)])
+def test_conv3d_c8_stack_unique_and_batch_independent(D, H, W):
+    """Regression for the plane-group kernel: a 126-voxel tile of a narrow volume wraps over several lines and, at the end of a
+    plane, into the next plane, whose own tile accumulates its kd taps in another order.  Exactly one tile may store each voxel:
+    re-running must give identical bits, and so must splitting the batch."""
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200.submodules import post_3dconvs
+    onet = O.post_3dconvs(4, 8)
+    holder = torch.nn.Module()
+    holder.net = onet
+    O.kaiming_normal_init_(holder, 5)
+    O.randomize_bn_(holder, 6)
+    net = post_3dconvs(4, 8)
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net = net.cuda()
+    x = (rnd(7, 4, D, H, W, scale=6.0).abs()).cuda()
+    a = net.run(x, add_skip=True)
+    for _ in range(3):
+        assert torch.equal(a, net.run(x, add_skip=True))
+    parts = torch.cat([net.run(x[:1].contiguous(), add_skip=True), net.run(x[1:].contiguous(), add_skip=True)])
+    assert torch.equal(a, parts)

@@ -182,7 +182,14 @@ def kernel_probes(model, pk, B=16):
         s = sets(nsets(B * (2 * C + 10) * h * w * 4), (B, C, h, w), (B, C, h, w))
         d = [torch.rand((B, 1, h, w), device=dev) * 20 for _ in s]
         us = time_rotating(lambda i: ops.warp_residual_volume_l1(s[i][0], s[i][1], d[i], 5), len(s))
-        add(f"K2 warp_residual_volume_l1 [{B},{C},{h},{w}] m=5", us, B * (2 * C + 1 + 9) * h * w * 4)
+        add(f"K2 warp_residual_volume_l1 [{B},{C},{h},{w}] m=5 (i.i.d. random disparity per pixel: worst case for the window gathers)",
+            us, B * (2 * C + 1 + 9) * h * w * 4)
+        # a smooth disparity field (what a trained network's previous stage produces): neighbouring pixels read neighbouring windows
+        yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32),
+                                indexing="ij")
+        smooth = (10.0 + 6.0 * torch.sin(xx / 37.0) * torch.cos(yy / 23.0)).expand(B, 1, h, w).contiguous()
+        us = time_rotating(lambda i: ops.warp_residual_volume_l1(s[i][0], s[i][1], smooth, 5), len(s))
+        add(f"K2 warp_residual_volume_l1 [{B},{C},{h},{w}] m=5 (smooth disparity)", us, B * (2 * C + 1 + 9) * h * w * 4)
     # K4
     for (D, h, w) in ((24, 46, 154), (9, 92, 308), (9, 184, 616)):
         s = sets(nsets(B * (D + 1) * h * w * 4), (B, D, h, w), scale=8.0)

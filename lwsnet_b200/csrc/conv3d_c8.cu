@@ -686,11 +686,13 @@ __global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
   const long long hw = (long long)H * W;
   const long long vox0 = (((long long)b * Dp + dp) * Hp + yp0) * Wp + xp;
   const bool zero_all = d < 0 || d >= D || x < 0 || x >= W;
-  float acc[NV][8];
+  // accumulators as float2 pairs: FFMA2 (fma.rn.f32x2, sm_100) does two output channels per issued instruction -- the kernel is
+  // bound by instruction issue (45 % of its instructions were scalar FFMAs), not by the FP32 pipe
+  float2 acc[NV][4];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[v][j] = make_float2(0.f, 0.f);
   if (!zero_all) {
     const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
     const float* cb = cost + (long long)b * D * hw;  // 32-bit offsets inside one pair's volume (host checks D*H*W < 2^31)
@@ -722,12 +724,13 @@ __global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
           const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8);
           const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8 + 4);
 #pragma unroll
+          const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+          const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
+#pragma unroll
           for (int vy = 0; vy < NV; ++vy) {
-            const float t = v[vy + kh];
-            acc[vy][0] = fmaf(t, wa.x, acc[vy][0]), acc[vy][1] = fmaf(t, wa.y, acc[vy][1]);
-            acc[vy][2] = fmaf(t, wa.z, acc[vy][2]), acc[vy][3] = fmaf(t, wa.w, acc[vy][3]);
-            acc[vy][4] = fmaf(t, wb.x, acc[vy][4]), acc[vy][5] = fmaf(t, wb.y, acc[vy][5]);
-            acc[vy][6] = fmaf(t, wb.z, acc[vy][6]), acc[vy][7] = fmaf(t, wb.w, acc[vy][7]);
+            const float2 t = make_float2(v[vy + kh], v[vy + kh]);
+            acc[vy][0] = __ffma2_rn(t, w01, acc[vy][0]), acc[vy][1] = __ffma2_rn(t, w23, acc[vy][1]);
+            acc[vy][2] = __ffma2_rn(t, w45, acc[vy][2]), acc[vy][3] = __ffma2_rn(t, w67, acc[vy][3]);
           }
         }
       }
@@ -744,8 +747,8 @@ __global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const float a0 = border ? 0.f : fmaxf(acc[vy][2 * p] + bv[2 * p], 0.f) * kDwsepActScale;
-      const float a1 = border ? 0.f : fmaxf(acc[vy][2 * p + 1] + bv[2 * p + 1], 0.f) * kDwsepActScale;
+      const float a0 = border ? 0.f : fmaxf(acc[vy][p].x + bv[2 * p], 0.f) * kDwsepActScale;
+      const float a1 = border ? 0.f : fmaxf(acc[vy][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
       const __half2 h = __floats2half2_rn(a0, a1);
       const float2 f = __half22float2(h);
       const __half2 l = __floats2half2_rn((a0 - f.x) * 2048.f, (a1 - f.y) * 2048.f);

@@ -539,11 +539,11 @@ __global__ void __launch_bounds__(256)
   const int y = blockIdx.y, b = blockIdx.z;
   const int x = xp - 1, dp0 = dpg * 4;
   const long long hw = (long long)H * W;
-  float acc[4][8];
+  float2 acc[4][4];  // float2 pairs: FFMA2 (fma.rn.f32x2) does two output channels per issued instruction
 #pragma unroll
   for (int v = 0; v < 4; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[v][j] = make_float2(0.f, 0.f);
   const bool xborder = x < 0 || x >= W;
   if (!xborder) {
     const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
@@ -576,12 +576,13 @@ __global__ void __launch_bounds__(256)
           const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8);
           const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8 + 4);
 #pragma unroll
+          const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+          const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
+#pragma unroll
           for (int vd = 0; vd < 4; ++vd) {
-            const float t = v[vd + kd];
-            acc[vd][0] = fmaf(t, wa.x, acc[vd][0]), acc[vd][1] = fmaf(t, wa.y, acc[vd][1]);
-            acc[vd][2] = fmaf(t, wa.z, acc[vd][2]), acc[vd][3] = fmaf(t, wa.w, acc[vd][3]);
-            acc[vd][4] = fmaf(t, wb.x, acc[vd][4]), acc[vd][5] = fmaf(t, wb.y, acc[vd][5]);
-            acc[vd][6] = fmaf(t, wb.z, acc[vd][6]), acc[vd][7] = fmaf(t, wb.w, acc[vd][7]);
+            const float2 t = make_float2(v[vd + kd], v[vd + kd]);
+            acc[vd][0] = __ffma2_rn(t, w01, acc[vd][0]), acc[vd][1] = __ffma2_rn(t, w23, acc[vd][1]);
+            acc[vd][2] = __ffma2_rn(t, w45, acc[vd][2]), acc[vd][3] = __ffma2_rn(t, w67, acc[vd][3]);
           }
         }
       }
@@ -599,8 +600,8 @@ __global__ void __launch_bounds__(256)
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const float a0 = border ? 0.f : fmaxf(acc[vd][2 * p] + bv[2 * p], 0.f) * kDwsepActScale;
-      const float a1 = border ? 0.f : fmaxf(acc[vd][2 * p + 1] + bv[2 * p + 1], 0.f) * kDwsepActScale;
+      const float a0 = border ? 0.f : fmaxf(acc[vd][p].x + bv[2 * p], 0.f) * kDwsepActScale;
+      const float a1 = border ? 0.f : fmaxf(acc[vd][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
       const __half2 h = __floats2half2_rn(a0, a1);
       const float2 f = __half22float2(h);
       const __half2 l = __floats2half2_rn((a0 - f.x) * 2048.f, (a1 - f.y) * 2048.f);

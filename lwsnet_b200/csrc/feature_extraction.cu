@@ -128,80 +128,9 @@ __global__ void __launch_bounds__(128) fe_conv_kernel(const FeConvArgs a) {
 }
 
 
-// ---- fast path 1: 3x3 conv with dilation DIL (pad = DIL), stride 1 or (DIL = 1) stride 2, Wi % 4 == 0 ---------------------------------------------
-// A thread owns 4 consecutive output pixels x all COUT.  Per (ci, ky) it issues three aligned, fully coalesced float4 loads
-// [x0-4, x0+8) that cover all three kx taps of its four pixels for DIL in {1, 2, 4} (the generic kernel issues 12 predicated
-// scalar loads for the same data and is LSU bound).
-template <int COUT, int DIL, int STRIDE>
-__global__ void __launch_bounds__(128) fe_conv_s1_kernel(const FeConvArgs a) {
-  extern __shared__ __align__(16) float sW[];  // [Cin][9][COUT]
-  for (int i = threadIdx.x; i < a.Cin * 9 * COUT; i += blockDim.x) sW[i] = __ldg(a.w + i);
-  __syncthreads();
-  const int wq = a.Wo >> 2;
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= wq * a.Ho) return;
-  const int yo = item / wq;
-  const int b = blockIdx.y;
-  const int x0 = (item - yo * wq) * 4;
-  const long long hw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
-  const float* in_b = a.in + (long long)b * a.Cin * hw;
-  const int xi0 = x0 * STRIDE;  // first input column of the aligned 12-wide window is xi0 - 4
-  const bool okL = xi0 >= 4, okM = xi0 + 4 <= a.Wi, okR = xi0 + 8 <= a.Wi;
-
-  float acc[4][COUT];
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int q = 0; q < COUT; ++q) acc[p][q] = 0.f;
-
-  for (int ci = 0; ci < a.Cin; ++ci) {
-    const float* plane = in_b + ci * hw;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yi = yo * STRIDE + (ky - 1) * DIL;
-      if ((unsigned)yi >= (unsigned)a.Hi) continue;
-      const float4* row = reinterpret_cast<const float4*>(plane + (long long)yi * a.Wi + xi0);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 L = okL ? __ldg(row - 1) : z, M = okM ? __ldg(row) : z, R = okR ? __ldg(row + 1) : z;
-      const float win[12] = {L.x, L.y, L.z, L.w, M.x, M.y, M.z, M.w, R.x, R.y, R.z, R.w};
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT;
-#pragma unroll
-        for (int q = 0; q < COUT; q += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float v = win[4 + p * STRIDE + (kx - 1) * DIL];
-            acc[p][q] = fmaf(v, w4.x, acc[p][q]);
-            acc[p][q + 1] = fmaf(v, w4.y, acc[p][q + 1]);
-            acc[p][q + 2] = fmaf(v, w4.z, acc[p][q + 2]);
-            acc[p][q + 3] = fmaf(v, w4.w, acc[p][q + 3]);
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < COUT; ++q) {
-    const float bias = __ldg(a.bias + q);
-    const long long o = ((long long)b * COUT + q) * ohw + (long long)yo * a.Wo + x0;
-    float r[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
-    if (a.res) {
-      const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
-      r[0] += rv.x, r[1] += rv.y, r[2] += rv.z, r[3] += rv.w;
-    }
-    if (a.relu) {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) r[p] = fmaxf(r[p], 0.f);
-    }
-    *reinterpret_cast<float4*>(a.out + o) = make_float4(r[0], r[1], r[2], r[3]);
-  }
-}
-
-// ---- fast path 1b: the same window scheme, software pipelined --------------------------------------------------------------------
+// ---- fast path 1: 3x3 conv with dilation DIL (pad = DIL), stride 1 or 2, even row pitch; software pipelined ---------------------
+// A thread owns 4 consecutive output pixels; per (ci, ky) three aligned, fully coalesced 128-bit loads [x0-4, x0+8) cover all
+// three kx taps of its four pixels for DIL in {1, 2, 4} (the generic kernel issues 12 predicated scalar loads for the same data).
 // The layers of the pyramid are small (a 1/8-resolution map of a few pairs is ~100k pixels), so a kernel whose threads wait for
 // their loads once per input channel is latency bound however many FLOPs the machine has.  Here a thread owns 4 consecutive output
 // pixels x CT output channels (blockIdx.z = channel group, so the small layers still fill the SMs), the three window rows of input
@@ -251,11 +180,11 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
       }
     }
   };
-  float acc[4][CT];
+  float2 acc[4][CT / 2];  // float2 pairs: FFMA2 (fma.rn.f32x2, sm_100) does two output channels per issued instruction
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int q = 0; q < CT; ++q) acc[p][q] = 0.f;
+    for (int q = 0; q < CT / 2; ++q) acc[p][q] = make_float2(0.f, 0.f);
   auto mac = [&](int ci, const float (&w)[3][WIN]) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -265,13 +194,13 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
 #pragma unroll
         for (int q = 0; q < CT; q += 4) {
           const float4 w4 = *reinterpret_cast<const float4*>(wp + q);
+          const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float v = w[ky][4 + p * STRIDE + (kx - 1) * DIL];
-            acc[p][q] = fmaf(v, w4.x, acc[p][q]);
-            acc[p][q + 1] = fmaf(v, w4.y, acc[p][q + 1]);
-            acc[p][q + 2] = fmaf(v, w4.z, acc[p][q + 2]);
-            acc[p][q + 3] = fmaf(v, w4.w, acc[p][q + 3]);
+            const float2 vv = make_float2(v, v);
+            acc[p][q / 2] = __ffma2_rn(vv, w01, acc[p][q / 2]);
+            acc[p][q / 2 + 1] = __ffma2_rn(vv, w23, acc[p][q / 2 + 1]);
           }
         }
       }
@@ -300,7 +229,7 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
     const long long o = ((long long)b * COUT + c0 + q) * ohw + (long long)yo * a.Wo + x0;
     float r[4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) r[p] = acc[p][q] + bias;
+    for (int p = 0; p < 4; ++p) r[p] = (q & 1 ? acc[p][q / 2].y : acc[p][q / 2].x) + bias;
     if constexpr (V4) {
       if (a.res) {
         const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
@@ -349,13 +278,13 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
   const float* in_b = a.in + (long long)b * a.Cin * ihw + (long long)i * a.Wi + 2 * j;
   const bool r1 = i + 1 < a.Hi, c2 = 2 * j + 2 < a.Wi;
 
-  float acc[2][4][8];
+  float2 acc[2][4][4];  // float2 pairs of output channels: FFMA2 (fma.rn.f32x2) halves the issued FMA instructions
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[r][p][q] = 0.f;
+      for (int q = 0; q < 4; ++q) acc[r][p][q] = make_float2(0.f, 0.f);
 
   // the six input values of channel ci + 1 are loaded while channel ci is multiplied (ping-pong register sets)
   auto load6 = [&](int ci, float (&v0)[3], float (&v1)[3]) {
@@ -383,14 +312,16 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
 #define LWS_ROW(ACC, IN, KY)                                                                                            \
   {                                                                                                                     \
     const float4 k0 = w[(KY) * 3], k1 = w[(KY) * 3 + 1], k2 = w[(KY) * 3 + 2];                                           \
-    ACC[0][q] = fmaf(IN[0], k1.x, ACC[0][q]), ACC[0][q + 1] = fmaf(IN[0], k1.y, ACC[0][q + 1]);                          \
-    ACC[0][q + 2] = fmaf(IN[0], k1.z, ACC[0][q + 2]), ACC[0][q + 3] = fmaf(IN[0], k1.w, ACC[0][q + 3]);                  \
-    ACC[1][q] = fmaf(IN[0], k2.x, fmaf(IN[1], k0.x, ACC[1][q])), ACC[1][q + 1] = fmaf(IN[0], k2.y, fmaf(IN[1], k0.y, ACC[1][q + 1])); \
-    ACC[1][q + 2] = fmaf(IN[0], k2.z, fmaf(IN[1], k0.z, ACC[1][q + 2])), ACC[1][q + 3] = fmaf(IN[0], k2.w, fmaf(IN[1], k0.w, ACC[1][q + 3])); \
-    ACC[2][q] = fmaf(IN[1], k1.x, ACC[2][q]), ACC[2][q + 1] = fmaf(IN[1], k1.y, ACC[2][q + 1]);                          \
-    ACC[2][q + 2] = fmaf(IN[1], k1.z, ACC[2][q + 2]), ACC[2][q + 3] = fmaf(IN[1], k1.w, ACC[2][q + 3]);                  \
-    ACC[3][q] = fmaf(IN[1], k2.x, fmaf(IN[2], k0.x, ACC[3][q])), ACC[3][q + 1] = fmaf(IN[1], k2.y, fmaf(IN[2], k0.y, ACC[3][q + 1])); \
-    ACC[3][q + 2] = fmaf(IN[1], k2.z, fmaf(IN[2], k0.z, ACC[3][q + 2])), ACC[3][q + 3] = fmaf(IN[1], k2.w, fmaf(IN[2], k0.w, ACC[3][q + 3])); \
+    const float2 k0a = make_float2(k0.x, k0.y), k0b = make_float2(k0.z, k0.w);                                           \
+    const float2 k1a = make_float2(k1.x, k1.y), k1b = make_float2(k1.z, k1.w);                                           \
+    const float2 k2a = make_float2(k2.x, k2.y), k2b = make_float2(k2.z, k2.w);                                           \
+    const float2 i0 = make_float2(IN[0], IN[0]), i1 = make_float2(IN[1], IN[1]), i2 = make_float2(IN[2], IN[2]);         \
+    ACC[0][q / 2] = __ffma2_rn(i0, k1a, ACC[0][q / 2]), ACC[0][q / 2 + 1] = __ffma2_rn(i0, k1b, ACC[0][q / 2 + 1]);       \
+    ACC[1][q / 2] = __ffma2_rn(i0, k2a, __ffma2_rn(i1, k0a, ACC[1][q / 2]));                                             \
+    ACC[1][q / 2 + 1] = __ffma2_rn(i0, k2b, __ffma2_rn(i1, k0b, ACC[1][q / 2 + 1]));                                     \
+    ACC[2][q / 2] = __ffma2_rn(i1, k1a, ACC[2][q / 2]), ACC[2][q / 2 + 1] = __ffma2_rn(i1, k1b, ACC[2][q / 2 + 1]);       \
+    ACC[3][q / 2] = __ffma2_rn(i1, k2a, __ffma2_rn(i2, k0a, ACC[3][q / 2]));                                             \
+    ACC[3][q / 2 + 1] = __ffma2_rn(i1, k2b, __ffma2_rn(i2, k0b, ACC[3][q / 2 + 1]));                                     \
   }
       LWS_ROW(acc[0], in0, 1)  // even output row: ky = 1 on input row i
       LWS_ROW(acc[1], in0, 2)  // odd output row: ky = 2 on input row i ...
@@ -407,7 +338,7 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
       const long long o = ((long long)b * COUT + co) * ohw + (long long)(2 * i + r) * a.Wo + 4 * j;
       float v[4];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) v[p] = acc[r][p][q] + bias;
+      for (int p = 0; p < 4; ++p) v[p] = (q & 1 ? acc[r][p][q / 2].y : acc[r][p][q / 2].x) + bias;
       if (a.res) {
         const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
         v[0] += rv.x, v[1] += rv.y, v[2] += rv.z, v[3] += rv.w;

@@ -352,7 +352,8 @@ constexpr int CP_OFF_STAGE = CP_OFF_RING + CP_NG * CP_GBYTES;
 constexpr int CP_OFF_XCH = CP_OFF_STAGE + C8_NGRP * 4096;
 constexpr int CP_OFF_BAR = CP_OFF_XCH + C8_NGRP * 4 * 3 * 8 * 4;
 constexpr int CP_SMEM = CP_OFF_BAR + 256 + 128;
-constexpr int CP_TCOLS = 192;                 // TMEM columns per step buffer
+constexpr int CP_TCOLS = 160;                 // TMEM columns per step buffer (144 used)
+constexpr int CP_NT = 3;                      // step buffers in TMEM (3 x 160 <= 512 columns)
 
 struct CPArgs {
   C8Args c;       // tensors, sizes, fast divisors (line0 / strip_len / total_tiles / ct_per_line unused)
@@ -426,15 +427,15 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CP_OFF_BAR);
   uint64_t* g_full = bars;              // [NG]
   uint64_t* g_empty = g_full + CP_NG;   // [NG]
-  uint64_t* t_full = g_empty + CP_NG;   // [2]
-  uint64_t* t_empty = t_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = g_empty + CP_NG;   // [NT]
+  uint64_t* t_empty = t_full + CP_NT;   // [NT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + CP_NT);
   constexpr uint32_t NB = LAST ? 16 : 48;  // accumulator columns per output tile = B rows per kd
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < CP_NG; ++i) mbar_init(g_full + i, 1), mbar_init(g_empty + i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, CP_L * 4);
+    for (int i = 0; i < CP_NT; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, CP_L * 4);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -489,8 +490,8 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
       while (sched.next(pa, w)) {
         for (int n = 0; n < w.nsteps; ++n, ++st) {
           const bool last = n == w.nsteps - 1;
-          const uint32_t tb = st & 1;
-          mbar_wait(t_empty + tb, ((st >> 1) & 1) ^ 1);
+          const uint32_t tb = st % CP_NT;
+          mbar_wait(t_empty + tb, ((st / CP_NT) & 1) ^ 1);
           uint32_t slot = bslot, ph = bph;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
@@ -546,8 +547,8 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
 #pragma unroll 1
         for (int i = 0; i < CP_L; ++i) {
           if ((int)((st * CP_L + i) & 3) != g) continue;
-          const uint32_t tb = st & 1;
-          mbar_wait(t_full + tb, (st >> 1) & 1);
+          const uint32_t tb = st % CP_NT;
+          mbar_wait(t_full + tb, (st / CP_NT) & 1);
           if (i >= w.L) {  // no such plane in this d group: only release the buffer
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + tb);

@@ -12,7 +12,8 @@ namespace lws {
 // (9 planes of a residual volume = one chunk, 24 planes of the stage-1 volume = two chunks of 12): on B200 the 16/clk/SM
 // MUFU.EX2 rate is within 2x of what the HBM stream asks for, so masked-out lanes of a partial chunk are not free.
 template <int VEC, int CH>
-__global__ void __launch_bounds__(256)
+// resident warps, not registers, bound this stream (measured at 64 pairs: 1 -> 3 -> 4 blocks / SM = 59 % -> 79 % -> 85 % of HBM for D = 9)
+__global__ void __launch_bounds__(256, CH == 9 ? 4 : 3)
     softmax_regression_kernel(const float* __restrict__ cost, float* __restrict__ low, int D, long long hw,
                               long long n_items_per_b, float start, float step) {
   const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;

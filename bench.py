@@ -207,6 +207,18 @@ def kernel_probes(model, pk, B=16):
         us = time_rotating(lambda i: stack.run(xs[i], add_skip=True), len(xs), iters=10, warm=3)
         flops = 2 * 27 * D * h * w * b * (C + 4 * C * C + C)
         add(f"K3 conv3d stack C={C} [{b},{D},{h},{w}] (6 launches, split-fp16 tcgen05)", us, flops=flops)
+    # BASELINE configs[1]: stage-1 path only = K1 volume + C=32 3D stack (+ skip) + K4 regression, [8,16,46,154], maxdisp 192 (D = 24)
+    f = sets(6, (8, 16, 46, 154), (8, 16, 46, 154))
+    st0 = model.volume_postprocess[0]
+
+    def stage1(i):
+        return ops.softmax_regression(st0.run(ops.cost_volume_l1(f[i][0], f[i][1], 24), add_skip=True), 0.0)
+
+    us = time_rotating(stage1, len(f), iters=12, warm=3)
+    rec = {"kernel": "configs[1] stage-1 path: K1 + 3D stack C=32 + K4, [8,16,46,154] D=24 (8 launches)", "us": round(us, 2),
+           "pairs_per_s": round(8 / us * 1e6, 1), "flops": 2 * 27 * 24 * 46 * 154 * 8 * (32 + 4 * 32 * 32 + 32)}
+    rec["tflops"] = round(rec["flops"] / us / 1e6, 2)
+    out.append(rec)
     # K6: one BN-ReLU-DW-PW block on its own (the step's dominant kernel, 12 launches per forward), then the whole refinement
     rp = model._refinement_packed(dev)
     Bk = 8
@@ -310,6 +322,15 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = timed(lambda: engine.infer_host(left_h, right_h, out_h), e2e_steps)
     e2e_value = world * BATCH * e2e_steps / (ms_e2e / 1e3)
 
+    # ---- the same with uint8 images in and uint8 disparities out (the reference's inference-loop body) ----------
+    g = torch.Generator().manual_seed(99 + rank)
+    lu8 = torch.randint(0, 256, (BATCH, 375, 1242, 3), dtype=torch.uint8, generator=g).pin_memory()
+    ru8 = torch.randint(0, 256, (BATCH, 375, 1242, 3), dtype=torch.uint8, generator=g).pin_memory()
+    gray_h = torch.empty((BATCH, 4, H_IMG, W_IMG), dtype=torch.uint8).pin_memory()
+    engine.infer_host_u8(lu8, ru8, H_IMG, W_IMG, out_gray=gray_h)
+    ms_u8 = timed(lambda: engine.infer_host_u8(lu8, ru8, H_IMG, W_IMG, out_gray=gray_h), e2e_steps)
+    u8_value = world * BATCH * e2e_steps / (ms_u8 / 1e3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -361,6 +382,10 @@ def run_ours(args, rank, world, local_rank):
                    "tflops_equiv": round(value * GFLOP_PER_PAIR / 1e3, 2)},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(left_h.nbytes + right_h.nbytes),
                 "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+        "e2e_u8": {"value": u8_value, "unit": "pairs/s", "h2d_bytes_per_step": int(lu8.nbytes + ru8.nbytes),
+                   "d2h_bytes_per_step": int(gray_h.nbytes), "steps": e2e_steps, "ms_per_step": ms_u8 / e2e_steps,
+                   "note": "uint8 HWC BGR 1242x375 images in, crop + normalise on the device, four uint8 disparity maps out "
+                           "(inference.py:93-115); random-noise images, so only the work, not the disparities, is meaningful"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -101,7 +101,15 @@ class LWSNet(nn.Module):
         # the reference runs the shared-weight extractor twice (models.py:110-111); one launch set over the stacked pair is
         # the same arithmetic per image (every kernel is batch-independent) and keeps the small 1/8-resolution layers fuller
         n = left_input.shape[0]
-        feats = self.feature_extraction(torch.cat([left_input, right_input.contiguous()]))
+        right_input = right_input.contiguous()
+        if (left_input.untyped_storage().data_ptr() == right_input.untyped_storage().data_ptr()
+                and right_input.storage_offset() == left_input.storage_offset() + left_input.numel()):
+            # the pair already sits back to back in one allocation (StereoEngine's buffers): view it as the stacked batch
+            stacked = left_input.new_empty(0).set_(left_input.untyped_storage(), left_input.storage_offset(),
+                                                   (2 * n,) + tuple(left_input.shape[1:]))
+        else:
+            stacked = torch.cat([left_input, right_input])
+        feats = self.feature_extraction(stacked)
         feats_l = [f[:n] for f in feats]
         feats_r = [f[n:] for f in feats]
         pred = []

@@ -80,8 +80,8 @@ class StereoEngine:
         g = self._graphs.get(key)
         if g is None:
             dev = self.device
-            left = torch.zeros((n, 3, H, W), device=dev)
-            right = torch.zeros((n, 3, H, W), device=dev)
+            both = torch.zeros((2 * n, 3, H, W), device=dev)  # left and right back to back: the model stacks them without a copy
+            left, right = both[:n], both[n:]
             out = torch.empty((n, 4, H, W), device=dev)
             s = torch.cuda.Stream(dev)
             s.wait_stream(torch.cuda.current_stream(dev))

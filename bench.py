@@ -250,6 +250,8 @@ def run_ours(args, rank, world, local_rank):
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     torch.cuda.set_device(local_rank)
+    from lwsnet_b200.runner import bind_to_gpu_cpus
+    cpus = bind_to_gpu_cpus(local_rank) if world > 1 and not args.no_bind else None  # before any pinned allocation
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator is created: keep stdout to the one JSON line
@@ -373,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": "configs[2]: full 4-stage LWSNet inference (volume build + warp + residual volumes + 3D stacks "
                                "+ regression + colour-guidance refinement), KITTI 1232x368, batch 64 per GPU",
-                   "batch_per_gpu": BATCH, "micro_batch": args.micro_batch,
+                   "batch_per_gpu": BATCH, "micro_batch": args.micro_batch, "cpu_binding": (f"{len(cpus)} NUMA-local cores per rank" if cpus else "none"),
                    "e2e_chunks": [hi - lo for lo, hi in engine._host_chunks(BATCH)], "maxdisplist": [24, 5, 5],
                    "weights": "random init (KaimingNormal, seed 0)", "cuda_graphs": not args.no_graphs,
                    "l2": "inputs (697 MB per step) and per-step activations exceed the 126 MB L2",
@@ -410,6 +412,7 @@ def main():
     ap.add_argument("--skip-probes", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--probes-only", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA-local CPU cores")
     ap.add_argument("--probe-batch", type=int, default=16, help="pairs per launch in the streaming-kernel probes")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

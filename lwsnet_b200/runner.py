@@ -14,6 +14,33 @@ import torch
 from . import ops
 
 
+def bind_to_gpu_cpus(device_index: int) -> Optional[list]:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so that
+    pinned host buffers allocated afterwards are first-touched on that node and H2D / D2H DMA does not cross the socket link.
+    With 8 ranks streaming ~24 GB/s each this is the difference between scaling and not.  Returns the CPU list, or None when NVML
+    or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:  # NVML enumerates by PCI bus id, CUDA may not: go through the bus id
+            pr = torch.cuda.get_device_properties(device_index)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous split of `total` pairs over `world` ranks; the first total % world ranks get one extra pair."""
     if world <= 0 or not (0 <= rank < world):

@@ -31,6 +31,27 @@ def _require_cuda(x: torch.Tensor, who: str) -> None:
         raise LwsError(f"{who}: lwsnet_b200 has no CPU path; move the model and its inputs to a CUDA device")
 
 
+# The per-layer classes below are parameter holders: their parents (feature_extraction, Post3DConvs, the refinement parts) execute
+# them fused through the C ABI.  A per-layer torch / cuDNN forward exists only as a GPU-side cross-check for the tests and is
+# refused outside `torch_crosscheck()`, so the product can never run a library kernel by accident.
+_CROSSCHECK = [False]
+
+
+class torch_crosscheck:
+    def __enter__(self):
+        self._old = _CROSSCHECK[0]
+        _CROSSCHECK[0] = True
+
+    def __exit__(self, *exc):
+        _CROSSCHECK[0] = self._old
+
+
+def _require_crosscheck(who: str) -> None:
+    if not _CROSSCHECK[0]:
+        raise LwsError(f"{who} is a parameter holder executed fused by its parent layer through liblws_b200; "
+                       "a stand-alone per-layer forward (torch / cuDNN) is not part of the product path")
+
+
 class BatchNorm(nn.Module):
     """Inference-mode BatchNorm2D/3D parameter holder with Paddle's state keys."""
 
@@ -52,6 +73,7 @@ class BatchNorm(nn.Module):
 
     def forward(self, x):
         _require_cuda(x, "BatchNorm")
+        _require_crosscheck("BatchNorm")
         s, t = self.scale_shift()
         shape = [1, -1] + [1] * (x.dim() - 2)
         return x * s.float().view(shape) + t.float().view(shape)
@@ -76,6 +98,7 @@ class Conv2D(_Conv):
 
     def forward(self, x):  # feature extractor only (off the hot path, see module docstring)
         _require_cuda(x, "Conv2D")
+        _require_crosscheck("Conv2D")
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # fp32 operands: TF32 moves disparities by px
             return F.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
 
@@ -86,6 +109,7 @@ class Conv2DTranspose(_Conv):
 
     def forward(self, x):
         _require_cuda(x, "Conv2DTranspose")
+        _require_crosscheck("Conv2DTranspose")
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             return F.conv_transpose2d(x, self.weight, None, self.stride, self.padding, self.output_padding)
 
@@ -98,6 +122,7 @@ class Conv3D(_Conv):
 class ReLU(nn.Module):
     def forward(self, x):
         _require_cuda(x, "ReLU")
+        _require_crosscheck("ReLU")
         return torch.relu(x)
 
 
@@ -182,11 +207,12 @@ class feature_extraction(nn.Module):
         """The same graph through torch's conv ops (cuDNN, fp32).  Not used by the product path; kept as a GPU-side
         cross-check for the tests of the feature-pyramid kernel."""
         _require_cuda(input, "feature_extraction")
-        output = self.dres0(input)
-        output = self.dres1(output) + output
-        res = self.dres2(output)
-        output = res[-1] + output
-        output = self.classif1(output)
+        with torch_crosscheck():
+            output = self.dres0(input)
+            output = self.dres1(output) + output
+            res = self.dres2(output)
+            output = res[-1] + output
+            output = self.classif1(output)
         res.pop(-1)
         res.append(output)
         return res

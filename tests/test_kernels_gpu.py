@@ -176,7 +176,7 @@ def _stack_from_golden(prefix, C):
     return net.cuda(), g
 
 
-# The C = 32 and C = 8 stacks have two implementations: the tcgen05 3xTF32 implicit GEMM (default) and the fp32 FFMA kernels
+# The C = 32 and C = 8 stacks have two implementations: the tcgen05 split-fp16 (x = hi + lo*2^-11, three exact products) implicit GEMM (default) and the fp32 FFMA kernels
 # (LWS_CONV3D_TC=0).  Operands of the tensor-core path are split exactly (x = xh + xl), but TMEM accumulation rounds toward
 # zero at each of its 108 MMA steps, which leaves a ~5e-6 relative drift per layer: its bound is 5e-4 * (1 + |y|), the FFMA
 # path keeps SURVEY 8(c)'s 1e-4 * (1 + |y|).
@@ -230,7 +230,7 @@ def test_conv3d_stack_vs_fp64_oracle(C, B, D, H, W, conv3d_path):
 
 
 # ------------------------------------------------------------------------------------------------ a8 + a9
-# Two implementations: channels-last tcgen05 3xTF32 (default; pointwise products are fp32-exact to a few ulps, the dense
+# Two implementations: channels-last tcgen05 split-fp16 (default; pointwise products are fp32-exact to a few ulps, the dense
 # 64->32 conv accumulates over 72 round-toward-zero MMA steps) and the fp32 FFMA kernels (LWS_REFINE_TC=0).
 REFINE_PATHS = [("tc", "1", 6.0, 1e-5), ("ffma", "0", 3.0, 2e-6)]
 

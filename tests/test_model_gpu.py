@@ -54,7 +54,7 @@ def test_stages_teacher_forced(models, H, W):
         e = err_stats(out.cpu(), pred64[s])
         floor = err_stats(pred32[s], pred64[s])
         print(f"stage {s + 1} teacher-forced {H}x{W}: {e}  | fp32-oracle floor (free-running): {floor}")
-        # stage 1 runs the tcgen05 3xTF32 stack by default (RZ accumulation in TMEM, see test_kernels_gpu.py): 4x floor;
+        # stage 1 runs the tcgen05 split-fp16 stack by default (RZ accumulation in TMEM, see test_kernels_gpu.py): 4x floor;
         # the FFMA stages keep 2x.  north_star's 1e-3 px holds on the mean and on >= 95 % of the pixels.
         k = 4 if s == 0 else 2
         assert e["mean"] <= k * floor["mean"] + 1e-4 and e["mean"] <= 1e-3
@@ -78,7 +78,7 @@ def test_end_to_end_vs_noise_floor(models):
         assert tuple(out[s].shape) == (2, 1, 128, 256)
         e, floor = err_stats(out[s].cpu(), p64[s]), err_stats(p32[s], p64[s])
         print(f"stage {s + 1} free-running: new {e} | fp32 oracle {floor}")
-        # 4x on mean / p99.9: stage 1 is the tcgen05 3xTF32 path (see test_stages_teacher_forced).  The free-running MAX is
+        # 4x on mean / p99.9: stage 1 is the tcgen05 split-fp16 path (see test_stages_teacher_forced).  The free-running MAX is
         # chaotic on random-init weights (stage-2/3 softmaxes are arg-min-like): 10x.
         for k, mult in (("max", 10), ("p999", 4), ("mean", 4)):
             assert e[k] <= mult * floor[k] + 1e-4 * (1 + p64[s].abs().max().item()), (s, k, e, floor)
@@ -209,3 +209,20 @@ def test_engine_schedules_agree_bitwise(models):
     out_e = eager.infer_host(left.pin_memory(), right.pin_memory())
     torch.cuda.synchronize()
     assert torch.equal(out_e, ref)
+
+
+def test_no_per_layer_library_forward(models):
+    """The per-layer holders (Conv2D, BatchNorm, ...) refuse a stand-alone torch / cuDNN forward: only the fused C-ABI paths run in
+    the product; the torch graph exists solely as a test cross-check behind `torch_crosscheck()`."""
+    from lwsnet_b200._lib import LwsError
+    from lwsnet_b200.submodules import torch_crosscheck
+    O, o32, o64, prod = models
+    x = torch.zeros(1, 3, 64, 128, device="cuda")
+    for layer in (prod.feature_extraction.dres0, prod.feature_extraction.dres0[0][0], prod.feature_extraction.dres2,
+                  prod.volume_postprocess[0][0][0]):
+        with pytest.raises(LwsError):
+            layer(x)
+    with pytest.raises(LwsError):
+        prod.refinement1_left(x)
+    with torch_crosscheck():
+        assert tuple(prod.feature_extraction.dres0(x).shape) == (1, 8, 32, 64)

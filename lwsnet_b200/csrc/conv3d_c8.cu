@@ -350,7 +350,8 @@ constexpr int CP_GBYTES = (CP_L + 2) * 4096;  // (L + 2) planes x (hi, lo) x 128
 constexpr int CP_OFF_RING = 14336;
 constexpr int CP_OFF_STAGE = CP_OFF_RING + CP_NG * CP_GBYTES;
 constexpr int CP_OFF_XCH = CP_OFF_STAGE + C8_NGRP * 4096;
-constexpr int CP_OFF_BAR = CP_OFF_XCH + C8_NGRP * 4 * 3 * 8 * 4;
+constexpr int CP_OFF_EX = CP_OFF_XCH + C8_NGRP * 4 * 3 * 8 * 4;   // [NGRP groups][4 planes: E1 lo/hi, E2 lo/hi channels][128 rows] float4
+constexpr int CP_OFF_BAR = CP_OFF_EX + C8_NGRP * 4 * 128 * 16;
 constexpr int CP_SMEM = CP_OFF_BAR + 256 + 128;
 constexpr int CP_TCOLS = 160;                 // TMEM columns per step buffer (144 used)
 constexpr int CP_NT = 3;                      // step buffers in TMEM (3 x 160 <= 512 columns)
@@ -599,36 +600,25 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
           if (lane == 0) mbar_arrive(t_empty + tb);
           // E = c0 * (main + corr * 2^-11) with c0 a power of two: the scale commutes with every rounding below, so it is applied
           // once, together with the bias, after the shifted sum (bit-identical to scaling each E)
+          // The Toeplitz shift out[r] = E0[r] + E1[r+1] + E2[r+2] goes through shared memory (4 conflict-free float4 planes per
+          // group): 4 stores + 4 loads per thread instead of 16 shuffles + 16 selects and a separate cross-quarter exchange.
           float out[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float e0 = fmaf(k0[c], 0x1p-11f, m0[c]);
+            out[c] = fmaf(k0[c], 0x1p-11f, m0[c]);
             m1[c] = fmaf(k1[c], 0x1p-11f, m1[c]);
             m2[c] = fmaf(k2[c], 0x1p-11f, m2[c]);
-            const float s1 = __shfl_down_sync(0xffffffffu, m1[c], 1);
-            const float s2 = __shfl_down_sync(0xffffffffu, m2[c], 2);
-            out[c] = e0 + (lane < 31 ? s1 : 0.f) + (lane < 30 ? s2 : 0.f);
           }
-          if (lane < 2) {
-            float4* d2 = reinterpret_cast<float4*>(xq + (1 + lane) * 8);
-            d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
-            if (lane == 0) {
-              float4* d1 = reinterpret_cast<float4*>(xq);
-              d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
-            }
-          }
+          float4* ex = reinterpret_cast<float4*>(smem + CP_OFF_EX) + g * (4 * 128);
+          ex[j] = make_float4(m1[0], m1[1], m1[2], m1[3]), ex[128 + j] = make_float4(m1[4], m1[5], m1[6], m1[7]);
+          ex[256 + j] = make_float4(m2[0], m2[1], m2[2], m2[3]), ex[384 + j] = make_float4(m2[4], m2[5], m2[6], m2[7]);
           // the bulk stores of this group's previous tile must have read the staging buffer
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           named_bar_sync(bar_id, 128);
-          if (q < 3 && lane >= 30) {
-            if (lane == 31) {
-              const float4* p1 = reinterpret_cast<const float4*>(xn);
-              const float4 u = p1[0], v = p1[1];
-              out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
-            }
-            const float4* p2 = reinterpret_cast<const float4*>(xn + (1 + lane - 30) * 8);
-            const float4 u = p2[0], v = p2[1];
-            out[0] += u.x, out[1] += u.y, out[2] += u.z, out[3] += u.w, out[4] += v.x, out[5] += v.y, out[6] += v.z, out[7] += v.w;
+          if (j < 126) {  // rows 126, 127 are the halo of the next tile
+            const float4 a0 = ex[j + 1], a1 = ex[128 + j + 1], b0 = ex[256 + j + 2], b1 = ex[384 + j + 2];
+            out[0] = out[0] + a0.x + b0.x, out[1] = out[1] + a0.y + b0.y, out[2] = out[2] + a0.z + b0.z, out[3] = out[3] + a0.w + b0.w;
+            out[4] = out[4] + a1.x + b1.x, out[5] = out[5] + a1.y + b1.y, out[6] = out[6] + a1.z + b1.z, out[7] = out[7] + a1.w + b1.w;
           }
           const bool border = xborder || yj + n < 1 || yj + n > a.H;  // beyond the plane end: not stored from this tile anyway
           uint32_t hi[4], lo[4];

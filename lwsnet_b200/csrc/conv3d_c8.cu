@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
     float* xq = xch + q * 24;                    // this quarter publishes e1 of lane 0, e2 of lanes 0 and 1
     const float* xn = xch + ((q + 1) & 3) * 24;  // next quarter's
     const int bar_id = 1 + g;
-    uint32_t st = 0, mine = 0;  // step counter; tiles this group has handled (double-buffers the LAST exchange rows)
+    uint32_t st0 = 0, mine = 0;  // first step of the current item; tiles this group has handled (double-buffers the LAST exchange rows)
     CPSched sched(pa);
     CPItem w;
     while (sched.next(pa, w)) {
@@ -544,10 +544,13 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
       fdivmod(w.x0 + j, a.fWp, carry, xj);
       const bool xborder = xj < 1 || xj > a.W || j >= 126;
       const int yj = w.y0 + carry;  // line of this thread's voxel at step 0; >= Hp: next plane (never stored from here)
-      for (int n = 0; n < w.nsteps; ++n, ++st) {
+      // this group's tiles of the item: k = 3 * step + i with k % 4 == g, visited directly (no skipped iterations)
+      const uint32_t k_begin = st0 * CP_L, k_end = (st0 + (uint32_t)w.nsteps) * CP_L;
 #pragma unroll 1
-        for (int i = 0; i < CP_L; ++i) {
-          if ((int)((st * CP_L + i) & 3) != g) continue;
+      for (uint32_t k = k_begin + (((uint32_t)g - k_begin) & 3u); k < k_end; k += 4) {
+        {
+          const uint32_t st = k / CP_L;
+          const int i = (int)(k - st * CP_L), n = (int)(st - st0);
           const uint32_t tb = st % CP_NT;
           mbar_wait(t_full + tb, (st / CP_NT) & 1);
           if (i >= w.L) {  // no such plane in this d group: only release the buffer
@@ -647,6 +650,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
           }
         }
       }
+      st0 += (uint32_t)w.nsteps;
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }

@@ -631,7 +631,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
             v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
             const __half2 h = __floats2half2_rn(v0, v1);
             const float2 f = __half22float2(h);
-            const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+            // (v - hi) * 2^11 on channel pairs (FADD2 + FMUL2)
+            const float2 d = split_lo2(v0, v1, f);
+            const __half2 l = __floats2half2_rn(d.x, d.y);
             hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
           }
           *reinterpret_cast<uint4*>(stage + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -746,7 +748,8 @@ __global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
       const float a1 = border ? 0.f : fmaxf(acc[vy][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
       const __half2 h = __floats2half2_rn(a0, a1);
       const float2 f = __half22float2(h);
-      const __half2 l = __floats2half2_rn((a0 - f.x) * 2048.f, (a1 - f.y) * 2048.f);
+      const float2 dl = split_lo2(a0, a1, f);
+      const __half2 l = __floats2half2_rn(dl.x, dl.y);
       hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
     }
     out_hi[vox0 + (long long)vy * Wp] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

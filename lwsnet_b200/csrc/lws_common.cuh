@@ -75,6 +75,12 @@ __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
+// low half of the split-fp16 operand of a channel pair: (v - hi) * 2^11 with FADD2 + FMUL2 (sm_100 packed fp32; same roundings as
+// the scalar form)
+__device__ __forceinline__ float2 split_lo2(float v0, float v1, float2 hi_as_float) {
+  return __fmul2_rn(__fadd2_rn(make_float2(v0, v1), make_float2(-hi_as_float.x, -hi_as_float.y)), make_float2(2048.f, 2048.f));
+}
+
 // ---- reference coordinate replay (models/models.py:44-53) ------------------------
 // Every operation is an explicitly rounded intrinsic so ptxas can never contract them into FMAs: the reference
 // issues one Paddle operator per arithmetic step and the tap indices must match it bit for bit.

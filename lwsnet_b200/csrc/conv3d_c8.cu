@@ -343,8 +343,10 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
 // t = -1 .. L feeds the accumulators i = max(0, t-1) .. min(L-1, t+1), which are neighbouring column blocks of TMEM, through ONE
 // MMA whose B operand is a row sub-range of that table:  N = 48, 96, 144, 96, 48 for L = 3  ->  15 MMAs / 1248 issue cycles per
 // three tiles instead of 27 / 1728.  The plane that feeds all L accumulators goes first with accumulate = 0.
-// Tiles are numbered k = 3 * step + i and handled round robin by the four epilogue groups; TMEM holds two steps (2 x 192 columns).
-constexpr int CP_L = 3;
+// Tiles are numbered k = CP_L * step + i and handled round robin by the four epilogue groups; TMEM holds two steps (2 x 192 columns).
+constexpr int CP_L = 3;                       // d planes per group.  The kernel is generic up to 5 (CP_L = 5, CP_NG = 5, CP_TCOLS = 256,
+                                              // CP_NT = 2: D = 9 as groups of 5 + 4, 13 input planes per 9 outputs instead of 15) --
+                                              // measured equal within noise (stage-3 stack 434 vs 442 us, stage-2 165 vs 159 per 4 pairs)
 constexpr int CP_NG = 6;                      // ring of line groups
 constexpr int CP_GBYTES = (CP_L + 2) * 4096;  // (L + 2) planes x (hi, lo) x 128 voxels x 16 B
 constexpr int CP_OFF_RING = 14336;
@@ -353,7 +355,7 @@ constexpr int CP_OFF_XCH = CP_OFF_STAGE + C8_NGRP * 4096;
 constexpr int CP_OFF_EX = CP_OFF_XCH + C8_NGRP * 4 * 3 * 8 * 4;   // [NGRP groups][4 planes: E1 lo/hi, E2 lo/hi channels][128 rows] float4
 constexpr int CP_OFF_BAR = CP_OFF_EX + C8_NGRP * 4 * 128 * 16;
 constexpr int CP_SMEM = CP_OFF_BAR + 256 + 128;
-constexpr int CP_TCOLS = 160;                 // TMEM columns per step buffer (144 used)
+constexpr int CP_TCOLS = 160;                 // TMEM columns per step buffer (CP_L x 48 = 144 used)
 constexpr int CP_NT = 3;                      // step buffers in TMEM (3 x 160 <= 512 columns)
 
 struct CPArgs {
@@ -397,26 +399,30 @@ struct CPSched {
   }
 };
 
-// MMAs of one line group (one kh) for L accumulators; INIT: the first one overwrites
+// MMAs of one line group (one kh) for L accumulators.  Input plane t = -1 .. L feeds accumulators max(0, t-1) .. min(L-1, t+1).
+// INIT (first kh of a step): the planes t = 1, 4, ... cover disjoint accumulator sets that together are all of them; they go first
+// and overwrite, everything else accumulates.
+template <uint32_t NB>
+__device__ __forceinline__ void cp_mma(uint32_t tmem_buf, uint32_t g_lo, uint32_t b_kh, uint64_t a_hi, uint64_t b_hi, int t, int L,
+                                       uint32_t acc) {
+  const int i_min = t - 1 > 0 ? t - 1 : 0, i_max = t + 1 < L - 1 ? t + 1 : L - 1;
+  const uint32_t N = NB * (uint32_t)(i_max - i_min + 1);
+  const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+  const uint64_t da = a_hi | (uint64_t)(g_lo + (uint32_t)(t + 1) * (4096 >> 4));
+  const uint64_t db = b_hi | (uint64_t)(b_kh + (uint32_t)(1 - t + i_min) * NB);  // row start (16-byte units)
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_buf + (uint32_t)i_min * NB),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
 template <int L, uint32_t NB>
 __device__ __forceinline__ void cp_issue_group(uint32_t tmem_buf, uint32_t g_lo, uint32_t b_kh, uint64_t a_hi, uint64_t b_hi, bool init) {
-  constexpr int t_init = L == 3 ? 1 : 0;
 #pragma unroll
-  for (int o = 0; o < L + 2; ++o) {
-    // issue order: the plane that covers every accumulator first
-    const int t = o == 0 ? t_init : (o - 2 < t_init ? o - 2 : o - 1);  // o = 0 -> t_init; then -1 .. L without t_init
-    const int i_min = t - 1 > 0 ? t - 1 : 0, i_max = t + 1 < L - 1 ? t + 1 : L - 1;
-    const uint32_t N = NB * (uint32_t)(i_max - i_min + 1);
-    const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t da = a_hi | (uint64_t)(g_lo + (uint32_t)(t + 1) * (4096 >> 4));
-    const uint64_t db = b_hi | (uint64_t)(b_kh + (uint32_t)(1 - t + i_min) * NB);  // row start (16-byte units)
-    const uint32_t acc = (init && o == 0) ? 0u : 1u;
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_buf + (uint32_t)i_min * NB),
-        "l"(da), "l"(db), "r"(idesc), "r"(acc)
-        : "memory");
-  }
+  for (int t = 1; t <= L; t += 3) cp_mma<NB>(tmem_buf, g_lo, b_kh, a_hi, b_hi, t, L, init ? 0u : 1u);
+#pragma unroll
+  for (int t = -1; t <= L; ++t)
+    if (!(t >= 1 && (t - 1) % 3 == 0)) cp_mma<NB>(tmem_buf, g_lo, b_kh, a_hi, b_hi, t, L, 1u);
 }
 
 template <bool LAST>
@@ -501,7 +507,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
             const uint32_t g_lo = ring_lo + slot * (CP_GBYTES >> 4);
             const uint32_t b_kh = b_lo + (uint32_t)kh * ((3 * NB * 32) >> 4);
             const uint32_t tbuf = tmem + tb * CP_TCOLS;
-            if (w.L == 3) cp_issue_group<3, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
+            if (w.L == 5) cp_issue_group<5, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
+            else if (w.L == 4) cp_issue_group<4, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
+            else if (w.L == 3) cp_issue_group<3, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
             else if (w.L == 2) cp_issue_group<2, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
             else cp_issue_group<1, NB>(tbuf, g_lo, b_kh, a_hi, b_hi, kh == 0);
             if (kh == 0 || last)

@@ -11,7 +11,8 @@
  *   - every tensor pointer is a DEVICE pointer to contiguous fp32, NCHW (NCDHW for volumes);
  *   - the caller owns every buffer including workspaces; nothing is allocated or freed here;
  *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no synchronisation;
- *   - re-entrant, no global mutable state;
+ *   - re-entrant; the only process-wide state is the option table below, changed only by lws_set_option (the library
+ *     never reads the environment), so concurrent calls see whatever options were set before them;
  *   - return 0 on success, <0 = LWS_ERR_*, >0 = the cudaError_t of a failed launch.
  *   - lws_pack_* functions are pure HOST functions (host pointers in, host blob out).
  */
@@ -45,6 +46,20 @@ enum {
 LWS_API const char* lws_status_string(int status);
 /* "lws_b200 <semver> sm_100a" */
 LWS_API const char* lws_version(void);
+
+/* ---- options ---------------------------------------------------------------------------------------------
+ * Explicit, process-wide switches (int values).  Unknown key: LWS_ERR_UNSUPPORTED; value out of range: LWS_ERR_BAD_SHAPE.
+ *   "conv3d_tc"       1   3D stacks on tcgen05 split-fp16 (1) or on the exact-fp32 FFMA kernels (0)
+ *   "refine_tc"       1   refinement on tcgen05 split-fp16 (1) or on the exact-fp32 FFMA kernels (0)
+ *   "refine_chain"    2   consecutive BN-ReLU-DW-PW blocks per L2-resident chain launch (0 / 1: one block per launch; 2; 4)
+ *   "chain_min_bands" 24  chains are used from this many (pair, 64-row band) units per launch on
+ *   "chain_sep_items" 160 chain kernel: queue distance between a producer band and its consumers (sizes the L2 rings;
+ *                         workspace sizes depend on it: set it before lws_refinement_workspace_bytes)
+ *   "warp_div_mode"   0   lws_warp_* coordinate normalisation x / (size-1): 0 = x * fl32(1/(size-1)) (Paddle 2.0 scalar
+ *                         division = scale op), 1 = IEEE division
+ *   "c8_v1" 0, "c8_chunk" 0, "k1_dt" 8   developer A/B switches of the C = 8 stack and the stage-1 volume kernel */
+LWS_API int lws_set_option(const char* key, int value);
+LWS_API int lws_get_option(const char* key, int* value);
 
 /* ---- a1: LWSNet._build_volume_2d  (models/models.py:58-76) ------------------------------------------
  * cost[b,d/stride,y,x] = sum_c | L[b,c,y,x] - (x-d >= 0 ? R[b,c,y,x-d] : 0) |,  d = 0,stride,..,maxdisp-stride.
@@ -128,6 +143,13 @@ LWS_API int lws_refinement_f32(const float* left, const float* pred3, const floa
 LWS_API size_t lws_refinement_clp_floats(int B, int H, int W);
 LWS_API int lws_refinement_block_clp_f32(const float* in_clp, float* out_clp, const float* packed_weights, int branch, int block,
                                          int B, int H, int W, lws_stream_t stream);
+
+/* blocks [block0, block0 + nblk) (nblk = 2..4) of a branch in ONE launch: the tensors between the blocks live in row rings that
+ * stay resident in L2 (dwsep_chain.cu).  Same layout as lws_refinement_block_clp_f32; the result is bit-identical to nblk
+ * single-block calls.  ws: lws_refinement_chain_workspace_bytes (256-byte aligned). */
+LWS_API size_t lws_refinement_chain_workspace_bytes(int branch, int block0, int nblk, int B, int H, int W);
+LWS_API int lws_refinement_chain_clp_f32(const float* in_clp, float* out_clp, const float* packed_weights, int branch, int block0,
+                                         int nblk, void* ws, size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
 
 /* ---- n1 (SURVEY.md 8(f) "next"): feature_extraction  (models/submodules.py:5-188) ----------------------------
  * img [B,3,H,W] -> f8 [B,16,H/8,W/8], f4 [B,16,H/4,W/4], f2 [B,8,H/2,W/2]; H, W multiples of 8.  12 launches, fp32.

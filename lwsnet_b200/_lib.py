@@ -22,6 +22,8 @@ _pp = POINTER(c_void_p)
 SIGNATURES = {
     "lws_status_string": (c_char_p, [c_int]),
     "lws_version": (c_char_p, []),
+    "lws_set_option": (c_int, [c_char_p, c_int]),
+    "lws_get_option": (c_int, [c_char_p, POINTER(c_int)]),
     "lws_cost_volume_l1_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_disp_to_scale_f32": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_warp_bilinear_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
@@ -40,6 +42,8 @@ SIGNATURES = {
     "lws_refinement_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lws_refinement_clp_floats": (c_size_t, [c_int, c_int, c_int]),
     "lws_refinement_block_clp_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "lws_refinement_chain_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "lws_refinement_chain_clp_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
     "lws_refinement_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
     "lws_preprocess_bgr_u8": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_disparity_to_u8": (c_int, [_fp, _fp, _fp, c_longlong, c_void_p]),
@@ -66,3 +70,31 @@ def check(status: int, what: str) -> None:
 
 def version() -> str:
     return lib.lws_version().decode()
+
+
+def set_option(key: str, value: int) -> None:
+    """lws_set_option: explicit process-wide switch of the C library (include/lws.h lists the keys)."""
+    check(lib.lws_set_option(key.encode(), int(value)), f"lws_set_option({key!r}, {value})")
+
+
+def get_option(key: str) -> int:
+    v = c_int(0)
+    check(lib.lws_get_option(key.encode(), ctypes.byref(v)), f"lws_get_option({key!r})")
+    return v.value
+
+
+class options:
+    """``with options(refine_tc=0, conv3d_tc=0): ...`` -- set library options for a block and restore them afterwards."""
+
+    def __init__(self, **kv):
+        self.kv, self.old = kv, {}
+
+    def __enter__(self):
+        for k, v in self.kv.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)

@@ -194,8 +194,7 @@ template <int CK, int COUT, int Q, int RG, int TW, int DIL, int EPI>
 static int launch_conv2d(Conv2dArgs a, int B, cudaStream_t st) {
   using Cfg = Conv2dCfg<CK, COUT, Q, RG, TW, DIL, EPI>;
   auto kern = conv2d_3x3_kernel<CK, COUT, Q, RG, TW, DIL, EPI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-  if (e != cudaSuccess) return (int)e;
+  LWS_SET_SMEM_ONCE(kern, Cfg::SMEM);  // `kern` is fixed by the template arguments: one static flag per instantiation
   a.tiles_w = cdiv(a.W, TW);
   a.tiles_h = cdiv(a.H, Cfg::TH);
   dim3 grid(a.tiles_w * a.tiles_h, B);

@@ -803,15 +803,13 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     conv3d_first_c8_kernel<NV><<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
-  const char* v1 = getenv("LWS_C8_V1");  // developer switch: the one-plane-per-tile kernel
-  const bool plane_groups = !(v1 && v1[0] == '1') && (long long)B * ((Wp + 125) / 126) * ((D + CP_L - 1) / CP_L) * Hp < (1ll << 31);
-  e = cudaFuncSetAttribute(conv3d_c8p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(conv3d_c8p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(conv3d_c8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(conv3d_c8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C8_SMEM);
+  // lws_set_option("c8_v1", 1): the one-plane-per-tile kernel
+  const bool plane_groups = opt(OPT_C8_V1) == 0 && (long long)B * ((Wp + 125) / 126) * ((D + CP_L - 1) / CP_L) * Hp < (1ll << 31);
+  LWS_SET_SMEM_ONCE(conv3d_c8p_kernel<false>, CP_SMEM);
+  LWS_SET_SMEM_ONCE(conv3d_c8p_kernel<true>, CP_SMEM);
+  LWS_SET_SMEM_ONCE(conv3d_c8_kernel<false>, C8_SMEM);
+  LWS_SET_SMEM_ONCE(conv3d_c8_kernel<true>, C8_SMEM);
+  e = cudaSuccess;
   if (e != cudaSuccess) return (int)e;
   int cur = 0;
   for (int l = 0; l <= layers; ++l) {  // l == layers: the closing 8 -> 1 conv
@@ -832,8 +830,8 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
       pa.c = a, pa.ct = ct, pa.ndg = (D + CP_L - 1) / CP_L;
       pa.total_steps = B * ct * pa.ndg * Hp;
       pa.fcolsteps = make_fastdiv(pa.ndg * Hp), pa.fct = make_fastdiv(ct);
-      const char* chs = getenv("LWS_C8_CH");  // developer override for tuning
-      pa.ch = chs && atoi(chs) > 0 ? atoi(chs) : Hp;
+      const int chs = opt(OPT_C8_CHUNK);  // lws_set_option("c8_chunk", n)
+      pa.ch = chs > 0 ? chs : Hp;
       const int grid = pa.total_steps < kNumSMs ? pa.total_steps : kNumSMs;
       if (last) conv3d_c8p_kernel<true><<<grid, C8_THREADS, CP_SMEM, st>>>(pa);
       else conv3d_c8p_kernel<false><<<grid, C8_THREADS, CP_SMEM, st>>>(pa);

@@ -484,11 +484,12 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1 && !L.last;
   const bool is2dlast = L.tz == 1 && L.nstages == 3 && L.nshift == 1 && L.last;
   if (!is3d && !is2d && !is2dlast) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = is2dlast  ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                  : is2d    ? cudaFuncSetAttribute(tz_gemm_kernel<8, 6, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                  : L.last  ? cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(tz_gemm_kernel<1, 3, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  // every variant may use up to the 227 KB cap (the per-call size is `smem`): set once per variant and device
+  if (is2dlast) LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 1, true>), 232448);
+  else if (is2d) LWS_SET_SMEM_ONCE((tz_gemm_kernel<8, 6, 1, false>), 232448);
+  else if (L.last) LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 3, true>), 232448);
+  else LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 3, false>), 232448);
+  cudaError_t e;
   a.bias = L.bias, a.scales = L.wtab + (L.last ? (size_t)nblk * 16 * 32 : (size_t)a.nbtiles * 192 * 32);
   a.skip = L.skip, a.out_f32 = L.out_f32, a.out_mode = L.out_mode;
   a.out_split = L.out_split, a.relu = L.relu;

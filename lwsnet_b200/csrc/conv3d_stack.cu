@@ -243,8 +243,7 @@ template <int CK, int COUT, int Q, int TD, int TW, bool FIRST, bool LAST>
 static int launch_conv3d(Conv3dArgs a, int B, cudaStream_t st) {
   using Cfg = Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>;
   auto kern = conv3d_k3_kernel<CK, COUT, Q, TD, TW, FIRST, LAST>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-  if (e != cudaSuccess) return (int)e;
+  LWS_SET_SMEM_ONCE(kern, Cfg::SMEM);  // `kern` is fixed by the template arguments: one static flag per instantiation
   a.tiles_w = cdiv(a.W, TW);
   a.tiles_h = cdiv(a.H, Cfg::TH);
   a.tiles_d = cdiv(a.D, TD);
@@ -276,8 +275,7 @@ static size_t packed_tc_offset(int C, int layers, int mid_layer) {
 static bool has_tc_tables(int C) { return C == 32 || C == 8; }
 static bool use_tc_path(int C) {
   if (!has_tc_tables(C)) return false;
-  const char* e = getenv("LWS_CONV3D_TC");
-  return !(e && e[0] == '0');
+  return opt(OPT_CONV3D_TC) != 0;
 }
 
 template <int C>

@@ -269,10 +269,7 @@ static int launch_tile(const float* L, const float* R, float* cost, int B, int C
                        cudaStream_t st) {
   if (t.smem > 200 * 1024) return LWS_ERR_UNSUPPORTED;
   auto kern = cost_volume_l1_tile_kernel<DT>;
-  if (t.smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
-    if (e != cudaSuccess) return (int)e;
-  }
+  if (t.smem > 48 * 1024) LWS_SET_SMEM_ONCE(kern, 200 * 1024);  // the cap checked above, once per DT instantiation
   const int vec2 = (W % 2 == 0) && ((((uintptr_t)L) | ((uintptr_t)R)) & 7) == 0;
   dim3 grid(t.n_xtiles * cdiv(H, t.nr), B * t.n_dtiles);
   kern<<<grid, t.threads, t.smem, st>>>(L, R, cost, C, H, W, D, t.n_xtiles, t.txq, t.nr, t.ck, t.n_dtiles, vec2);
@@ -299,9 +296,9 @@ extern "C" int lws_cost_volume_l1_f32(const float* L, const float* R, float* cos
     if (direct) {
       // DT = 8 measured fastest at every batch size (B = 64: 37 us against 41 us for DT = 12 and 55 us for DT = 24): the kernel is
       // bound by resident warps (96 registers -> 20 warps / SM against 8 at DT = 24) and L1 wavefronts, not by window re-reads
-      const char* force = getenv("LWS_K1_DT");  // developer override for tuning
-      if (force && atoi(force) == 24 && D % 24 == 0) return launch_direct<24>(L, R, cost, B, C, H, W, D, st);
-      if (force && atoi(force) == 12 && D % 12 == 0) return launch_direct<12>(L, R, cost, B, C, H, W, D, st);
+      const int force = opt(OPT_K1_DT);  // lws_set_option("k1_dt", 8 | 12 | 24)
+      if (force == 24 && D % 24 == 0) return launch_direct<24>(L, R, cost, B, C, H, W, D, st);
+      if (force == 12 && D % 12 == 0) return launch_direct<12>(L, R, cost, B, C, H, W, D, st);
       return launch_direct<8>(L, R, cost, B, C, H, W, D, st);
     }
     // otherwise the shared-memory tile kernel: widest disparity tile that still puts >= 3 blocks on every SM

@@ -16,80 +16,9 @@
 //     shared memory and TMA-stores it (clipped at the line end by the tensor map), so the tile's critical path has no
 //     cross-warp barrier.
 // The y-border lines of the output are zero-filled by all threads at kernel start.
-#include <cuda_fp16.h>
-#include <math.h>
-#include <string.h>
-
-#include "lws_common.cuh"
-#include "tma_utils.cuh"
+#include "dwsep_common.cuh"
 
 namespace lws {
-
-constexpr int DS_RP = 16;          // border of the refinement CLP tensors
-constexpr int DS_DW_WARPS = 8;     // warps 0..7
-constexpr int DS_EPI_WARP0 = 8;    // warps 8..11 (warp % 4 = TMEM lane quarter)
-constexpr int DS_PROD_WARP = 12;
-constexpr int DS_MMA_WARP = 13;
-constexpr int DS_THREADS = 14 * 32;
-constexpr int DS_NIN = 5;                   // input ring slots
-constexpr int DS_INBYTES = 160 * 128;       // (128 + 2*16) pixels x 128 B
-constexpr int DS_NA = 3;                    // A-operand tiles
-constexpr int DS_NT = 2;                    // TMEM accumulators (64 columns each)
-constexpr int DS_NOUT = 2;                  // output staging tiles
-constexpr int DS_TILE = 128 * 128;          // 16 KB
-constexpr int DS_OFF_A = 0;
-constexpr int DS_OFF_OUT = DS_OFF_A + DS_NA * DS_TILE;
-constexpr int DS_OFF_B = DS_OFF_OUT + DS_NOUT * DS_TILE;
-constexpr int DS_OFF_IN = DS_OFF_B + 8192;
-constexpr int DS_OFF_W = DS_OFF_IN + DS_NIN * DS_INBYTES;   // depthwise weights [9][32] fp32
-constexpr int DS_OFF_BAR = DS_OFF_W + 9 * 32 * 4;
-constexpr int DS_SMEM = DS_OFF_BAR + 256 + 1024 /*align slack*/;
-// the im2col modes (CIN > 0) have no input ring: their shared memory ends 100 KB earlier, which the SM gives to L1 -- the front end's
-// tap loads are L1 hits only if the few image lines in flight stay resident
-constexpr int DS_SMEM_IM2COL = DS_SMEM - DS_NIN * DS_INBYTES;
-constexpr float DS_ACT_SCALE = kDwsepActScale;
-
-struct DsArgs {
-  const float* dw;      // [32][9] depthwise weights
-  const __half* pwh;    // [64][32]: rows 0..31 = fp16(w*sw) (row = cout, col = cin), rows 32..63 = fp16((w*sw - hi) * 2^11)
-  const float* scales;  // [2]: c0 = 1 / (DS_ACT_SCALE * sw), c1 = c0 * 2^-11
-  const float* bias;    // [32]
-  float* out;           // CLP [B][Hp][Wp][32] (for the y-border zero fill; the interior goes through the TMA store map)
-  const float* img;     // CIN > 0 (first conv of a refinement branch): NCHW fp32 input [B][CIN][H][W]
-  int W;
-  int B, Hp, Wp, H, dil, relu;
-  int out_split;        // 1: write rows as [32 hi | 32 lo] halves of act * 2^-6 (operand format of conv3d_f16.cu) instead of fp32
-  int nxt, rows_phase;     // x tiles per line; lines per row phase (max over phases)
-  long long total_rows;     // B * nxt * dil * rows_phase tile-rows, split evenly (contiguously) over the CTAs
-};
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-__device__ __forceinline__ void ds_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-      "%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
 
 // Schedule: a strip = (b, x tile, row phase py) = the image lines yi = py + i*dil, i in [0, rows_phase), of one 128-pixel
 // column tile.  All B * nxt * dil * rows_phase tile-rows are numbered strip-major and every CTA takes one contiguous range of
@@ -515,8 +444,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
                      int H, int W, int dil, int relu, int out_split, cudaStream_t st) {
   if (dil < 1 || dil > DS_RP || (32 % dil) != 0) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(dwsep_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
-  if (e != cudaSuccess) return (int)e;
+  LWS_SET_SMEM_ONCE(dwsep_f16_kernel<0>, DS_SMEM);
+  cudaError_t e;
   DsArgs a;
   memset(&a, 0, sizeof(a));
   a.dw = dw, a.pwh = (const __half*)pwh, a.scales = scales, a.bias = bias, a.out = out;
@@ -543,9 +472,9 @@ int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* p
 int launch_conv0_f16(const float* img, float* out, const void* wtab, const float* scales, const float* bias, int B, int CIN, int H,
                      int W, cudaStream_t st) {
   if (CIN != 1 && CIN != 3) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = CIN == 3 ? cudaFuncSetAttribute(dwsep_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_IM2COL)
-                           : cudaFuncSetAttribute(dwsep_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_IM2COL);
-  if (e != cudaSuccess) return (int)e;
+  if (CIN == 3) LWS_SET_SMEM_ONCE(dwsep_f16_kernel<3>, DS_SMEM_IM2COL);
+  else LWS_SET_SMEM_ONCE(dwsep_f16_kernel<1>, DS_SMEM_IM2COL);
+  cudaError_t e;
   DsArgs a;
   memset(&a, 0, sizeof(a));
   a.dw = bias /*unused*/, a.pwh = (const __half*)wtab, a.scales = scales, a.bias = bias, a.out = out, a.img = img, a.W = W;

@@ -1,4 +1,7 @@
-// Status strings / version of the lws_b200 C ABI (include/lws.h).
+// Status strings / version / explicit options of the lws_b200 C ABI (include/lws.h).
+#include <atomic>
+#include <string.h>
+
 #include "lws_common.cuh"
 
 extern "C" const char* lws_status_string(int status) {
@@ -15,4 +18,59 @@ extern "C" const char* lws_status_string(int status) {
   return "LWS_ERR_UNKNOWN";
 }
 
-extern "C" const char* lws_version(void) { return "lws_b200 0.1.0 sm_100a"; }
+extern "C" const char* lws_version(void) { return "lws_b200 0.2.0 sm_100a"; }
+
+// ---- options: the only process-wide state of the library, changed only through lws_set_option (never read from the environment) ----
+namespace lws {
+struct OptDesc {
+  const char* key;
+  int def, lo, hi;
+};
+static const OptDesc kOpts[OPT_COUNT] = {
+    {"conv3d_tc", 1, 0, 1},           // 3D stacks on tcgen05 split-fp16 (1) or on the fp32 FFMA kernels (0)
+    {"refine_tc", 1, 0, 1},           // refinement on tcgen05 split-fp16 (1) or on the fp32 FFMA kernels (0)
+    {"c8_v1", 0, 0, 1},               // C = 8 stacks: one-plane-per-tile kernel instead of the plane-group kernel
+    {"c8_chunk", 0, 0, 1 << 20},      // plane-group kernel: lines per chunk of the work order (0 = whole strips)
+    {"k1_dt", 8, 8, 24},              // disparity tile of the direct stage-1 volume kernel (8, 12 or 24)
+    {"refine_chain", 2, 0, 4},        // consecutive depthwise-separable blocks per L2-resident chain launch (0 / 1 = one block per launch)
+    {"chain_sep_items", 160, 1, 100000},  // chain kernel: queue distance between a producer band and its consumers
+    {"warp_div_mode", 0, 0, 1},       // warp coordinate normalisation: 0 = x * fl32(1/c) (Paddle 2.0 scale op), 1 = true division x / c
+    {"chain_min_bands", 24, 0, 1 << 20},  // chains are used when the launch has at least this many (pair, band) units
+};
+static std::atomic<int> g_opts[OPT_COUNT];
+static std::atomic<bool> g_opts_init{false};
+static void opts_init() {
+  if (g_opts_init.load(std::memory_order_acquire)) return;
+  for (int i = 0; i < OPT_COUNT; ++i) g_opts[i].store(kOpts[i].def, std::memory_order_relaxed);
+  g_opts_init.store(true, std::memory_order_release);
+}
+int opt(int id) {
+  opts_init();
+  return g_opts[id].load(std::memory_order_relaxed);
+}
+}  // namespace lws
+
+extern "C" int lws_set_option(const char* key, int value) {
+  using namespace lws;
+  if (!key) return LWS_ERR_NULL_PTR;
+  opts_init();
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(key, kOpts[i].key) == 0) {
+      if (value < kOpts[i].lo || value > kOpts[i].hi) return LWS_ERR_BAD_SHAPE;
+      g_opts[i].store(value, std::memory_order_relaxed);
+      return LWS_OK;
+    }
+  return LWS_ERR_UNSUPPORTED;
+}
+
+extern "C" int lws_get_option(const char* key, int* value) {
+  using namespace lws;
+  if (!key || !value) return LWS_ERR_NULL_PTR;
+  opts_init();
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(key, kOpts[i].key) == 0) {
+      *value = g_opts[i].load(std::memory_order_relaxed);
+      return LWS_OK;
+    }
+  return LWS_ERR_UNSUPPORTED;
+}

@@ -18,6 +18,34 @@
 
 namespace lws {
 
+// explicit library options (lws_set_option / lws_get_option, lws_api.cu); the library never reads the environment
+enum {
+  OPT_CONV3D_TC = 0,
+  OPT_REFINE_TC,
+  OPT_C8_V1,
+  OPT_C8_CHUNK,
+  OPT_K1_DT,
+  OPT_REFINE_CHAIN,
+  OPT_CHAIN_SEP_ITEMS,
+  OPT_WARP_DIV_MODE,
+  OPT_CHAIN_MIN_BANDS,
+  OPT_COUNT
+};
+int opt(int id);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and device context instead of once per launch
+#define LWS_SET_SMEM_ONCE(kernel, bytes)                                                                        \
+  do {                                                                                                          \
+    static int done__[16];                                                                                      \
+    int dev__ = 0;                                                                                              \
+    cudaGetDevice(&dev__);                                                                                      \
+    if (dev__ < 0 || dev__ >= 16 || !done__[dev__]) {                                                           \
+      cudaError_t e__ = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      if (e__ != cudaSuccess) return (int)e__;                                                                  \
+      if (dev__ >= 0 && dev__ < 16) done__[dev__] = 1;                                                          \
+    }                                                                                                           \
+  } while (0)
+
 constexpr int kNumSMs = 148;  // B200
 // split-fp16 tensor-core operands (x = hi + lo * 2^-11, both fp16): activations are pre-scaled by this power of two so that
 // values up to 4.19e6 stay finite in fp16; weights carry their own per-layer power-of-two scale (see the pack functions)

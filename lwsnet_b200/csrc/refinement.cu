@@ -176,8 +176,8 @@ constexpr size_t DW_SMEM = (size_t)(2 * DW_CK * DW_ROWS * DW_PWMAX + DW_C * DW_C
 
 static int launch_dwsep(DwsepArgs a, int B, cudaStream_t st) {
   if (a.dil < 1 || a.dil > 16) return LWS_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(dwsep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_SMEM);
-  if (e != cudaSuccess) return (int)e;
+  LWS_SET_SMEM_ONCE(dwsep_block_kernel, DW_SMEM);
+  cudaError_t e;
   dim3 grid(cdiv(a.W, DW_TX) * cdiv(a.H, DW_TI * a.dil) * a.dil, B);
   dwsep_block_kernel<<<grid, DW_THREADS, DW_SMEM, st>>>(a);
   e = cudaPeekAtLastError();
@@ -401,6 +401,16 @@ extern "C" size_t lws_refinement_workspace_bytes(int B, int H, int W) {
 namespace lws {
 int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
                      int H, int W, int dil, int relu, int out_split, cudaStream_t st);
+struct ChainBlockDesc {
+  const float* dw;
+  const void* pwh;
+  const float* scales;
+  const float* bias;
+  int dil, relu, out_split;
+};
+size_t dwsep_chain_workspace_bytes(const int* dil, int nblk, int B, int H, int W);
+int launch_dwsep_chain(const float* in, float* out, const ChainBlockDesc* blocks, int nblk, void* ws, size_t ws_bytes, int B,
+                       int H, int W, cudaStream_t st);
 }
 extern "C" size_t lws_refinement_clp_floats(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
@@ -423,6 +433,35 @@ extern "C" int lws_refinement_block_clp_f32(const float* in_clp, float* out_clp,
   return launch_dwsep_f16(in_clp, out_clp, dw, tc, tc + 1024, bias, B, H, W, dil, branch < 2 || block < 3, 0, (cudaStream_t)stream);
 }
 
+static const int kBlockDil[3][4] = {{2, 4, 8, 16}, {2, 4, 8, 16}, {8, 4, 2, 1}};
+
+extern "C" size_t lws_refinement_chain_workspace_bytes(int branch, int block0, int nblk, int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0 || branch < 0 || branch > 2 || block0 < 0 || nblk < 2 || block0 + nblk > 4) return 0;
+  return lws::dwsep_chain_workspace_bytes(kBlockDil[branch] + block0, nblk, B, H, W);
+}
+
+extern "C" int lws_refinement_chain_clp_f32(const float* in_clp, float* out_clp, const float* pk, int branch, int block0, int nblk,
+                                            void* ws, size_t ws_bytes, int B, int H, int W, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(in_clp);
+  LWS_CHECK_PTR(out_clp);
+  LWS_CHECK_PTR(pk);
+  LWS_CHECK_PTR(ws);
+  if (B <= 0 || H <= 0 || W <= 0 || branch < 0 || branch > 2 || block0 < 0 || nblk < 2 || block0 + nblk > 4) return LWS_ERR_BAD_SHAPE;
+  if ((((uintptr_t)in_clp) | ((uintptr_t)out_clp) | ((uintptr_t)pk)) & 15) return LWS_ERR_BAD_ALIGN;
+  const RefLayout L = ref_layout();
+  ChainBlockDesc blk[4];
+  for (int k = 0; k < nblk; ++k) {
+    const int j = block0 + k;
+    const float* tc = pk + (branch < 2 ? L.r1_pwtc[branch][j] : L.r2_pwtc[j]);
+    blk[k].dw = pk + (branch < 2 ? L.r1_dw[branch][j] : L.r2_dw[j]);
+    blk[k].pwh = tc, blk[k].scales = tc + 1024;
+    blk[k].bias = pk + (branch < 2 ? L.r1_b[branch][j] : L.r2_bb[j]);
+    blk[k].dil = kBlockDil[branch][j], blk[k].relu = branch < 2 || j < 3, blk[k].out_split = 0;
+  }
+  return launch_dwsep_chain(in_clp, out_clp, blk, nblk, ws, ws_bytes, B, H, W, (cudaStream_t)stream);
+}
+
 extern "C" int lws_refinement_f32(const float* left, const float* pred3, const float* pk, float* pred4, void* ws,
                                   size_t ws_bytes, int B, int H, int W, lws_stream_t stream) {
   using namespace lws;
@@ -437,8 +476,7 @@ extern "C" int lws_refinement_f32(const float* left, const float* pred3, const f
   cudaStream_t st = (cudaStream_t)stream;
   const RefLayout L = ref_layout();
   {
-    const char* env = getenv("LWS_REFINE_TC");
-    if (!(env && env[0] == '0')) {
+    if (opt(OPT_REFINE_TC) != 0) {
       RefTcWeights wt;
       for (int br = 0; br < 2; ++br) {
         wt.w0[br] = pk + L.r1_w0[br], wt.b0[br] = pk + L.r1_b0[br];

@@ -10,19 +10,12 @@
 #include <math.h>
 #include <string.h>
 
-#include "lws_common.cuh"
-#include "tma_utils.cuh"
+#include "dwsep_common.cuh"
 #include "conv3d_f16.cuh"
 
 namespace lws {
 
 constexpr int RP = 16;  // border of the refinement CLP tensors
-
-// BN-ReLU-DW(dil)-PW block on CLP (dwsep_tc.cu)
-int launch_conv0_f16(const float* img, float* out, const void* wtab, const float* scales, const float* bias, int B, int CIN, int H,
-                     int W, cudaStream_t st);
-int launch_dwsep_f16(const float* in, float* out, const float* dw, const void* pwh, const float* scales, const float* bias, int B,
-                     int H, int W, int dil, int relu, int out_split, cudaStream_t st);
 
 // ---- host ------------------------------------------------------------------------------------------------------------------
 struct RefTcWeights {
@@ -33,8 +26,62 @@ struct RefTcWeights {
   const float* last_tc;
 };
 
-size_t refinement_tc_workspace_bytes(int B, int H, int W) {
-  return (size_t)4 * B * (H + 2 * RP) * (W + 2 * RP) * 32 * sizeof(float);
+static const int kR1Dil[4] = {2, 4, 8, 16};
+static const int kR2Dil[4] = {8, 4, 2, 1};
+
+// Blocks per chain launch (option "refine_chain": 0 / 1 = one block per launch).  Chains pay a pipeline fill of a few bands, so a
+// launch with few (pair, band) units stays on the per-block kernel.
+static int chain_len(int B, int H) {
+  int n = opt(OPT_REFINE_CHAIN);
+  if (n < 2) return 1;
+  if (n == 3) n = 2;  // four blocks split 2 + 2 or run as one chain of 4
+  if ((long long)B * ((H + 63) / 64) < opt(OPT_CHAIN_MIN_BANDS)) return 1;
+  return n;
+}
+static size_t chain_ws_bytes(int B, int H, int W) {
+  size_t m = 0;
+  for (int n = 2; n <= 4; n += 2)
+    for (int br = 0; br < 2; ++br)
+      for (int j = 0; j + n <= 4; j += n) {
+        const size_t b = dwsep_chain_workspace_bytes((br ? kR2Dil : kR1Dil) + j, n, B, H, W);
+        m = b > m ? b : m;
+      }
+  return (m + 255) / 256 * 256;
+}
+static size_t clp_bytes(int B, int H, int W) {
+  return ((size_t)B * (H + 2 * RP) * (W + 2 * RP) * 32 * sizeof(float) + 255) / 256 * 256;
+}
+
+size_t refinement_tc_workspace_bytes(int B, int H, int W) { return 4 * clp_bytes(B, H, W) + chain_ws_bytes(B, H, W); }
+
+// blocks [j0, j0 + n) of branch br (0 / 1 = refinement1_left / _disp, 2 = refinement2): src -> dst, one block per launch through
+// `tmp` ping-pong buffers or as L2-resident chains
+static int run_blocks(const RefTcWeights& wt, int br, const float* src, float* dst, float* tmp0, float* tmp1, void* chain_ws,
+                      size_t chain_bytes, int B, int H, int W, bool last_relu, bool last_split, cudaStream_t st) {
+  const int* dil = br < 2 ? kR1Dil : kR2Dil;
+  const int n = chain_len(B, H);
+  int rc;
+  const float* cur = src;
+  for (int j = 0; j < 4; j += n) {
+    float* out = j + n >= 4 ? dst : (cur == tmp0 ? tmp1 : tmp0);
+    if (n == 1) {
+      const bool last = j == 3;
+      rc = launch_dwsep_f16(cur, out, wt.dw[br][j], wt.pwtc[br][j], wt.pwtc[br][j] + 1024, wt.bias[br][j], B, H, W, dil[j],
+                            last ? last_relu : 1, last ? last_split : 0, st);
+    } else {
+      ChainBlockDesc blk[4];
+      for (int k = 0; k < n; ++k) {
+        const bool last = j + k == 3;
+        blk[k].dw = wt.dw[br][j + k], blk[k].pwh = wt.pwtc[br][j + k], blk[k].scales = wt.pwtc[br][j + k] + 1024;
+        blk[k].bias = wt.bias[br][j + k], blk[k].dil = dil[j + k], blk[k].relu = last ? last_relu : 1;
+        blk[k].out_split = last ? last_split : 0;
+      }
+      rc = launch_dwsep_chain(cur, out, blk, n, chain_ws, chain_bytes, B, H, W, st);
+    }
+    if (rc) return rc;
+    cur = out;
+  }
+  return LWS_OK;
 }
 
 int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt, float* pred4, void* ws, int B, int H,
@@ -42,27 +89,19 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
   const int Hp = H + 2 * RP, Wp = W + 2 * RP;
   const long long R = (long long)Hp * Wp;
   if (R >= (1ll << 31) - 65536 || B * R * 32 >= (1ll << 40)) return LWS_ERR_BAD_SHAPE;
-  const long long buf_floats = (long long)B * R * 32;
+  const size_t cb = clp_bytes(B, H, W);
   float* catL = (float*)ws;
-  float* catD = catL + buf_floats;
-  float* ping = catD + buf_floats;
-  float* pong = ping + buf_floats;
-  static const int r1_dil[4] = {2, 4, 8, 16};
-  static const int r2_dil[4] = {8, 4, 2, 1};
+  float* catD = (float*)((char*)ws + cb);
+  float* ping = (float*)((char*)ws + 2 * cb);
+  float* pong = (float*)((char*)ws + 3 * cb);
+  void* chain_ws = (char*)ws + 4 * cb;
+  const size_t chain_bytes = chain_ws_bytes(B, H, W);
   int rc;
   for (int br = 0; br < 2; ++br) {
-    if ((rc = launch_conv0_f16(br == 0 ? left : pred3, ping, wt.w0tc[br], wt.w0tc[br] + 1024, wt.b0[br], B, br == 0 ? 3 : 1, H, W, st)))
+    // first conv -> pong; blocks 1..4 -> the branch's half of the concat (split-fp16 rows: it feeds the dense conv)
+    if ((rc = launch_conv0_f16(br == 0 ? left : pred3, pong, wt.w0tc[br], wt.w0tc[br] + 1024, wt.b0[br], B, br == 0 ? 3 : 1, H, W, st)))
       return rc;
-    float* cur = ping;
-    float* nxt = pong;
-    for (int j = 0; j < 4; ++j) {
-      float* dst = j < 3 ? nxt : (br == 0 ? catL : catD);
-      if ((rc = launch_dwsep_f16(cur, dst, wt.dw[br][j], wt.pwtc[br][j], wt.pwtc[br][j] + 1024, wt.bias[br][j], B, H, W,
-                                 r1_dil[j], 1, j == 3 /* the concat halves feed the dense conv: split-fp16 rows */, st)))
-        return rc;
-      float* t = cur;
-      cur = nxt, nxt = t;
-    }
+    if ((rc = run_blocks(wt, br, pong, br == 0 ? catL : catD, ping, pong, chain_ws, chain_bytes, B, H, W, true, true, st))) return rc;
   }
   {
     // dense 64 -> 32, dilation 8: stages = (kh, source), kw folded into N (Toeplitz shift 8 pixels), strips down the image
@@ -75,15 +114,9 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
     L.out_split = 0, L.relu = 1;
     if ((rc = launch_tz_gemm(L, st))) return rc;
   }
-  float* cur = ping;
-  float* nxt = pong;
-  for (int j = 0; j < 4; ++j) {
-    if ((rc = launch_dwsep_f16(cur, nxt, wt.dw[2][j], wt.pwtc[2][j], wt.pwtc[2][j] + 1024, wt.bias[2][j], B, H, W, r2_dil[j],
-                               j < 3, j == 3 /* the last block feeds the closing conv: split-fp16 rows */, st)))
-      return rc;
-    float* t = cur;
-    cur = nxt, nxt = t;
-  }
+  // blocks 1..4 of refinement2: ping -> catL (free by now); the last block has no ReLU and feeds the closing conv (split-fp16 rows)
+  if ((rc = run_blocks(wt, 2, ping, catL, pong, catD, chain_ws, chain_bytes, B, H, W, false, true, st))) return rc;
+  float* cur = catL;
   {
     // closing 32 -> 1 conv + skip (pred4 = pred3 + r): stages = kh, kw folded into N = 16, strips down the image
     TzLayer L;

@@ -312,12 +312,10 @@ extern "C" int lws_warp_residual_volume_l1_f32(const float* L, const float* R, c
     const int threads = round_up(cdiv(W, passes), 32);
     dim3 grid(H, B);
     if (C == 8) {
-      if (row_smem > 48 * 1024)
-        cudaFuncSetAttribute(warp_residual_volume_row_kernel<8, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (row_smem > 48 * 1024) LWS_SET_SMEM_ONCE((warp_residual_volume_row_kernel<8, 9>), 96 * 1024);
       warp_residual_volume_row_kernel<8, 9><<<grid, threads, row_smem, st>>>(L, R, disp, cost, H, W, m, (float)stride, ax, ay);
     } else {
-      if (row_smem > 48 * 1024)
-        cudaFuncSetAttribute(warp_residual_volume_row_kernel<16, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (row_smem > 48 * 1024) LWS_SET_SMEM_ONCE((warp_residual_volume_row_kernel<16, 9>), 96 * 1024);
       warp_residual_volume_row_kernel<16, 9><<<grid, threads, row_smem, st>>>(L, R, disp, cost, H, W, m, (float)stride, ax, ay);
     }
   } else if (m == 5) {

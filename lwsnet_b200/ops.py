@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 
 import torch
 
-from ._lib import LwsError, check, lib
+from ._lib import LwsError, check, get_option, lib, options, set_option  # noqa: F401  (options API re-exported)
 
 LAUNCHES = [0]  # kernels of liblws_b200 enqueued through this module (bench.py reports it as gpu_launches)
 _workspaces: dict = {}
@@ -274,6 +274,26 @@ def refinement_block_clp(in_clp: torch.Tensor, packed: torch.Tensor, branch: int
                                                block, B, H, W, _stream(in_clp)), "lws_refinement_block_clp_f32")
     LAUNCHES[0] += 1
     return out
+
+
+def refinement_chain_clp(in_clp: torch.Tensor, packed: torch.Tensor, branch: int, block0: int, nblk: int, B: int, H: int, W: int,
+                         out: Optional[torch.Tensor] = None, return_ws: bool = False):
+    """Blocks [block0, block0 + nblk) of a refinement branch in ONE launch (dwsep_chain.cu): the tensors between the blocks stay
+    in L2-resident row rings.  Same layout and bit-identical results as nblk calls of refinement_block_clp."""
+    n = int(lib.lws_refinement_clp_floats(B, H, W))
+    if in_clp.numel() != n:
+        raise ValueError(f"in_clp must hold {n} floats")
+    out = out if out is not None else torch.empty_like(in_clp)
+    nbytes = int(lib.lws_refinement_chain_workspace_bytes(branch, block0, nblk, B, H, W))
+    if nbytes == 0:
+        raise ValueError("bad chain arguments")
+    ws = workspace(in_clp.device, "chain", nbytes)
+    with torch.cuda.device(in_clp.device):
+        check(lib.lws_refinement_chain_clp_f32(_ptr(in_clp, "in_clp"), _ptr(out, "out_clp"), _ptr(packed, "packed"), branch, block0,
+                                               nblk, ctypes.c_void_p(ws.data_ptr()), nbytes, B, H, W, _stream(in_clp)),
+              "lws_refinement_chain_clp_f32")
+    LAUNCHES[0] += 1
+    return (out, ws) if return_ws else out
 
 
 # ------------------------------------------------------------------------------------------------ n1 feature pyramid

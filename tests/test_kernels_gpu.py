@@ -177,17 +177,17 @@ def _stack_from_golden(prefix, C):
 
 
 # The C = 32 and C = 8 stacks have two implementations: the tcgen05 split-fp16 (x = hi + lo*2^-11, three exact products) implicit GEMM (default) and the fp32 FFMA kernels
-# (LWS_CONV3D_TC=0).  Operands of the tensor-core path are split exactly (x = xh + xl), but TMEM accumulation rounds toward
+# (option "conv3d_tc" = 0).  Operands of the tensor-core path are split exactly (x = xh + xl), but TMEM accumulation rounds toward
 # zero at each of its 108 MMA steps, which leaves a ~5e-6 relative drift per layer: its bound is 5e-4 * (1 + |y|), the FFMA
 # path keeps SURVEY 8(c)'s 1e-4 * (1 + |y|).
 CONV3D_PATHS = [("tc", "1", 5e-4), ("ffma", "0", 1e-4)]
 
 
 @pytest.fixture(params=CONV3D_PATHS, ids=[p[0] for p in CONV3D_PATHS])
-def conv3d_path(request, monkeypatch):
+def conv3d_path(request):
     name, env, tol = request.param
-    monkeypatch.setenv("LWS_CONV3D_TC", env)
-    return name, tol
+    with ops().options(conv3d_tc=int(env)):
+        yield name, tol
 
 
 @pytest.mark.parametrize("name,C", [("c8", 8), ("c32", 32)])
@@ -231,15 +231,15 @@ def test_conv3d_stack_vs_fp64_oracle(C, B, D, H, W, conv3d_path):
 
 # ------------------------------------------------------------------------------------------------ a8 + a9
 # Two implementations: channels-last tcgen05 split-fp16 (default; pointwise products are fp32-exact to a few ulps, the dense
-# 64->32 conv accumulates over 72 round-toward-zero MMA steps) and the fp32 FFMA kernels (LWS_REFINE_TC=0).
+# 64->32 conv accumulates over 72 round-toward-zero MMA steps) and the fp32 FFMA kernels (option "refine_tc" = 0).
 REFINE_PATHS = [("tc", "1", 6.0, 1e-5), ("ffma", "0", 3.0, 2e-6)]
 
 
 @pytest.fixture(params=REFINE_PATHS, ids=[p[0] for p in REFINE_PATHS])
-def refine_path(request, monkeypatch):
+def refine_path(request):
     name, env, floor_mult, scale_tol = request.param
-    monkeypatch.setenv("LWS_REFINE_TC", env)
-    return name, floor_mult, scale_tol
+    with ops().options(refine_tc=int(env)):
+        yield name, floor_mult, scale_tol
 
 
 def _check_refine(out, ref, fp32_floor, path):
@@ -309,6 +309,62 @@ def test_refinement_block_clp_vs_fp64(B, H, W):
     border = out.clone()
     border[:, 16:16 + H, 16:16 + W, :] = 0
     assert border.abs().max().item() == 0.0
+
+
+def _clp_input(seed, B, H, W, scale=3.0):
+    x = rnd(seed, B, 32, H, W, scale=scale).abs()
+    clp = torch.zeros(B, H + 32, W + 32, 32)
+    clp[:, 16:16 + H, 16:16 + W, :] = x.permute(0, 2, 3, 1)
+    return clp.cuda().reshape(-1)
+
+
+@pytest.mark.parametrize("branch,block0,nblk,B,H,W", [
+    (0, 0, 2, 2, 40, 150),     # dil 2,4: 16-row bands, ragged width
+    (0, 2, 2, 1, 72, 130),     # dil 8,16: 64-row bands, last band partial (8 rows)
+    (2, 0, 2, 2, 50, 260),     # refinement2 dil 8,4 (descending), 32-row bands
+    (2, 2, 2, 3, 33, 70),      # dil 2,1, last block without ReLU
+    (1, 0, 4, 2, 100, 200),    # the whole branch as one chain of four
+    (2, 0, 4, 1, 368, 1232),   # KITTI size
+    (0, 0, 2, 1, 5, 9),        # smaller than one band / one tile
+])
+def test_refinement_chain_bit_identical_to_blocks(branch, block0, nblk, B, H, W):
+    """dwsep_chain.cu: blocks kept in L2-resident rings inside one launch == the same blocks launched one by one, BITWISE (the
+    per-pixel arithmetic is identical; only the schedule and where the intermediate rows live differ).  Also checks the kernel's
+    watchdog flag (a dependency wait that would have hung sets it) and that the zero border survives."""
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=True))
+    packed = model._refinement_packed(torch.device("cuda"))
+    x = _clp_input(61, B, H, W)
+    ref = x
+    for j in range(block0, block0 + nblk):
+        ref = ops().refinement_block_clp(ref, packed, branch, j, B, H, W)
+    for sep in (160, 8):  # default queue distance, and a tiny one that forces consumers to wait for their producers
+        with ops().options(chain_sep_items=sep):
+            out, ws = ops().refinement_chain_clp(x, packed, branch, block0, nblk, B, H, W, return_ws=True)
+            torch.cuda.synchronize()
+            ctrl = ws[:8].view(torch.int32).cpu()
+        assert int(ctrl[1]) == 0, "chain kernel watchdog fired (a dependency wait timed out)"
+        assert torch.equal(out, ref), f"sep={sep}: max diff {(out - ref).abs().max().item():.3e}"
+    o4 = out.reshape(B, H + 32, W + 32, 32).clone()
+    o4[:, 16:16 + H, 16:16 + W, :] = 0
+    assert o4.abs().max().item() == 0.0
+
+
+def test_refinement_chain_option_is_bit_identical():
+    """lws_refinement_f32 with chains of 2 / 4 blocks == one block per launch, bitwise, at a shape large enough to use chains."""
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=True))
+    left = rnd(71, 2, 3, 200, 328).cuda()
+    pred3 = (rnd(72, 2, 1, 200, 328, scale=10.0) + 20.0).cuda()
+    with ops().options(refine_chain=0):
+        ref = model._refine(left, pred3).clone()
+    for n in (2, 4):
+        with ops().options(refine_chain=n, chain_min_bands=0):
+            out = model._refine(left, pred3)
+            torch.cuda.synchronize()
+        assert torch.equal(out, ref), n
 
 
 # ------------------------------------------------------------------------------------------------ n1 feature pyramid

@@ -108,16 +108,17 @@ def test_batch_shard_equivalence(models):
         assert torch.equal(full[s], torch.cat([p[s] for p in parts]))
 
 
-def test_exact_fp32_mode_end_to_end(models, monkeypatch):
-    """LWS_CONV3D_TC=0 LWS_REFINE_TC=0 select the fp32 FFMA kernels everywhere: every stage within 2x the fp32 oracle's floor."""
-    monkeypatch.setenv("LWS_CONV3D_TC", "0")
-    monkeypatch.setenv("LWS_REFINE_TC", "0")
+def test_exact_fp32_mode_end_to_end(models):
+    """Options conv3d_tc=0 refine_tc=0 select the fp32 FFMA kernels everywhere: every stage within 2x the fp32 oracle's floor."""
+    from lwsnet_b200 import ops
     O, o32, o64, prod = models
     left, right = O.synthetic_pair(1, 128, 256, seed=3, max_disp=30.0)
     with torch.no_grad():
         p64 = o64(left.double(), right.double())
         p32 = o32(left, right)
-    out = prod(left.cuda(), right.cuda())
+    with ops.options(conv3d_tc=0, refine_tc=0):
+        out = prod(left.cuda(), right.cuda())
+        torch.cuda.synchronize()
     for s in range(4):
         e, floor = err_stats(out[s].cpu(), p64[s]), err_stats(p32[s], p64[s])
         for k in ("max", "p999", "mean"):

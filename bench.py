@@ -250,6 +250,11 @@ def run_ours(args, rank, world, local_rank):
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     torch.cuda.set_device(local_rank)
+    lib_opts = {}
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ops.set_option(k, int(v))
+        lib_opts[k] = int(v)
     from lwsnet_b200.runner import bind_to_gpu_cpus
     cpus = bind_to_gpu_cpus(local_rank) if world > 1 and not args.no_bind else None  # before any pinned allocation
     dev = torch.device("cuda", local_rank)
@@ -378,6 +383,7 @@ def run_ours(args, rank, world, local_rank):
                    "batch_per_gpu": BATCH, "micro_batch": args.micro_batch, "cpu_binding": (f"{len(cpus)} NUMA-local cores per rank" if cpus else "none"),
                    "e2e_chunks": [hi - lo for lo, hi in engine._host_chunks(BATCH)], "maxdisplist": [24, 5, 5],
                    "weights": "random init (KaimingNormal, seed 0)", "cuda_graphs": not args.no_graphs,
+                   "library_options": {**{k: ops.get_option(k) for k in ("conv3d_tc", "refine_tc", "refine_chain", "chain_sep_items")}, **lib_opts},
                    "l2": "inputs (697 MB per step) and per-step activations exceed the 126 MB L2",
                    "numerics": "fp32 storage at the ABI; conv stacks and pointwise convs on tcgen05 with split-fp16 operands "
                                "(x = hi + lo*2^-11, 3 exact products, fp32 accumulation)",
@@ -414,6 +420,8 @@ def main():
     ap.add_argument("--probes-only", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA-local CPU cores")
     ap.add_argument("--probe-batch", type=int, default=16, help="pairs per launch in the streaming-kernel probes")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="library option for A/B runs (lws_set_option, include/lws.h), e.g. --opt refine_chain=0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

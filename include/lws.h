@@ -51,7 +51,8 @@ LWS_API const char* lws_version(void);
  * Explicit, process-wide switches (int values).  Unknown key: LWS_ERR_UNSUPPORTED; value out of range: LWS_ERR_BAD_SHAPE.
  *   "conv3d_tc"       1   3D stacks on tcgen05 split-fp16 (1) or on the exact-fp32 FFMA kernels (0)
  *   "refine_tc"       1   refinement on tcgen05 split-fp16 (1) or on the exact-fp32 FFMA kernels (0)
- *   "refine_chain"    2   consecutive BN-ReLU-DW-PW blocks per L2-resident chain launch (0 / 1: one block per launch; 2; 4)
+ *   "refine_chain"    0   consecutive BN-ReLU-DW-PW blocks per L2-resident chain launch (0 / 1: one block per launch; 2; 4).
+ *                         Off by default: it cuts the blocks' DRAM traffic 1.7x but is slower (profiles/r02_chain_ab.txt)
  *   "chain_min_bands" 24  chains are used from this many (pair, 64-row band) units per launch on
  *   "chain_sep_items" 160 chain kernel: queue distance between a producer band and its consumers (sizes the L2 rings;
  *                         workspace sizes depend on it: set it before lws_refinement_workspace_bytes)
@@ -133,6 +134,8 @@ LWS_API size_t lws_refinement_packed_floats(void);
  * n_tensors must be 80. */
 LWS_API int lws_pack_refinement_weights(const float* const* tensors, int n_tensors, float eps, float* packed);
 LWS_API size_t lws_refinement_workspace_bytes(int B, int H, int W);
+/* kernel launches lws_refinement_f32 enqueues for this shape under the current options (16 with one block per launch) */
+LWS_API int lws_refinement_launches(int B, int H, int W);
 LWS_API int lws_refinement_f32(const float* left, const float* pred3, const float* packed_weights, float* pred4, void* ws,
                        size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
 

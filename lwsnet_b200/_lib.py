@@ -40,6 +40,7 @@ SIGNATURES = {
     "lws_refinement_packed_floats": (c_size_t, []),
     "lws_pack_refinement_weights": (c_int, [_pp, c_int, c_float, _fp]),
     "lws_refinement_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lws_refinement_launches": (c_int, [c_int, c_int, c_int]),
     "lws_refinement_clp_floats": (c_size_t, [c_int, c_int, c_int]),
     "lws_refinement_block_clp_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_refinement_chain_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),

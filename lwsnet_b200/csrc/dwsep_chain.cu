@@ -54,6 +54,7 @@ struct ChainArgs {
   int items_per_step;    // nblk * per_blk
   int total_items;
   unsigned done_target;  // per_blk * 4 epilogue-warp arrivals complete a band
+  int debug;             // option "chain_debug" (timing experiments)
 };
 struct ChainMaps {
   CUtensorMap in[CH_MAXBLK];   // block k input: k = 0 the CLP input tensor, k > 0 ring k-1 (box = 128 + 2*dil_k pixels)
@@ -216,11 +217,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
         if (!end) {
           if (!chain_decode(a, n, w)) continue;
           const int m = w.g - w.b * a.nmb;
-          if (w.k > 0) {  // the bands of block k-1 this item reads (one band of halo either side, inside the pair)
+          if (!(a.debug & 1) && w.k > 0) {  // the bands of block k-1 this item reads (one band of halo either side, inside the pair)
             const unsigned* d = done + (w.k - 1) * a.nbands + w.b * a.nmb;
             for (int mm = max(m - 1, 0); mm <= min(m + 1, a.nmb - 1); ++mm) chain_wait(d + mm, a.done_target, flag);
           }
-          if (w.k + 1 < a.nblk) {  // block k+1 is done with the ring rows this band overwrites (global band g - RB and its halo readers)
+          if (!(a.debug & 1) && w.k + 1 < a.nblk) {  // block k+1 is done with the ring rows this band overwrites (global band g - RB and its halo readers)
             const unsigned* d = done + (w.k + 1) * a.nbands;
             for (int gg = max(w.g - a.RB - 1, 0); gg <= w.g - a.RB + 1; ++gg) chain_wait(d + gg, a.done_target, flag);
           }
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
       // the deferred signal must not wait for an item that is not there yet: this CTA's own scheduler thread may be spinning on
       // exactly that band counter before it publishes the next item
       if (lane == 0 && pend && !item_published()) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (!(a.debug & 2)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         signal(pend);
         pend = nullptr;
       }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
       // end of the item: its band counter is signalled once its stores are known to have completed
       if (lane == 0) {
         if (pend) {  // the item before was too short for the deferred path
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          if (!(a.debug & 2)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           signal(pend);
           pend = nullptr;
           signal(done + w.k * a.nbands + w.g);
@@ -582,6 +583,7 @@ int launch_dwsep_chain(const float* in, float* out, const ChainBlockDesc* blocks
   if (steps * a.items_per_step >= (1ll << 30)) return LWS_ERR_BAD_SHAPE;
   a.total_items = (int)(steps * a.items_per_step);
   a.done_target = (unsigned)a.per_blk * 4u;
+  a.debug = opt(OPT_CHAIN_DEBUG);
 
   cudaError_t e = cudaMemsetAsync(ws, 0, g.ctrl_bytes, st);
   if (e != cudaSuccess) return (int)e;

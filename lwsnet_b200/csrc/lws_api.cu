@@ -32,10 +32,12 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"c8_v1", 0, 0, 1},               // C = 8 stacks: one-plane-per-tile kernel instead of the plane-group kernel
     {"c8_chunk", 0, 0, 1 << 20},      // plane-group kernel: lines per chunk of the work order (0 = whole strips)
     {"k1_dt", 8, 8, 24},              // disparity tile of the direct stage-1 volume kernel (8, 12 or 24)
-    {"refine_chain", 2, 0, 4},        // consecutive depthwise-separable blocks per L2-resident chain launch (0 / 1 = one block per launch)
+    {"refine_chain", 0, 0, 4},        // consecutive depthwise-separable blocks per L2-resident chain launch (0 / 1 = one block per launch;
+                                      // default off: halves the DRAM traffic of the blocks but measured slower, profiles/r02_chain_ab.txt)
     {"chain_sep_items", 160, 1, 100000},  // chain kernel: queue distance between a producer band and its consumers
     {"warp_div_mode", 0, 0, 1},       // warp coordinate normalisation: 0 = x * fl32(1/c) (Paddle 2.0 scale op), 1 = true division x / c
     {"chain_min_bands", 24, 0, 1 << 20},  // chains are used when the launch has at least this many (pair, band) units
+    {"chain_debug", 0, 0, 255},       // TIMING EXPERIMENTS ONLY (results are wrong): 1 = skip dependency waits, 2 = signal without store completion
 };
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::atomic<bool> g_opts_init{false};

@@ -29,6 +29,7 @@ enum {
   OPT_CHAIN_SEP_ITEMS,
   OPT_WARP_DIV_MODE,
   OPT_CHAIN_MIN_BANDS,
+  OPT_CHAIN_DEBUG,
   OPT_COUNT
 };
 int opt(int id);
@@ -112,26 +113,36 @@ __device__ __forceinline__ float2 split_lo2(float v0, float v1, float2 hi_as_flo
 // ---- reference coordinate replay (models/models.py:44-53) ------------------------
 // Every operation is an explicitly rounded intrinsic so ptxas can never contract them into FMAs: the reference
 // issues one Paddle operator per arithmetic step and the tap indices must match it bit for bit.
+// The normalisation `2*v / max(size-1, 1)` of models/models.py:44-45 is a tensor divided by a Python scalar.  Paddle 2.0 dygraph
+// lowers that to a `scale` op, x * fl32(1/c) (the survey's least verifiable assumption); later Paddle
+// versions run a true elementwise division.  Both are implemented; option "warp_div_mode" selects (0 = reciprocal multiply).
 struct WarpAxis {
   float recip;  // fl32(1 / max(size-1, 1))
   float half;   // (size-1) * 0.5
+  float denom;  // max(size-1, 1)
+  int div;      // 1: IEEE division by denom instead of the multiplication by recip
 };
 
 __host__ inline WarpAxis make_warp_axis(int size) {
   WarpAxis a;
   a.recip = (float)(1.0 / (double)(size - 1 > 1 ? size - 1 : 1));
   a.half = (float)((double)(size - 1) * 0.5);
+  a.denom = (float)(size - 1 > 1 ? size - 1 : 1);
+  a.div = opt(OPT_WARP_DIV_MODE);
   return a;
 }
 
+__device__ __forceinline__ float warp_normalise(float two_v, WarpAxis a) {
+  return a.div ? __fdiv_rn(two_v, a.denom) : __fmul_rn(two_v, a.recip);  // warp-uniform branch
+}
 // un-normalised sampling coordinate for pixel coordinate `pix` displaced by `dsp`
 __device__ __forceinline__ float warp_coord(float pix, float dsp, WarpAxis a) {
   float v = __fsub_rn(pix, dsp);
-  float g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, v), a.recip), 1.0f);
+  float g = __fsub_rn(warp_normalise(__fmul_rn(2.0f, v), a), 1.0f);
   return __fmul_rn(__fadd_rn(g, 1.0f), a.half);
 }
 __device__ __forceinline__ float warp_coord_nodisp(float pix, WarpAxis a) {
-  float g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, pix), a.recip), 1.0f);
+  float g = __fsub_rn(warp_normalise(__fmul_rn(2.0f, pix), a), 1.0f);
   return __fmul_rn(__fadd_rn(g, 1.0f), a.half);
 }
 

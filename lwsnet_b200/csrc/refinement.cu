@@ -26,6 +26,7 @@ struct RefTcWeights {
   const float* last_tc;
 };
 size_t refinement_tc_workspace_bytes(int B, int H, int W);
+int refinement_tc_launches(int B, int H);
 int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt, float* pred4, void* ws, int B, int H,
                   int W, cudaStream_t st);
 
@@ -411,6 +412,10 @@ struct ChainBlockDesc {
 size_t dwsep_chain_workspace_bytes(const int* dil, int nblk, int B, int H, int W);
 int launch_dwsep_chain(const float* in, float* out, const ChainBlockDesc* blocks, int nblk, void* ws, size_t ws_bytes, int B,
                        int H, int W, cudaStream_t st);
+}
+extern "C" int lws_refinement_launches(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return lws::opt(lws::OPT_REFINE_TC) ? lws::refinement_tc_launches(B, H) : 16;
 }
 extern "C" size_t lws_refinement_clp_floats(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;

@@ -52,6 +52,8 @@ static size_t clp_bytes(int B, int H, int W) {
   return ((size_t)B * (H + 2 * RP) * (W + 2 * RP) * 32 * sizeof(float) + 255) / 256 * 256;
 }
 
+int refinement_tc_launches(int B, int H) { return 4 + 12 / chain_len(B, H); }
+
 size_t refinement_tc_workspace_bytes(int B, int H, int W) { return 4 * clp_bytes(B, H, W) + chain_ws_bytes(B, H, W); }
 
 // blocks [j0, j0 + n) of branch br (0 / 1 = refinement1_left / _disp, 2 = refinement2): src -> dst, one block per launch through

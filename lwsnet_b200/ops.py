@@ -257,7 +257,7 @@ def refinement(left: torch.Tensor, pred3: torch.Tensor, packed: torch.Tensor,
         check(lib.lws_refinement_f32(_ptr(left, "left"), _ptr(pred3, "pred3"), _ptr(packed, "packed"),
                                      _ptr(pred4, "pred4"), ctypes.c_void_p(ws.data_ptr()), nbytes, B, H, W,
                                      _stream(left)), "lws_refinement_f32")
-    LAUNCHES[0] += 16
+    LAUNCHES[0] += int(lib.lws_refinement_launches(B, H, W))
     return pred4
 
 

@@ -58,17 +58,24 @@ def disp_to_scale(pred_full, h, w):
     return (r * f32(h)) * f32(1.0 / H_img)
 
 
-def warp_taps(dsp, H, W):
+def warp_taps(dsp, H, W, div_mode=0):
     """A.3: dsp [N,H,W] fp32 (the *argument* of warp, i.e. disp - shift).
+
+    div_mode 0: `2*v / max(size-1,1)` as the reciprocal multiply of Paddle 2.0's scale op (SURVEY.md C.2, the oracle's choice);
+    div_mode 1: as a true IEEE division (later Paddle versions).
 
     Returns x0 [N,H,W] int32, y0 [H] int32, (wx0, wx1) [N,H,W] fp32 = (x1-ix, ix-x0), (wy0, wy1) [H] fp32.
     """
     xs = np.arange(W, dtype=f32)[None, None, :]
     ys = np.arange(H, dtype=f32)
-    rW = f32(1.0 / max(W - 1, 1))
-    rH = f32(1.0 / max(H - 1, 1))
-    gx = (f32(2.0) * (xs - dsp)) * rW - f32(1.0)
-    gy = (f32(2.0) * ys) * rH - f32(1.0)
+    if div_mode:
+        gx = ((f32(2.0) * (xs - dsp)) / f32(max(W - 1, 1))).astype(f32) - f32(1.0)
+        gy = ((f32(2.0) * ys) / f32(max(H - 1, 1))).astype(f32) - f32(1.0)
+    else:
+        rW = f32(1.0 / max(W - 1, 1))
+        rH = f32(1.0 / max(H - 1, 1))
+        gx = (f32(2.0) * (xs - dsp)) * rW - f32(1.0)
+        gy = (f32(2.0) * ys) * rH - f32(1.0)
     ix = (gx + f32(1.0)) * f32((W - 1) * 0.5)
     iy = (gy + f32(1.0)) * f32((H - 1) * 0.5)
     x0f = np.floor(ix)

@@ -82,13 +82,17 @@ def test_warp_taps_bit_exact(H, W):
     disp[0, 0, 0, 0] = 0.0
     disp[1, 0, -1, -1] = 1e9   # wildly out of range both ways
     disp[1, 0, 0, -1] = -1e9
-    for shift in (-4.0, 0.0, 3.0):
-        x0, y0, wx, wy = ops().warp_taps(disp.cuda(), shift)
-        ex0, ey0, (ewx0, ewx1), (ewy0, ewy1) = S.warp_taps(disp[:, 0].numpy() - np.float32(shift), H, W)
-        assert np.array_equal(x0.cpu().numpy(), ex0)
-        assert np.array_equal(y0.cpu().numpy(), ey0)
-        assert np.array_equal(wx.cpu().numpy().view(np.uint32), np.stack([ewx0, ewx1], -1).view(np.uint32))
-        assert np.array_equal(wy.cpu().numpy().view(np.uint32), np.stack([ewy0, ewy1], -1).view(np.uint32))
+    # both readings of the reference's `tensor / python scalar`: reciprocal multiply (Paddle 2.0, the oracle's
+    # choice and the library default) and true division -- bit-exact under each
+    for div_mode in (0, 1):
+        with ops().options(warp_div_mode=div_mode):
+            for shift in (-4.0, 0.0, 3.0):
+                x0, y0, wx, wy = ops().warp_taps(disp.cuda(), shift)
+                ex0, ey0, (ewx0, ewx1), (ewy0, ewy1) = S.warp_taps(disp[:, 0].numpy() - np.float32(shift), H, W, div_mode)
+                assert np.array_equal(x0.cpu().numpy(), ex0)
+                assert np.array_equal(y0.cpu().numpy(), ey0)
+                assert np.array_equal(wx.cpu().numpy().view(np.uint32), np.stack([ewx0, ewx1], -1).view(np.uint32))
+                assert np.array_equal(wy.cpu().numpy().view(np.uint32), np.stack([ewy0, ewy1], -1).view(np.uint32))
 
 
 def test_warp_and_residual_volume_golden():

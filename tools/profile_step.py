@@ -18,6 +18,9 @@ ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--warm", type=int, default=1)
 a = ap.parse_args()
 torch.cuda.set_device(0)
+for kv in filter(None, os.environ.get("LWS_PROFILE_OPTS", "").split(",")):  # e.g. LWS_PROFILE_OPTS=refine_chain=0,conv3d_tc=1
+    from lwsnet_b200 import ops
+    ops.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 m = LWSNet(O.default_args())
 m.load_state_dict(O.build_oracle(0).state_dict())
 m = m.cuda()

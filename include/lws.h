@@ -92,7 +92,9 @@ LWS_API int lws_warp_residual_volume_l1_f32(const float* L, const float* R, cons
 /* ---- a5: post_3dconvs + skip  (models/submodules.py:190-221, models/models.py:136-138) ---------------
  * out = cost + Conv_{n-1}(ReLU(BN_{n-1}( ... Conv_0(ReLU(BN_0(cost))) ... ))),  n = layers + 2 convs,
  * channels 1 -> C -> ... -> C -> 1, every conv 3x3x3 / stride 1 / zero pad 1 / no bias, BN in inference mode.
- * cost,out [B,D,H,W] (the singleton channel is implicit).  C must be 8, 16 or 32.
+ * cost,out [B,D,H,W] (the singleton channel is implicit).  Any C >= 1 (the reference takes any channels_3d * growth_rate,
+ * models/models.py:19-22): C = 8 and 32 (the reference's configuration) have tcgen05 kernels, every other width runs on the
+ * exact-fp32 FFMA kernel (16 natively, the rest in groups of 8 output channels, zero-padded to a multiple of 8).
  * add_skip != 0 fuses the `+ cost` of models/models.py:137 into the last conv; add_skip == 0 returns the bare
  * post_3dconvs(cost) (what calling the reference's nn.Sequential alone returns). */
 LWS_API size_t lws_conv3d_stack_packed_floats(int C, int layers);
@@ -104,6 +106,8 @@ LWS_API int lws_pack_conv3d_stack_weights(const float* const* conv_w, const floa
                                   const float* const* bn_bias, const float* const* bn_mean,
                                   const float* const* bn_var, float eps, int C, int layers, float* packed);
 LWS_API size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, int C, int layers);
+/* kernel launches lws_conv3d_stack_f32 enqueues (layers + 2 for C = 8, 16, 32) */
+LWS_API int lws_conv3d_stack_launches(int C, int layers);
 LWS_API int lws_conv3d_stack_f32(const float* cost, const float* packed_weights, float* out, void* ws, size_t ws_bytes, int B,
                          int D, int H, int W, int C, int layers, int add_skip, lws_stream_t stream);
 
@@ -116,6 +120,12 @@ LWS_API int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folded, 
  * low[b,0,y,x] = sum_j softmax_j(-cost[b,:,y,x]) * (start + j*step).  One pass over the volume. */
 LWS_API int lws_softmax_regression_f32(const float* cost, float* low, int B, int D, int H, int W, float start, float step,
                                lws_stream_t stream);
+
+/* The stand-alone class disparity_regression(start, end, stride).forward(input) (models/models.py:167-179) on an ALREADY
+ * soft-maxed (or any other) volume: out[b,0,y,x] = sum_j input[b,j,y,x] * (start + j*step), no renormalisation, fp32
+ * left-to-right sum like paddle.sum over axis 1. */
+LWS_API int lws_disparity_regression_f32(const float* prob, float* out, int B, int D, int H, int W, float start, float step,
+                                         lws_stream_t stream);
 
 /* ---- a7: rescale + upsample + skip  (models/models.py:145-148,153-156) ------------------------------
  * pred = bilinear_resize_halfpixel((low * float(H)) * fl32(1/h), H, W) (+ prev if prev != NULL).
@@ -138,6 +148,24 @@ LWS_API size_t lws_refinement_workspace_bytes(int B, int H, int W);
 LWS_API int lws_refinement_launches(int B, int H, int W);
 LWS_API int lws_refinement_f32(const float* left, const float* pred3, const float* packed_weights, float* pred4, void* ws,
                        size_t ws_bytes, int B, int H, int W, lws_stream_t stream);
+
+/* ---- a8 / a9 as stand-alone layers: the reference calls refinement1_left(x), refinement1_disp(x), refinement2(x) as layers
+ *      (models/models.py:158-160).  Module-local BN folding, NCHW in / out, exact-fp32 FFMA kernels; the model's forward uses the
+ *      fused lws_refinement_f32 above.
+ * lws_refinement1_f32: x [B,in_channels,H,W] (in_channels 1 or 3) -> out [B,32,H,W]  (models/submodules.py:282-300)
+ *   HOST pack, 25 tensors: conv0 [32,in,3,3]; blocks 1..4: BN(32) weight, bias, _mean, _variance, dw [32,1,3,3], pw [32,32,1,1]
+ * lws_refinement2_f32: x [B,64,H,W] -> out [B,1,H,W] (no skip add; models/submodules.py:302-327)
+ *   HOST pack, 30 tensors: BN(64) x4; conv [32,64,3,3]; blocks 1..4 as above; conv_last [1,32,3,3] */
+LWS_API size_t lws_refinement1_packed_floats(int in_channels);
+LWS_API int lws_pack_refinement1_weights(const float* const* tensors, int n_tensors, int in_channels, float eps, float* packed);
+LWS_API size_t lws_refinement1_workspace_bytes(int B, int H, int W);
+LWS_API int lws_refinement1_f32(const float* x, const float* packed_weights, float* out, void* ws, size_t ws_bytes, int B,
+                                int in_channels, int H, int W, lws_stream_t stream);
+LWS_API size_t lws_refinement2_packed_floats(void);
+LWS_API int lws_pack_refinement2_weights(const float* const* tensors, int n_tensors, float eps, float* packed);
+LWS_API size_t lws_refinement2_workspace_bytes(int B, int H, int W);
+LWS_API int lws_refinement2_f32(const float* x, const float* packed_weights, float* out, void* ws, size_t ws_bytes, int B, int H,
+                                int W, lws_stream_t stream);
 
 /* One BN-ReLU-DW3x3(dil)-PW1x1 block of the refinement (models/submodules.py:236-261) on its own, on the channels-last bordered
  * tensors the refinement uses internally: act[b][H+32][W+32][32] fp32, 16-pixel zero border (lws_refinement_clp_floats elements).

@@ -32,6 +32,7 @@ SIGNATURES = {
     "lws_conv3d_stack_packed_floats": (c_size_t, [c_int, c_int]),
     "lws_pack_conv3d_stack_weights": (c_int, [_pp, _pp, _pp, _pp, _pp, c_float, c_int, c_int, _fp]),
     "lws_conv3d_stack_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "lws_conv3d_stack_launches": (c_int, [c_int, c_int]),
     "lws_conv3d_stack_f32": (c_int, [_fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "lws_conv3d_bnrelu_layer_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -46,6 +47,15 @@ SIGNATURES = {
     "lws_refinement_chain_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "lws_refinement_chain_clp_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
     "lws_refinement_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "lws_refinement1_packed_floats": (c_size_t, [c_int]),
+    "lws_pack_refinement1_weights": (c_int, [_pp, c_int, c_int, c_float, _fp]),
+    "lws_refinement1_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lws_refinement1_f32": (c_int, [_fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
+    "lws_refinement2_packed_floats": (c_size_t, []),
+    "lws_pack_refinement2_weights": (c_int, [_pp, c_int, c_float, _fp]),
+    "lws_refinement2_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lws_refinement2_f32": (c_int, [_fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "lws_disparity_regression_f32": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "lws_preprocess_bgr_u8": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_disparity_to_u8": (c_int, [_fp, _fp, _fp, c_longlong, c_void_p]),
     "lws_feature_extraction_packed_floats": (c_size_t, []),

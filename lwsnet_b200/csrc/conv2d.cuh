@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(Conv2dCfg<CK, COUT, Q, RG, TW, DIL, EPI>::THRE
     if constexpr (EPI == EPI_SKIP_ADD) {
       const float* sk = a.skip + (long long)b * hw + pix;
 #pragma unroll
-      for (int p = 0; p < P; ++p) r[p] = acc[p][q] + ((gw + p < W) ? __ldg(sk + p) : 0.f);
+      for (int p = 0; p < P; ++p) r[p] = acc[p][q] + ((a.skip && gw + p < W) ? __ldg(sk + p) : 0.f);
     } else {
       const float bias = __ldg(a.bias + co);
 #pragma unroll

@@ -309,9 +309,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
         for (int p = 0; p < 4; ++p) {
           float v0 = fmaxf(out[2 * p] + bias[2 * p], 0.f), v1 = fmaxf(out[2 * p + 1] + bias[2 * p + 1], 0.f);
           v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
-          const __half2 h = __floats2half2_rn(v0, v1);
+          const __half2 h = f2h2_sat(v0, v1);
           const float2 f = __half22float2(h);
-          const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+          const __half2 l = f2h2_sat((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
           hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
         }
         *reinterpret_cast<uint4*>(stage + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -637,11 +637,11 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
           for (int p = 0; p < 4; ++p) {
             float v0 = fmaxf(fmaf(out[2 * p], c0, bias[2 * p]), 0.f), v1 = fmaxf(fmaf(out[2 * p + 1], c0, bias[2 * p + 1]), 0.f);
             v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
-            const __half2 h = __floats2half2_rn(v0, v1);
+            const __half2 h = f2h2_sat(v0, v1);
             const float2 f = __half22float2(h);
             // (v - hi) * 2^11 on channel pairs (FADD2 + FMUL2)
             const float2 d = split_lo2(v0, v1, f);
-            const __half2 l = __floats2half2_rn(d.x, d.y);
+            const __half2 l = f2h2_sat(d.x, d.y);
             hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
           }
           *reinterpret_cast<uint4*>(stage + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -754,10 +754,10 @@ __global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
     for (int p = 0; p < 4; ++p) {
       const float a0 = border ? 0.f : fmaxf(acc[vy][p].x + bv[2 * p], 0.f) * kDwsepActScale;
       const float a1 = border ? 0.f : fmaxf(acc[vy][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
-      const __half2 h = __floats2half2_rn(a0, a1);
+      const __half2 h = f2h2_sat(a0, a1);
       const float2 f = __half22float2(h);
       const float2 dl = split_lo2(a0, a1, f);
-      const __half2 l = __floats2half2_rn(dl.x, dl.y);
+      const __half2 l = f2h2_sat(dl.x, dl.y);
       hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
     }
     out_hi[vox0 + (long long)vy * Wp] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

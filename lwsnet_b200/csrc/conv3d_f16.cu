@@ -401,10 +401,10 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
               float v0 = fmaxf(out[c] + bias[c], relu_lo);
               float v1 = fmaxf(out[c + 1] + bias[c + 1], relu_lo);
               v0 = border ? 0.f : v0, v1 = border ? 0.f : v1;
-              const __half2 h = __floats2half2_rn(v0, v1);
+              const __half2 h = f2h2_sat(v0, v1);
               const float2 f = __half22float2(h);
               const float2 dl = split_lo2(v0, v1, f);
-              const __half2 l = __floats2half2_rn(dl.x, dl.y);
+              const __half2 l = f2h2_sat(dl.x, dl.y);
               hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c8 ^ (j & 7)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
@@ -604,10 +604,10 @@ __global__ void __launch_bounds__(256)
     for (int p = 0; p < 4; ++p) {
       const float a0 = border ? 0.f : fmaxf(acc[vd][p].x + bv[2 * p], 0.f) * kDwsepActScale;
       const float a1 = border ? 0.f : fmaxf(acc[vd][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
-      const __half2 h = __floats2half2_rn(a0, a1);
+      const __half2 h = f2h2_sat(a0, a1);
       const float2 f = __half22float2(h);
       const float2 dl = split_lo2(a0, a1, f);
-      const __half2 l = __floats2half2_rn(dl.x, dl.y);
+      const __half2 l = f2h2_sat(dl.x, dl.y);
       hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
     }
     out[(row0 + vd) * 8 + sub] = make_uint4(hi[0], hi[1], hi[2], hi[3]);

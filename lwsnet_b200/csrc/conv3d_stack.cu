@@ -44,6 +44,7 @@ struct Conv3dArgs {
   int Cin, D, H, W;
   int tiles_w, tiles_h, tiles_d;
   const float* affine;  // device [s0, t0]: BN_0 scalar affine (FIRST only)
+  int cout_total, cout_off;  // the launch writes channels [cout_off, cout_off + COUT) of an output with cout_total channels
 };
 
 template <int CK, int COUT, int Q, int TD, int TW, bool FIRST, bool LAST>
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>::T
     for (int q = 0; q < Q; ++q) {
       const int co = cg * Q + q;
       const float bias = __ldg(a.bias + co);
-      float* o = a.out + ((long long)b * COUT + co) * dhw + vox;
+      float* o = a.out + ((long long)b * a.cout_total + a.cout_off + co) * dhw + vox;
       float r[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) r[p] = fmaxf(acc[p][q] + bias, 0.f);
@@ -244,6 +245,7 @@ static int launch_conv3d(Conv3dArgs a, int B, cudaStream_t st) {
   using Cfg = Conv3dCfg<CK, COUT, Q, TD, TW, FIRST, LAST>;
   auto kern = conv3d_k3_kernel<CK, COUT, Q, TD, TW, FIRST, LAST>;
   LWS_SET_SMEM_ONCE(kern, Cfg::SMEM);  // `kern` is fixed by the template arguments: one static flag per instantiation
+  if (a.cout_total == 0) a.cout_total = COUT, a.cout_off = 0;
   a.tiles_w = cdiv(a.W, TW);
   a.tiles_h = cdiv(a.H, Cfg::TH);
   a.tiles_d = cdiv(a.D, TD);
@@ -255,10 +257,16 @@ static int launch_conv3d(Conv3dArgs a, int B, cudaStream_t st) {
 
 // packed layout (floats): [s0, t0, 0, 0] then per conv i: weights [Cin_i][27][Cout_i] (rounded up to 4 floats),
 // bias [Cout_i] (rounded up to 4; zeros for the last conv)
+// Widths other than 8 / 16 / 32 (the reference takes any channels_3d * growth_rate, models/models.py:19-22) run on the FP32 FFMA
+// kernel in groups of 8 output channels: C is padded to Cp = round_up(C, 8) with zero weights / zero bias (the padded activations
+// are exactly 0), and the packed weights of a conv are stored group-major [Cp/8][Cin_p][27][8].
+static bool native_width(int C) { return C == 8 || C == 16 || C == 32; }
+static int padded_width(int C) { return native_width(C) ? C : round_up(C, 8); }
 static size_t conv_w_floats(int cin, int cout) { return (size_t)round_up(cin * 27 * cout, 4); }
 static size_t packed_offset(int C, int layers, int conv, bool bias) {
   size_t off = 4;
   const int n = layers + 2;
+  C = padded_width(C);
   for (int i = 0; i < n; ++i) {
     const int cin = i == 0 ? 1 : C, cout = i == n - 1 ? 1 : C;
     if (i == conv && !bias) return off;
@@ -309,7 +317,42 @@ static int run_stack(const float* cost, const float* pk, float* out, float* bufA
   return launch_conv3d<4, 1, 1, 4, 64, false, true>(a, B, st);
 }
 
+// any other width: groups of 8 output channels on the FFMA kernel (Cp = padded width)
+static int run_stack_grouped(const float* cost, const float* pk, float* out, float* bufA, float* bufB, int B, int D, int H, int W,
+                             int C, int layers, int add_skip, cudaStream_t st) {
+  const int Cp = padded_width(C), ng = Cp / 8;
+  Conv3dArgs a;
+  int rc;
+  for (int g = 0; g < ng; ++g) {
+    memset(&a, 0, sizeof(a));
+    a.D = D, a.H = H, a.W = W, a.in = cost, a.Cin = 1, a.out = bufA, a.affine = pk, a.cout_total = Cp, a.cout_off = g * 8;
+    a.w = pk + packed_offset(C, layers, 0, false) + (size_t)g * 27 * 8, a.bias = pk + packed_offset(C, layers, 0, true) + g * 8;
+    if ((rc = launch_conv3d<1, 8, 8, 3, 64, true, false>(a, B, st))) return rc;
+  }
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int i = 1; i <= layers; ++i) {
+    for (int g = 0; g < ng; ++g) {
+      memset(&a, 0, sizeof(a));
+      a.D = D, a.H = H, a.W = W, a.in = cur, a.Cin = Cp, a.out = nxt, a.cout_total = Cp, a.cout_off = g * 8;
+      a.w = pk + packed_offset(C, layers, i, false) + (size_t)g * Cp * 27 * 8, a.bias = pk + packed_offset(C, layers, i, true) + g * 8;
+      if ((rc = launch_conv3d<4, 8, 8, 3, 64, false, false>(a, B, st))) return rc;
+    }
+    float* t = cur;
+    cur = nxt, nxt = t;
+  }
+  memset(&a, 0, sizeof(a));
+  a.D = D, a.H = H, a.W = W, a.in = cur, a.Cin = Cp, a.out = out, a.skip = add_skip ? cost : nullptr;
+  a.w = pk + packed_offset(C, layers, layers + 1, false), a.bias = nullptr;
+  return launch_conv3d<4, 1, 1, 4, 64, false, true>(a, B, st);
+}
+
 }  // namespace lws
+
+extern "C" int lws_conv3d_stack_launches(int C, int layers) {
+  if (C <= 0 || layers < 0) return 0;
+  return lws::native_width(C) ? layers + 2 : (layers + 1) * (lws::padded_width(C) / 8) + 1;
+}
 
 extern "C" size_t lws_conv3d_stack_packed_floats(int C, int layers) {
   if (C <= 0 || layers < 0) return 0;
@@ -329,16 +372,22 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
   auto bn_shift = [&](int i, int c) { return (double)bn_bias[i][c] - (double)bn_mean[i][c] * bn_scale(i, c); };
   packed[0] = (float)bn_scale(0, 0);
   packed[1] = (float)bn_shift(0, 0);
+  const bool native = native_width(C);
+  const int Cp = padded_width(C);
   for (int i = 0; i < n; ++i) {
     const int cin = i == 0 ? 1 : C, cout = i == n - 1 ? 1 : C;
+    const int cinp = i == 0 ? 1 : Cp;  // padded input width the kernels iterate over (padding weights stay 0)
     float* w = packed + packed_offset(C, layers, i, false);
     float* bias = packed + packed_offset(C, layers, i, true);
     for (int co = 0; co < cout; ++co) {
       const double s = (i < n - 1) ? bn_scale(i + 1, co) : 1.0;
       if (i < n - 1) bias[co] = (float)bn_shift(i + 1, co);
       for (int ci = 0; ci < cin; ++ci)
-        for (int t = 0; t < 27; ++t)
-          w[((size_t)ci * 27 + t) * cout + co] = (float)((double)conv_w[i][((size_t)co * cin + ci) * 27 + t] * s);
+        for (int t = 0; t < 27; ++t) {
+          const float v = (float)((double)conv_w[i][((size_t)co * cin + ci) * 27 + t] * s);
+          if (native || cout == 1) w[((size_t)ci * 27 + t) * cout + co] = v;
+          else w[(((size_t)(co >> 3) * cinp + ci) * 27 + t) * 8 + (co & 7)] = v;  // group-major [Cp/8][Cin_p][27][8]
+        }
     }
   }
   if (C == 32) {
@@ -462,7 +511,7 @@ extern "C" int lws_pack_conv3d_stack_weights(const float* const* conv_w, const f
 extern "C" size_t lws_conv3d_stack_workspace_bytes(int B, int D, int H, int W, int C, int layers) {
   (void)layers;
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
-  const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
+  const size_t act = ((size_t)B * lws::padded_width(C) * D * H * W * sizeof(float) + 255) / 256 * 256;
   size_t tc = 0;
   if (C == 32 && lws::conv3d_f16_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_f16_workspace_bytes(B, D, H, W);
   if (C == 8 && lws::conv3d_c8_workspace_bytes(B, D, H, W) > tc) tc = lws::conv3d_c8_workspace_bytes(B, D, H, W);
@@ -478,7 +527,7 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
   LWS_CHECK_PTR(out);
   LWS_CHECK_PTR(ws);
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || layers < 0 || B > 65535) return LWS_ERR_BAD_SHAPE;
-  if (C != 8 && C != 16 && C != 32) return LWS_ERR_UNSUPPORTED;
+  if (C <= 0) return LWS_ERR_BAD_SHAPE;
   if (ws_bytes < lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers)) return LWS_ERR_WORKSPACE_TOO_SMALL;
   if ((((uintptr_t)ws) | ((uintptr_t)packed_weights)) & 15) return LWS_ERR_BAD_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
@@ -500,9 +549,10 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
                              layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
     return LWS_ERR_UNSUPPORTED;
   }
-  const size_t act = ((size_t)B * C * D * H * W * sizeof(float) + 255) / 256 * 256;
+  const size_t act = ((size_t)B * padded_width(C) * D * H * W * sizeof(float) + 255) / 256 * 256;
   float* bufA = (float*)ws;
   float* bufB = (float*)((char*)ws + act);
+  if (!native_width(C)) return run_stack_grouped(cost, packed_weights, out, bufA, bufB, B, D, H, W, C, layers, add_skip, st);
   // BN_0's scalar affine is the first two floats of the device blob; the first conv kernel reads it from there.
   switch (C) {
     case 8:

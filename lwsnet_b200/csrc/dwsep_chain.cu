@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float v0 = m[c8 * 8 + 2 * k] * DS_ACT_SCALE, v1 = m[c8 * 8 + 2 * k + 1] * DS_ACT_SCALE;
-                const __half2 h = __floats2half2_rn(v0, v1);
+                const __half2 h = f2h2_sat(v0, v1);
                 const float2 f = __half22float2(h);
                 const float2 d = split_lo2(v0, v1, f);
-                hi[k] = h2_bits(h), lw[k] = h2_bits(__floats2half2_rn(d.x, d.y));
+                hi[k] = h2_bits(h), lw[k] = h2_bits(f2h2_sat(d.x, d.y));
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + ((c8 ^ (p & 7)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
                            "r"(hi[3])
@@ -487,11 +487,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
           const uint32_t dst = a_base + ab * DS_TILE;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const __half2 h01 = __floats2half2_rn(acc[j].x, acc[j].y), h23 = __floats2half2_rn(acc[j].z, acc[j].w);
+            const __half2 h01 = f2h2_sat(acc[j].x, acc[j].y), h23 = f2h2_sat(acc[j].z, acc[j].w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const float2 d01 = split_lo2(acc[j].x, acc[j].y, f01), d23 = split_lo2(acc[j].z, acc[j].w, f23);
-            const __half2 l01 = __floats2half2_rn(d01.x, d01.y);
-            const __half2 l23 = __floats2half2_rn(d23.x, d23.y);
+            const __half2 l01 = f2h2_sat(d01.x, d01.y);
+            const __half2 l23 = f2h2_sat(d23.x, d23.y);
             sts64(dst + a_off[j], h2_bits(h01), h2_bits(h23));
             sts64(dst + (a_off[j] ^ 64u), h2_bits(l01), h2_bits(l23));  // chunk + 4 (bit 6 of the swizzled offset)
           }

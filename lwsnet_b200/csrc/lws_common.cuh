@@ -1,5 +1,6 @@
 // Shared helpers for the lws_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -102,6 +103,16 @@ __device__ __forceinline__ void cp_async_wait() {
 // streaming (evict-first) 128-bit store for write-once outputs
 __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+
+// fp32 pair -> fp16 pair, round to nearest, SATURATING to +-65504 instead of overflowing to inf (F2FP.SATFINITE: the same single
+// instruction as the plain conversion).  Split-fp16 operands carry activations * 2^-6, so values beyond +-4.19e6 saturate: the
+// tensor-core paths can never produce inf / NaN from finite inputs (finite but clipped there; options conv3d_tc = 0 / refine_tc = 0
+// select the exact-fp32 kernels, which take the whole fp32 range).
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
 }
 
 // low half of the split-fp16 operand of a channel pair: (v - hi) * 2^11 with FADD2 + FMUL2 (sm_100 packed fp32; same roundings as

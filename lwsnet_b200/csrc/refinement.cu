@@ -550,3 +550,207 @@ extern "C" int lws_refinement_f32(const float* left, const float* pred3, const f
     return launch_conv2d<8, 1, 1, 4, 64, 1, EPI_SKIP_ADD>(c, B, st);
   }
 }
+
+// ---- stand-alone refinement1 / refinement2 (the reference calls them as layers, models/models.py:158-160) -----------------------
+// Module-local BN folding (nothing is folded across the module boundary, unlike the fused lws_refinement_f32), NCHW in / out, on
+// the exact-fp32 FFMA kernels above.  These entries exist for API parity; the model's forward uses the fused path.
+namespace lws {
+struct PartBN {
+  const float *w, *b, *m, *v;
+};
+static double part_scale(const PartBN& bn, int c, float eps) { return (double)bn.w[c] / sqrt((double)bn.v[c] + (double)eps); }
+static double part_shift(const PartBN& bn, int c, float eps) { return (double)bn.b[c] - (double)bn.m[c] * part_scale(bn, c, eps); }
+// one BN-ReLU-DW-PW block: BN of THIS block is folded into the producer; here: dw copy + pw scaled by the NEXT block's BN (or none)
+static void part_pack_block(const float* dw, const float* pw, const PartBN* next, float eps, float* dst /*288 + 1024 + 32*/) {
+  memcpy(dst, dw, 288 * sizeof(float));
+  for (int co = 0; co < 32; ++co) {
+    const double s = next ? part_scale(*next, co, eps) : 1.0;
+    dst[288 + 1024 + co] = next ? (float)part_shift(*next, co, eps) : 0.f;
+    for (int ci = 0; ci < 32; ++ci) dst[288 + ci * 32 + co] = (float)((double)pw[co * 32 + ci] * s);
+  }
+}
+constexpr size_t kPartBlock = 288 + 1024 + 32;
+
+__global__ void bnrelu_nchw_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                   float* __restrict__ y, int C, long long hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / hw) % C);
+    y[i] = fmaxf(fmaf(x[i], __ldg(scale + c), __ldg(shift + c)), 0.f);
+  }
+}
+}  // namespace lws
+
+extern "C" size_t lws_refinement1_packed_floats(int in_channels) {
+  if (in_channels != 1 && in_channels != 3) return 0;
+  return (size_t)in_channels * 288 + 32 + 4 * lws::kPartBlock;
+}
+// tensors (25): conv0 [32,cin,3,3]; then for blocks 1..4: BN(32) weight, bias, _mean, _variance, dw [32,1,3,3], pw [32,32,1,1]
+extern "C" int lws_pack_refinement1_weights(const float* const* t, int n_tensors, int in_channels, float eps, float* packed) {
+  using namespace lws;
+  if (!t || !packed) return LWS_ERR_NULL_PTR;
+  if (n_tensors != 25 || (in_channels != 1 && in_channels != 3)) return LWS_ERR_BAD_SHAPE;
+  for (int i = 0; i < n_tensors; ++i)
+    if (!t[i]) return LWS_ERR_NULL_PTR;
+  auto bn = [&](int j) { PartBN b = {t[1 + (j - 1) * 6], t[2 + (j - 1) * 6], t[3 + (j - 1) * 6], t[4 + (j - 1) * 6]}; return b; };
+  const PartBN b1 = bn(1);
+  float* w0 = packed;
+  float* bias0 = packed + (size_t)in_channels * 288;
+  for (int co = 0; co < 32; ++co) {
+    const double s = part_scale(b1, co, eps);
+    bias0[co] = (float)part_shift(b1, co, eps);
+    for (int ci = 0; ci < in_channels; ++ci)
+      for (int k = 0; k < 9; ++k) w0[((size_t)ci * 9 + k) * 32 + co] = (float)((double)t[0][((size_t)co * in_channels + ci) * 9 + k] * s);
+  }
+  for (int j = 1; j <= 4; ++j) {
+    PartBN nb;
+    if (j < 4) nb = bn(j + 1);
+    part_pack_block(t[5 + (j - 1) * 6], t[6 + (j - 1) * 6], j < 4 ? &nb : nullptr, eps, bias0 + 32 + (j - 1) * kPartBlock);
+  }
+  return LWS_OK;
+}
+extern "C" size_t lws_refinement1_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)2 * B * 32 * H * W * sizeof(float);
+}
+// refinement1(in_channels, 32)(x): x [B,in_channels,H,W] -> out [B,32,H,W]  (models/submodules.py:282-300)
+extern "C" int lws_refinement1_f32(const float* x, const float* pk, float* out, void* ws, size_t ws_bytes, int B, int in_channels,
+                                   int H, int W, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(x);
+  LWS_CHECK_PTR(pk);
+  LWS_CHECK_PTR(out);
+  LWS_CHECK_PTR(ws);
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || (in_channels != 1 && in_channels != 3)) return LWS_ERR_BAD_SHAPE;
+  if (ws_bytes < lws_refinement1_workspace_bytes(B, H, W)) return LWS_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)ws) | ((uintptr_t)pk) | ((uintptr_t)out)) & 15) return LWS_ERR_BAD_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long hw = (long long)H * W;
+  float* bufA = (float*)ws;
+  float* bufB = bufA + (long long)B * 32 * hw;
+  static const int dil[4] = {2, 4, 8, 16};
+  Conv2dArgs c;
+  memset(&c, 0, sizeof(c));
+  c.H = H, c.W = W, c.in = x, c.Cin = in_channels, c.in_bs = in_channels * hw;
+  c.w = pk, c.bias = pk + (size_t)in_channels * 288, c.out = bufA, c.out_bs = 32 * hw;
+  int rc = in_channels == 3 ? launch_conv2d<3, 32, 8, 1, 64, 1, EPI_BIAS_RELU>(c, B, st)
+                            : launch_conv2d<1, 32, 8, 1, 64, 1, EPI_BIAS_RELU>(c, B, st);
+  if (rc) return rc;
+  const float* blocks = pk + (size_t)in_channels * 288 + 32;
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int j = 0; j < 4; ++j) {
+    DwsepArgs d;
+    d.in = cur, d.in_bs = 32 * hw, d.H = H, d.W = W, d.dil = dil[j], d.relu = j < 3;
+    d.dw = blocks + j * kPartBlock, d.pw = d.dw + 288, d.bias = d.pw + 1024;
+    d.out = j < 3 ? nxt : out, d.out_bs = 32 * hw;
+    if ((rc = launch_dwsep(d, B, st))) return rc;
+    float* tt = cur;
+    cur = nxt, nxt = tt;
+  }
+  return LWS_OK;
+}
+
+extern "C" size_t lws_refinement2_packed_floats(void) { return 128 + 64 * 288 + 32 + 4 * lws::kPartBlock + 288; }
+// tensors (30): BN(64) weight, bias, _mean, _variance; conv [32,64,3,3]; blocks 1..4 as above; conv_last [1,32,3,3]
+extern "C" int lws_pack_refinement2_weights(const float* const* t, int n_tensors, float eps, float* packed) {
+  using namespace lws;
+  if (!t || !packed) return LWS_ERR_NULL_PTR;
+  if (n_tensors != 30) return LWS_ERR_BAD_SHAPE;
+  for (int i = 0; i < n_tensors; ++i)
+    if (!t[i]) return LWS_ERR_NULL_PTR;
+  const PartBN b64 = {t[0], t[1], t[2], t[3]};
+  for (int c = 0; c < 64; ++c) packed[c] = (float)part_scale(b64, c, eps), packed[64 + c] = (float)part_shift(b64, c, eps);
+  auto bn = [&](int j) { PartBN b = {t[5 + (j - 1) * 6], t[6 + (j - 1) * 6], t[7 + (j - 1) * 6], t[8 + (j - 1) * 6]}; return b; };
+  const PartBN b1 = bn(1);
+  float* w = packed + 128;
+  float* bias = w + 64 * 288;
+  for (int co = 0; co < 32; ++co) {
+    const double s = part_scale(b1, co, eps);
+    bias[co] = (float)part_shift(b1, co, eps);
+    for (int ci = 0; ci < 64; ++ci)
+      for (int k = 0; k < 9; ++k) w[((size_t)ci * 9 + k) * 32 + co] = (float)((double)t[4][((size_t)co * 64 + ci) * 9 + k] * s);
+  }
+  for (int j = 1; j <= 4; ++j) {
+    PartBN nb;
+    if (j < 4) nb = bn(j + 1);
+    part_pack_block(t[9 + (j - 1) * 6], t[10 + (j - 1) * 6], j < 4 ? &nb : nullptr, eps, bias + 32 + (j - 1) * kPartBlock);
+  }
+  float* last = bias + 32 + 4 * kPartBlock;  // [32][9][1]
+  for (int ci = 0; ci < 32; ++ci)
+    for (int k = 0; k < 9; ++k) last[ci * 9 + k] = t[29][ci * 9 + k];
+  return LWS_OK;
+}
+extern "C" size_t lws_refinement2_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * (64 + 32 + 32) * H * W * sizeof(float);
+}
+// refinement2(64, 32)(x): x [B,64,H,W] -> out [B,1,H,W]  (models/submodules.py:302-327; no skip: the caller adds it, models.py:160-162)
+extern "C" int lws_refinement2_f32(const float* x, const float* pk, float* out, void* ws, size_t ws_bytes, int B, int H, int W,
+                                   lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(x);
+  LWS_CHECK_PTR(pk);
+  LWS_CHECK_PTR(out);
+  LWS_CHECK_PTR(ws);
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535) return LWS_ERR_BAD_SHAPE;
+  if (ws_bytes < lws_refinement2_workspace_bytes(B, H, W)) return LWS_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)ws) | ((uintptr_t)pk) | ((uintptr_t)out)) & 15) return LWS_ERR_BAD_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long hw = (long long)H * W;
+  float* act = (float*)ws;  // ReLU(BN64(x)): the conv pads the activated tensor with zeros
+  float* bufA = act + (long long)B * 64 * hw;
+  float* bufB = bufA + (long long)B * 32 * hw;
+  const long long total = (long long)B * 64 * hw;
+  bnrelu_nchw_kernel<<<(int)min((total + 255) / 256, (long long)kNumSMs * 16), 256, 0, st>>>(x, pk, pk + 64, act, 64, hw, total);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return (int)e;
+  static const int dil[4] = {8, 4, 2, 1};
+  Conv2dArgs c;
+  memset(&c, 0, sizeof(c));
+  c.H = H, c.W = W, c.in = act, c.Cin = 64, c.in_bs = 64 * hw;
+  c.w = pk + 128, c.bias = pk + 128 + 64 * 288, c.out = bufA, c.out_bs = 32 * hw;
+  int rc = launch_conv2d<8, 32, 8, 1, 64, 8, EPI_BIAS_RELU>(c, B, st);
+  if (rc) return rc;
+  const float* blocks = pk + 128 + 64 * 288 + 32;
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int j = 0; j < 4; ++j) {
+    DwsepArgs d;
+    d.in = cur, d.in_bs = 32 * hw, d.H = H, d.W = W, d.dil = dil[j], d.relu = j < 3;
+    d.dw = blocks + j * kPartBlock, d.pw = d.dw + 288, d.bias = d.pw + 1024;
+    d.out = nxt, d.out_bs = 32 * hw;
+    if ((rc = launch_dwsep(d, B, st))) return rc;
+    float* tt = cur;
+    cur = nxt, nxt = tt;
+  }
+  memset(&c, 0, sizeof(c));
+  c.H = H, c.W = W, c.in = cur, c.Cin = 32, c.in_bs = 32 * hw;
+  c.w = blocks + 4 * kPartBlock, c.skip = nullptr, c.out = out, c.out_bs = hw;
+  return launch_conv2d<8, 1, 1, 4, 64, 1, EPI_SKIP_ADD>(c, B, st);
+}
+
+// ---- stand-alone disparity_regression.forward (models/models.py:167-179): out = sum_j input[:, j] * (start + j * step) ----------
+namespace lws {
+__global__ void weighted_sum_kernel(const float* __restrict__ p, float* __restrict__ out, int D, long long hw, long long total,
+                                    float start, float step) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, r = i - b * hw;
+    const float* src = p + b * D * hw + r;
+    float acc = 0.f;
+    // the reference multiplies by the expanded arange and reduces with paddle.sum over axis 1: plain left-to-right fp32 sum
+    for (int j = 0; j < D; ++j) acc = __fadd_rn(acc, __fmul_rn(__ldg(src + j * hw), __fadd_rn(start, __fmul_rn((float)j, step))));
+    out[i] = acc;
+  }
+}
+}  // namespace lws
+extern "C" int lws_disparity_regression_f32(const float* prob, float* out, int B, int D, int H, int W, float start, float step,
+                                            lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(prob);
+  LWS_CHECK_PTR(out);
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return LWS_ERR_BAD_SHAPE;
+  const long long hw = (long long)H * W, total = B * hw;
+  weighted_sum_kernel<<<(int)min((total + 255) / 256, (long long)kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(prob, out, D, hw, total,
+                                                                                                              start, step);
+  LWS_RETURN_LAUNCH_STATUS();
+}

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import LwsError
-from .submodules import BN_EPS, feature_extraction, post_3dconvs, refinement1, refinement2, refinement_tensor_list
+from .submodules import BN_EPS, _pack_key, feature_extraction, post_3dconvs, refinement1, refinement2, refinement_tensor_list
 
 
 class LWSNet(nn.Module):
@@ -39,7 +39,9 @@ class LWSNet(nn.Module):
         """``model.set_state_dict(paddle.load(path))``: accepts {key: ndarray | tensor | (name, ndarray)} with the Paddle key
         grammar; unlike Paddle, a key or shape mismatch raises instead of warning."""
         from .checkpoint import convert_state
-        return self.load_state_dict(convert_state(state_dict, self.state_dict()), strict=True)
+        res = self.load_state_dict(convert_state(state_dict, self.state_dict()), strict=True)
+        self.repack()
+        return res
 
     set_dict = set_state_dict  # Paddle 2.0 alias
 
@@ -64,15 +66,29 @@ class LWSNet(nn.Module):
 
     def _refinement_packed(self, device):
         mods = (self.refinement1_left, self.refinement1_disp, self.refinement2)
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for m in mods
-                                     for p in list(m.parameters()) + list(m.buffers()))
+        key = tuple(_pack_key(m, device) for m in mods)
         if self._ref_packed is None or self._ref_key != key:
             self._ref_packed = ops.pack_refinement(refinement_tensor_list(*mods), BN_EPS).to(device)
             self._ref_key = key
         return self._ref_packed
 
+    def repack(self):
+        """Drop every cached BN-folded weight blob.  The caches notice ordinary weight updates by themselves (load_state_dict,
+        set_state_dict, in-place tensor ops); edits through ``p.data`` bypass torch's version counter and need this call."""
+        self._ref_packed = None
+        for m in self.modules():
+            if m is not self and hasattr(m, "repack"):
+                m.repack()
+
+    def pack_state(self, device):
+        """Identity of the packed weight blobs the next forward on `device` will read (StereoEngine compares it with what a
+        captured CUDA graph baked in)."""
+        blobs = [self.feature_extraction.packed(device), self._refinement_packed(device)]
+        blobs += [vp.packed(device) for vp in self.volume_postprocess]
+        return tuple((b.data_ptr(), b._version) for b in blobs)
+
     # one iteration of the stage loop, reference models/models.py:115-156
-    def _stage(self, scale, feat_l, feat_r, prev_pred, img_h, img_w):
+    def _stage(self, scale, feat_l, feat_r, prev_pred, img_h, img_w, out=None):
         if scale > 0:
             wflow = ops.disp_to_scale(prev_pred, feat_l.shape[2], feat_l.shape[3])                 # models.py:119-121
             cost = self._build_volume_2d3(feat_l, feat_r, self.maxdisplist[scale], wflow, stride=1)  # :123-127
@@ -82,14 +98,16 @@ class LWSNet(nn.Module):
             start = 0.0
         cost = self.volume_postprocess[scale].run(cost, add_skip=True)                               # :136-138
         low = ops.softmax_regression(cost, start, 1.0)                                              # :142 / :151-152
-        return ops.scale_upsample_add(low, prev_pred if scale > 0 else None, img_h, img_w)          # :145-148 / :153-156
+        return ops.scale_upsample_add(low, prev_pred if scale > 0 else None, img_h, img_w, out=out)  # :145-148 / :153-156
 
-    def _refine(self, left_input, pred3):
-        return ops.refinement(left_input, pred3, self._refinement_packed(left_input.device))        # :158-162
+    def _refine(self, left_input, pred3, out=None):
+        return ops.refinement(left_input, pred3, self._refinement_packed(left_input.device), out=out)  # :158-162
 
     # -- reference models/models.py:106-164 ----------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, left_input, right_input):
+    def forward(self, left_input, right_input, out=None):
+        """Returns the list of 4 stage disparities [B,1,H,W] like the reference.  `out` (optional, an extension used by
+        StereoEngine): a preallocated [4,B,1,H,W] fp32 tensor the four stages are written into (the returned list are its views)."""
         if not (left_input.is_cuda and right_input.is_cuda):
             raise LwsError("LWSNet.forward: lwsnet_b200 has no CPU path; inputs must be CUDA tensors")
         if left_input.shape != right_input.shape or left_input.dim() != 4 or left_input.shape[1] != 3:
@@ -112,11 +130,14 @@ class LWSNet(nn.Module):
         feats = self.feature_extraction(stacked)
         feats_l = [f[:n] for f in feats]
         feats_r = [f[n:] for f in feats]
+        if out is not None and (tuple(out.shape) != (4, n, 1, img_h, img_w) or out.dtype != torch.float32 or not out.is_contiguous()
+                                or out.device != left_input.device):
+            raise ValueError("out must be a contiguous fp32 [4,B,1,H,W] tensor on the inputs' device")
         pred = []
         for scale in range(len(feats_l)):
             pred.append(self._stage(scale, feats_l[scale].contiguous(), feats_r[scale].contiguous(),
-                                    pred[scale - 1] if scale > 0 else None, img_h, img_w))
-        pred.append(self._refine(left_input, pred[2]))
+                                    pred[scale - 1] if scale > 0 else None, img_h, img_w, out=None if out is None else out[scale]))
+        pred.append(self._refine(left_input, pred[2], out=None if out is None else out[3]))
         return pred
 
 
@@ -124,8 +145,8 @@ class disparity_regression(nn.Module):
     """reference models/models.py:167-179: expectation of arange(start*stride, end*stride, stride) under `input`.
 
     `input` is the already soft-maxed volume (as in the reference).  Inside LWSNet the softmax and this expectation run
-    as one fused kernel (ops.softmax_regression); this stand-alone class is kept for API compatibility and evaluates
-    the same fused kernel on log(input), which is mathematically the identity softmax(log p) = p for a normalised p.
+    as one fused kernel (ops.softmax_regression); this stand-alone class evaluates exactly what the reference's class does,
+    sum_j input[:, j] * disp_j, with no renormalisation of `input` (ops.disparity_regression).
     """
 
     def __init__(self, start, end, stride=1):
@@ -138,4 +159,4 @@ class disparity_regression(nn.Module):
             raise LwsError("disparity_regression: no CPU path")
         if input.shape[1] != self.my_steplength:
             raise ValueError(f"expected {self.my_steplength} disparity planes, got {input.shape[1]}")
-        return ops.softmax_regression(-torch.log(input), float(self.start * self.stride), float(self.stride))
+        return ops.disparity_regression(input, float(self.start * self.stride), float(self.stride))

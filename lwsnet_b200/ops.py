@@ -15,7 +15,7 @@ from ._lib import LwsError, check, get_option, lib, options, set_option  # noqa:
 
 LAUNCHES = [0]  # kernels of liblws_b200 enqueued through this module (bench.py reports it as gpu_launches)
 _workspaces: dict = {}
-_retired: list = []  # outgrown buffers stay alive: captured CUDA graphs may still hold their addresses
+_retired: dict = {}  # outgrown buffers stay alive while a captured CUDA graph may still hold their addresses (see release_retired)
 
 
 def _ptr(t: Optional[torch.Tensor], name: str, dtype=torch.float32):
@@ -47,15 +47,24 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, tag).  Reuse is stream-ordered, so use one stream per tag."""
-    key = (device.index, tag)
+    """Grow-only scratch buffer per (device, STREAM, tag): calls on one stream are ordered, so they may share scratch memory;
+    two engines / threads working on different streams of one device get different buffers and cannot race."""
+    stream = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index, stream, tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
-            _retired.append(buf)
+            _retired.setdefault((device.index, stream), []).append(buf)
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+def release_retired(device: Optional[torch.device] = None) -> None:
+    """Free outgrown scratch buffers.  Call when the CUDA graphs that captured them have been dropped (StereoEngine does)."""
+    for key in list(_retired):
+        if device is None or key[0] == device.index:
+            del _retired[key]
 
 
 def release_workspaces() -> None:
@@ -187,7 +196,7 @@ def conv3d_stack(cost: torch.Tensor, packed: torch.Tensor, C: int, layers: int, 
         check(lib.lws_conv3d_stack_f32(_ptr(cost, "cost"), _ptr(packed, "packed"), _ptr(out, "out"),
                                        ctypes.c_void_p(ws.data_ptr()), nbytes, B, D, H, W, C, layers, int(add_skip),
                                        _stream(cost)), "lws_conv3d_stack_f32")
-    LAUNCHES[0] += layers + 2
+    LAUNCHES[0] += int(lib.lws_conv3d_stack_launches(C, layers))
     return out
 
 
@@ -233,7 +242,73 @@ def scale_upsample_add(low: torch.Tensor, prev: Optional[torch.Tensor], H: int, 
     return pred
 
 
+def disparity_regression(prob: torch.Tensor, start: float, step: float = 1.0) -> torch.Tensor:
+    """disparity_regression(start, end, stride).forward(prob) (reference models/models.py:167-179) on an already soft-maxed
+    volume: sum_j prob[:, j] * (start + j * step), without renormalising `prob`."""
+    prob = _f32c(prob)
+    B, D, H, W = prob.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=prob.device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(prob.device):
+        check(lib.lws_disparity_regression_f32(_ptr(prob, "prob"), _ptr(out, "out"), B, D, H, W, float(start), float(step),
+                                               _stream(prob)), "lws_disparity_regression_f32")
+    LAUNCHES[0] += 1
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ a8 + a9
+def pack_refinement1(tensors: Sequence[torch.Tensor], in_channels: int, eps: float) -> torch.Tensor:
+    """Module-local BN folding of a stand-alone refinement1 (25 tensors, order: include/lws.h)."""
+    hs = [_host_f32(t) for t in tensors]
+    n = int(lib.lws_refinement1_packed_floats(in_channels))
+    if n == 0:
+        raise LwsError(f"refinement1: in_channels must be 1 or 3 (the reference's two uses), got {in_channels}")
+    packed = torch.zeros(n, dtype=torch.float32)
+    check(lib.lws_pack_refinement1_weights(_ptr_array(hs), len(hs), in_channels, float(eps), ctypes.c_void_p(packed.data_ptr())),
+          "lws_pack_refinement1_weights")
+    return packed
+
+
+def refinement1(x: torch.Tensor, packed: torch.Tensor) -> torch.Tensor:
+    """refinement1(in, 32)(x) as a layer (reference models/submodules.py:282-300, called at models/models.py:158-159)."""
+    x = _f32c(x)
+    B, cin, H, W = x.shape
+    out = torch.empty((B, 32, H, W), dtype=torch.float32, device=x.device)
+    nbytes = int(lib.lws_refinement1_workspace_bytes(B, H, W))
+    ws = workspace(x.device, "refine_part", nbytes)
+    with torch.cuda.device(x.device):
+        check(lib.lws_refinement1_f32(_ptr(x, "x"), _ptr(packed, "packed"), _ptr(out, "out"), ctypes.c_void_p(ws.data_ptr()), nbytes,
+                                      B, cin, H, W, _stream(x)), "lws_refinement1_f32")
+    LAUNCHES[0] += 5
+    return out
+
+
+def pack_refinement2(tensors: Sequence[torch.Tensor], eps: float) -> torch.Tensor:
+    """Module-local BN folding of a stand-alone refinement2 (30 tensors, order: include/lws.h)."""
+    hs = [_host_f32(t) for t in tensors]
+    packed = torch.zeros(int(lib.lws_refinement2_packed_floats()), dtype=torch.float32)
+    check(lib.lws_pack_refinement2_weights(_ptr_array(hs), len(hs), float(eps), ctypes.c_void_p(packed.data_ptr())),
+          "lws_pack_refinement2_weights")
+    return packed
+
+
+def refinement2(x: torch.Tensor, packed: torch.Tensor) -> torch.Tensor:
+    """refinement2(64, 32)(x) as a layer (reference models/submodules.py:302-327, called at models/models.py:160): no skip add."""
+    x = _f32c(x)
+    B, c, H, W = x.shape
+    if c != 64:
+        raise ValueError("refinement2 expects [B,64,H,W]")
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    nbytes = int(lib.lws_refinement2_workspace_bytes(B, H, W))
+    ws = workspace(x.device, "refine_part", nbytes)
+    with torch.cuda.device(x.device):
+        check(lib.lws_refinement2_f32(_ptr(x, "x"), _ptr(packed, "packed"), _ptr(out, "out"), ctypes.c_void_p(ws.data_ptr()), nbytes,
+                                      B, H, W, _stream(x)), "lws_refinement2_f32")
+    LAUNCHES[0] += 7
+    return out
+
+
 def pack_refinement(tensors: Sequence[torch.Tensor], eps: float) -> torch.Tensor:
     """Fold the BNs of refinement1_left / refinement1_disp / refinement2 (host); tensor order: include/lws.h."""
     hs = [_host_f32(t) for t in tensors]

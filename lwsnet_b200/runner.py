@@ -77,9 +77,12 @@ def ramp_batches(n: int, mb: int, edge: int) -> List[Tuple[int, int]]:
 class StereoEngine:
     """Runs ``model`` (lwsnet_b200.LWSNet on one CUDA device) over batches.
 
-    infer_device: inputs already resident in HBM  ->  preds [B,4,H,W] on the device.
-    infer_host  : inputs in (pinned) host memory   ->  preds written to a (pinned) host tensor; H2D of micro-batch
-                  i+1 and D2H of micro-batch i-1 overlap the compute of micro-batch i (three streams, two buffer sets).
+    infer_device : inputs already resident in HBM  ->  preds [B,4,H,W] on the device.
+    infer_host   : inputs in (pinned) host memory   ->  preds written to a (pinned) host tensor; H2D of micro-batch
+                   i+1 and D2H of micro-batch i-1 overlap the compute of micro-batch i (three streams, two buffer sets).
+    infer_host_u8: the reference's inference-loop body (inference.py:90-137): uint8 images in, uint8 / JET disparities out.
+    ``stages`` selects which of the four stage outputs leave the device (the reference's directory mode keeps only the last,
+    inference.py:133-137); the forward always computes all four.
     """
 
     def __init__(self, model, micro_batch: int = 2, device: Optional[torch.device] = None, use_graphs: bool = True,
@@ -93,14 +96,25 @@ class StereoEngine:
         self.use_graphs = use_graphs
         self._graphs = {}
         self._graph_launches = {}
+        self._pack_state = None
         self._h2d = torch.cuda.Stream(self.device)
         self._d2h = torch.cuda.Stream(self.device)
 
     # ------------------------------------------------------------------------------------------ device-resident
     def _forward_into(self, left, right, out):
-        preds = self.model(left, right)
-        for s in range(4):
-            out[:, s].copy_(preds[s][:, 0])
+        """out: [4,n,1,H,W] stage-major, so every stage is one contiguous block and the model writes into it directly."""
+        self.model(left, right, out=out)
+
+    def _check_weights(self):
+        """Captured graphs bake in the device addresses of the BN-folded weight blobs: drop them when the model's weights (and
+        with them the blobs) have changed since capture, so a replay can never read stale or freed weights."""
+        state = self.model.pack_state(self.device)
+        if state != self._pack_state:
+            if self._graphs:
+                self._graphs.clear()
+                self._graph_launches.clear()
+                ops.release_retired(self.device)
+            self._pack_state = state
 
     def _graph_for(self, n, H, W, slot=0):
         key = (n, H, W, slot)
@@ -109,7 +123,7 @@ class StereoEngine:
             dev = self.device
             both = torch.zeros((2 * n, 3, H, W), device=dev)  # left and right back to back: the model stacks them without a copy
             left, right = both[:n], both[n:]
-            out = torch.empty((n, 4, H, W), device=dev)
+            out = torch.empty((4, n, 1, H, W), device=dev)
             s = torch.cuda.Stream(dev)
             s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s):
@@ -135,15 +149,18 @@ class StereoEngine:
         B, _, H, W = left.shape
         if out is None:
             out = torch.empty((B, 4, H, W), device=left.device)
+        self._check_weights()
         for lo, hi in micro_batches(B, self.mb):
             if self.use_graphs:
                 graph, gl, gr, go = self._graph_for(hi - lo, H, W)
                 gl.copy_(left[lo:hi])
                 gr.copy_(right[lo:hi])
                 self._replay(graph)
-                out[lo:hi].copy_(go)
+                out[lo:hi].copy_(go[:, :, 0].transpose(0, 1))
             else:
-                self._forward_into(left[lo:hi].contiguous(), right[lo:hi].contiguous(), out[lo:hi])
+                go = torch.empty((4, hi - lo, 1, H, W), device=left.device)
+                self._forward_into(left[lo:hi].contiguous(), right[lo:hi].contiguous(), go)
+                out[lo:hi].copy_(go[:, :, 0].transpose(0, 1))
         return out
 
     # ------------------------------------------------------------------------------------------ host-resident
@@ -159,19 +176,27 @@ class StereoEngine:
         if buf is None:
             dev = self.device
             buf = (None, torch.empty((n, 3, H, W), device=dev), torch.empty((n, 3, H, W), device=dev),
-                   torch.empty((n, 4, H, W), device=dev))
+                   torch.empty((4, n, 1, H, W), device=dev))
             self._graphs[key] = buf
         return buf
 
     @torch.no_grad()
-    def infer_host(self, left: torch.Tensor, right: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """left/right: CPU tensors [B,3,H,W] (pinned for async copies).  Returns a CPU tensor [B,4,H,W]."""
+    def infer_host(self, left: torch.Tensor, right: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   stages=(0, 1, 2, 3)) -> torch.Tensor:
+        """left/right: CPU tensors [B,3,H,W] (pinned for async copies).  Returns a CPU tensor [B,len(stages),H,W] with the selected
+        stage disparities (fp32)."""
         B, _, H, W = left.shape
         dev = self.device
+        stages = tuple(stages)
+        if not stages or any(s not in (0, 1, 2, 3) for s in stages):
+            raise ValueError("stages must be a non-empty subset of (0, 1, 2, 3)")
         if out is None:
-            out = torch.empty((B, 4, H, W), pin_memory=True)
+            out = torch.empty((B, len(stages), H, W), pin_memory=True)
+        if tuple(out.shape) != (B, len(stages), H, W):
+            raise ValueError("out must be [B,len(stages),H,W]")
         cur = torch.cuda.current_stream(dev)
         chunks = self._host_chunks(B)
+        self._check_weights()
         bufs = [self._host_slot(hi - lo, H, W, i & 1) for i, (lo, hi) in enumerate(chunks)]  # before the timed copies start
         in_ready = [torch.cuda.Event() for _ in chunks]
         done = [torch.cuda.Event() for _ in chunks]
@@ -199,7 +224,8 @@ class StereoEngine:
             in_free[key] = done[i]
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done[i])
-                out[lo:hi].copy_(go, non_blocking=True)
+                for j, st in enumerate(stages):
+                    out[lo:hi, j].copy_(go[st, :, 0], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._d2h)
                 out_free[key] = ev
@@ -211,32 +237,42 @@ class StereoEngine:
     @torch.no_grad()
     def infer_host_u8(self, left: torch.Tensor, right: torch.Tensor, th: int = 368, tw: int = 1232,
                       out_gray: Optional[torch.Tensor] = None, out_color: Optional[torch.Tensor] = None,
-                      color: bool = False):
+                      color: bool = False, stages=(0, 1, 2, 3), gray: bool = True):
         """The reference's whole inference loop body (inference.py:90-115) with only uint8 crossing PCIe.
 
         left/right: CPU uint8 [B,h,w,3] HWC BGR images as cv2.imread returns them (pinned for async copies).  Crop, BGR->RGB,
         ToTensor and Normalize run on the device (ops.preprocess_bgr_u8), the four stage disparities are cast to uint8 on the
-        device (ops.disparity_to_u8) and, when ``color``, JET colour-mapped.  Returns (gray [B,4,th,tw] uint8 CPU,
-        color [B,4,th,tw,3] uint8 CPU or None).  H2D / compute / D2H of neighbouring micro-batches overlap as in infer_host.
+        device (ops.disparity_to_u8) and, when ``color``, JET colour-mapped.  Returns (gray [B,S,th,tw] uint8 CPU or None,
+        color [B,S,th,tw,3] uint8 CPU or None) for the S selected ``stages`` (``stages=(3,), gray=False, color=True`` is the
+        reference's directory mode: one colour image per pair, inference.py:133-137).  H2D / compute / D2H of neighbouring
+        micro-batches overlap as in infer_host.
         """
         B, h, w, _ = left.shape
         dev = self.device
-        if out_gray is None:
-            out_gray = torch.empty((B, 4, th, tw), dtype=torch.uint8, pin_memory=True)
+        stages = tuple(stages)
+        S = len(stages)
+        if not stages or any(s not in (0, 1, 2, 3) for s in stages) or list(stages) != sorted(set(stages)):
+            raise ValueError("stages must be a non-empty ascending subset of (0, 1, 2, 3)")
+        if not (gray or color):
+            raise ValueError("ask for gray and/or color")
+        if gray and out_gray is None:
+            out_gray = torch.empty((B, S, th, tw), dtype=torch.uint8, pin_memory=True)
         if color and out_color is None:
-            out_color = torch.empty((B, 4, th, tw, 3), dtype=torch.uint8, pin_memory=True)
+            out_color = torch.empty((B, S, th, tw, 3), dtype=torch.uint8, pin_memory=True)
+        contiguous_stages = stages == tuple(range(stages[0], stages[0] + S))
         cur = torch.cuda.current_stream(dev)
         chunks = self._host_chunks(B)
+        self._check_weights()
         bufs = []
         for i, (lo, hi) in enumerate(chunks):
             n, slot = hi - lo, i & 1
-            key = ("u8", n, h, w, th, tw, color, slot)
+            key = ("u8", n, h, w, th, tw, gray, color, S, slot)
             io = self._graphs.get(key)
             if io is None:
                 io = (torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
                       torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
-                      torch.empty((n, 4, th, tw), dtype=torch.uint8, device=dev),
-                      torch.empty((n, 4, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
+                      torch.empty((S, n, th, tw), dtype=torch.uint8, device=dev) if gray else None,
+                      torch.empty((S, n, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
                 self._graphs[key] = io
             bufs.append((io, self._host_slot(n, th, tw, slot)))
         in_ready = [torch.cuda.Event() for _ in chunks]
@@ -262,17 +298,25 @@ class StereoEngine:
                 self._replay(graph)
             else:
                 self._forward_into(gl, gr, go)
-            ops.disparity_to_u8(go, gray=True, color=color, out_gray=ug, out_color=uc if color else None)
+            # go is stage-major [4,n,1,th,tw]: a run of consecutive stages is one contiguous block -> one conversion launch
+            if contiguous_stages:
+                ops.disparity_to_u8(go[stages[0]:stages[0] + S], gray=gray, color=color, out_gray=ug, out_color=uc)
+            else:
+                for j, st in enumerate(stages):
+                    ops.disparity_to_u8(go[st], gray=gray, color=color, out_gray=ug[j] if gray else None,
+                                        out_color=uc[j] if color else None)
             done[i].record(cur)
             in_free[key] = done[i]
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done[i])
-                out_gray[lo:hi].copy_(ug, non_blocking=True)
-                if color:
-                    out_color[lo:hi].copy_(uc, non_blocking=True)
+                for j in range(S):
+                    if gray:
+                        out_gray[lo:hi, j].copy_(ug[j], non_blocking=True)
+                    if color:
+                        out_color[lo:hi, j].copy_(uc[j], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._d2h)
                 out_free[key] = ev
         cur.wait_stream(self._d2h)
         cur.wait_stream(self._h2d)
-        return out_gray, out_color
+        return (out_gray if gray else None), (out_color if color else None)

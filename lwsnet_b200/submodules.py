@@ -26,6 +26,12 @@ from ._lib import LwsError
 BN_EPS = 1e-5  # paddle.nn.BatchNorm2D/3D default epsilon
 
 
+def _pack_key(module, device):
+    """Cache key of a folded-weight blob: storage address and in-place version of every tensor.  In-place edits through
+    ``p.data`` do not bump the version: call ``repack()`` (or ``model.repack()``) after such weight surgery."""
+    return (str(device),) + tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+
+
 def _require_cuda(x: torch.Tensor, who: str) -> None:
     if not x.is_cuda:
         raise LwsError(f"{who}: lwsnet_b200 has no CPU path; move the model and its inputs to a CUDA device")
@@ -192,8 +198,11 @@ class feature_extraction(nn.Module):
         out.append(self.classif1[2].weight)
         return out
 
+    def repack(self):
+        self._packed = None
+
     def packed(self, device):
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        key = _pack_key(self, device)
         if self._packed is None or self._packed_key != key:
             self._packed = ops.pack_feature_extraction(self.tensor_list(), BN_EPS).to(device)
             self._packed_key = key
@@ -239,8 +248,11 @@ class Post3DConvs(nn.Sequential):
         self._packed = None
         self._packed_key = None
 
+    def repack(self):
+        self._packed = None
+
     def packed(self, device):
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        key = _pack_key(self, device)
         if self._packed is None or self._packed_key != key:
             convs = [blk[2].weight for blk in self]
             bns = [blk[0].tensors() for blk in self]
@@ -284,24 +296,58 @@ def preconv2d_depthseperated(in_channels, out_channels, kernel_size, stride, pad
 
 
 class _RefinementPart(nn.Sequential):
-    """refinement1 / refinement2 stacks.  Inside LWSNet they execute fused (lws_refinement_f32); a stand-alone call
-    is not a hot-path entry of the reference (the model is their only caller) and is refused rather than emulated."""
+    """refinement1 / refinement2 stacks.  Inside LWSNet.forward they execute fused (lws_refinement_f32, BN folded across the
+    module boundaries); called as a layer, like the reference does at models/models.py:158-160, they run their own C-ABI entry
+    (lws_refinement1_f32 / lws_refinement2_f32, module-local BN folding, NCHW in / out)."""
 
-    def forward(self, input):
-        raise LwsError(f"{type(self).__name__}: executes fused inside LWSNet.forward (ops.refinement); "
-                       "a stand-alone forward is not built")
+    def __init__(self, *layers):
+        super().__init__(*layers)
+        self._packed = None
+        self._packed_key = None
+
+    def repack(self):
+        self._packed = None
+
+    def _cached(self, device, make):
+        key = _pack_key(self, device)
+        if self._packed is None or self._packed_key != key:
+            self._packed = make().to(device)
+            self._packed_key = key
+        return self._packed
 
 
 class Refinement1(_RefinementPart):
-    pass
+    def tensor_list(self):
+        out = [self[0].weight]
+        for j in range(1, 5):
+            out += list(self[j][0].tensors()) + [self[j][2].weight, self[j][3].weight]
+        return out
+
+    def forward(self, input):
+        _require_cuda(input, "refinement1")
+        cin = self[0].weight.shape[1]
+        if input.dim() != 4 or input.shape[1] != cin:
+            raise ValueError(f"refinement1 expects [B,{cin},H,W], got {tuple(input.shape)}")
+        return ops.refinement1(input, self._cached(input.device, lambda: ops.pack_refinement1(self.tensor_list(), cin, BN_EPS)))
 
 
 class Refinement2(_RefinementPart):
-    pass
+    def tensor_list(self):
+        out = list(self[0][0].tensors()) + [self[0][2].weight]
+        for j in range(1, 5):
+            out += list(self[j][0].tensors()) + [self[j][2].weight, self[j][3].weight]
+        out.append(self[5].weight)
+        return out
+
+    def forward(self, input):
+        _require_cuda(input, "refinement2")
+        return ops.refinement2(input, self._cached(input.device, lambda: ops.pack_refinement2(self.tensor_list(), BN_EPS)))
 
 
 def refinement1(in_channels, out_channels):
     """reference models/submodules.py:282-300."""
+    if in_channels not in (1, 3) or out_channels != 32:
+        raise LwsError("refinement1: built for the reference's two uses, refinement1(3, 32) and refinement1(1, 32)")
     net = [Conv2D(in_channels, out_channels, 3, 1, 1)]
     net += [preconv2d_depthseperated(out_channels, out_channels, 3, 1, 1, dilation=2 ** (k + 1)) for k in range(4)]
     return Refinement1(*net)
@@ -309,6 +355,8 @@ def refinement1(in_channels, out_channels):
 
 def refinement2(in_channels, out_channels):
     """reference models/submodules.py:302-327."""
+    if in_channels != 64 or out_channels != 32:
+        raise LwsError("refinement2: built for the reference's use, refinement2(64, 32)")
     net = [preconv2d(in_channels, out_channels, 3, 1, 1, dilation=8)]
     net += [preconv2d_depthseperated(out_channels, out_channels, 3, 1, 1, dilation=2 ** k) for k in reversed(range(4))]
     net += [Conv2D(out_channels, 1, 3, 1, 1)]

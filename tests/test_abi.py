@@ -38,7 +38,16 @@ def test_status_strings_and_validation_without_gpu():
     dummy = ctypes.c_void_p(16)
     assert lib.lws_cost_volume_l1_f32(dummy, dummy, dummy, 1, 4, 4, 8, 13, 2, None) == -1  # maxdisp % stride
     assert lib.lws_conv3d_stack_f32(dummy, dummy, dummy, dummy, 0, 1, 4, 4, 4, 8, 4, 1, None) == -4
-    assert lib.lws_conv3d_stack_f32(dummy, dummy, dummy, dummy, 1 << 40, 1, 4, 4, 4, 7, 4, 1, None) == -5
+    assert lib.lws_conv3d_stack_f32(dummy, dummy, dummy, dummy, 1 << 40, 1, 4, 4, 4, 0, 4, 1, None) == -1  # C must be >= 1
+    # explicit options instead of environment switches
+    v = ctypes.c_int(-1)
+    assert lib.lws_get_option(b"conv3d_tc", ctypes.byref(v)) == 0 and v.value == 1
+    assert lib.lws_set_option(b"conv3d_tc", 0) == 0 and lib.lws_get_option(b"conv3d_tc", ctypes.byref(v)) == 0 and v.value == 0
+    assert lib.lws_set_option(b"conv3d_tc", 1) == 0
+    assert lib.lws_set_option(b"conv3d_tc", 7) == -1 and lib.lws_set_option(b"no_such_option", 1) == -5
+    assert lib.lws_set_option(None, 1) == -3
+    assert lib.lws_conv3d_stack_launches(8, 4) == 6 and lib.lws_conv3d_stack_launches(24, 4) == 16
+    assert lib.lws_refinement1_packed_floats(2) == 0 and lib.lws_refinement1_packed_floats(3) > 0
     assert lib.lws_refinement_f32(dummy, dummy, dummy, dummy, dummy, 0, 1, 8, 8, None) == -4
     assert lib.lws_conv3d_stack_workspace_bytes(2, 24, 46, 154, 32, 4) >= 2 * 2 * 32 * 24 * 46 * 154 * 4
     assert lib.lws_refinement_workspace_bytes(1, 368, 1232) >= 128 * 368 * 1232 * 4

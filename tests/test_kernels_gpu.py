@@ -180,11 +180,11 @@ def _stack_from_golden(prefix, C):
     return net.cuda(), g
 
 
-# The C = 32 and C = 8 stacks have two implementations: the tcgen05 split-fp16 (x = hi + lo*2^-11, three exact products) implicit GEMM (default) and the fp32 FFMA kernels
-# (option "conv3d_tc" = 0).  Operands of the tensor-core path are split exactly (x = xh + xl), but TMEM accumulation rounds toward
-# zero at each of its 108 MMA steps, which leaves a ~5e-6 relative drift per layer: its bound is 5e-4 * (1 + |y|), the FFMA
-# path keeps SURVEY 8(c)'s 1e-4 * (1 + |y|).
-CONV3D_PATHS = [("tc", "1", 5e-4), ("ffma", "0", 1e-4)]
+# The C = 32 and C = 8 stacks have two implementations: the tcgen05 split-fp16 (x = hi + lo*2^-11, three exact products) implicit
+# GEMM (default) and the fp32 FFMA kernels (option "conv3d_tc" = 0).  Both meet SURVEY 8(c)'s 1e-4 * (1 + |y|) against the fp64
+# oracle (measured r02: max |d| 5.8e-5 tensor-core vs 6.0e-5 FFMA on the C = 32 KITTI volume, fp32 oracle 3.3e-5), and both must
+# stay within 2.5x of the fp32 oracle's own worst error (+1e-6 absolute) so that a regression of a few ulps per layer is caught.
+CONV3D_PATHS = [("tc", "1", 1e-4), ("ffma", "0", 1e-4)]
 
 
 @pytest.fixture(params=CONV3D_PATHS, ids=[p[0] for p in CONV3D_PATHS])
@@ -231,12 +231,13 @@ def test_conv3d_stack_vs_fp64_oracle(C, B, D, H, W, conv3d_path):
     err = (out.cpu().double() - ref).abs()
     print(f"conv3d stack C={C} [{B},{D},{H},{W}] path={conv3d_path[0]}: max err {err.max().item():.3e} (fp32 oracle max err {floor:.3e})")
     assert (err <= tol * (1 + ref.abs())).all(), f"max err {err.max().item():.3e}"
+    assert err.max().item() <= 2.5 * floor + 1e-6, f"max err {err.max().item():.3e} vs fp32 oracle {floor:.3e}"
 
 
 # ------------------------------------------------------------------------------------------------ a8 + a9
-# Two implementations: channels-last tcgen05 split-fp16 (default; pointwise products are fp32-exact to a few ulps, the dense
-# 64->32 conv accumulates over 72 round-toward-zero MMA steps) and the fp32 FFMA kernels (option "refine_tc" = 0).
-REFINE_PATHS = [("tc", "1", 6.0, 1e-5), ("ffma", "0", 3.0, 2e-6)]
+# Two implementations: channels-last tcgen05 split-fp16 (default) and the fp32 FFMA kernels (option "refine_tc" = 0).  Same bars
+# for both (measured r02: tensor-core max |d| 1.07x the fp32 oracle's own max error, FFMA 0.95x).
+REFINE_PATHS = [("tc", "1", 2.0, 2e-6), ("ffma", "0", 2.0, 2e-6)]
 
 
 @pytest.fixture(params=REFINE_PATHS, ids=[p[0] for p in REFINE_PATHS])
@@ -250,7 +251,7 @@ def _check_refine(out, ref, fp32_floor, path):
     """|d| <= 1e-4 * (1 + |y|) + scale_tol * max|y| against the fp64 oracle.  The second term is the cancellation floor:
     the refinement sums ~600 products of O(100) activations into outputs that are O(1) at many pixels while max|y| is
     O(1000) with random-init weights; the fp32 oracle itself misses the pure relative bound (its max error is printed
-    next to ours, and ours must stay within floor_mult x of it: 3x for the FFMA kernels, 6x for the tensor-core path)."""
+    next to ours, and ours must stay within 2x of it on both paths)."""
     name, floor_mult, scale_tol = path
     err = (out.cpu().double() - ref).abs()
     bound = 1e-4 * (1 + ref.abs()) + scale_tol * ref.abs().max()

@@ -54,9 +54,9 @@ def test_stages_teacher_forced(models, H, W):
         e = err_stats(out.cpu(), pred64[s])
         floor = err_stats(pred32[s], pred64[s])
         print(f"stage {s + 1} teacher-forced {H}x{W}: {e}  | fp32-oracle floor (free-running): {floor}")
-        # stage 1 runs the tcgen05 split-fp16 stack by default (RZ accumulation in TMEM, see test_kernels_gpu.py): 4x floor;
-        # the FFMA stages keep 2x.  north_star's 1e-3 px holds on the mean and on >= 95 % of the pixels.
-        k = 4 if s == 0 else 2
+        # every stage (all on the tcgen05 split-fp16 stacks by default) within 2x the fp32 oracle's floor; north_star's 1e-3 px
+        # holds on the mean and on >= 95 % of the pixels (measured r02: 0.5-1.4x the floor on max, <= 1x on mean).
+        k = 2
         assert e["mean"] <= k * floor["mean"] + 1e-4 and e["mean"] <= 1e-3
         assert e["max"] <= k * floor["max"] + 5e-3
         assert e["frac_le_1e3"] >= 0.95
@@ -78,9 +78,8 @@ def test_end_to_end_vs_noise_floor(models):
         assert tuple(out[s].shape) == (2, 1, 128, 256)
         e, floor = err_stats(out[s].cpu(), p64[s]), err_stats(p32[s], p64[s])
         print(f"stage {s + 1} free-running: new {e} | fp32 oracle {floor}")
-        # 4x on mean / p99.9: stage 1 is the tcgen05 split-fp16 path (see test_stages_teacher_forced).  The free-running MAX is
-        # chaotic on random-init weights (stage-2/3 softmaxes are arg-min-like): 10x.
-        for k, mult in (("max", 10), ("p999", 4), ("mean", 4)):
+        # SURVEY.md 8(c) protocol 3: every statistic within 2x the fp32 oracle's own error (measured r02: 0.4-0.75x)
+        for k, mult in (("max", 2), ("p999", 2), ("mean", 2)):
             assert e[k] <= mult * floor[k] + 1e-4 * (1 + p64[s].abs().max().item()), (s, k, e, floor)
 
 
@@ -93,7 +92,7 @@ def test_end_to_end_golden(models):
         floor = err_stats(torch.from_numpy(g[f"pred32_{s}"]), ref64)
         e = err_stats(out[s].cpu(), ref64)
         for k in ("max", "mean"):
-            assert e[k] <= 4 * floor[k] + 1e-4 * (1 + ref64.abs().max().item()), (s, k, e, floor)
+            assert e[k] <= 2 * floor[k] + 1e-4 * (1 + ref64.abs().max().item()), (s, k, e, floor)
 
 
 def test_batch_shard_equivalence(models):
@@ -154,15 +153,46 @@ def test_infer_host_u8_matches_fp32_path(models):
     assert np.array_equal(color.numpy(), lut[ref_u8])
 
 
+def _free_running_check(name, prod, left, right, pred64, pred32):
+    """SURVEY.md 8(c) protocol 3: free-running product vs the fp64 oracle, every statistic <= 2x the fp32 oracle's own error."""
+    out = prod(left.cuda(), right.cuda())
+    torch.cuda.synchronize()
+    for s in range(4):
+        e, floor = err_stats(out[s].cpu(), pred64[s]), err_stats(pred32[s], pred64[s])
+        print(f"{name} stage {s + 1} free-running: new {e} | fp32 oracle {floor}")
+        for k in ("max", "p999", "mean"):
+            assert e[k] <= 2 * floor[k] + 1e-4 * (1 + pred64[s].abs().max().item()), (name, s, k, e, floor)
+
+
+def _teacher_forced_check(name, prod, left, H, W, pred64, pred32, tr):
+    for s in range(3):
+        fl, fr = tr[f"feat_l{s}"].float().cuda(), tr[f"feat_r{s}"].float().cuda()
+        prev = pred64[s - 1].float().cuda() if s > 0 else None
+        out = prod._stage(s, fl, fr, prev, H, W)
+        e, floor = err_stats(out.cpu(), pred64[s]), err_stats(pred32[s], pred64[s])
+        print(f"{name} stage {s + 1} teacher-forced: {e} | fp32-oracle floor (free-running): {floor}")
+        assert e["mean"] <= 2 * floor["mean"] + 1e-4 and e["mean"] <= 1e-3, (name, s, e, floor)
+        assert e["max"] <= 2 * floor["max"] + 5e-3, (name, s, e, floor)
+        assert e["frac_le_1e3"] >= 0.95, (name, s, e)
+    out4 = prod._refine(left.cuda(), pred64[2].float().cuda())
+    e = err_stats(out4.cpu(), pred64[3])
+    assert e["mean"] <= 1e-3 * (1 + pred64[3].abs().mean().item()), (name, e)
+    feats = prod.feature_extraction(left.cuda())
+    for s in range(3):
+        ref = tr[f"feat_l{s}"]
+        d = (feats[s].cpu().double() - ref).abs()
+        assert (d <= 1e-4 * (1 + ref.abs()) + 2e-6 * ref.abs().max()).all(), (name, s, d.max().item())
+
+
 @pytest.mark.parametrize("name,H,W,maxdisplist", [
+    ("configs[2] KITTI 1232x368", 368, 1232, (24, 5, 5)),
     ("configs[3] SceneFlow 960x544", 544, 960, (24, 5, 5)),
-    ("configs[4] 1920 wide, maxdisp 384 (D = 48 at 1/8), quarter height", 272, 1920, (48, 5, 5)),
+    ("configs[4] 1920x1088, maxdisp 384 (D = 48 at 1/8)", 1088, 1920, (48, 5, 5)),
 ])
-def test_other_baseline_configs_teacher_forced(name, H, W, maxdisplist):
-    """BASELINE.json configs[3] / configs[4] shapes (the parity-test cases next to the benchmarked configs[2]): every stage, fed
-    the fp64 oracle's features and previous prediction, against the fp64 oracle; same bars as test_stages_teacher_forced.
-    configs[4] keeps its full width and its D = 48 stage-1 volume but a quarter of its 1088 rows so that the CPU oracle
-    finishes in seconds (no kernel's tiling depends on the image height beyond the row count)."""
+def test_baseline_configs_full_size(name, H, W, maxdisplist):
+    """BASELINE.json configs[2..4] at their FULL image sizes, one pair each: every stage teacher-forced (fed the fp64 oracle's
+    features and previous prediction) and the whole model free-running, against the fp64 oracle with the fp32 oracle's own error
+    as the floor (SURVEY.md 8(c) protocols 2 and 3)."""
     from oracle import lwsnet_torch as O
     args = O.default_args(maxdisplist=maxdisplist)
     o32 = O.build_oracle(seed=0, args=args, random_bn=True)
@@ -172,25 +202,44 @@ def test_other_baseline_configs_teacher_forced(name, H, W, maxdisplist):
     with torch.no_grad():
         pred64, tr = o64.forward_trace(left.double(), right.double())
         pred32, _ = o32.forward_trace(left, right)
+    _teacher_forced_check(name, prod, left, H, W, pred64, pred32, tr)
+    _free_running_check(name, prod, left, right, pred64, pred32)
+
+
+def test_config0_reference_test_pair():
+    """BASELINE.json configs[0]: the reference's own test pair (reference/left_test.png + right_test.png, committed losslessly as
+    tests/golden/kitti_test_pair.npz by oracle/make_kitti_fixture.py) through the reference's inference-loop body
+    (inference.py:90-115) at batch 1: device-side crop / BGR->RGB / normalise byte-identical to the host preprocessing, the four
+    disparities within 2x the fp32 oracle's floor, and the uint8 maps the loop would write."""
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200 import ops
+    from lwsnet_b200.runner import StereoEngine
+    g = golden("kitti_test_pair")
+    lb, rb = g["left_bgr"], g["right_bgr"]
+    assert lb.shape == (375, 1242, 3) and lb.dtype == np.uint8
+    left, right = O.preprocess_bgr_uint8(lb), O.preprocess_bgr_uint8(rb)         # inference.py:93-103 on the host
+    assert torch.equal(ops.preprocess_bgr_u8(cu(lb[None])).cpu(), left)          # ... and on the device: same bytes
+    assert torch.equal(ops.preprocess_bgr_u8(cu(rb[None])).cpu(), right)
+    o32 = O.build_oracle(seed=0)
+    o64 = O.build_oracle(seed=0, dtype=torch.float64)
+    prod = product_from_oracle(o32)
+    with torch.no_grad():
+        pred64 = o64(left.double(), right.double())
+        pred32 = o32(left, right)
+    _free_running_check("configs[0] left_test.png/right_test.png", prod, left, right, pred64, pred32)
+    # the loop body end to end with uint8 I/O (batch 1, no CUDA graph needed)
+    eng = StereoEngine(prod, micro_batch=1)
+    gray, color = eng.infer_host_u8(torch.from_numpy(lb[None]).pin_memory(), torch.from_numpy(rb[None]).pin_memory(), color=True)
+    torch.cuda.synchronize()
+    out = torch.cat(prod(left.cuda(), right.cuda()), 1).cpu().numpy()
+    assert np.array_equal(gray.numpy(), out.astype(np.int64).astype(np.uint8))   # inference.py:114 astype(np.uint8)
+    last, _ = eng.infer_host_u8(torch.from_numpy(lb[None]).pin_memory(), torch.from_numpy(rb[None]).pin_memory(), stages=(3,))
+    torch.cuda.synchronize()
+    assert np.array_equal(last.numpy()[:, 0], gray.numpy()[:, 3])                 # directory mode: the last stage only
+    # uint8 disparities against the fp32 oracle's: equal except where the fp32 noise crosses an integer boundary
+    ref_u8 = torch.cat(pred32, 1).numpy().astype(np.int64).astype(np.uint8)
     for s in range(3):
-        fl, fr = tr[f"feat_l{s}"].float().cuda(), tr[f"feat_r{s}"].float().cuda()
-        prev = pred64[s - 1].float().cuda() if s > 0 else None
-        out = prod._stage(s, fl, fr, prev, H, W)
-        e, floor = err_stats(out.cpu(), pred64[s]), err_stats(pred32[s], pred64[s])
-        print(f"{name} stage {s + 1} teacher-forced: {e} | fp32-oracle floor (free-running): {floor}")
-        k = 4 if s == 0 else 2
-        assert e["mean"] <= k * floor["mean"] + 1e-4 and e["mean"] <= 1e-3, (name, s, e, floor)
-        assert e["max"] <= k * floor["max"] + 5e-3, (name, s, e, floor)
-        assert e["frac_le_1e3"] >= 0.95, (name, s, e)
-    out4 = prod._refine(left.cuda(), pred64[2].float().cuda())
-    e = err_stats(out4.cpu(), pred64[3])
-    assert e["mean"] <= 1e-3 * (1 + pred64[3].abs().mean().item()), (name, e)
-    # the feature pyramid at this shape
-    feats = prod.feature_extraction(left.cuda())
-    for s in range(3):
-        ref = tr[f"feat_l{s}"]
-        d = (feats[s].cpu().double() - ref).abs()
-        assert (d <= 1e-4 * (1 + ref.abs()) + 2e-6 * ref.abs().max()).all(), (name, s, d.max().item())
+        assert (gray.numpy()[:, s] == ref_u8[:, s]).mean() >= 0.995, s
 
 
 def test_engine_schedules_agree_bitwise(models):
@@ -223,7 +272,6 @@ def test_no_per_layer_library_forward(models):
                   prod.volume_postprocess[0][0][0]):
         with pytest.raises(LwsError):
             layer(x)
-    with pytest.raises(LwsError):
-        prod.refinement1_left(x)
+    # (refinement1 / refinement2 ARE callable as layers, like in the reference: tests/test_boundary_gpu.py)
     with torch_crosscheck():
         assert tuple(prod.feature_extraction.dres0(x).shape) == (1, 8, 32, 64)

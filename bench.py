@@ -28,7 +28,18 @@ if ROOT not in sys.path:
 H_IMG, W_IMG = 368, 1232
 BATCH = 64
 METRIC = "stereo pairs/sec, 4-stage KITTI 1232x368"
-GFLOP_PER_PAIR = 91.6
+GFLOP_PER_PAIR = {0: 91.6, 1: 38.19 + 0.0016, 2: 91.6, 3: 105.5, 4: 598.2}
+
+
+def ncu_traffic(key):
+    """dram__bytes_read + write of one launch of `key` (kernel + shape) from the committed ncu extract profiles/ncu_traffic.json
+    (tools/ncu_traffic.py); None when this kernel / shape has not been captured, so the figure cannot go stale silently."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(path)).get(key)
+    except Exception:
+        return None, None
+    return (rec["traffic_bytes"], rec["source"]) if rec else (None, None)
 
 
 def peaks():
@@ -93,25 +104,35 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import lwsnet_torch as O
+    from lwsnet_b200.synthetic import CONFIGS
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = O.build_oracle(seed=0)
+    model = O.build_oracle(seed=0, args=O.default_args(maxdisplist=cfg["maxdisplist"]))
     sample_pairs = 1
-    left, right = O.synthetic_pair(sample_pairs, H_IMG, W_IMG, seed=1234)
+    left, right = O.synthetic_pair(sample_pairs, cfg["H"], cfg["W"], seed=1234)
+    if args.config == 1:  # stage-1 path only: feature maps in, low-res disparity out
+        g = torch.Generator().manual_seed(1234)
+        fl, fr = torch.randn(1, 16, 46, 154, generator=g) * 2, torch.randn(1, 16, 46, 154, generator=g) * 2
+        step = lambda: model.stage(0, fl, fr, None, (cfg["H"], cfg["W"]))
+    else:
+        step = lambda: model(left, right)
     with torch.no_grad():
         for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
-            model(left, right)
+            step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            model(left, right)
+            step()
         dt = time.perf_counter() - t0
     value = sample_pairs * args.steps / dt
-    sample = f"{sample_pairs} KITTI-shaped pair per step (of the 64-pair batch), torch-CPU restatement of the Paddle model, fp32"
+    sample = (f"{sample_pairs} pair per step of {cfg['name']} (the full batch would take minutes on the CPU), torch-CPU restatement "
+              "of the Paddle model (Paddle is not installable offline), fp32, all host threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.config in (3, 4) else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: full 4-stage LWSNet inference, KITTI 1232x368", "sample": sample},
+        "config": {"workload": cfg["name"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -244,9 +265,9 @@ def kernel_probes(model, pk, B=16):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from oracle import lwsnet_torch as O   # input/weight generation + cpu_baseline leg only (never on the timed GPU path)
-    from lwsnet_b200 import LWSNet, ops
-    from lwsnet_b200.runner import StereoEngine
+    from lwsnet_b200 import ops
+    from lwsnet_b200.runner import StereoEngine, bind_to_gpu_cpus, shard_range
+    from lwsnet_b200.synthetic import CONFIGS, default_args, random_init_model, synthetic_images_u8, synthetic_pair
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     torch.cuda.set_device(local_rank)
@@ -255,7 +276,6 @@ def run_ours(args, rank, world, local_rank):
         k, v = kv.split("=")
         ops.set_option(k, int(v))
         lib_opts[k] = int(v)
-    from lwsnet_b200.runner import bind_to_gpu_cpus
     cpus = bind_to_gpu_cpus(local_rank) if world > 1 and not args.no_bind else None  # before any pinned allocation
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -272,25 +292,29 @@ def run_ours(args, rank, world, local_rank):
             os.dup2(saved, 1)
             os.close(saved)
     pk = peaks()
-
-    oracle_model = O.build_oracle(seed=0)
-    model = LWSNet(O.default_args())
-    model.load_state_dict(oracle_model.state_dict(), strict=True)
-    model = model.to(dev)
-    engine = StereoEngine(model, micro_batch=args.micro_batch, device=dev, use_graphs=not args.no_graphs,
-                          host_edge=args.host_edge if args.host_edge > 0 else None)
+    cfg = CONFIGS[args.config]
+    H, W = cfg["H"], cfg["W"]
+    margs = default_args(maxdisplist=cfg["maxdisplist"])
+    model = random_init_model(seed=0, args=margs, device=dev)  # the package's own seeded KaimingNormal init (identity BatchNorm)
     if args.probes_only:  # developer mode: the per-kernel probes alone
         for rec in kernel_probes(model, pk, args.probe_batch):
             print(json.dumps(rec))
         return
 
-    # synthetic batch: 8 distinct pairs tiled to 64 (content does not change the work); rank-dependent seed
-    base_l, base_r = O.synthetic_pair(8, H_IMG, W_IMG, seed=1234 + 8 * rank)
-    left_h = base_l.repeat(BATCH // 8, 1, 1, 1).pin_memory()
-    right_h = base_r.repeat(BATCH // 8, 1, 1, 1).pin_memory()
-    left_d, right_d = left_h.to(dev), right_h.to(dev)
-    out_d = torch.empty((BATCH, 4, H_IMG, W_IMG), device=dev)
-    out_h = torch.empty((BATCH, 4, H_IMG, W_IMG)).pin_memory()
+    # pairs per rank: configs[0..2] give every rank its own batch (weak scaling), configs[3] / [4] shard one batch (strong scaling)
+    strong = args.config in (3, 4)
+    if strong:
+        lo, hi = shard_range(cfg["batch"], rank, world)
+        n_local, n_total = hi - lo, cfg["batch"]
+    elif args.config == 0:
+        # batch 1: one step = 64 consecutive single-pair inferences (micro-batch 1), so that a step is long enough to time
+        n_local, n_total = 64, 64 * world
+    else:
+        n_local, n_total = cfg["batch"], cfg["batch"] * world
+    mb = args.micro_batch if args.micro_batch > 0 else {0: 1, 1: 8, 2: 24, 3: 16, 4: 4}[args.config]
+    mb = max(1, min(mb, n_local))
+    engine = StereoEngine(model, micro_batch=mb, device=dev, use_graphs=not args.no_graphs,
+                          host_edge=(args.host_edge if 0 < args.host_edge < mb else None))
 
     def barrier():
         if world > 1:
@@ -310,33 +334,142 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    # ---- device-resident throughput ("value") -------------------------------------------------------------
-    for _ in range(args.warmup):
-        engine.infer_device(left_d, right_d, out_d)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    n0 = ops.LAUNCHES[0]
-    ms = timed(lambda: engine.infer_device(left_d, right_d, out_d), args.steps)
-    launches = ops.LAUNCHES[0] - n0
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * BATCH * args.steps / (ms / 1e3)
-
-    # ---- end to end through the public API with host buffers ("e2e") --------------------------------------------
-    for _ in range(max(1, min(2, args.warmup))):
-        engine.infer_host(left_h, right_h, out_h)
+    extra = {}
     e2e_steps = max(2, args.steps // 2)
-    ms_e2e = timed(lambda: engine.infer_host(left_h, right_h, out_h), e2e_steps)
-    e2e_value = world * BATCH * e2e_steps / (ms_e2e / 1e3)
+    if args.config == 1:
+        # ---- configs[1]: the stage-1 path alone (cost volume + C=32 3D stack + regression + upsample), feature maps resident -------
+        nset = 6
+        gen = torch.Generator().manual_seed(1234 + rank)
+        feats = [(torch.randn(n_local, 16, H // 8, W // 8, generator=gen) * 2, torch.randn(n_local, 16, H // 8, W // 8, generator=gen) * 2)
+                 for _ in range(nset)]
+        feats_h = [(a.pin_memory(), b.pin_memory()) for a, b in feats]
+        feats_d = [(a.to(dev), b.to(dev)) for a, b in feats]
+        out_h = torch.empty((n_local, 1, H, W)).pin_memory()
+        graphs = []
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for a, b in feats_d:
+                model._stage(0, a, b, None, H, W)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        outs = []
+        n0 = ops.LAUNCHES[0]
+        for a, b in feats_d:  # one graph per rotating input set: inputs (23 MB per set) are never L2 resident
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs.append(model._stage(0, a, b, None, H, W))
+            graphs.append(g)
+        per_step_launches = (ops.LAUNCHES[0] - n0) // nset
+        it = [0]
+        passes = 8  # one step = 8 passes of the batch-8 stage-1 path (64 pairs, ~8 ms): long enough to time and to sample clocks
+        n_total *= passes
 
-    # ---- the same with uint8 images in and uint8 disparities out (the reference's inference-loop body) ----------
-    g = torch.Generator().manual_seed(99 + rank)
-    lu8 = torch.randint(0, 256, (BATCH, 375, 1242, 3), dtype=torch.uint8, generator=g).pin_memory()
-    ru8 = torch.randint(0, 256, (BATCH, 375, 1242, 3), dtype=torch.uint8, generator=g).pin_memory()
-    gray_h = torch.empty((BATCH, 4, H_IMG, W_IMG), dtype=torch.uint8).pin_memory()
-    engine.infer_host_u8(lu8, ru8, H_IMG, W_IMG, out_gray=gray_h)
-    ms_u8 = timed(lambda: engine.infer_host_u8(lu8, ru8, H_IMG, W_IMG, out_gray=gray_h), e2e_steps)
-    u8_value = world * BATCH * e2e_steps / (ms_u8 / 1e3)
+        def step_dev():
+            for _ in range(passes):
+                graphs[it[0] % nset].replay()
+                it[0] += 1
+
+        def step_host():
+            for _ in range(passes):
+                k = it[0] % nset
+                feats_d[k][0].copy_(feats_h[k][0], non_blocking=True)
+                feats_d[k][1].copy_(feats_h[k][1], non_blocking=True)
+                graphs[k].replay()
+                out_h.copy_(outs[k], non_blocking=True)
+                it[0] += 1
+
+        for _ in range(args.warmup):
+            step_dev()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        steps = args.steps
+        ms = timed(step_dev, steps)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = per_step_launches * passes * steps
+        value = n_total * steps / (ms / 1e3)
+        ms_per_step = ms / steps
+        ms_e2e = timed(step_host, steps)
+        e2e = {"value": n_total * steps / (ms_e2e / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(passes * 2 * feats_h[0][0].nbytes),
+               "d2h_bytes_per_step": int(passes * out_h.nbytes), "steps": steps, "ms_per_step": ms_e2e / steps,
+               "path": "pinned fp32 feature maps in, model._stage(0, ...) (a1 + a5 + a6 + a7), fp32 stage-1 disparity out"}
+        extra["step"] = f"{passes} passes of the batch-{n_local} stage-1 path"
+        reported_steps = steps
+        l2_note = f"{nset} rotating input sets; the stack's activations (2 x {n_local * 23.9:.0f} MB) exceed the 126 MB L2" \
+            if n_local * 23.9 * 2 > 126 else f"{nset} rotating input sets (L2 is flushed by the 3D stack's own activations)"
+    else:
+        # ---- configs[0], [2], [3], [4]: the full 4-stage model ------------------------------------------------------------------
+        base = min(n_local, 8)
+        base_l, base_r = synthetic_pair(base, H, W, seed=1234 + 8 * rank, max_disp=min(150.0, W / 8))
+        if args.config == 0:
+            fixture = os.path.join(ROOT, "tests", "golden", "kitti_test_pair.npz")
+            if os.path.isfile(fixture):  # the reference's own test pair (reference/left_test.png + right_test.png)
+                import numpy as np
+                g = np.load(fixture)
+                lu = torch.from_numpy(g["left_bgr"][None]).to(dev)
+                ru = torch.from_numpy(g["right_bgr"][None]).to(dev)
+                base_l, base_r = ops.preprocess_bgr_u8(lu, H, W).cpu(), ops.preprocess_bgr_u8(ru, H, W).cpu()
+                extra["input"] = "reference/left_test.png + right_test.png (tests/golden/kitti_test_pair.npz), inference.py:93-103 preprocessing"
+        reps = -(-n_local // base_l.shape[0])
+        left_h = base_l.repeat(reps, 1, 1, 1)[:n_local].contiguous().pin_memory()
+        right_h = base_r.repeat(reps, 1, 1, 1)[:n_local].contiguous().pin_memory()
+        left_d, right_d = left_h.to(dev), right_h.to(dev)
+        out_d = torch.empty((n_local, 4, H, W), device=dev)
+
+        # device-resident throughput ("value")
+        for _ in range(args.warmup):
+            engine.infer_device(left_d, right_d, out_d)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        n0 = ops.LAUNCHES[0]
+        steps = args.steps
+        ms = timed(lambda: engine.infer_device(left_d, right_d, out_d), steps)
+        launches = ops.LAUNCHES[0] - n0
+        clocks = sampler.stop() if rank == 0 else None
+        value = n_total * steps / (ms / 1e3)
+        ms_per_step = ms / steps
+        reported_steps = steps
+
+        # end to end through the public API with host buffers ("e2e"): the reference's inference-loop body (inference.py:90-115),
+        # uint8 BGR frames in (pinned), device-side crop / normalise, the four stage disparities out as uint8 (astype(np.uint8))
+        fh, fw = (375, 1242) if (H, W) == (368, 1232) else (H, W)
+        lu8, ru8 = synthetic_images_u8(n_local, fh, fw, seed=99 + rank)
+        lu8, ru8 = lu8.pin_memory(), ru8.pin_memory()
+        gray_h = torch.empty((n_local, 4, H, W), dtype=torch.uint8).pin_memory()
+        for _ in range(max(1, min(2, args.warmup))):
+            engine.infer_host_u8(lu8, ru8, H, W, out_gray=gray_h)
+        es = e2e_steps
+        ms_u8 = timed(lambda: engine.infer_host_u8(lu8, ru8, H, W, out_gray=gray_h), es)
+        h2d, d2h = int(lu8.nbytes + ru8.nbytes), int(gray_h.nbytes)
+        e2e = {"value": n_total * es / (ms_u8 / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": es, "ms_per_step": ms_u8 / es,
+               "h2d_gbs_per_rank": round(h2d / (ms_u8 / es) / 1e6, 2), "d2h_gbs_per_rank": round(d2h / (ms_u8 / es) / 1e6, 2),
+               "path": "StereoEngine.infer_host_u8: pinned uint8 HWC BGR frames in (cv2.imread layout), crop + BGR->RGB + normalise on "
+                       "the device, 4-stage model, four uint8 disparity maps out (the reference's loop body, inference.py:90-115)"}
+        # the same with fp32 tensors across PCIe (the reference's model(left, right) -> .numpy() boundary): extra key
+        out_h = torch.empty((n_local, 4, H, W)).pin_memory()
+        for _ in range(max(1, min(2, args.warmup))):
+            engine.infer_host(left_h, right_h, out_h)
+        ms_f32 = timed(lambda: engine.infer_host(left_h, right_h, out_h), es)
+        extra["e2e_f32"] = {"value": n_total * es / (ms_f32 / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(left_h.nbytes + right_h.nbytes),
+                            "d2h_bytes_per_step": int(out_h.nbytes), "steps": es, "ms_per_step": ms_f32 / es,
+                            "path": "StereoEngine.infer_host: pinned fp32 [B,3,H,W] tensors in, four fp32 disparity maps out"}
+        if args.config == 0:
+            # batch-1 latency, the only number the reference publishes (README.md:136, inference.py:107-111): with / without CUDA graph
+            eager = StereoEngine(model, micro_batch=1, device=dev, use_graphs=False)
+            for _ in range(3):
+                eager.infer_device(left_d, right_d, out_d)
+            ms_eager = timed(lambda: eager.infer_device(left_d, right_d, out_d), 2)
+            extra["step"] = "64 consecutive batch-1 inferences"
+            extra["latency_ms_per_pair"] = {"cuda_graph": round(ms_per_step / n_local, 4), "eager_launches": round(ms_eager / 2 / n_local, 4),
+                                            "e2e_uint8_io": round(ms_u8 / es / n_local, 4),
+                                            "note": "batch-1 latency, the figure the reference prints (inference.py:107-111, README.md:136)"}
+        in_mb = (left_d.nbytes + right_d.nbytes) / 1e6
+        l2_note = (f"inputs ({in_mb:.0f} MB per step) and per-step activations exceed the 126 MB L2" if in_mb > 126 else
+                   f"inputs are {in_mb:.0f} MB, but every forward streams > 1 GB of activations per pair through the 126 MB L2 "
+                   "(the refinement alone writes 12 x 58 MB per pair), which flushes them between steps")
 
     if rank != 0:
         if world > 1:
@@ -346,60 +479,62 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the kernels (rank 0, timed alone) ----------------------------------------------------------------
     kernels, roofline = [], None
     if not args.skip_probes:
-        kernels = kernel_probes(model, pk, args.probe_batch)
+        kernels = kernel_probes(model if args.config != 4 else random_init_model(0, default_args(), dev), pk, args.probe_batch)
         dom = next(k for k in kernels if k["kernel"].startswith("K6 dwsep block"))
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full (profiles/r01_ncu_*dwsep*)
+        traffic, src = ncu_traffic("dwsep_f16_kernel<0> dil=4 [8,32,368,1232]")
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": round(dom["gbs"] / pk["hbm"], 4), "traffic": 987819520,
+                    "frac": round(dom["gbs"] / pk["hbm"], 4), "traffic": traffic,
+                    "traffic_source": src and (src + " via profiles/ncu_traffic.json (dram__bytes_read + write of one launch at this shape)"),
                     "peak_source": pk["source"] + " copy bandwidth",
-                    "note": "dominant kernel by time (12 launches per forward, ~34% of the step); timed alone (CUDA-graph replay "
+                    "note": "dominant kernel by time (12 launches per forward, ~35% of the KITTI step); timed alone (CUDA-graph replay "
                             "between CUDA events) over 3 rotating 518 MB tensors (> L2) at 8 pairs per launch; algorithmic bytes = "
-                            "interior pixels x 32 channels x 4 B, read once + written once; traffic = ncu dram read + write of one "
-                            "launch at the same shape (profiles/r01_ncu_full_dwsep_f16_q42_8pairs.txt); the conv stacks are "
-                            "tensor-core kernels, see `kernels`"}
+                            "interior pixels x 32 channels x 4 B, read once + written once; the conv stacks are tensor-core "
+                            "kernels, see `kernels`"}
 
     # ---- CPU baseline beside it (N=1 only): the oracle port on the host cores, bounded sample -----------------------
     cpu = None
     if world == 1 and not args.skip_cpu:
+        from oracle import lwsnet_torch as O   # cpu_baseline leg only (never on the timed GPU path)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        l1, r1 = base_l[:1], base_r[:1]
+        oracle_model = O.LWSNet(O.default_args(maxdisplist=cfg["maxdisplist"])).eval()
+        oracle_model.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)  # same weights
+        reps = 3 if args.config != 4 else 1
         with torch.no_grad():
-            oracle_model(l1, r1)
+            if args.config == 1:
+                fl, fr = feats[0][0][:1], feats[0][1][:1]
+                fn = lambda: oracle_model.stage(0, fl, fr, None, (H, W))
+            else:
+                l1, r1 = base_l[:1], base_r[:1]
+                fn = lambda: oracle_model(l1, r1)
+            fn()
             t0 = time.perf_counter()
-            reps = 3
             for _ in range(reps):
-                oracle_model(l1, r1)
+                fn()
             dt = (time.perf_counter() - t0) / reps
         cpu = {"value": 1.0 / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-               "sample": f"{reps} forwards of 1 KITTI-shaped pair (of the 64-pair batch), torch-CPU restatement of the Paddle reference, fp32"}
+               "sample": f"{reps} forwards of 1 pair of this workload, torch-CPU restatement of the Paddle reference, fp32, same weights"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "configs[2]: full 4-stage LWSNet inference (volume build + warp + residual volumes + 3D stacks "
-                               "+ regression + colour-guidance refinement), KITTI 1232x368, batch 64 per GPU",
-                   "batch_per_gpu": BATCH, "micro_batch": args.micro_batch, "cpu_binding": (f"{len(cpus)} NUMA-local cores per rank" if cpus else "none"),
-                   "e2e_chunks": [hi - lo for lo, hi in engine._host_chunks(BATCH)], "maxdisplist": [24, 5, 5],
-                   "weights": "random init (KaimingNormal, seed 0)", "cuda_graphs": not args.no_graphs,
-                   "library_options": {**{k: ops.get_option(k) for k in ("conv3d_tc", "refine_tc", "refine_chain", "chain_sep_items")}, **lib_opts},
-                   "l2": "inputs (697 MB per step) and per-step activations exceed the 126 MB L2",
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": reported_steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "image": [H, W], "pairs_per_step_total": n_total, "pairs_per_step_per_gpu": n_local,
+                   "micro_batch": mb, "cpu_binding": (f"{len(cpus)} NUMA-local cores per rank" if cpus else "none"),
+                   "maxdisplist": list(cfg["maxdisplist"]), "weights": "random init (package KaimingNormal, seed 0)",
+                   "cuda_graphs": not args.no_graphs, "l2": l2_note,
+                   "library_options": {**{k: ops.get_option(k) for k in ("conv3d_tc", "refine_tc", "refine_chain")}, **lib_opts},
                    "numerics": "fp32 storage at the ABI; conv stacks and pointwise convs on tcgen05 with split-fp16 operands "
                                "(x = hi + lo*2^-11, 3 exact products, fp32 accumulation)",
-                   "tflops_equiv": round(value * GFLOP_PER_PAIR / 1e3, 2)},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(left_h.nbytes + right_h.nbytes),
-                "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
-        "e2e_u8": {"value": u8_value, "unit": "pairs/s", "h2d_bytes_per_step": int(lu8.nbytes + ru8.nbytes),
-                   "d2h_bytes_per_step": int(gray_h.nbytes), "steps": e2e_steps, "ms_per_step": ms_u8 / e2e_steps,
-                   "note": "uint8 HWC BGR 1242x375 images in, crop + normalise on the device, four uint8 disparity maps out "
-                           "(inference.py:93-115); random-noise images, so only the work, not the disparities, is meaningful"},
+                   "tflops_equiv": round(value * GFLOP_PER_PAIR[args.config] / 1e3, 2)},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "kernels": kernels,
         "cpu_baseline": cpu,
     }
+    line.update(extra)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -411,7 +546,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=24, help="pairs per forward (one CUDA-graph replay)")
+    ap.add_argument("--config", type=int, default=2, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs index (default 2: the configuration the metric is quoted on)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="pairs per forward (one CUDA-graph replay); 0 = per-config default")
     ap.add_argument("--host-edge", type=int, default=8,
                     help="e2e: pairs in the first / last chunk of the host-resident schedule (0 = all chunks are --micro-batch)")
     ap.add_argument("--no-graphs", action="store_true")

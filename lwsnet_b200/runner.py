@@ -101,9 +101,13 @@ class StereoEngine:
         self._d2h = torch.cuda.Stream(self.device)
 
     # ------------------------------------------------------------------------------------------ device-resident
-    def _forward_into(self, left, right, out):
-        """out: [4,n,1,H,W] stage-major, so every stage is one contiguous block and the model writes into it directly."""
+    def _forward_into(self, left, right, out, user=None):
+        """out: [4,n,1,H,W] stage-major, so every stage is one contiguous block and the model writes into it directly;
+        user (optional): [n,4,H,W], the layout handed to the caller (one transposing device copy, so that the D2H copy of a
+        chunk is a single contiguous transfer)."""
         self.model(left, right, out=out)
+        if user is not None:
+            user.copy_(out[:, :, 0].transpose(0, 1))
 
     def _check_weights(self):
         """Captured graphs bake in the device addresses of the BN-folded weight blobs: drop them when the model's weights (and
@@ -124,19 +128,20 @@ class StereoEngine:
             both = torch.zeros((2 * n, 3, H, W), device=dev)  # left and right back to back: the model stacks them without a copy
             left, right = both[:n], both[n:]
             out = torch.empty((4, n, 1, H, W), device=dev)
+            user = torch.empty((n, 4, H, W), device=dev)
             s = torch.cuda.Stream(dev)
             s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s):
-                for _ in range(2):  # warm-up: cuDNN autotune, cudaFuncSetAttribute, workspace growth
-                    self._forward_into(left, right, out)
+                for _ in range(2):  # warm-up: cudaFuncSetAttribute, workspace growth
+                    self._forward_into(left, right, out, user)
             torch.cuda.current_stream(dev).wait_stream(s)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES[0]
             with torch.cuda.graph(graph):
-                self._forward_into(left, right, out)
+                self._forward_into(left, right, out, user)
             self._graph_launches[id(graph)] = ops.LAUNCHES[0] - n0
-            g = (graph, left, right, out)
+            g = (graph, left, right, out, user)
             self._graphs[key] = g
         return g
 
@@ -152,15 +157,14 @@ class StereoEngine:
         self._check_weights()
         for lo, hi in micro_batches(B, self.mb):
             if self.use_graphs:
-                graph, gl, gr, go = self._graph_for(hi - lo, H, W)
+                graph, gl, gr, go, gu = self._graph_for(hi - lo, H, W)
                 gl.copy_(left[lo:hi])
                 gr.copy_(right[lo:hi])
                 self._replay(graph)
-                out[lo:hi].copy_(go[:, :, 0].transpose(0, 1))
+                out[lo:hi].copy_(gu)
             else:
                 go = torch.empty((4, hi - lo, 1, H, W), device=left.device)
-                self._forward_into(left[lo:hi].contiguous(), right[lo:hi].contiguous(), go)
-                out[lo:hi].copy_(go[:, :, 0].transpose(0, 1))
+                self._forward_into(left[lo:hi].contiguous(), right[lo:hi].contiguous(), go, out[lo:hi])
         return out
 
     # ------------------------------------------------------------------------------------------ host-resident
@@ -168,7 +172,7 @@ class StereoEngine:
         return ramp_batches(B, self.mb, self.host_edge) if self.host_edge else micro_batches(B, self.mb)
 
     def _host_slot(self, n, H, W, slot):
-        """(graph | None, left, right, out) device buffers for an n-pair chunk in pipeline slot 0/1."""
+        """(graph | None, left, right, out [4,n,1,H,W], user [n,4,H,W]) device buffers for an n-pair chunk in pipeline slot 0/1."""
         if self.use_graphs:
             return self._graph_for(n, H, W, slot)
         key = ("eager", n, H, W, slot)
@@ -176,8 +180,24 @@ class StereoEngine:
         if buf is None:
             dev = self.device
             buf = (None, torch.empty((n, 3, H, W), device=dev), torch.empty((n, 3, H, W), device=dev),
-                   torch.empty((4, n, 1, H, W), device=dev))
+                   torch.empty((4, n, 1, H, W), device=dev), torch.empty((n, 4, H, W), device=dev))
             self._graphs[key] = buf
+        return buf
+
+    def _select_stages(self, go, gu, stages):
+        """Contiguous device tensor [n,S,H,W] holding the selected stages: all four = the user-layout buffer, a single stage = its
+        block of the stage-major buffer (no copy), anything else = a small gathered staging tensor."""
+        if len(stages) == 4:
+            return gu
+        if len(stages) == 1:
+            return go[stages[0]]
+        key = ("sel", id(gu), stages)
+        buf = self._graphs.get(key)
+        if buf is None:
+            buf = torch.empty((gu.shape[0], len(stages)) + tuple(gu.shape[2:]), device=gu.device)
+            self._graphs[key] = buf
+        for j, st in enumerate(stages):
+            buf[:, j].copy_(go[st, :, 0])
         return buf
 
     @torch.no_grad()
@@ -205,7 +225,7 @@ class StereoEngine:
         self._h2d.wait_stream(cur)
         self._d2h.wait_stream(cur)
         for i, (lo, hi) in enumerate(chunks):
-            graph, gl, gr, go = bufs[i]
+            graph, gl, gr, go, gu = bufs[i]
             key = id(gl)
             with torch.cuda.stream(self._h2d):
                 if key in in_free:
@@ -219,13 +239,13 @@ class StereoEngine:
             if graph is not None:
                 self._replay(graph)
             else:
-                self._forward_into(gl, gr, go)
+                self._forward_into(gl, gr, go, gu)
+            src = self._select_stages(go, gu, stages)  # contiguous [n,S,H,W] on the device: one contiguous D2H transfer
             done[i].record(cur)
             in_free[key] = done[i]
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done[i])
-                for j, st in enumerate(stages):
-                    out[lo:hi, j].copy_(go[st, :, 0], non_blocking=True)
+                out[lo:hi].copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._d2h)
                 out_free[key] = ev
@@ -259,7 +279,6 @@ class StereoEngine:
             out_gray = torch.empty((B, S, th, tw), dtype=torch.uint8, pin_memory=True)
         if color and out_color is None:
             out_color = torch.empty((B, S, th, tw, 3), dtype=torch.uint8, pin_memory=True)
-        contiguous_stages = stages == tuple(range(stages[0], stages[0] + S))
         cur = torch.cuda.current_stream(dev)
         chunks = self._host_chunks(B)
         self._check_weights()
@@ -271,8 +290,8 @@ class StereoEngine:
             if io is None:
                 io = (torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
                       torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
-                      torch.empty((S, n, th, tw), dtype=torch.uint8, device=dev) if gray else None,
-                      torch.empty((S, n, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
+                      torch.empty((n, S, th, tw), dtype=torch.uint8, device=dev) if gray else None,
+                      torch.empty((n, S, th, tw, 3), dtype=torch.uint8, device=dev) if color else None)
                 self._graphs[key] = io
             bufs.append((io, self._host_slot(n, th, tw, slot)))
         in_ready = [torch.cuda.Event() for _ in chunks]
@@ -281,7 +300,7 @@ class StereoEngine:
         self._h2d.wait_stream(cur)
         self._d2h.wait_stream(cur)
         for i, (lo, hi) in enumerate(chunks):
-            (ul, ur, ug, uc), (graph, gl, gr, go) = bufs[i]
+            (ul, ur, ug, uc), (graph, gl, gr, go, gu) = bufs[i]
             key = id(ul)
             with torch.cuda.stream(self._h2d):
                 if key in in_free:
@@ -297,23 +316,17 @@ class StereoEngine:
             if graph is not None:
                 self._replay(graph)
             else:
-                self._forward_into(gl, gr, go)
-            # go is stage-major [4,n,1,th,tw]: a run of consecutive stages is one contiguous block -> one conversion launch
-            if contiguous_stages:
-                ops.disparity_to_u8(go[stages[0]:stages[0] + S], gray=gray, color=color, out_gray=ug, out_color=uc)
-            else:
-                for j, st in enumerate(stages):
-                    ops.disparity_to_u8(go[st], gray=gray, color=color, out_gray=ug[j] if gray else None,
-                                        out_color=uc[j] if color else None)
+                self._forward_into(gl, gr, go, gu)
+            # one conversion launch over the selected stages in the caller's [n,S,...] layout, then one contiguous D2H per output
+            ops.disparity_to_u8(self._select_stages(go, gu, stages), gray=gray, color=color, out_gray=ug, out_color=uc)
             done[i].record(cur)
             in_free[key] = done[i]
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done[i])
-                for j in range(S):
-                    if gray:
-                        out_gray[lo:hi, j].copy_(ug[j], non_blocking=True)
-                    if color:
-                        out_color[lo:hi, j].copy_(uc[j], non_blocking=True)
+                if gray:
+                    out_gray[lo:hi].copy_(ug, non_blocking=True)
+                if color:
+                    out_color[lo:hi].copy_(uc, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._d2h)
                 out_free[key] = ev

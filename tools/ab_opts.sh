@@ -9,7 +9,7 @@ for o in "$@"; do
 import json
 try:
     d = json.loads(open("gpurun_out/bench_${tag}_$i.log").read().strip().splitlines()[-1])
-    print("[$o] value %.1f e2e %.1f u8 %.1f launches %d sm_mhz %s %s" % (d["value"], d["e2e"]["value"], d.get("e2e_u8", {}).get("value", 0), d["gpu_launches"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
+    print("[$o] value %.1f e2e(u8) %.1f e2e_f32 %.1f launches %d sm_mhz %s %s" % (d["value"], d["e2e"]["value"], d.get("e2e_f32", {}).get("value", 0), d["gpu_launches"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
 except Exception as e:
     print("[$o] failed", e)
 PY

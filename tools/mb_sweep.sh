@@ -8,7 +8,7 @@ for mb in $mbs; do
 import json
 try:
     d = json.loads(open("gpurun_out/bench_${tag}_mb$mb.log").read().strip().splitlines()[-1])
-    print("mb=$mb value %.1f e2e %.1f u8 %.1f launches %d clocks %s" % (d["value"], d["e2e"]["value"], d.get("e2e_u8", {}).get("value", 0), d["gpu_launches"], d["clocks"]))
+    print("mb=$mb value %.1f e2e(u8) %.1f e2e_f32 %.1f launches %d clocks %s" % (d["value"], d["e2e"]["value"], d.get("e2e_f32", {}).get("value", 0), d["gpu_launches"], d["clocks"]))
 except Exception as e:
     print("mb=$mb failed", e)
 PY

@@ -171,3 +171,21 @@ def test_jet_table_in_kernel_source_equals_cv2_fixture():
     body = body[:body.index("};")]
     table = np.array([[int(v) for v in m] for m in re.findall(r"\{(\d+),(\d+),(\d+)\}", body)], np.uint8)
     assert np.array_equal(table, np.load(os.path.join(ROOT, "tests", "golden", "jet_lut_bgr.npy")))
+
+
+def test_paddle_binding_compiles():
+    """paddle_binding/lws_paddle_ops.cc (the Paddle custom-op binding a maintainer of the reference would build) type-checks against
+    include/lws.h and the minimal paddle/extension.h stand-in, and binds every compute entry point of the header."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "paddle_binding", "lws_paddle_ops.cc")
+    gxx = shutil.which("g++")
+    assert gxx, "g++ not found"
+    subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "paddle_binding", "stub"),
+                    "-I", os.path.join(root, "include"), src], check=True)
+    text = open(src).read()
+    compute = [n for n in header_functions() if n.endswith(("_f32", "_u8")) and not n.startswith("lws_pack")]
+    internal = {"lws_warp_taps_f32", "lws_conv3d_bnrelu_layer_f32", "lws_refinement_block_clp_f32", "lws_refinement_chain_clp_f32"}
+    missing = [n for n in compute if n not in internal and n + "(" not in text]
+    assert not missing, f"entry points without a Paddle op: {missing}"

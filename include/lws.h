@@ -133,6 +133,17 @@ LWS_API int lws_disparity_regression_f32(const float* prob, float* out, int B, i
 LWS_API int lws_scale_upsample_add_f32(const float* low, const float* prev_or_null, float* pred, int B, int h, int w, int H,
                                int W, lws_stream_t stream);
 
+/* ---- a6 + a7 (+ a2 of the next stage) fused: the tail of one iteration of the stage loop (models/models.py:142-156, :119-121) ----
+ * pred = bilinear_resize_halfpixel((softmax_regression(cost) * float(H)) * fl32(1/h), H, W) (+ prev);
+ * wflow_next = (bilinear_resize_halfpixel(pred, hn, wn) * float(hn)) * fl32(1/H)   (only if wflow_next_or_null != NULL).
+ * One pass: the filtered volume is streamed once, the low-resolution disparity never reaches HBM and pred is not read back.
+ * Bit-identical to lws_softmax_regression_f32 + lws_scale_upsample_add_f32 + lws_disp_to_scale_f32.  Applies when H/h == W/w is
+ * an integer <= 8 dividing 32 and hn, wn decimate H, W by 1 or an even factor dividing the 32 x 256 tile
+ * (lws_regression_tail_supported == 0); otherwise LWS_ERR_UNSUPPORTED and the caller runs the three stand-alone entries. */
+LWS_API int lws_regression_tail_supported(int h, int w, int H, int W, int hn, int wn);
+LWS_API int lws_regression_tail_f32(const float* cost, const float* prev_or_null, float* pred, float* wflow_next_or_null, int B,
+                                    int D, int h, int w, int H, int W, int hn, int wn, float start, float step, lws_stream_t stream);
+
 /* ---- a8+a9: refinement1_left / refinement1_disp / refinement2 + skip
  *             (models/submodules.py:223-327, models/models.py:158-162) --------------------------------
  * pred4 = pred3 + R2(concat[R1_left(left), R1_disp(pred3)]).  left [B,3,H,W], pred3/pred4 [B,1,H,W]. */

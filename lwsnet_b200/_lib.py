@@ -38,6 +38,9 @@ SIGNATURES = {
     "lws_conv3d_bnrelu_layer_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_softmax_regression_f32": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "lws_scale_upsample_add_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "lws_regression_tail_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "lws_regression_tail_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                        c_void_p]),
     "lws_refinement_packed_floats": (c_size_t, []),
     "lws_pack_refinement_weights": (c_int, [_pp, c_int, c_float, _fp]),
     "lws_refinement_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -188,4 +188,36 @@ __device__ __forceinline__ ResizeTap resize_tap(int dst, float scale, int in_siz
   return t;
 }
 
+
+// half-pixel bilinear blend of the four taps (a00 a01 / a10 a11) with explicitly rounded operations, so that every kernel that
+// upsamples (K5, K2a, the fused regression tail) produces the same bits for the same inputs whatever the surrounding code is
+__device__ __forceinline__ float bilinear_blend(float a00, float a01, float a10, float a11, const ResizeTap& tx, const ResizeTap& ty) {
+  const float top = __fmaf_rn(tx.l1, a01, __fmul_rn(tx.l0, a00));
+  const float bot = __fmaf_rn(tx.l1, a11, __fmul_rn(tx.l0, a10));
+  return __fmaf_rn(ty.l1, bot, __fmul_rn(ty.l0, top));
+}
+
+// chunked online softmax regression over the disparity axis (K4 and the fused tail share it: same bits).  z[j] = -cost of plane
+// d0 + j (-inf beyond D); state (m, s, ws) = running max, sum of exp, sum of exp * disparity.
+template <int CH>
+__device__ __forceinline__ void softmax_chunk_update(const float (&z)[CH], int d0, float start, float step, float& m, float& s,
+                                                     float& ws) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  float cm = z[0];
+#pragma unroll
+  for (int j = 1; j < CH; ++j) cm = fmaxf(cm, z[j]);
+  const float nm = fmaxf(m, cm);
+  const float r = exp2f(__fmul_rn(__fsub_rn(m, nm), kLog2e));  // exp2f(-inf) = 0 on the first chunk
+  float cs = 0.f, cws = 0.f;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    const float e = exp2f(__fmul_rn(__fsub_rn(z[j], nm), kLog2e));
+    cs = __fadd_rn(cs, e);
+    cws = __fmaf_rn(e, __fmaf_rn(step, (float)(d0 + j), start), cws);
+  }
+  s = __fmaf_rn(s, r, cs);
+  ws = __fmaf_rn(ws, r, cws);
+  m = nm;
+}
+
 }  // namespace lws

@@ -20,7 +20,6 @@ __global__ void __launch_bounds__(256, CH == 9 ? 4 : 3)
   if (item >= n_items_per_b) return;
   const int b = blockIdx.y;
   const float* p = cost + (long long)b * D * hw + item * VEC;
-  constexpr float kLog2e = 1.4426950408889634f;
   float m[VEC], s[VEC], ws[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) m[v] = -INFINITY, s[v] = 0.f, ws[v] = 0.f;
@@ -44,29 +43,18 @@ __global__ void __launch_bounds__(256, CH == 9 ? 4 : 3)
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      float cm = z[0][v];
+      float zc[CH];
 #pragma unroll
-      for (int j = 1; j < CH; ++j) cm = fmaxf(cm, z[j][v]);
-      const float nm = fmaxf(m[v], cm);
-      const float r = exp2f((m[v] - nm) * kLog2e);  // exp2f(-inf) = 0 on the first chunk
-      float cs = 0.f, cws = 0.f;
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        const float e = exp2f((z[j][v] - nm) * kLog2e);
-        cs += e;
-        cws += e * (start + step * (float)(d0 + j));
-      }
-      s[v] = s[v] * r + cs;
-      ws[v] = ws[v] * r + cws;
-      m[v] = nm;
+      for (int j = 0; j < CH; ++j) zc[j] = z[j][v];
+      softmax_chunk_update<CH>(zc, d0, start, step, m[v], s[v], ws[v]);
     }
   }
   float* o = low + (long long)b * hw + item * VEC;
   if constexpr (VEC == 4) {
-    *reinterpret_cast<float4*>(o) = make_float4(ws[0] / s[0], ws[1] / s[1], ws[2] / s[2], ws[3] / s[3]);
+    *reinterpret_cast<float4*>(o) = make_float4(__fdiv_rn(ws[0], s[0]), __fdiv_rn(ws[1], s[1]), __fdiv_rn(ws[2], s[2]), __fdiv_rn(ws[3], s[3]));
   } else {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) o[v] = ws[v] / s[v];
+    for (int v = 0; v < VEC; ++v) o[v] = __fdiv_rn(ws[v], s[v]);
   }
 }
 
@@ -92,7 +80,7 @@ __global__ void __launch_bounds__(256)
     const float a01 = __fmul_rn(__fmul_rn(__ldg(l0 + tx.i1), fH), rh);
     const float a10 = __fmul_rn(__fmul_rn(__ldg(l1 + tx.i0), fH), rh);
     const float a11 = __fmul_rn(__fmul_rn(__ldg(l1 + tx.i1), fH), rh);
-    out[p] = ty.l0 * (tx.l0 * a00 + tx.l1 * a01) + ty.l1 * (tx.l0 * a10 + tx.l1 * a11);
+    out[p] = bilinear_blend(a00, a01, a10, a11, tx, ty);
   }
   const long long base = ((long long)b * H + y) * W + xq * 4;
   const bool vec = ((W & 3) == 0);
@@ -100,13 +88,13 @@ __global__ void __launch_bounds__(256)
     float4 o = make_float4(out[0], out[1], out[2], out[3]);
     if (prev) {
       const float4 pv = __ldcs(reinterpret_cast<const float4*>(prev + base));
-      o.x += pv.x, o.y += pv.y, o.z += pv.z, o.w += pv.w;
+      o.x = __fadd_rn(o.x, pv.x), o.y = __fadd_rn(o.y, pv.y), o.z = __fadd_rn(o.z, pv.z), o.w = __fadd_rn(o.w, pv.w);
     }
     *reinterpret_cast<float4*>(pred + base) = o;
   } else {
 #pragma unroll
     for (int p = 0; p < 4; ++p)
-      if (xq * 4 + p < W) pred[base + p] = out[p] + (prev ? prev[base + p] : 0.f);
+      if (xq * 4 + p < W) pred[base + p] = prev ? __fadd_rn(out[p], prev[base + p]) : out[p];
   }
 }
 
@@ -122,12 +110,147 @@ __global__ void __launch_bounds__(256)
   const ResizeTap tx = resize_tap(x, sx, W);
   const float* p0 = pred + ((long long)b * H + ty.i0) * W;
   const float* p1 = pred + ((long long)b * H + ty.i1) * W;
-  const float v = ty.l0 * (tx.l0 * __ldg(p0 + tx.i0) + tx.l1 * __ldg(p0 + tx.i1)) +
-                  ty.l1 * (tx.l0 * __ldg(p1 + tx.i0) + tx.l1 * __ldg(p1 + tx.i1));
+  const float v = bilinear_blend(__ldg(p0 + tx.i0), __ldg(p0 + tx.i1), __ldg(p1 + tx.i0), __ldg(p1 + tx.i1), tx, ty);
   wflow[((long long)b * h + y) * w + x] = __fmul_rn(__fmul_rn(v, fh), rH);
 }
 
+// ---- fused tail of a stage: K4 + K5 (+ K2a of the NEXT stage) in one pass --------------------------------------------------------
+// pred = upsample((softmax-regression(cost) * H) * (1/h)) (+ prev);  wflow_next = (resize(pred, hn, wn) * hn) * (1/H)
+// (reference models/models.py:142-156 and, for the next iteration of the stage loop, :119-121).  The filtered volume is streamed
+// once, the low-resolution disparity never exists in HBM, and the full-resolution prediction is not read back for the next wflow.
+// A block owns a 32 x 256 full-resolution tile (scale s = H/h = W/w: (32/s + 2) x (256/s + 2) low-resolution pixels incl. the
+// one-pixel halo the half-pixel bilinear taps reach): phase 1 regresses those pixels into shared memory with the same chunked online
+// softmax as K4, phase 2 writes the tile with 128-bit stores, phase 3 decimates it to the next stage's wflow.  The arithmetic is
+// that of the three stand-alone kernels (shared device functions with explicit roundings): the results are bit-identical.
+constexpr int RT_TH = 32, RT_TW = 256, RT_THREADS = 256;
+
+template <int CH>
+__global__ void __launch_bounds__(RT_THREADS)
+    regression_tail_kernel(const float* __restrict__ cost, const float* __restrict__ prev, float* __restrict__ pred,
+                           float* __restrict__ wflow, int D, int h, int w, int H, int W, int hn, int wn, int s, float start, float step,
+                           float fH, float rh, float fhn, float rH) {
+  extern __shared__ float sLow[];  // [(RT_TH/s + 2)][(RT_TW/s + 2)] low-resolution disparities, already scaled by H/h
+  const int lth = RT_TH / s + 2, ltw = RT_TW / s + 2;
+  const int b = blockIdx.z;
+  const int Y0 = blockIdx.y * RT_TH, X0 = blockIdx.x * RT_TW;
+  const int ly0 = Y0 / s - 1, lx0 = X0 / s - 1;  // low-resolution origin of the shared tile
+  const long long hw = (long long)h * w;
+  const float* cb = cost + (long long)b * D * hw;
+  // ---- phase 1: softmax regression of the tile's low-resolution pixels ----------------------------------------------------------
+  for (int i = threadIdx.x; i < lth * ltw; i += RT_THREADS) {
+    const int ly = ly0 + i / ltw, lx = lx0 + i % ltw;
+    float v = 0.f;
+    if (ly >= 0 && ly < h && lx >= 0 && lx < w) {
+      const float* p = cb + (long long)ly * w + lx;
+      float m = -INFINITY, sum = 0.f, ws = 0.f;
+      for (int d0 = 0; d0 < D; d0 += CH) {
+        float z[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) z[j] = d0 + j < D ? -__ldg(p + (long long)(d0 + j) * hw) : -INFINITY;
+        softmax_chunk_update<CH>(z, d0, start, step, m, sum, ws);
+      }
+      v = __fmul_rn(__fmul_rn(__fdiv_rn(ws, sum), fH), rh);  // (low * float(H)) * fl32(1/h), as K5
+    }
+    sLow[i] = v;
+  }
+  __syncthreads();
+  // ---- phase 2: upsample (+ prev) -> pred, 4 pixels per thread and row -------------------------------------------------------------
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  auto pred_at = [&](int y, int x) -> float {  // the prediction at full-resolution pixel (y, x) inside this tile
+    const ResizeTap ty = resize_tap(y, sy, h), tx = resize_tap(x, sx, w);
+    const float* r0 = sLow + (ty.i0 - ly0) * ltw - lx0;
+    const float* r1 = sLow + (ty.i1 - ly0) * ltw - lx0;
+    const float up = bilinear_blend(r0[tx.i0], r0[tx.i1], r1[tx.i0], r1[tx.i1], tx, ty);
+    return prev ? __fadd_rn(up, __ldg(prev + ((long long)b * H + y) * W + x)) : up;
+  };
+  const bool vec = (W & 3) == 0;
+  for (int i = threadIdx.x; i < RT_TH * (RT_TW / 4); i += RT_THREADS) {
+    const int y = Y0 + i / (RT_TW / 4), x = X0 + (i % (RT_TW / 4)) * 4;
+    if (y >= H || x >= W) continue;
+    const ResizeTap ty = resize_tap(y, sy, h);
+    const float* r0 = sLow + (ty.i0 - ly0) * ltw - lx0;
+    const float* r1 = sLow + (ty.i1 - ly0) * ltw - lx0;
+    float out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const ResizeTap tx = resize_tap(min(x + q, W - 1), sx, w);
+      out[q] = bilinear_blend(r0[tx.i0], r0[tx.i1], r1[tx.i0], r1[tx.i1], tx, ty);
+    }
+    const long long base = ((long long)b * H + y) * W + x;
+    if (vec) {
+      float4 o = make_float4(out[0], out[1], out[2], out[3]);
+      if (prev) {
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(prev + base));
+        o.x = __fadd_rn(o.x, pv.x), o.y = __fadd_rn(o.y, pv.y), o.z = __fadd_rn(o.z, pv.z), o.w = __fadd_rn(o.w, pv.w);
+      }
+      *reinterpret_cast<float4*>(pred + base) = o;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (x + q < W) pred[base + q] = prev ? __fadd_rn(out[q], prev[base + q]) : out[q];
+    }
+  }
+  // ---- phase 3: the next stage's wflow from this tile's predictions (its taps never leave the tile: host-checked) -------------------
+  if (wflow) {
+    const int fy = H / hn, fx = W / wn;
+    const float syn = (float)H / (float)hn, sxn = (float)W / (float)wn;
+    const int nty = RT_TH / fy, ntx = RT_TW / fx;
+    for (int i = threadIdx.x; i < nty * ntx; i += RT_THREADS) {
+      const int yn = Y0 / fy + i / ntx, xn = X0 / fx + i % ntx;
+      if (yn >= hn || xn >= wn) continue;
+      const ResizeTap ty = resize_tap(yn, syn, H), tx = resize_tap(xn, sxn, W);
+      const float v = bilinear_blend(pred_at(ty.i0, tx.i0), pred_at(ty.i0, tx.i1), pred_at(ty.i1, tx.i0), pred_at(ty.i1, tx.i1), tx, ty);
+      wflow[((long long)b * hn + yn) * wn + xn] = __fmul_rn(__fmul_rn(v, fhn), rH);
+    }
+  }
+}
+
 }  // namespace lws
+
+// 0: the fused kernel applies (integer scale H/h == W/w dividing the 32 x 256 tile; next-stage decimation by 1 or an even factor
+// that divides the tile); otherwise LWS_ERR_UNSUPPORTED (the caller runs the three stand-alone kernels)
+extern "C" int lws_regression_tail_supported(int h, int w, int H, int W, int hn, int wn) {
+  using namespace lws;
+  if (h <= 0 || w <= 0 || H <= 0 || W <= 0) return LWS_ERR_BAD_SHAPE;
+  if (H % h || W % w || H / h != W / w) return LWS_ERR_UNSUPPORTED;
+  const int s = H / h;
+  if (s > 8 || RT_TH % s || RT_TW % s) return LWS_ERR_UNSUPPORTED;
+  if (hn > 0 || wn > 0) {
+    if (hn <= 0 || wn <= 0 || H % hn || W % wn) return LWS_ERR_UNSUPPORTED;
+    const int fy = H / hn, fx = W / wn;
+    if ((fy != 1 && (fy & 1)) || (fx != 1 && (fx & 1)) || RT_TH % fy || RT_TW % fx) return LWS_ERR_UNSUPPORTED;
+  }
+  return LWS_OK;
+}
+
+extern "C" int lws_regression_tail_f32(const float* cost, const float* prev_or_null, float* pred, float* wflow_next_or_null, int B,
+                                       int D, int h, int w, int H, int W, int hn, int wn, float start, float step,
+                                       lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(cost);
+  LWS_CHECK_PTR(pred);
+  if (B <= 0 || D <= 0 || B > 65535) return LWS_ERR_BAD_SHAPE;
+  if (!wflow_next_or_null) hn = wn = 0;
+  const int rc = lws_regression_tail_supported(h, w, H, W, hn, wn);
+  if (rc) return rc;
+  if ((W & 3) == 0 && (((uintptr_t)pred | (uintptr_t)prev_or_null) & 15) != 0) return LWS_ERR_BAD_ALIGN;
+  const int s = H / h;
+  dim3 grid(cdiv(W, RT_TW), cdiv(H, RT_TH), B);
+  if (grid.y > 65535) return LWS_ERR_BAD_SHAPE;
+  const size_t smem = (size_t)(RT_TH / s + 2) * (RT_TW / s + 2) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float fH = (float)H, rh = (float)(1.0 / (double)h), fhn = (float)hn, rH = (float)(1.0 / (double)H);
+  if (D % 9 == 0)
+    regression_tail_kernel<9><<<grid, RT_THREADS, smem, st>>>(cost, prev_or_null, pred, wflow_next_or_null, D, h, w, H, W, hn, wn, s,
+                                                              start, step, fH, rh, fhn, rH);
+  else if (D % 12 == 0)
+    regression_tail_kernel<12><<<grid, RT_THREADS, smem, st>>>(cost, prev_or_null, pred, wflow_next_or_null, D, h, w, H, W, hn, wn, s,
+                                                               start, step, fH, rh, fhn, rH);
+  else
+    regression_tail_kernel<8><<<grid, RT_THREADS, smem, st>>>(cost, prev_or_null, pred, wflow_next_or_null, D, h, w, H, W, hn, wn, s,
+                                                              start, step, fH, rh, fhn, rH);
+  LWS_RETURN_LAUNCH_STATUS();
+}
 
 extern "C" int lws_softmax_regression_f32(const float* cost, float* low, int B, int D, int H, int W, float start,
                                           float step, lws_stream_t stream) {
@@ -147,8 +270,11 @@ extern "C" int lws_softmax_regression_f32(const float* cost, float* low, int B, 
     else if (D % 12 == 0) softmax_regression_kernel<4, 12><<<grid, threads, 0, st>>>(cost, low, D, hw, n, start, step);
     else softmax_regression_kernel<4, 8><<<grid, threads, 0, st>>>(cost, low, D, hw, n, start, step);
   } else {
+    // same chunk length per D as the vector path and the fused tail: the chunking decides the rounding, and all three agree bitwise
     dim3 grid((unsigned)((hw + 255) / 256), B);
-    softmax_regression_kernel<1, 8><<<grid, 256, 0, st>>>(cost, low, D, hw, hw, start, step);
+    if (D % 9 == 0) softmax_regression_kernel<1, 9><<<grid, 256, 0, st>>>(cost, low, D, hw, hw, start, step);
+    else if (D % 12 == 0) softmax_regression_kernel<1, 12><<<grid, 256, 0, st>>>(cost, low, D, hw, hw, start, step);
+    else softmax_regression_kernel<1, 8><<<grid, 256, 0, st>>>(cost, low, D, hw, hw, start, step);
   }
   LWS_RETURN_LAUNCH_STATUS();
 }

@@ -88,17 +88,22 @@ class LWSNet(nn.Module):
         return tuple((b.data_ptr(), b._version) for b in blobs)
 
     # one iteration of the stage loop, reference models/models.py:115-156
-    def _stage(self, scale, feat_l, feat_r, prev_pred, img_h, img_w, out=None):
+    def _stage(self, scale, feat_l, feat_r, prev_pred, img_h, img_w, out=None, wflow=None, next_hw=None):
+        """One iteration of the stage loop.  ``wflow``: this stage's wflow if the previous stage's fused tail already produced it;
+        ``next_hw``: feature size of the next stage -- then the tail also emits the next wflow and (pred, wflow_next) is returned."""
         if scale > 0:
-            wflow = ops.disp_to_scale(prev_pred, feat_l.shape[2], feat_l.shape[3])                 # models.py:119-121
+            if wflow is None:
+                wflow = ops.disp_to_scale(prev_pred, feat_l.shape[2], feat_l.shape[3])             # models.py:119-121
             cost = self._build_volume_2d3(feat_l, feat_r, self.maxdisplist[scale], wflow, stride=1)  # :123-127
             start = float(-self.maxdisplist[scale] + 1)
         else:
             cost = self._build_volume_2d(feat_l, feat_r, self.maxdisplist[scale], stride=1)          # :131-134
             start = 0.0
         cost = self.volume_postprocess[scale].run(cost, add_skip=True)                               # :136-138
-        low = ops.softmax_regression(cost, start, 1.0)                                              # :142 / :151-152
-        return ops.scale_upsample_add(low, prev_pred if scale > 0 else None, img_h, img_w, out=out)  # :145-148 / :153-156
+        # :142 / :151-152 softmax + regression, :145-148 / :153-156 rescale + upsample + skip, and the next stage's :119-121
+        pred, wflow_next = ops.regression_tail(cost, prev_pred if scale > 0 else None, img_h, img_w, start, 1.0, next_hw=next_hw,
+                                               out=out)
+        return pred if next_hw is None else (pred, wflow_next)
 
     def _refine(self, left_input, pred3, out=None):
         return ops.refinement(left_input, pred3, self._refinement_packed(left_input.device), out=out)  # :158-162
@@ -133,10 +138,14 @@ class LWSNet(nn.Module):
         if out is not None and (tuple(out.shape) != (4, n, 1, img_h, img_w) or out.dtype != torch.float32 or not out.is_contiguous()
                                 or out.device != left_input.device):
             raise ValueError("out must be a contiguous fp32 [4,B,1,H,W] tensor on the inputs' device")
-        pred = []
+        pred, wflow = [], None
         for scale in range(len(feats_l)):
-            pred.append(self._stage(scale, feats_l[scale].contiguous(), feats_r[scale].contiguous(),
-                                    pred[scale - 1] if scale > 0 else None, img_h, img_w, out=None if out is None else out[scale]))
+            nxt = tuple(feats_l[scale + 1].shape[2:]) if scale + 1 < len(feats_l) else None
+            res = self._stage(scale, feats_l[scale].contiguous(), feats_r[scale].contiguous(),
+                              pred[scale - 1] if scale > 0 else None, img_h, img_w, out=None if out is None else out[scale],
+                              wflow=wflow, next_hw=nxt)
+            p, wflow = res if nxt is not None else (res, None)
+            pred.append(p)
         pred.append(self._refine(left_input, pred[2], out=None if out is None else out[3]))
         return pred
 

@@ -242,6 +242,32 @@ def scale_upsample_add(low: torch.Tensor, prev: Optional[torch.Tensor], H: int, 
     return pred
 
 
+def regression_tail(cost: torch.Tensor, prev: Optional[torch.Tensor], H: int, W: int, start: float, step: float = 1.0,
+                    next_hw: Optional[tuple] = None, out: Optional[torch.Tensor] = None, fused: bool = True):
+    """Tail of one stage-loop iteration (reference models/models.py:142-156) and the head of the next (:119-121):
+    pred = upsample(softmax_regression(cost) * H / h) (+ prev)  and, when ``next_hw`` is given, the next stage's
+    wflow = resize(pred, next_hw) * h_next / H.  One fused launch where the shapes allow it (lws_regression_tail_f32), otherwise
+    the three stand-alone kernels; both give the same bits.  Returns (pred [B,1,H,W], wflow [B,1,hn,wn] or None)."""
+    cost = _f32c(cost)
+    B, D, h, w = cost.shape
+    if prev is not None:
+        prev = _f32c(prev)
+        if tuple(prev.shape) != (B, 1, H, W):
+            raise ValueError("prev must be [B,1,H,W]")
+    hn, wn = (int(next_hw[0]), int(next_hw[1])) if next_hw is not None else (0, 0)
+    if fused and lib.lws_regression_tail_supported(h, w, H, W, hn, wn) == 0:
+        pred = out if out is not None else torch.empty((B, 1, H, W), dtype=torch.float32, device=cost.device)
+        wflow = torch.empty((B, 1, hn, wn), dtype=torch.float32, device=cost.device) if next_hw is not None else None
+        with torch.cuda.device(cost.device):
+            check(lib.lws_regression_tail_f32(_ptr(cost, "cost"), _ptr(prev, "prev"), _ptr(pred, "pred"), _ptr(wflow, "wflow"), B, D, h,
+                                              w, H, W, hn, wn, float(start), float(step), _stream(cost)), "lws_regression_tail_f32")
+        LAUNCHES[0] += 1
+        return pred, wflow
+    low = softmax_regression(cost, start, step)
+    pred = scale_upsample_add(low, prev, H, W, out=out)
+    return pred, (disp_to_scale(pred, hn, wn) if next_hw is not None else None)
+
+
 def disparity_regression(prob: torch.Tensor, start: float, step: float = 1.0) -> torch.Tensor:
     """disparity_regression(start, end, stride).forward(prob) (reference models/models.py:167-179) on an already soft-maxed
     volume: sum_j prob[:, j] * (start + j * step), without renormalising `prob`."""

@@ -107,6 +107,20 @@ std::vector<paddle::Tensor> ScaleUpsampleAdd(const paddle::Tensor& low, const pa
   return {pred};
 }
 
+// ---- a6 + a7 (+ a2 of the next stage) fused: the tail of one stage-loop iteration (models/models.py:142-156, :119-121) ----------
+// has_prev = 0 for the first stage; hn = wn = 0 when there is no next stage (Wflow is then an empty [B,1,0,0] tensor)
+std::vector<paddle::Tensor> RegressionTail(const paddle::Tensor& cost, const paddle::Tensor& prev, int H, int W, int hn, int wn,
+                                           float start, float step, int has_prev) {
+  const auto s = cost.shape();  // [B,D,h,w]
+  auto pred = paddle::empty({s[0], 1, H, W}, paddle::DataType::FLOAT32, cost.place());
+  auto wflow = paddle::empty({s[0], 1, hn, wn}, paddle::DataType::FLOAT32, cost.place());
+  lws_check(lws_regression_tail_f32(cost.data<float>(), has_prev ? prev.data<float>() : nullptr, pred.data<float>(),
+                                    hn > 0 ? wflow.data<float>() : nullptr, i32(s[0]), i32(s[1]), i32(s[2]), i32(s[3]), H, W, hn, wn,
+                                    start, step, cost.stream()),
+            "lws_regression_tail_f32");
+  return {pred, wflow};
+}
+
 // ---- a8 + a9 fused: pred3 + refinement2(concat[refinement1_left(left), refinement1_disp(pred3)]) (models/models.py:158-162) ----
 std::vector<paddle::Tensor> Refinement(const paddle::Tensor& left, const paddle::Tensor& pred3, const paddle::Tensor& packed) {
   const auto s = left.shape();  // [B,3,H,W]
@@ -184,6 +198,7 @@ PD_BUILD_OP(lws_conv3d_stack).Inputs({"Cost", "Packed"}).Outputs({"Out"}).Attrs(
 PD_BUILD_OP(lws_softmax_regression).Inputs({"Cost"}).Outputs({"Low"}).Attrs({"start: float", "step: float"}).SetKernelFn(PD_KERNEL(SoftmaxRegression));
 PD_BUILD_OP(lws_disparity_regression).Inputs({"Prob"}).Outputs({"Out"}).Attrs({"start: float", "step: float"}).SetKernelFn(PD_KERNEL(DisparityRegression));
 PD_BUILD_OP(lws_scale_upsample_add).Inputs({"Low", "Prev"}).Outputs({"Pred"}).Attrs({"H: int", "W: int", "has_prev: int"}).SetKernelFn(PD_KERNEL(ScaleUpsampleAdd));
+PD_BUILD_OP(lws_regression_tail).Inputs({"Cost", "Prev"}).Outputs({"Pred", "WflowNext"}).Attrs({"H: int", "W: int", "hn: int", "wn: int", "start: float", "step: float", "has_prev: int"}).SetKernelFn(PD_KERNEL(RegressionTail));
 PD_BUILD_OP(lws_refinement).Inputs({"Left", "Pred3", "Packed"}).Outputs({"Pred4"}).SetKernelFn(PD_KERNEL(Refinement));
 PD_BUILD_OP(lws_refinement1).Inputs({"X", "Packed"}).Outputs({"Out"}).SetKernelFn(PD_KERNEL(Refinement1));
 PD_BUILD_OP(lws_refinement2).Inputs({"X", "Packed"}).Outputs({"Out"}).SetKernelFn(PD_KERNEL(Refinement2));

@@ -170,6 +170,39 @@ def test_scale_upsample_add(B, h, w, H, W):
     close_rel(ops().scale_upsample_add(low.cuda(), prev.cuda(), H, W), S.scale_upsample_add(low.numpy(), prev.numpy(), H, W), 1e-5)
 
 
+@pytest.mark.parametrize("B,D,h,w,H,W,nhw,start", [
+    (2, 24, 46, 154, 368, 1232, (92, 308), 0.0),     # stage 1 -> wflow of stage 2 (decimation 4)
+    (1, 9, 92, 308, 368, 1232, (184, 616), -4.0),    # stage 2 -> wflow of stage 3 (decimation 2)
+    (2, 9, 184, 616, 368, 1232, None, -4.0),         # stage 3: no next stage
+    (1, 48, 136, 240, 1088, 1920, (272, 480), 0.0),  # configs[4]
+    (1, 9, 16, 32, 64, 128, (32, 64), -4.0),         # smaller than one tile
+    (1, 24, 17, 30, 136, 240, (34, 60), 0.0),        # ragged tiles
+    (1, 9, 40, 56, 40, 56, None, -4.0),              # scale 1
+])
+def test_regression_tail_fused_is_bit_identical(B, D, h, w, H, W, nhw, start):
+    """lws_regression_tail_f32 (K4 + K5 + the next stage's K2a in one pass) == the three stand-alone kernels, BITWISE, with and
+    without the previous-stage skip; and against the numpy spec within the K4 / K5 tolerances."""
+    from oracle import spec_np as S
+    for scale in (1.0, 30.0):
+        cost = rnd(18, B, D, h, w, scale=scale).cuda()
+        prev = rnd(19, B, 1, H, W, scale=30.0).cuda()
+        for pv in (None, prev):
+            pf, wf = ops().regression_tail(cost, pv, H, W, start, 1.0, next_hw=nhw)
+            pu, wu = ops().regression_tail(cost, pv, H, W, start, 1.0, next_hw=nhw, fused=False)
+            assert torch.equal(pf, pu)
+            assert (wf is None and wu is None) or torch.equal(wf, wu)
+        low = S.softmax_regression(cost.cpu().double().numpy(), start)
+        ref = S.scale_upsample_add(low.astype(np.float32), prev.cpu().numpy(), H, W)
+        # K4's bar is 2e-5 LOW-resolution pixels; the rescale by H/h turns it into 2e-5 * H/h full-resolution pixels (+ K5's 1e-5 rel)
+        err = (pf.cpu().double() - torch.from_numpy(ref).double()).abs()
+        assert (err <= 2e-5 * (H / h) + 1e-5 * torch.from_numpy(ref).double().abs()).all(), err.max().item()
+        if nhw is not None:
+            close_rel(wf, S.disp_to_scale(pf.cpu().numpy(), *nhw), 1e-5)
+    assert ops().lib.lws_regression_tail_supported(5, 7, 40, 56, 0, 0) == 0
+    assert ops().lib.lws_regression_tail_supported(6, 9, 13, 31, 0, 0) == -5       # non-integer scale -> stand-alone kernels
+    assert ops().lib.lws_regression_tail_supported(46, 154, 368, 1232, 123, 411) == -5
+
+
 # ------------------------------------------------------------------------------------------------ a5
 def _stack_from_golden(prefix, C):
     from lwsnet_b200.submodules import post_3dconvs

@@ -216,6 +216,15 @@ def kernel_probes(model, pk, B=16):
         s = sets(nsets(B * (D + 1) * h * w * 4), (B, D, h, w), scale=8.0)
         us = time_rotating(lambda i: ops.softmax_regression(s[i][0], 0.0), len(s))
         add(f"K4 softmax_regression [{B},{D},{h},{w}]", us, B * (D + 1) * h * w * 4)
+    # fused stage tail (what the engine runs instead of K4 + K5 + K2a): volume + prev in, pred + next wflow out
+    for (D, h, w, nhw, has_prev) in ((24, 46, 154, (92, 308), False), (9, 92, 308, (184, 616), True), (9, 184, 616, None, True)):
+        per = (D * h * w + (H_IMG * W_IMG if has_prev else 0) + H_IMG * W_IMG + (nhw[0] * nhw[1] if nhw else 0)) * 4
+        s = sets(nsets(B * per), (B, D, h, w), (B, 1, H_IMG, W_IMG), scale=8.0)
+        o = torch.empty((B, 1, H_IMG, W_IMG), device=dev)
+        us = time_rotating(lambda i: ops.regression_tail(s[i][0], s[i][1] if has_prev else None, H_IMG, W_IMG, 0.0, 1.0, next_hw=nhw, out=o),
+                           len(s))
+        add(f"TAIL regression_tail [{B},{D},{h},{w}] -> pred [{B},1,368,1232]{' + prev' if has_prev else ''}{' + next wflow' if nhw else ''} "
+            "(K4 + K5 + K2a fused)", us, B * per)
     # K5
     s = sets(nsets(B * (184 * 616 + H_IMG * W_IMG) * 4), (B, 1, 184, 616), (B, 1, H_IMG, W_IMG))
     o = torch.empty((B, 1, H_IMG, W_IMG), device=dev)

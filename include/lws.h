@@ -58,7 +58,10 @@ LWS_API const char* lws_version(void);
  *                         workspace sizes depend on it: set it before lws_refinement_workspace_bytes)
  *   "warp_div_mode"   0   lws_warp_* coordinate normalisation x / (size-1): 0 = x * fl32(1/(size-1)) (Paddle 2.0 scalar
  *                         division = scale op), 1 = IEEE division
- *   "c8_v1" 0, "c8_chunk" 0, "k1_dt" 8   developer A/B switches of the C = 8 stack and the stage-1 volume kernel */
+ *   "first_conv"      1   first 1 -> C conv of a 3D stack: 0 = taps read from global memory, 1 = C = 32 with the tap window staged
+ *                         in shared memory (default), 4 / 8 = C = 8 staged as well (measured slower; A/B)
+ *   "c8_v1" 0, "c8_chunk" 0, "k1_dt" 8   developer A/B switches of the C = 8 stack and the stage-1 volume kernel
+ *   "chain_debug"     0   TIMING EXPERIMENTS ONLY (wrong results): chain kernel without dependency waits */
 LWS_API int lws_set_option(const char* key, int value);
 LWS_API int lws_get_option(const char* key, int* value);
 

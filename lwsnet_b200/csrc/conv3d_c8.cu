@@ -765,6 +765,115 @@ __global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
   }
 }
 
+// ---- first conv 1 -> 8, version 2: the activated tap window staged once in shared memory --------------------------------------
+// Version 1 above fetches its 54 taps per thread straight from global memory: 3 address instructions + 1 predicate per load and
+// the BN_0 affine + ReLU recomputed for every use (ncu: 28 % of its instructions are the FFMA2s that do the work).  Here a block
+// (one padded output plane dp, NV rows, 128 columns) first stages ReLU(BN_0(cost)) of the 3 x (NV + 2) x 130 window, zero outside
+// the volume (the conv pads the ACTIVATED tensor), so the taps are immediate-offset LDS and the activation is applied once per
+// element.  Thread = one column x NV rows x 8 channels (channel pairs through FFMA2).
+template <int NV>
+__global__ void __launch_bounds__(128, NV == 8 ? 4 : 6)
+    conv3d_first_c8_v2_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][8]*/, const float* __restrict__ bias,
+                              const float* __restrict__ affine, uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, int D, int H,
+                              int W) {
+  constexpr int TR = NV + 2, TC = 130;
+  __shared__ __align__(16) float sW[27 * 8];
+  __shared__ float sIn[3 * TR * TC];
+  const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+  const int b = blockIdx.x / Dp, dp = blockIdx.x - b * Dp;
+  const int yp0 = blockIdx.y * NV;
+  const int xp0 = blockIdx.z * 128;
+  const int tid = threadIdx.x;
+  const int xp = xp0 + tid;
+  const int d = dp - 1;
+  const long long vox0 = (((long long)b * Dp + dp) * Hp + yp0) * Wp + xp;
+  if (d < 0 || d >= D) {  // padding plane: zeros only (block-uniform)
+    if (xp < Wp)
+      for (int vy = 0; vy < NV && yp0 + vy < Hp; ++vy)
+        out_hi[vox0 + (long long)vy * Wp] = make_uint4(0, 0, 0, 0), out_lo[vox0 + (long long)vy * Wp] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  for (int i = tid; i < 27 * 8; i += 128) sW[i] = __ldg(w + i);
+  {
+    const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+    const long long hw = (long long)H * W;
+    const float* cb = cost + (long long)b * D * hw;
+    // tile element (kd, r, c) = activated cost at plane d + kd - 1, row yp0 + r - 2, column xp0 + c - 2; a thread stages column
+    // c = tid of every (kd, r) row (threads 0 and 1 also the two halo columns 128, 129): no index arithmetic per element
+    const int xx0 = xp0 + tid - 2, xx1 = xp0 + 128 + tid - 2;
+    const bool okx0 = (unsigned)xx0 < (unsigned)W, okx1 = tid < 2 && (unsigned)xx1 < (unsigned)W;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int dd = d + kd - 1;
+      const bool okd = (unsigned)dd < (unsigned)D;
+      const float* cd = cb + (long long)dd * hw;
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        const int yy = yp0 + r - 2;
+        const bool ok = okd && (unsigned)yy < (unsigned)H;  // block-uniform
+        const float* row = cd + (long long)yy * W;
+        sIn[(kd * TR + r) * TC + tid] = (ok && okx0) ? fmaxf(fmaf(__ldg(row + xx0), s0, t0), 0.f) : 0.f;
+        if (tid < 2) sIn[(kd * TR + r) * TC + 128 + tid] = (ok && okx1) ? fmaxf(fmaf(__ldg(row + xx1), s0, t0), 0.f) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  if (xp >= Wp) return;
+  float2 acc[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[v][j] = make_float2(0.f, 0.f);
+  const int x = xp - 1;
+  const bool zero_all = x < 0 || x >= W;
+  if (!zero_all) {
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float v[TR];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) v[r] = sIn[(kd * TR + r) * TC + tid + kw];  // column xp0 + tid + kw - 2 = x + kw - 1
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 8 + 4);
+          const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+          const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
+#pragma unroll
+          for (int vy = 0; vy < NV; ++vy) {
+            const float2 t = make_float2(v[vy + kh], v[vy + kh]);
+            acc[vy][0] = __ffma2_rn(t, w01, acc[vy][0]), acc[vy][1] = __ffma2_rn(t, w23, acc[vy][1]);
+            acc[vy][2] = __ffma2_rn(t, w45, acc[vy][2]), acc[vy][3] = __ffma2_rn(t, w67, acc[vy][3]);
+          }
+        }
+      }
+    }
+  }
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + j);
+#pragma unroll
+  for (int vy = 0; vy < NV; ++vy) {
+    const int yp = yp0 + vy;
+    if (yp >= Hp) break;
+    const bool border = zero_all || yp == 0 || yp == Hp - 1;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float a0 = border ? 0.f : fmaxf(acc[vy][p].x + bv[2 * p], 0.f) * kDwsepActScale;
+      const float a1 = border ? 0.f : fmaxf(acc[vy][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
+      const __half2 h = f2h2_sat(a0, a1);
+      const float2 f = __half22float2(h);
+      const float2 dl = split_lo2(a0, a1, f);
+      const __half2 l = f2h2_sat(dl.x, dl.y);
+      hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    out_hi[vox0 + (long long)vy * Wp] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    out_lo[vox0 + (long long)vy * Wp] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ---- host -------------------------------------------------------------------------------------------------------------------
 static long long c8_plane_bytes(int B, int D, int H, int W) {
   const long long vox = (long long)B * (D + 2) * (H + 2) * (W + 2);
@@ -797,10 +906,24 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
     if ((e = cudaMemset2DAsync(plane[i] + (size_t)(Dp - 1) * pl, vox_b * 16, 0, pl, B, st)) != cudaSuccess) return (int)e;
   }
   {
-    constexpr int NV = 4;  // NV = 8 (168 registers, 2-3 blocks / SM) measured slower
-    if ((Hp + NV - 1) / NV > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
-    dim3 grid(B * Dp, (Hp + NV - 1) / NV, (Wp + 127) / 128);
-    conv3d_first_c8_kernel<NV><<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
+    // C = 8: the global-memory version stays the default (measured r02i, 8 pairs: 52 + 178 us against 61 + 201 us (NV = 4) and
+    // 74 + 238 us (NV = 8) for the staged version: with 4-6 resident blocks the staging phase is not overlapped); option
+    // "first_conv" = 4 / 8 selects the staged version for A/B.  (C = 32 uses its staged version by default: 152 -> 125 us.)
+    const int ver = opt(OPT_FIRST_CONV);
+    if (ver != 4 && ver != 8) {
+      constexpr int NV = 4;  // NV = 8 (168 registers, 2-3 blocks / SM) measured slower
+      if ((Hp + NV - 1) / NV > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
+      dim3 grid(B * Dp, (Hp + NV - 1) / NV, (Wp + 127) / 128);
+      conv3d_first_c8_kernel<NV><<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
+    } else if (ver == 4) {
+      if ((Hp + 3) / 4 > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
+      dim3 grid(B * Dp, (Hp + 3) / 4, (Wp + 127) / 128);
+      conv3d_first_c8_v2_kernel<4><<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
+    } else {
+      if ((Hp + 7) / 8 > 65535 || (Wp + 127) / 128 > 65535) return LWS_ERR_BAD_SHAPE;
+      dim3 grid(B * Dp, (Hp + 7) / 8, (Wp + 127) / 128);
+      conv3d_first_c8_v2_kernel<8><<<grid, 128, 0, st>>>(cost, w_first, b_first, affine, (uint4*)plane[0], (uint4*)plane[1], D, H, W);
+    }
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   // lws_set_option("c8_v1", 1): the one-plane-per-tile kernel

@@ -615,6 +615,107 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- first conv 1 -> 32, version 2: the activated tap window of a (row, 64-column chunk) staged once in shared memory ----------------
+// Version 1 above loads its 54 taps per lane from global memory (address + predicate instructions per load, the BN_0 affine + ReLU
+// recomputed per use).  Here a block = (y, 64 padded columns, pair) stages ReLU(BN_0(cost)) of rows y-1..y+1, all planes (two zero
+// planes either side, so no tap needs a predicate) and 66 columns; the 64 voxel groups of the block (4 lanes x 8 output channels
+// each) then walk the (4-plane group, column) items with immediate-offset LDS taps.
+constexpr int F32V2_XT = 64;
+__global__ void __launch_bounds__(256, 2)
+    conv3d_first_ydx_v2_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][32]*/, const float* __restrict__ bias,
+                               const float* __restrict__ affine, uint4* __restrict__ out, int D, int H, int W) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* sW = smem_f;             // [27][32]
+  float* sIn = smem_f + 27 * 32;  // [3 kh][NP planes][66 cols]
+  constexpr int TC = F32V2_XT + 2;
+  const int Wp = W + 2, Dp = D + 2;
+  const int ngd = (Dp + 3) >> 2;
+  const int NP = 4 * ngd + 2;     // tile plane pi holds input plane pi - 2; the last plane group reads planes up to 4*ngd + 1
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int xc0 = blockIdx.x * F32V2_XT;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * 32; i += 256) sW[i] = __ldg(w + i);
+  {
+    const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+    const long long hw = (long long)H * W;
+    const float* cb = cost + (long long)b * D * hw;
+    const int rr = tid / TC, cc = tid - rr * TC;  // 3 tile rows of 66 columns per pass (198 of the 256 threads)
+    const int xx = xc0 + cc - 2;
+    const bool okx = rr < 3 && (unsigned)xx < (unsigned)W;
+    for (int row = rr; row < 3 * NP && rr < 3; row += 3) {
+      const int kh = row / NP, pi = row - kh * NP;
+      const int dd = pi - 2, yy = y + kh - 1;
+      float v = 0.f;
+      if (okx && (unsigned)dd < (unsigned)D && (unsigned)yy < (unsigned)H)
+        v = fmaxf(fmaf(__ldg(cb + (long long)dd * hw + (long long)yy * W + xx), s0, t0), 0.f);
+      sIn[row * TC + cc] = v;
+    }
+  }
+  __syncthreads();
+  const int sub = tid & 3, grp = tid >> 2;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
+  const int ncols = min(F32V2_XT, Wp - xc0);
+  const int nitems = ngd * ncols;
+  for (int item = grp; item < nitems; item += 64) {
+    const int dpg = item / ncols, i = item - dpg * ncols;  // x fastest: the 8 groups of a warp read 8 neighbouring columns
+    const int xp = xc0 + i, dp0 = dpg * 4;
+    float2 acc[4][4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[v][j] = make_float2(0.f, 0.f);
+    const bool xborder = xp == 0 || xp == Wp - 1;
+    if (!xborder) {
+      // voxel vd (padded plane dp0 + vd, d = dp - 1), tap kd: input plane d + kd - 1 = dp0 + (vd + kd) - 2 -> tile plane dp0 + vd + kd
+      const float* base = sIn + dp0 * TC + i;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float v[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) v[r] = base[(kh * NP + r) * TC + kw];
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8 + 4);
+            const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+            const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
+#pragma unroll
+            for (int vd = 0; vd < 4; ++vd) {
+              const float2 t = make_float2(v[vd + kd], v[vd + kd]);
+              acc[vd][0] = __ffma2_rn(t, w01, acc[vd][0]), acc[vd][1] = __ffma2_rn(t, w23, acc[vd][1]);
+              acc[vd][2] = __ffma2_rn(t, w45, acc[vd][2]), acc[vd][3] = __ffma2_rn(t, w67, acc[vd][3]);
+            }
+          }
+        }
+      }
+    }
+    const long long row0 = (((long long)b * H + y) * Wp + xp) * Dp + dp0;
+#pragma unroll
+    for (int vd = 0; vd < 4; ++vd) {
+      const int dp = dp0 + vd;
+      if (dp >= Dp) break;
+      const bool border = xborder || dp == 0 || dp == Dp - 1;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float a0 = border ? 0.f : fmaxf(acc[vd][p].x + bv[2 * p], 0.f) * kDwsepActScale;
+        const float a1 = border ? 0.f : fmaxf(acc[vd][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
+        const __half2 h = f2h2_sat(a0, a1);
+        const float2 f = __half22float2(h);
+        const float2 dl = split_lo2(a0, a1, f);
+        const __half2 l = f2h2_sat(dl.x, dl.y);
+        hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      out[(row0 + vd) * 8 + sub] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      out[(row0 + vd) * 8 + 4 + sub] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W) {
   const size_t rows = (size_t)B * H * (W + 2) * (D + 2);
   return 2 * (rows * 128 + 1024);
@@ -635,9 +736,15 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
   cudaError_t e;
   {
     if (H > 65535 || B > 65535) return LWS_ERR_BAD_SHAPE;
-    const int groups = Wp * ((Dp + 3) / 4);
-    dim3 grid((groups + 63) / 64, H, B);
-    conv3d_first_ydx_kernel<<<grid, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W, make_fastdiv(Wp));
+    const size_t smem2 = (size_t)(27 * 32 + 3 * (4 * ((Dp + 3) / 4) + 2) * (F32V2_XT + 2)) * sizeof(float);
+    if (opt(OPT_FIRST_CONV) != 0 && smem2 <= 48 * 1024) {  // shared-memory staged tap window
+      dim3 grid((Wp + F32V2_XT - 1) / F32V2_XT, H, B);
+      conv3d_first_ydx_v2_kernel<<<grid, 256, smem2, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W);
+    } else {
+      const int groups = Wp * ((Dp + 3) / 4);
+      dim3 grid((groups + 63) / 64, H, B);
+      conv3d_first_ydx_kernel<<<grid, 256, 0, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W, make_fastdiv(Wp));
+    }
     if ((e = cudaPeekAtLastError()) != cudaSuccess) return (int)e;
   }
   float* cur = bufA;

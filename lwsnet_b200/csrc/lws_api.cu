@@ -38,6 +38,8 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"warp_div_mode", 0, 0, 1},       // warp coordinate normalisation: 0 = x * fl32(1/c) (Paddle 2.0 scale op), 1 = true division x / c
     {"chain_min_bands", 24, 0, 1 << 20},  // chains are used when the launch has at least this many (pair, band) units
     {"chain_debug", 0, 0, 255},       // TIMING EXPERIMENTS ONLY (results are wrong): 1 = skip dependency waits, 2 = signal without store completion
+    {"first_conv", 1, 0, 8},          // first 3D conv (1 -> C): 0 = taps from global memory (r01 kernels); 1 = C = 32 with its tap window
+                                      // staged in shared memory (default); 4 / 8 = also C = 8 staged, 4 / 8 rows per thread (slower, A/B)
 };
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::atomic<bool> g_opts_init{false};

@@ -31,6 +31,7 @@ enum {
   OPT_WARP_DIV_MODE,
   OPT_CHAIN_MIN_BANDS,
   OPT_CHAIN_DEBUG,
+  OPT_FIRST_CONV,
   OPT_COUNT
 };
 int opt(int id);

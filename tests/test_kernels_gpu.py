@@ -267,6 +267,28 @@ def test_conv3d_stack_vs_fp64_oracle(C, B, D, H, W, conv3d_path):
     assert err.max().item() <= 2.5 * floor + 1e-6, f"max err {err.max().item():.3e} vs fp32 oracle {floor:.3e}"
 
 
+@pytest.mark.parametrize("C,B,D,H,W", [(32, 2, 24, 46, 154), (8, 2, 9, 92, 308), (8, 1, 9, 13, 150), (32, 1, 48, 9, 70), (8, 1, 3, 5, 9)])
+def test_first_conv_versions_bit_identical(C, B, D, H, W):
+    """The first 1 -> C conv with its tap window staged in shared memory (option first_conv = 8 / 4) performs the same FMAs in the
+    same order as the version that reads its taps from global memory (first_conv = 0): identical stack output bits."""
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200.submodules import post_3dconvs
+    onet = O.post_3dconvs(4, C)
+    holder = torch.nn.Module()
+    holder.net = onet
+    O.kaiming_normal_init_(holder, 31)
+    O.randomize_bn_(holder, 32)
+    net = post_3dconvs(4, C)
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net = net.cuda()
+    x = (rnd(33, B, D, H, W, scale=6.0).abs()).cuda()
+    with ops().options(first_conv=0):
+        ref = net.run(x, add_skip=True).clone()
+    for ver in (1, 8, 4):
+        with ops().options(first_conv=ver):
+            assert torch.equal(net.run(x, add_skip=True), ref), ver
+
+
 # ------------------------------------------------------------------------------------------------ a8 + a9
 # Two implementations: channels-last tcgen05 split-fp16 (default) and the fp32 FFMA kernels (option "refine_tc" = 0).  Same bars
 # for both (measured r02: tensor-core max |d| 1.07x the fp32 oracle's own max error, FFMA 0.95x).

@@ -221,7 +221,7 @@ def kernel_probes(model, pk, B=16):
         per = (D * h * w + (H_IMG * W_IMG if has_prev else 0) + H_IMG * W_IMG + (nhw[0] * nhw[1] if nhw else 0)) * 4
         s = sets(nsets(B * per), (B, D, h, w), (B, 1, H_IMG, W_IMG), scale=8.0)
         o = torch.empty((B, 1, H_IMG, W_IMG), device=dev)
-        us = time_rotating(lambda i: ops.regression_tail(s[i][0], s[i][1] if has_prev else None, H_IMG, W_IMG, 0.0, 1.0, next_hw=nhw, out=o),
+        us = time_rotating(lambda i: ops.regression_tail(s[i][0], s[i][1] if has_prev else None, H_IMG, W_IMG, 0.0, 1.0, next_hw=nhw, out=o, fused=True),
                            len(s))
         add(f"TAIL regression_tail [{B},{D},{h},{w}] -> pred [{B},1,368,1232]{' + prev' if has_prev else ''}{' + next wflow' if nhw else ''} "
             "(K4 + K5 + K2a fused)", us, B * per)

@@ -60,6 +60,8 @@ LWS_API const char* lws_version(void);
  *                         division = scale op), 1 = IEEE division
  *   "first_conv"      1   first 1 -> C conv of a 3D stack: 0 = taps read from global memory, 1 = C = 32 with the tap window staged
  *                         in shared memory (default), 4 / 8 = C = 8 staged as well (measured slower; A/B)
+ *   "fused_tail"      0   hint for hosts: run the stage tail through lws_regression_tail_f32 (one kernel) instead of the three
+ *                         stand-alone entries.  Bit-identical; measured slower at 24 pairs per launch (profiles/r02_tail_ab.txt)
  *   "c8_v1" 0, "c8_chunk" 0, "k1_dt" 8   developer A/B switches of the C = 8 stack and the stage-1 volume kernel
  *   "chain_debug"     0   TIMING EXPERIMENTS ONLY (wrong results): chain kernel without dependency waits */
 LWS_API int lws_set_option(const char* key, int value);

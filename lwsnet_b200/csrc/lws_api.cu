@@ -40,6 +40,8 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"chain_debug", 0, 0, 255},       // TIMING EXPERIMENTS ONLY (results are wrong): 1 = skip dependency waits, 2 = signal without store completion
     {"first_conv", 1, 0, 8},          // first 3D conv (1 -> C): 0 = taps from global memory (r01 kernels); 1 = C = 32 with its tap window
                                       // staged in shared memory (default); 4 / 8 = also C = 8 staged, 4 / 8 rows per thread (slower, A/B)
+    {"fused_tail", 0, 0, 1},          // stage tail (softmax regression + upsample + skip + next wflow) as ONE kernel instead of three.
+                                      // Off by default: bit-identical but slower at the engine's micro-batch (profiles/r02_tail_ab.txt)
 };
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::atomic<bool> g_opts_init{false};

@@ -32,6 +32,7 @@ enum {
   OPT_CHAIN_MIN_BANDS,
   OPT_CHAIN_DEBUG,
   OPT_FIRST_CONV,
+  OPT_FUSED_TAIL,
   OPT_COUNT
 };
 int opt(int id);

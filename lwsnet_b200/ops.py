@@ -243,11 +243,12 @@ def scale_upsample_add(low: torch.Tensor, prev: Optional[torch.Tensor], H: int, 
 
 
 def regression_tail(cost: torch.Tensor, prev: Optional[torch.Tensor], H: int, W: int, start: float, step: float = 1.0,
-                    next_hw: Optional[tuple] = None, out: Optional[torch.Tensor] = None, fused: bool = True):
+                    next_hw: Optional[tuple] = None, out: Optional[torch.Tensor] = None, fused: Optional[bool] = None):
     """Tail of one stage-loop iteration (reference models/models.py:142-156) and the head of the next (:119-121):
     pred = upsample(softmax_regression(cost) * H / h) (+ prev)  and, when ``next_hw`` is given, the next stage's
-    wflow = resize(pred, next_hw) * h_next / H.  One fused launch where the shapes allow it (lws_regression_tail_f32), otherwise
-    the three stand-alone kernels; both give the same bits.  Returns (pred [B,1,H,W], wflow [B,1,hn,wn] or None)."""
+    wflow = resize(pred, next_hw) * h_next / H.  Either one fused launch (lws_regression_tail_f32, where the shapes allow it) or
+    the three stand-alone kernels; both give the same bits.  ``fused=None`` follows the library option "fused_tail" (default 0: the
+    stand-alone kernels are faster at the engine's micro-batch).  Returns (pred [B,1,H,W], wflow [B,1,hn,wn] or None)."""
     cost = _f32c(cost)
     B, D, h, w = cost.shape
     if prev is not None:
@@ -255,6 +256,8 @@ def regression_tail(cost: torch.Tensor, prev: Optional[torch.Tensor], H: int, W:
         if tuple(prev.shape) != (B, 1, H, W):
             raise ValueError("prev must be [B,1,H,W]")
     hn, wn = (int(next_hw[0]), int(next_hw[1])) if next_hw is not None else (0, 0)
+    if fused is None:
+        fused = get_option("fused_tail") != 0
     if fused and lib.lws_regression_tail_supported(h, w, H, W, hn, wn) == 0:
         pred = out if out is not None else torch.empty((B, 1, H, W), dtype=torch.float32, device=cost.device)
         wflow = torch.empty((B, 1, hn, wn), dtype=torch.float32, device=cost.device) if next_hw is not None else None

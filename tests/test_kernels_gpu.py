@@ -187,7 +187,7 @@ def test_regression_tail_fused_is_bit_identical(B, D, h, w, H, W, nhw, start):
         cost = rnd(18, B, D, h, w, scale=scale).cuda()
         prev = rnd(19, B, 1, H, W, scale=30.0).cuda()
         for pv in (None, prev):
-            pf, wf = ops().regression_tail(cost, pv, H, W, start, 1.0, next_hw=nhw)
+            pf, wf = ops().regression_tail(cost, pv, H, W, start, 1.0, next_hw=nhw, fused=True)
             pu, wu = ops().regression_tail(cost, pv, H, W, start, 1.0, next_hw=nhw, fused=False)
             assert torch.equal(pf, pu)
             assert (wf is None and wu is None) or torch.equal(wf, wu)

@@ -219,6 +219,30 @@ LWS_API int lws_preprocess_bgr_u8(const uint8_t* img, const float* lut, float* o
                                   lws_stream_t stream);
 LWS_API int lws_disparity_to_u8(const float* disp, uint8_t* gray_or_null, uint8_t* bgr_or_null, long long n, lws_stream_t stream);
 
+/* ---- n4 (SURVEY.md 8(f) "next"): training path of the hot-path kernels (reference train.py:127-166) ---------------------------
+ * Backward of a1 / a4 / a6 and the multi-stage smooth-L1 loss.  Gradients are those autograd gives the reference's formulation:
+ * d|x| = sign(x) (0 at 0); bilinear sampling with zero padding differentiated w.r.t. the sampled features and the disparity.
+ * The convolution stacks' backward is not part of this tier.
+ * lws_cost_volume_l1_bwd_f32: gcost [B,maxdisp/stride,H,W] -> gL, gR [B,C,H,W]
+ * lws_warp_residual_volume_l1_bwd_f32: gcost [B,2m-1,H,W] -> gL, gR [B,C,H,W] (gR is zero-filled here, then accumulated with
+ *   atomics: the summation order, hence the last bits, may vary from run to run), gdisp [B,1,H,W]
+ * lws_softmax_regression_bwd_f32: cost [B,D,H,W], glow [B,1,H,W] -> gcost [B,D,H,W]
+ * lws_smooth_l1_multistage_loss_f32: out[s] = weights[s] * mean_{gt < maxdisp} smooth_l1(preds[s] - gt), s < n_stages <= 4, and
+ *   out[4] = number of masked pixels (all losses 0 when it is 0: the reference skips such batches, train.py:139-140);
+ *   grads[s] (optional) = d out[s] / d preds[s].  preds / grads: HOST arrays of n_stages device pointers to n floats each;
+ *   weights: HOST array; out: DEVICE float[5]; deterministic (fixed reduction order). */
+LWS_API int lws_cost_volume_l1_bwd_f32(const float* L, const float* R, const float* gcost, float* gL, float* gR, int B, int C, int H,
+                                       int W, int maxdisp, int stride, lws_stream_t stream);
+LWS_API int lws_warp_residual_volume_l1_bwd_f32(const float* L, const float* R, const float* disp, const float* gcost, float* gL,
+                                                float* gR, float* gdisp, int B, int C, int H, int W, int m, int stride,
+                                                lws_stream_t stream);
+LWS_API int lws_softmax_regression_bwd_f32(const float* cost, const float* glow, float* gcost, int B, int D, int H, int W, float start,
+                                           float step, lws_stream_t stream);
+LWS_API size_t lws_smooth_l1_loss_workspace_bytes(long long n);
+LWS_API int lws_smooth_l1_multistage_loss_f32(const float* const* preds, const float* gt, const float* weights, int n_stages,
+                                              long long n, float maxdisp, float* out, float* const* grads_or_null, void* ws,
+                                              size_t ws_bytes, lws_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,13 @@ SIGNATURES = {
     "lws_refinement2_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lws_refinement2_f32": (c_int, [_fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_void_p]),
     "lws_disparity_regression_f32": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "lws_cost_volume_l1_bwd_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "lws_warp_residual_volume_l1_bwd_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                    c_void_p]),
+    "lws_softmax_regression_bwd_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "lws_smooth_l1_loss_workspace_bytes": (c_size_t, [c_longlong]),
+    "lws_smooth_l1_multistage_loss_f32": (c_int, [_pp, _fp, POINTER(c_float), c_int, c_longlong, c_float, _fp, _pp, _fp, c_size_t,
+                                                  c_void_p]),
     "lws_preprocess_bgr_u8": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_disparity_to_u8": (c_int, [_fp, _fp, _fp, c_longlong, c_void_p]),
     "lws_feature_extraction_packed_floats": (c_size_t, []),

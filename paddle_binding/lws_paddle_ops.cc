@@ -188,8 +188,59 @@ std::vector<paddle::Tensor> DisparityToU8(const paddle::Tensor& disp) {
   return {gray, bgr};
 }
 
+// ---- n4: backward of a1 / a4 / a6 (registered as the grad ops of the forward ops) and the loss of train.py:145-155 --------------
+std::vector<paddle::Tensor> CostVolumeL1Grad(const paddle::Tensor& L, const paddle::Tensor& R, const paddle::Tensor& gcost, int maxdisp,
+                                             int stride) {
+  const auto s = L.shape();
+  auto gL = paddle::empty_like(L), gR = paddle::empty_like(R);
+  lws_check(lws_cost_volume_l1_bwd_f32(L.data<float>(), R.data<float>(), gcost.data<float>(), gL.data<float>(), gR.data<float>(),
+                                       i32(s[0]), i32(s[1]), i32(s[2]), i32(s[3]), maxdisp, stride, L.stream()),
+            "lws_cost_volume_l1_bwd_f32");
+  return {gL, gR};
+}
+std::vector<paddle::Tensor> WarpResidualVolumeL1Grad(const paddle::Tensor& L, const paddle::Tensor& R, const paddle::Tensor& disp,
+                                                     const paddle::Tensor& gcost, int maxdisp, int stride) {
+  const auto s = L.shape();
+  auto gL = paddle::empty_like(L), gR = paddle::empty_like(R), gdisp = paddle::empty_like(disp);
+  lws_check(lws_warp_residual_volume_l1_bwd_f32(L.data<float>(), R.data<float>(), disp.data<float>(), gcost.data<float>(),
+                                                gL.data<float>(), gR.data<float>(), gdisp.data<float>(), i32(s[0]), i32(s[1]),
+                                                i32(s[2]), i32(s[3]), maxdisp, stride, L.stream()),
+            "lws_warp_residual_volume_l1_bwd_f32");
+  return {gL, gR, gdisp};
+}
+std::vector<paddle::Tensor> SoftmaxRegressionGrad(const paddle::Tensor& cost, const paddle::Tensor& glow, float start, float step) {
+  const auto s = cost.shape();
+  auto gcost = paddle::empty_like(cost);
+  lws_check(lws_softmax_regression_bwd_f32(cost.data<float>(), glow.data<float>(), gcost.data<float>(), i32(s[0]), i32(s[1]),
+                                           i32(s[2]), i32(s[3]), start, step, cost.stream()),
+            "lws_softmax_regression_bwd_f32");
+  return {gcost};
+}
+// loss[s] = w_s * smooth_l1(pred_s[gt < maxdisp], gt[gt < maxdisp], mean) for the four stage outputs, with their gradients
+std::vector<paddle::Tensor> SmoothL1MultistageLoss(const paddle::Tensor& p0, const paddle::Tensor& p1, const paddle::Tensor& p2,
+                                                   const paddle::Tensor& p3, const paddle::Tensor& gt, float w0, float w1, float w2,
+                                                   float w3, float maxdisp) {
+  int64_t n = 1;
+  for (auto d : gt.shape()) n *= d;
+  auto out = paddle::empty({5}, paddle::DataType::FLOAT32, gt.place());
+  auto g0 = paddle::empty_like(p0), g1 = paddle::empty_like(p1), g2 = paddle::empty_like(p2), g3 = paddle::empty_like(p3);
+  const float* preds[4] = {p0.data<float>(), p1.data<float>(), p2.data<float>(), p3.data<float>()};
+  float* grads[4] = {g0.data<float>(), g1.data<float>(), g2.data<float>(), g3.data<float>()};
+  const float w[4] = {w0, w1, w2, w3};
+  const size_t ws_bytes = lws_smooth_l1_loss_workspace_bytes(n);
+  auto ws = scratch(ws_bytes, gt);
+  lws_check(lws_smooth_l1_multistage_loss_f32(preds, gt.data<float>(), w, 4, n, maxdisp, out.data<float>(), grads, ws.data<uint8_t>(),
+                                              ws_bytes, gt.stream()),
+            "lws_smooth_l1_multistage_loss_f32");
+  return {out, g0, g1, g2, g3};
+}
+
 }  // namespace
 
+PD_BUILD_GRAD_OP(lws_cost_volume_l1).Inputs({"L", "R", "Cost@GRAD"}).Outputs({"L@GRAD", "R@GRAD"}).Attrs({"maxdisp: int", "stride: int"}).SetKernelFn(PD_KERNEL(CostVolumeL1Grad));
+PD_BUILD_GRAD_OP(lws_warp_residual_volume_l1).Inputs({"L", "R", "Disp", "Cost@GRAD"}).Outputs({"L@GRAD", "R@GRAD", "Disp@GRAD"}).Attrs({"maxdisp: int", "stride: int"}).SetKernelFn(PD_KERNEL(WarpResidualVolumeL1Grad));
+PD_BUILD_GRAD_OP(lws_softmax_regression).Inputs({"Cost", "Low@GRAD"}).Outputs({"Cost@GRAD"}).Attrs({"start: float", "step: float"}).SetKernelFn(PD_KERNEL(SoftmaxRegressionGrad));
+PD_BUILD_OP(lws_smooth_l1_multistage_loss).Inputs({"P0", "P1", "P2", "P3", "Gt"}).Outputs({"Loss", "G0", "G1", "G2", "G3"}).Attrs({"w0: float", "w1: float", "w2: float", "w3: float", "maxdisp: float"}).SetKernelFn(PD_KERNEL(SmoothL1MultistageLoss));
 PD_BUILD_OP(lws_cost_volume_l1).Inputs({"L", "R"}).Outputs({"Cost"}).Attrs({"maxdisp: int", "stride: int"}).SetKernelFn(PD_KERNEL(CostVolumeL1));
 PD_BUILD_OP(lws_disp_to_scale).Inputs({"PredFull"}).Outputs({"Wflow"}).Attrs({"h: int", "w: int"}).SetKernelFn(PD_KERNEL(DispToScale));
 PD_BUILD_OP(lws_warp_bilinear).Inputs({"X", "Disp"}).Outputs({"Out"}).SetKernelFn(PD_KERNEL(WarpBilinear));

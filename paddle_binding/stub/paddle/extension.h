@@ -36,4 +36,5 @@ struct PdOpBuilder {
 #define PD_BUILD_OP_CAT2(a, b) a##b
 #define PD_BUILD_OP_CAT(a, b) PD_BUILD_OP_CAT2(a, b)
 #define PD_BUILD_OP(name) static PdOpBuilder& PD_BUILD_OP_CAT(pd_op_builder_##name##_, __LINE__) = PdOpBuilder::Make(#name)
+#define PD_BUILD_GRAD_OP(name) static PdOpBuilder& PD_BUILD_OP_CAT(pd_grad_op_builder_##name##_, __LINE__) = PdOpBuilder::Make(#name "_grad")
 #define PD_KERNEL(fn) (&fn)

@@ -544,9 +544,20 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
     if (C == 32)
       return conv3d_stack_f16(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
                               layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
-    if (C == 8)
-      return conv3d_stack_c8(cost, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
-                             layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip, st);
+    if (C == 8) {
+      // option "c8_group" = G > 0: depth-first over groups of G pairs (all six layers of a group before the next group), so that a
+      // group's ping-pong activation planes are overwritten while they are still in L2 instead of streaming through HBM
+      const int G = opt(OPT_C8_GROUP) > 0 ? opt(OPT_C8_GROUP) : B;
+      const long long dhw = (long long)D * H * W;
+      for (int b0 = 0; b0 < B; b0 += G) {
+        const int nb = B - b0 < G ? B - b0 : G;
+        const int rc = conv3d_stack_c8(cost + b0 * dhw, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true),
+                                       wtc, bmid, layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out + b0 * dhw, ws, nb, D, H,
+                                       W, add_skip, st);
+        if (rc) return rc;
+      }
+      return LWS_OK;
+    }
     return LWS_ERR_UNSUPPORTED;
   }
   const size_t act = ((size_t)B * padded_width(C) * D * H * W * sizeof(float) + 255) / 256 * 256;

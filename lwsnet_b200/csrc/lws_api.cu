@@ -42,6 +42,7 @@ static const OptDesc kOpts[OPT_COUNT] = {
                                       // staged in shared memory (default); 4 / 8 = also C = 8 staged, 4 / 8 rows per thread (slower, A/B)
     {"fused_tail", 0, 0, 1},          // stage tail (softmax regression + upsample + skip + next wflow) as ONE kernel instead of three.
                                       // Off by default: bit-identical but slower at the engine's micro-batch (profiles/r02_tail_ab.txt)
+    {"c8_group", 0, 0, 4096},         // C = 8 stacks: depth-first over groups of this many pairs (0 = whole batch layer by layer)
 };
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::atomic<bool> g_opts_init{false};

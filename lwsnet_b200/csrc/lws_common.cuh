@@ -33,6 +33,7 @@ enum {
   OPT_CHAIN_DEBUG,
   OPT_FIRST_CONV,
   OPT_FUSED_TAIL,
+  OPT_C8_GROUP,
   OPT_COUNT
 };
 int opt(int id);

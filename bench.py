@@ -535,7 +535,8 @@ def run_ours(args, rank, world, local_rank):
                    "library_options": {**{k: ops.get_option(k) for k in ("conv3d_tc", "refine_tc", "refine_chain")}, **lib_opts},
                    "numerics": "fp32 storage at the ABI; conv stacks and pointwise convs on tcgen05 with split-fp16 operands "
                                "(x = hi + lo*2^-11, 3 exact products, fp32 accumulation)",
-                   "tflops_equiv": round(value * GFLOP_PER_PAIR[args.config] / 1e3, 2)},
+                   "tflops_equiv": round(value * GFLOP_PER_PAIR[args.config] / 1e3, 2),
+                   "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -100,6 +100,9 @@ class StereoEngine:
         self._pack_state = None
         self._h2d = torch.cuda.Stream(self.device)
         self._d2h = torch.cuda.Stream(self.device)
+        # ONE stream for every warm-up and capture of this engine: scratch buffers are keyed by (device, stream) in ops.workspace,
+        # so all graphs of the engine share one set (their replays are serialised on the caller's stream anyway)
+        self._cap = torch.cuda.Stream(self.device)
 
     # ------------------------------------------------------------------------------------------ device-resident
     def _forward_into(self, left, right, out, user=None):
@@ -130,7 +133,7 @@ class StereoEngine:
             left, right = both[:n], both[n:]
             out = torch.empty((4, n, 1, H, W), device=dev)
             user = torch.empty((n, 4, H, W), device=dev)
-            s = torch.cuda.Stream(dev)
+            s = self._cap
             s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s):
                 for _ in range(2):  # warm-up: cudaFuncSetAttribute, workspace growth
@@ -139,7 +142,7 @@ class StereoEngine:
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES[0]
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=s):
                 self._forward_into(left, right, out, user)
             self._graph_launches[id(graph)] = ops.LAUNCHES[0] - n0
             g = (graph, left, right, out, user)

@@ -116,6 +116,17 @@ LWS_API int lws_conv3d_stack_launches(int C, int layers);
 LWS_API int lws_conv3d_stack_f32(const float* cost, const float* packed_weights, float* out, void* ws, size_t ws_bytes, int B,
                          int D, int H, int W, int C, int layers, int add_skip, lws_stream_t stream);
 
+/* a2 + a5 in one call (north_star item 2: "volume build fused into the first conv"): stage 1 of LWSNet.forward,
+ * models/models.py:126-138 with _build_volume_2d (models/models.py:58-76) computed inside the first conv kernel's shared-memory
+ * tap window.  L,R [B,Cf,H,W] features, maxdisp = the stage's disparity count D (stride 1); cost_out [B,D,H,W] receives the raw
+ * volume (the skip input), out [B,D,H,W] the stack's result; bit-identical to lws_cost_volume_l1_f32 + lws_conv3d_stack_f32.
+ * _supported returns LWS_OK when the fused kernel applies (C = 32 tensor-core path, even W, window fits in shared memory),
+ * LWS_ERR_UNSUPPORTED otherwise -- the caller then issues the two calls. */
+LWS_API int lws_cost_volume_conv3d_stack_supported(int B, int Cf, int H, int W, int maxdisp, int C, int layers);
+LWS_API int lws_cost_volume_conv3d_stack_f32(const float* L, const float* R, const float* packed_weights, float* cost_out,
+                                     float* out, void* ws, size_t ws_bytes, int B, int Cf, int H, int W, int maxdisp, int C,
+                                     int layers, int add_skip, lws_stream_t stream);
+
 /* One BN-folded C -> C layer of the stack (out = ReLU(conv3x3x3(in, w_folded) + bias)), in/out [B,C,D,H,W] post-activation,
  * w_folded [Cin][27][Cout].  The stack's dominant kernel on its own: for per-layer tests and for timing it in isolation. */
 LWS_API int lws_conv3d_bnrelu_layer_f32(const float* in, const float* w_folded, const float* bias, float* out, int B, int C,

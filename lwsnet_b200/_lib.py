@@ -35,6 +35,9 @@ SIGNATURES = {
     "lws_conv3d_stack_launches": (c_int, [c_int, c_int]),
     "lws_conv3d_stack_f32": (c_int, [_fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
+    "lws_cost_volume_conv3d_stack_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "lws_cost_volume_conv3d_stack_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                 c_int, c_int, c_void_p]),
     "lws_conv3d_bnrelu_layer_f32": (c_int, [_fp, _fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "lws_softmax_regression_f32": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "lws_scale_upsample_add_f32": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -716,6 +716,165 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ---- north_star item 2: the stage-1 volume build FUSED into the first conv ------------------------------------------------------
+// cost[b,d,y,x] = sum_c |L[b,c,y,x] - R[b,c,y,x-d]| (LWSNet._build_volume_2d, models/models.py:58-76) is computed straight into the
+// shared-memory tap window of the first 1 -> 32 conv (post_3dconvs, models/submodules.py:216-218): a block = (TY = 4 output rows,
+// 64 padded columns, pair) builds rows y0-1 .. y0+TY of the volume with the register-window scheme of cost_volume.cu (a thread-tile
+// = 1 row x 4 pixels x 8 disparities, 64-bit loads of L and of the aligned R window, 2*C FADD-class operations per value), writes
+// the rows it owns to HBM once (the skip connection of models/models.py:137 needs the raw volume) and keeps ReLU(BN_0(cost)) for the
+// conv.  The volume is rebuilt (TY+2)/TY = 1.5x (halo rows), which costs ~8 % more instructions than the conv alone; in exchange the
+// stand-alone volume launch and its re-read disappear.  Same FMA order as the unfused kernels: bit-identical.
+constexpr int FUS_TY = 4;
+template <int DT>
+__global__ void __launch_bounds__(256, 2)
+    cost_first_conv_fused_kernel(const float* __restrict__ L, const float* __restrict__ R, float* __restrict__ cost,
+                                 const float* __restrict__ w /*[27][32]*/, const float* __restrict__ bias, const float* __restrict__ affine,
+                                 uint4* __restrict__ out, int Cf, int D, int H, int W) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* sW = smem_f;             // [27][32]
+  float* sIn = smem_f + 27 * 32;  // [TY + 2 rows][NP planes][66 cols]: ReLU(BN_0(cost)), zero outside the volume
+  constexpr int TC = F32V2_XT + 2, TR = FUS_TY + 2;
+  const int Wp = W + 2, Dp = D + 2;
+  const int ngd = (Dp + 3) >> 2;
+  const int NP = 4 * ngd + 2;  // tile plane pi holds input plane d = pi - 2
+  const int y0 = blockIdx.y * FUS_TY, b = blockIdx.z;
+  const int xc0 = blockIdx.x * F32V2_XT;
+  const int tid = threadIdx.x;
+  const long long hw = (long long)H * W;
+  for (int i = tid; i < 27 * 32; i += 256) sW[i] = __ldg(w + i);
+  for (int i = tid; i < TR * NP * TC; i += 256) sIn[i] = 0.f;
+  __syncthreads();
+  {
+    // ---- phase 1: the cost window.  thread-tile = (row r, pixel quad xq, disparity tile dt of DT); window column c <-> x = xc0 - 2 + c
+    const float s0 = __ldg(affine), t0 = __ldg(affine + 1);
+    constexpr int NQ = (TC + 3) / 4;  // 17 pixel quads (the last one covers 2 columns beyond the window)
+    const int ndt = (D + DT - 1) / DT;
+    const float* Lb = L + (long long)b * Cf * hw;
+    const float* Rb = R + (long long)b * Cf * hw;
+    float* cb = cost + (long long)b * D * hw;
+    for (int tile = tid; tile < TR * NQ * ndt; tile += 256) {
+      const int dt = tile % ndt, rq = tile / ndt, xq = rq % NQ, r = rq / NQ;
+      const int yy = y0 + r - 1, x0 = xc0 - 2 + xq * 4, d0 = dt * DT;
+      if ((unsigned)yy >= (unsigned)H || x0 >= W || x0 + 3 < 0) continue;  // rows / quads outside the image stay zero
+      const float* Lp = Lb + (long long)yy * W + x0;
+      const int xs = x0 - d0 - DT;  // wv[i] = R[xs + i]; R[x0 + p - (d0 + j)] = wv[p - j + DT]
+      const float* Rp = Rb + (long long)yy * W + xs;
+      constexpr int NW = (DT + 4) / 2;
+      bool okw[NW];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) okw[i] = xs + 2 * i >= 0 && xs + 2 * i < W;  // xs and W are even: a pair is wholly in or out
+      const bool okl0 = x0 >= 0, okl1 = x0 + 2 < W;  // x0 is even
+      float acc[4][DT];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < DT; ++j) acc[p][j] = 0.f;
+      for (int c = 0; c < Cf; ++c) {
+        const float2 a = okl0 ? __ldg(reinterpret_cast<const float2*>(Lp + c * hw)) : make_float2(0.f, 0.f);
+        const float2 bq = okl1 ? __ldg(reinterpret_cast<const float2*>(Lp + c * hw + 2)) : make_float2(0.f, 0.f);
+        const float l[4] = {a.x, a.y, bq.x, bq.y};
+        float wv[DT + 4];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const float2 v = okw[i] ? __ldg(reinterpret_cast<const float2*>(Rp + c * hw) + i) : make_float2(0.f, 0.f);
+          wv[2 * i] = v.x, wv[2 * i + 1] = v.y;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int j = 0; j < DT; ++j) acc[p][j] += fabsf(l[p] - wv[p - j + DT]);
+      }
+      const bool own_row = r >= 1 && r <= FUS_TY;  // rows y0 .. y0+TY-1 belong to this block (the halo rows to its neighbours)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int col = xq * 4 + p, xx = x0 + p;
+        if (col >= TC || (unsigned)xx >= (unsigned)W) continue;
+        const bool own = own_row && col >= 1 && col <= F32V2_XT;  // x = xp - 1 for this chunk's padded columns xp
+#pragma unroll
+        for (int j = 0; j < DT; ++j) {
+          const int d = d0 + j;
+          if (d >= D) break;
+          if (own) cb[(long long)d * hw + (long long)yy * W + xx] = acc[p][j];
+          sIn[(r * NP + d + 2) * TC + col] = fmaxf(fmaf(acc[p][j], s0, t0), 0.f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: the 1 -> 32 conv from the window (as conv3d_first_ydx_v2_kernel, over TY rows) ---------------------------------------
+  const int sub = tid & 3, grp = tid >> 2;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + sub * 8 + j);
+  const int ncols = min(F32V2_XT, Wp - xc0);
+  const int per_row = ngd * ncols;
+  const int nrows = min(FUS_TY, H - y0);
+  for (int item = grp; item < nrows * per_row; item += 64) {
+    const int ty = item / per_row, rem = item - ty * per_row;
+    const int dpg = rem / ncols, i = rem - dpg * ncols;
+    const int xp = xc0 + i, dp0 = dpg * 4, y = y0 + ty;
+    float2 acc[4][4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[v][j] = make_float2(0.f, 0.f);
+    const bool xborder = xp == 0 || xp == Wp - 1;
+    if (!xborder) {
+      const float* base = sIn + (ty * NP + dp0) * TC + i;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float v[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) v[r] = base[(kh * NP + r) * TC + kw];
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const float4 wa = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sW + (kd * 9 + kh * 3 + kw) * 32 + sub * 8 + 4);
+            const float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w);
+            const float2 w45 = make_float2(wb.x, wb.y), w67 = make_float2(wb.z, wb.w);
+#pragma unroll
+            for (int vd = 0; vd < 4; ++vd) {
+              const float2 t = make_float2(v[vd + kd], v[vd + kd]);
+              acc[vd][0] = __ffma2_rn(t, w01, acc[vd][0]), acc[vd][1] = __ffma2_rn(t, w23, acc[vd][1]);
+              acc[vd][2] = __ffma2_rn(t, w45, acc[vd][2]), acc[vd][3] = __ffma2_rn(t, w67, acc[vd][3]);
+            }
+          }
+        }
+      }
+    }
+    const long long row0 = (((long long)b * H + y) * Wp + xp) * Dp + dp0;
+#pragma unroll
+    for (int vd = 0; vd < 4; ++vd) {
+      const int dp = dp0 + vd;
+      if (dp >= Dp) break;
+      const bool border = xborder || dp == 0 || dp == Dp - 1;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float a0 = border ? 0.f : fmaxf(acc[vd][p].x + bv[2 * p], 0.f) * kDwsepActScale;
+        const float a1 = border ? 0.f : fmaxf(acc[vd][p].y + bv[2 * p + 1], 0.f) * kDwsepActScale;
+        const __half2 h = f2h2_sat(a0, a1);
+        const float2 f = __half22float2(h);
+        const float2 dl = split_lo2(a0, a1, f);
+        const __half2 l = f2h2_sat(dl.x, dl.y);
+        hi[p] = *reinterpret_cast<const uint32_t*>(&h), lo[p] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      out[(row0 + vd) * 8 + sub] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      out[(row0 + vd) * 8 + 4 + sub] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// 0 when the fused volume + first-conv kernel applies: stride 1, even W and even feature-channel count (64-bit loads), window fits
+int cost_first_conv_fused_supported(int Cf, int D, int H, int W) {
+  const int Dp = D + 2;
+  const size_t smem = (size_t)(27 * 32 + (FUS_TY + 2) * (4 * ((Dp + 3) / 4) + 2) * (F32V2_XT + 2)) * sizeof(float);
+  if ((W & 1) || Cf <= 0 || D <= 0 || smem > 100 * 1024 || H > 65535 * FUS_TY) return LWS_ERR_UNSUPPORTED;
+  return LWS_OK;
+}
+
 size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W) {
   const size_t rows = (size_t)B * H * (W + 2) * (D + 2);
   return 2 * (rows * 128 + 1024);
@@ -723,9 +882,10 @@ size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W) {
 
 // wtab[l]: per mid layer the Toeplitz operand table (5 tiles x 192 rows x 128 B, then scales[2]); bias_mid[l]: [32];
 // w_last_tab: operand table of the closing 32 -> 1 conv (9 blocks x 16 rows x 128 B, then scales[2])
+// featL / featR non-null: `cost` is an OUTPUT -- the stage-1 volume is built inside the first conv kernel (cost_first_conv_fused_kernel)
 int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
                      const float* const* bias_mid, int layers, const float* w_last_tab, float* out, void* ws, int B, int D, int H,
-                     int W, int add_skip, cudaStream_t st) {
+                     int W, int add_skip, cudaStream_t st, const float* featL, const float* featR, int Cf) {
   const int Wp = W + 2, Dp = D + 2;
   const long long R = (long long)H * Wp * Dp;
   if (R >= (1ll << 31) - 65536 || 128 + 2 * Dp > 256 || (long long)D * H * W >= (1ll << 31)) return LWS_ERR_UNSUPPORTED;
@@ -737,7 +897,20 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
   {
     if (H > 65535 || B > 65535) return LWS_ERR_BAD_SHAPE;
     const size_t smem2 = (size_t)(27 * 32 + 3 * (4 * ((Dp + 3) / 4) + 2) * (F32V2_XT + 2)) * sizeof(float);
-    if (opt(OPT_FIRST_CONV) != 0 && smem2 <= 48 * 1024) {  // shared-memory staged tap window
+    if (featL) {
+      if (cost_first_conv_fused_supported(Cf, D, H, W) != LWS_OK) return LWS_ERR_UNSUPPORTED;
+      const size_t smemf = (size_t)(27 * 32 + (FUS_TY + 2) * (4 * ((Dp + 3) / 4) + 2) * (F32V2_XT + 2)) * sizeof(float);
+      dim3 grid((Wp + F32V2_XT - 1) / F32V2_XT, (H + FUS_TY - 1) / FUS_TY, B);
+      if (opt(OPT_FUSE_VOLUME) != 2 && D % 12 == 0) {  // 12-disparity tiles: the 6 x 17 x D/12 tiles of a block fit one pass of its 256 threads at D = 24
+        LWS_SET_SMEM_ONCE(cost_first_conv_fused_kernel<12>, 100 * 1024);
+        cost_first_conv_fused_kernel<12><<<grid, 256, smemf, st>>>(featL, featR, const_cast<float*>(cost), w_first, b_first, affine,
+                                                                   (uint4*)bufA, Cf, D, H, W);
+      } else {
+        LWS_SET_SMEM_ONCE(cost_first_conv_fused_kernel<8>, 100 * 1024);
+        cost_first_conv_fused_kernel<8><<<grid, 256, smemf, st>>>(featL, featR, const_cast<float*>(cost), w_first, b_first, affine,
+                                                                  (uint4*)bufA, Cf, D, H, W);
+      }
+    } else if (opt(OPT_FIRST_CONV) != 0 && smem2 <= 48 * 1024) {  // shared-memory staged tap window
       dim3 grid((Wp + F32V2_XT - 1) / F32V2_XT, H, B);
       conv3d_first_ydx_v2_kernel<<<grid, 256, smem2, st>>>(cost, w_first, b_first, affine, (uint4*)bufA, D, H, W);
     } else {

@@ -29,9 +29,10 @@ int conv3d_stack_c8(const float* cost, const float* affine, const float* w_first
                     int add_skip, cudaStream_t st);
 // conv3d_f16.cu: tcgen05 split-fp16 Toeplitz-N path for C = 32
 size_t conv3d_f16_workspace_bytes(int B, int D, int H, int W);
+int cost_first_conv_fused_supported(int Cf, int D, int H, int W);
 int conv3d_stack_f16(const float* cost, const float* affine, const float* w_first, const float* b_first, const float* const* wtab,
                      const float* const* bias_mid, int layers, const float* w_last, float* out, void* ws, int B, int D, int H, int W,
-                     int add_skip, cudaStream_t st);
+                     int add_skip, cudaStream_t st, const float* featL = nullptr, const float* featR = nullptr, int Cf = 0);
 constexpr int kTcLayerFloats = 9 * 192 * 32;
 constexpr int kTcLastOff = 32768;  // C = 32: table of the closing 32 -> 1 conv inside the first mid layer's slot  // per 32->32 layer: [9 (kd,kh)][3 kw][32 hi + 32 lo rows][32 ci]
 
@@ -573,6 +574,43 @@ extern "C" int lws_conv3d_stack_f32(const float* cost, const float* packed_weigh
     default:
       return run_stack<32>(cost, packed_weights, out, bufA, bufB, B, D, H, W, layers, add_skip, st);
   }
+}
+
+// Stage 1 of the network in one call: the L1 volume (a2) is built inside the stack's first conv kernel (north_star item 2).
+// cost_out receives the raw volume (it is the skip input, models/models.py:137, and what a caller of _build_volume_2d gets).
+extern "C" int lws_cost_volume_conv3d_stack_supported(int B, int Cf, int H, int W, int maxdisp, int C, int layers) {
+  using namespace lws;
+  if (B <= 0 || Cf <= 0 || H <= 0 || W <= 0 || maxdisp <= 0 || layers <= 0 || layers > 16 || B > 65535) return LWS_ERR_BAD_SHAPE;
+  if (C != 32 || !use_tc_path(C) || 128 + 2 * (maxdisp + 2) > 256) return LWS_ERR_UNSUPPORTED;
+  return cost_first_conv_fused_supported(Cf, maxdisp, H, W);
+}
+
+extern "C" int lws_cost_volume_conv3d_stack_f32(const float* L, const float* R, const float* packed_weights, float* cost_out,
+                                                float* out, void* ws, size_t ws_bytes, int B, int Cf, int H, int W, int maxdisp,
+                                                int C, int layers, int add_skip, lws_stream_t stream) {
+  using namespace lws;
+  LWS_CHECK_PTR(L);
+  LWS_CHECK_PTR(R);
+  LWS_CHECK_PTR(packed_weights);
+  LWS_CHECK_PTR(cost_out);
+  LWS_CHECK_PTR(out);
+  LWS_CHECK_PTR(ws);
+  const int rc = lws_cost_volume_conv3d_stack_supported(B, Cf, H, W, maxdisp, C, layers);
+  if (rc) return rc;
+  const int D = maxdisp;
+  if (ws_bytes < lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers)) return LWS_ERR_WORKSPACE_TOO_SMALL;
+  if ((((uintptr_t)ws) | ((uintptr_t)packed_weights)) & 15) return LWS_ERR_BAD_ALIGN;
+  if ((((uintptr_t)L) | ((uintptr_t)R)) & 7) return LWS_ERR_BAD_ALIGN;
+  const float* pk = packed_weights;
+  const float* wtc[16];
+  const float* bmid[16];
+  for (int l = 0; l < layers; ++l) {
+    wtc[l] = pk + packed_tc_offset(C, layers, l);
+    bmid[l] = pk + packed_offset(C, layers, l + 1, true);
+  }
+  return conv3d_stack_f16(cost_out, pk, pk + packed_offset(C, layers, 0, false), pk + packed_offset(C, layers, 0, true), wtc, bmid,
+                          layers, pk + packed_tc_offset(C, layers, 0) + kTcLastOff, out, ws, B, D, H, W, add_skip,
+                          (cudaStream_t)stream, L, R, Cf);
 }
 
 // One BN-folded C -> C layer of the stack on its own (the kernel the stack spends its time in): used by bench.py to

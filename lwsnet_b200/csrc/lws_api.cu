@@ -43,6 +43,8 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"fused_tail", 0, 0, 1},          // stage tail (softmax regression + upsample + skip + next wflow) as ONE kernel instead of three.
                                       // Off by default: bit-identical but slower at the engine's micro-batch (profiles/r02_tail_ab.txt)
     {"c8_group", 0, 0, 4096},         // C = 8 stacks: depth-first over groups of this many pairs (0 = whole batch layer by layer)
+    {"fuse_volume", 1, 0, 2},         // stage 1 through lws_cost_volume_conv3d_stack_f32 (volume built inside the first conv kernel; the
+                                      // model reads this, profiles/r02_fuse_volume_ab.txt): 0 = two calls, 1 = fused, 2 = fused with 8-disparity tiles
 };
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::atomic<bool> g_opts_init{false};

@@ -34,6 +34,7 @@ enum {
   OPT_FIRST_CONV,
   OPT_FUSED_TAIL,
   OPT_C8_GROUP,
+  OPT_FUSE_VOLUME,
   OPT_COUNT
 };
 int opt(int id);

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import LwsError
+from ._lib import LwsError, get_option
 from .submodules import BN_EPS, _pack_key, feature_extraction, post_3dconvs, refinement1, refinement2, refinement_tensor_list
 
 
@@ -96,10 +96,17 @@ class LWSNet(nn.Module):
                 wflow = ops.disp_to_scale(prev_pred, feat_l.shape[2], feat_l.shape[3])             # models.py:119-121
             cost = self._build_volume_2d3(feat_l, feat_r, self.maxdisplist[scale], wflow, stride=1)  # :123-127
             start = float(-self.maxdisplist[scale] + 1)
+            cost = self.volume_postprocess[scale].run(cost, add_skip=True)                          # :136-138
         else:
-            cost = self._build_volume_2d(feat_l, feat_r, self.maxdisplist[scale], stride=1)          # :131-134
             start = 0.0
-        cost = self.volume_postprocess[scale].run(cost, add_skip=True)                               # :136-138
+            vp, D = self.volume_postprocess[scale], self.maxdisplist[scale]
+            B, Cf, h, w = feat_l.shape
+            if get_option("fuse_volume") and ops.cost_volume_conv3d_stack_supported(B, Cf, h, w, D, vp.channels, vp.layers):
+                # :131-138 in one call: the volume is built inside the first conv kernel's shared-memory tap window
+                _, cost = ops.cost_volume_conv3d_stack(feat_l, feat_r, D, vp.packed(feat_l.device), vp.channels, vp.layers)
+            else:
+                cost = self._build_volume_2d(feat_l, feat_r, D, stride=1)                            # :131-134
+                cost = vp.run(cost, add_skip=True)                                                   # :136-138
         # :142 / :151-152 softmax + regression, :145-148 / :153-156 rescale + upsample + skip, and the next stage's :119-121
         pred, wflow_next = ops.regression_tail(cost, prev_pred if scale > 0 else None, img_h, img_w, start, 1.0, next_hw=next_hw,
                                                out=out)

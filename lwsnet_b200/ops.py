@@ -200,6 +200,30 @@ def conv3d_stack(cost: torch.Tensor, packed: torch.Tensor, C: int, layers: int, 
     return out
 
 
+def cost_volume_conv3d_stack_supported(B: int, Cf: int, H: int, W: int, maxdisp: int, C: int, layers: int) -> bool:
+    """True when the fused stage-1 call applies (C = 32 tensor-core path, even W, tap window fits in shared memory)."""
+    return int(lib.lws_cost_volume_conv3d_stack_supported(B, Cf, H, W, maxdisp, C, layers)) == 0
+
+
+def cost_volume_conv3d_stack(L: torch.Tensor, R: torch.Tensor, maxdisp: int, packed: torch.Tensor, C: int, layers: int,
+                             add_skip: bool = True):
+    """Stage 1 in one call: _build_volume_2d (reference models/models.py:58-76) built inside the first conv kernel of
+    post_3dconvs (+ skip, models/models.py:136-138).  Returns (raw volume [B,D,H,W], stack output [B,D,H,W])."""
+    L, R = _f32c(L), _f32c(R)
+    B, Cf, H, W = L.shape
+    D = int(maxdisp)
+    cost = torch.empty((B, D, H, W), dtype=torch.float32, device=L.device)
+    out = torch.empty_like(cost)
+    nbytes = int(lib.lws_conv3d_stack_workspace_bytes(B, D, H, W, C, layers))
+    ws = workspace(L.device, "conv3d", nbytes)
+    with torch.cuda.device(L.device):
+        check(lib.lws_cost_volume_conv3d_stack_f32(_ptr(L, "L"), _ptr(R, "R"), _ptr(packed, "packed"), _ptr(cost, "cost"),
+                                                   _ptr(out, "out"), ctypes.c_void_p(ws.data_ptr()), nbytes, B, Cf, H, W, D, C,
+                                                   layers, int(add_skip), _stream(L)), "lws_cost_volume_conv3d_stack_f32")
+    LAUNCHES[0] += int(lib.lws_conv3d_stack_launches(C, layers))
+    return cost, out
+
+
 def conv3d_bnrelu_layer(x: torch.Tensor, w_folded: torch.Tensor, bias: torch.Tensor,
                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One BN-folded C->C layer: ReLU(conv3x3x3(x, w) + bias); x [B,C,D,H,W], w_folded [C][27][C]."""

@@ -78,6 +78,21 @@ std::vector<paddle::Tensor> Conv3dStack(const paddle::Tensor& cost, const paddle
   return {out};
 }
 
+// ---- a2 + a5 fused: stage 1 of LWSNet.forward (models/models.py:131-138), the volume built inside the first conv kernel ----------
+std::vector<paddle::Tensor> CostVolumeConv3dStack(const paddle::Tensor& L, const paddle::Tensor& R, const paddle::Tensor& packed,
+                                                  int maxdisp, int C, int layers, int add_skip) {
+  const auto s = L.shape();  // [B,Cf,H,W]
+  auto cost = paddle::empty({s[0], maxdisp, s[2], s[3]}, paddle::DataType::FLOAT32, L.place());
+  auto out = paddle::empty_like(cost);
+  const size_t ws_bytes = lws_conv3d_stack_workspace_bytes(i32(s[0]), maxdisp, i32(s[2]), i32(s[3]), C, layers);
+  auto ws = scratch(ws_bytes, L);
+  lws_check(lws_cost_volume_conv3d_stack_f32(L.data<float>(), R.data<float>(), packed.data<float>(), cost.data<float>(),
+                                             out.data<float>(), ws.data<uint8_t>(), ws_bytes, i32(s[0]), i32(s[1]), i32(s[2]),
+                                             i32(s[3]), maxdisp, C, layers, add_skip, L.stream()),
+            "lws_cost_volume_conv3d_stack_f32");
+  return {cost, out};
+}
+
 // ---- a6: F.softmax(-cost, axis=1) + disparity_regression (models/models.py:142,151-152,167-179) --------------------------------
 std::vector<paddle::Tensor> SoftmaxRegression(const paddle::Tensor& cost, float start, float step) {
   const auto s = cost.shape();  // [B,D,H,W]
@@ -246,6 +261,7 @@ PD_BUILD_OP(lws_disp_to_scale).Inputs({"PredFull"}).Outputs({"Wflow"}).Attrs({"h
 PD_BUILD_OP(lws_warp_bilinear).Inputs({"X", "Disp"}).Outputs({"Out"}).SetKernelFn(PD_KERNEL(WarpBilinear));
 PD_BUILD_OP(lws_warp_residual_volume_l1).Inputs({"L", "R", "Disp"}).Outputs({"Cost"}).Attrs({"maxdisp: int", "stride: int"}).SetKernelFn(PD_KERNEL(WarpResidualVolumeL1));
 PD_BUILD_OP(lws_conv3d_stack).Inputs({"Cost", "Packed"}).Outputs({"Out"}).Attrs({"C: int", "layers: int", "add_skip: int"}).SetKernelFn(PD_KERNEL(Conv3dStack));
+PD_BUILD_OP(lws_cost_volume_conv3d_stack).Inputs({"L", "R", "Packed"}).Outputs({"Cost", "Out"}).Attrs({"maxdisp: int", "C: int", "layers: int", "add_skip: int"}).SetKernelFn(PD_KERNEL(CostVolumeConv3dStack));
 PD_BUILD_OP(lws_softmax_regression).Inputs({"Cost"}).Outputs({"Low"}).Attrs({"start: float", "step: float"}).SetKernelFn(PD_KERNEL(SoftmaxRegression));
 PD_BUILD_OP(lws_disparity_regression).Inputs({"Prob"}).Outputs({"Out"}).Attrs({"start: float", "step: float"}).SetKernelFn(PD_KERNEL(DisparityRegression));
 PD_BUILD_OP(lws_scale_upsample_add).Inputs({"Low", "Prev"}).Outputs({"Pred"}).Attrs({"H: int", "W: int", "has_prev: int"}).SetKernelFn(PD_KERNEL(ScaleUpsampleAdd));

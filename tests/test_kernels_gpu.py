@@ -289,6 +289,40 @@ def test_first_conv_versions_bit_identical(C, B, D, H, W):
             assert torch.equal(net.run(x, add_skip=True), ref), ver
 
 
+@pytest.mark.parametrize("B,Cf,D,H,W", [(2, 32, 24, 46, 154), (1, 32, 24, 7, 66), (3, 16, 12, 9, 130), (1, 32, 40, 5, 64), (1, 2, 3, 4, 6)])
+def test_fused_volume_first_conv_bit_identical(B, Cf, D, H, W):
+    """Stage 1 as ONE call (lws_cost_volume_conv3d_stack_f32: the volume is built inside the first conv kernel's shared-memory
+    window) performs the same additions / FMAs in the same order as lws_cost_volume_l1_f32 + lws_conv3d_stack_f32: identical raw
+    volume and identical stack output bits, ragged widths and heights included."""
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200.submodules import post_3dconvs
+    onet = O.post_3dconvs(4, 32)
+    holder = torch.nn.Module()
+    holder.net = onet
+    O.kaiming_normal_init_(holder, 41)
+    O.randomize_bn_(holder, 42)
+    net = post_3dconvs(4, 32)
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net = net.cuda()
+    L, R = rnd(43, B, Cf, H, W).cuda(), rnd(44, B, Cf, H, W).cuda()
+    o = ops()
+    assert o.cost_volume_conv3d_stack_supported(B, Cf, H, W, D, 32, 4)
+    cost_ref = o.cost_volume_l1(L, R, D, 1)
+    out_ref = net.run(cost_ref, add_skip=True).clone()
+    for mode in (1, 2):  # 12-disparity tiles where D % 12 == 0 / 8-disparity tiles
+        with o.options(fuse_volume=mode):
+            cost, out = o.cost_volume_conv3d_stack(L, R, D, net.packed(L.device), 32, 4)
+        assert torch.equal(cost, cost_ref), mode
+        assert torch.equal(out, out_ref), mode
+
+
+def test_fused_volume_first_conv_unsupported_cases():
+    o = ops()
+    assert not o.cost_volume_conv3d_stack_supported(1, 32, 8, 153, 24, 32, 4)   # odd W: no 64-bit row loads
+    assert not o.cost_volume_conv3d_stack_supported(1, 32, 8, 154, 9, 8, 4)     # C = 8 stack
+    assert not o.cost_volume_conv3d_stack_supported(1, 32, 8, 154, 24, 32, 0)   # no mid layer: FFMA path
+
+
 # ------------------------------------------------------------------------------------------------ a8 + a9
 # Two implementations: channels-last tcgen05 split-fp16 (default) and the fp32 FFMA kernels (option "refine_tc" = 0).  Same bars
 # for both (measured r02: tensor-core max |d| 1.07x the fp32 oracle's own max error, FFMA 0.95x).

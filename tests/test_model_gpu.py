@@ -107,6 +107,23 @@ def test_batch_shard_equivalence(models):
         assert torch.equal(full[s], torch.cat([p[s] for p in parts]))
 
 
+def test_schedule_options_bit_identical_end_to_end(models):
+    """The schedule variants (stage 1 volume fused into the first conv, one-kernel stage tail) only move work between launches:
+    every stage's output is bitwise what the default schedule produces."""
+    from lwsnet_b200 import ops
+    O, o32, o64, prod = models
+    left, right = O.synthetic_pair(2, 64, 144, seed=23, max_disp=20.0)
+    left, right = left.cuda(), right.cuda()
+    with ops.options(fuse_volume=0, fused_tail=0):
+        ref = [t.clone() for t in prod(left, right)]
+    for kw in ({"fuse_volume": 1}, {"fuse_volume": 2}, {"fused_tail": 1}, {"fuse_volume": 1, "fused_tail": 1}):
+        with ops.options(**kw):
+            out = prod(left, right)
+            torch.cuda.synchronize()
+        for s in range(4):
+            assert torch.equal(out[s], ref[s]), (kw, s)
+
+
 def test_exact_fp32_mode_end_to_end(models):
     """Options conv3d_tc=0 refine_tc=0 select the fp32 FFMA kernels everywhere: every stage within 2x the fp32 oracle's floor."""
     from lwsnet_b200 import ops

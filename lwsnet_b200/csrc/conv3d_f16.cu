@@ -53,6 +53,9 @@ struct TzArgs {
   // a strip outputs rows ct*OUTR + n*srow + [0, OUTR) and shares all but its last `G` stage boxes with tile n-1, so they stay
   // in the shared-memory ring.  srow = R gives plain linear tiling (strips of one tile).
   int srow, strip_len, total_tiles;  // total_tiles = B * ct_per_sl * strip_len, split evenly (contiguously) over the CTAs
+  int seg_len, segs_per_strip, nseg;  // segment schedule (TzSched): nseg = B * segs_per_strip * ct_per_sl
+  int dbg;  // option tz_debug, TIMING EXPERIMENTS ONLY (results are wrong): 1 = no A loads after the first ring fill, 2 = epilogue only frees
+            // the accumulator, 4 = epilogue without staging / TMA store
   FastDiv ct_per_sl;
   int nstages, G, nshift, nbtiles, nslot;
   int slot_bytes, box_bytes;
@@ -64,22 +67,40 @@ struct TzArgs {
 struct TzItem {
   int b, orow0, ntiles;
 };
-// A strip = (b, column tile ct) walked down all strip_len super lines; tiles are numbered strip-major and every CTA takes one
-// contiguous range (balanced to one tile; a CTA reloads the shared stage boxes only at the start of a (partial) strip).
-template <int OUTR>
+// A strip = (b, column tile ct) walked down all strip_len super lines.  Two ways of handing strips to the CTAs:
+//  * seg_len == 0: tiles are numbered strip-major and every CTA takes one contiguous range (balanced to one tile; a CTA reloads the
+//    shared stage boxes only at the start of a (partial) strip);
+//  * seg_len > 0: a strip is cut into segments of seg_len super lines; segments are numbered (b, segment of the strip, ct) with ct
+//    fastest and dealt round-robin, so CTAs k and k+1 walk NEIGHBOURING column tiles down the SAME super lines at the same time:
+//    the rows their boxes share (the halo of the middle-axis taps) are fetched from DRAM once and hit L2 for the neighbour.
+// NCTA = 2: a CTA pair walks the schedule together (OUTR = rows of the pair's double tile; CTA r of the pair takes its r-th half).
+template <int OUTR, int NCTA = 1>
 struct TzSched {
   int g, g1, step;
   __device__ __forceinline__ TzSched(const TzArgs& a) {
+    const int bid = blockIdx.x / NCTA, nb = gridDim.x / NCTA;
     if (a.strip_len == 1) {  // linear tiling: interleave the tiles over the CTAs (neighbouring tiles run concurrently: L2 reuse)
-      g = blockIdx.x, g1 = a.total_tiles, step = gridDim.x;
+      g = bid, g1 = a.total_tiles, step = nb;
+    } else if (a.seg_len > 0) {
+      g = bid, g1 = a.nseg, step = nb;
     } else {
-      g = (int)((long long)a.total_tiles * blockIdx.x / gridDim.x);
-      g1 = (int)((long long)a.total_tiles * (blockIdx.x + 1) / gridDim.x);
+      g = (int)((long long)a.total_tiles * bid / nb);
+      g1 = (int)((long long)a.total_tiles * (bid + 1) / nb);
       step = 0;
     }
   }
   __device__ __forceinline__ bool next(const TzArgs& a, TzItem& it) {
     if (g >= g1) return false;
+    if (a.seg_len > 0) {
+      int bs, ct;
+      fdivmod(g, a.ct_per_sl, bs, ct);
+      it.b = bs / a.segs_per_strip;
+      const int n0 = (bs - it.b * a.segs_per_strip) * a.seg_len;
+      it.ntiles = min(a.seg_len, a.strip_len - n0);
+      it.orow0 = ct * OUTR + n0 * a.srow;
+      g += step;
+      return true;
+    }
     const int strip = g / a.strip_len, n0 = g - strip * a.strip_len;
     int ct;
     fdivmod(strip, a.ct_per_sl, it.b, ct);
@@ -100,6 +121,50 @@ __device__ __forceinline__ void tz_mma(uint32_t d, uint64_t da, uint64_t db, uin
 __device__ __forceinline__ void tz_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA over M = 256 = the two CTAs' 128-row A tiles; each CTA supplies half of B's N rows from
+// its own shared memory at the descriptor's address, so the B operand bytes per CTA (the shared-memory port load) are halved.
+__device__ __forceinline__ void tz_mma2(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void tz_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+// arrive on the barrier at this offset in the pair's leader CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+constexpr int TZ_BTILE2 = 144 * 128;  // pair: a CTA's share of one weight tile = 96 rows (its half of N = 192) + 48 rows (its half of N = 96)
+
 __device__ __forceinline__ void tz_ld8(uint32_t taddr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -116,7 +181,10 @@ __device__ __forceinline__ void tz_ld8(uint32_t taddr, float* v) {
 // LAST: the C -> 1 convolution that closes the stack.  Same pipeline with N = 16 per MMA: the weight block of a (stage,
 // window) is 16 rows x [B1 | B2] with B1 = rows {t: wh_t, 8+t: wl_t} for the xh operand and B2 = rows {8+t: wh_t} for the xl
 // operand, so acc[:, t] = main and acc[:, 8+t] = corr of Toeplitz tap t; the epilogue writes fp32 NCDHW (+ skip).
-template <int TZ, int NST, int NSH, bool LAST>
+// PAIR: launched as clusters of two CTAs that walk the schedule together on double tiles (CTA r = the r-th 128-row half); the leader's
+// single thread issues every MMA for both (cta_group::2), each CTA's producer fills its own A ring and its half of the weights, each
+// CTA's epilogue drains its own TMEM.
+template <int TZ, int NST, int NSH, bool LAST, bool PAIR = false>
 __global__ void __launch_bounds__(TZ_THREADS, 1)
     tz_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut, const TzArgs a) {
@@ -124,7 +192,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;                                   // [nbtiles][24576]
-  uint8_t* sOut = sB + a.nbtiles * TZ_BTILE;             // [16384] staging tile
+  uint8_t* sOut = sB + a.nbtiles * (PAIR ? TZ_BTILE2 : TZ_BTILE);  // [16384] staging tile
   uint8_t* sA = sOut + 16384;                            // [nslot][slot_bytes]
   uint8_t* tail = sA + a.nslot * a.slot_bytes;
   float* xch = reinterpret_cast<float*>(tail);           // [4 quarters][3*TZ rows][32] boundary rows for the Toeplitz shifts
@@ -137,19 +205,31 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  constexpr int SOUTR = PAIR ? 2 * OUTR : OUTR;  // rows of a schedule tile
+  constexpr int NCTA = PAIR ? 2 : 1;
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(a_full + i, 1), mbar_init(a_empty + i, 1);
     mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, LAST ? 4 : 8);
+    for (int i = 0; i < 2; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, LAST ? 4 : 8 * NCTA);
     mbar_fence_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     tma_prefetch_desc(&mapOut);
   }
+  if (PAIR) {  // the peer's barriers must exist before anything of this CTA signals them
+    __syncthreads();
+    cluster_sync_all();
+  }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -161,7 +241,14 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one_sync()) {
-      if (LAST) {  // one box: NST*NSH blocks x 16 rows
+      if (PAIR) {  // mapB's box is 48 rows here: rows [96 r, 96 r + 96) and [48 r, 48 r + 48) of every 192-row weight tile
+        if (rank == 0) mbar_expect_tx(b_full, (uint32_t)a.nbtiles * TZ_BTILE2 * 2);
+        for (int i = 0; i < a.nbtiles; ++i) {
+          tma2_load_2d(sB + i * TZ_BTILE2, &mapB, b_full, 0, i * 192 + (int)rank * 96);
+          tma2_load_2d(sB + i * TZ_BTILE2 + 48 * 128, &mapB, b_full, 0, i * 192 + (int)rank * 96 + 48);
+          tma2_load_2d(sB + i * TZ_BTILE2 + 96 * 128, &mapB, b_full, 0, i * 192 + (int)rank * 48);
+        }
+      } else if (LAST) {  // one box: NST*NSH blocks x 16 rows
         mbar_expect_tx(b_full, (uint32_t)(NST * NSH) * 2048);
         tma_load_2d(sB, &mapB, b_full, 0, 0);
       } else {
@@ -169,15 +256,26 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         for (int i = 0; i < a.nbtiles; ++i) tma_load_2d(sB + i * TZ_BTILE, &mapB, b_full, 0, i * 192);
       }
       uint32_t slot = 0, ph = 0;  // ring position and phase of the next entry
-      TzSched<OUTR> sched(a);
+      TzSched<SOUTR, NCTA> sched(a);
         TzItem w;
         while (sched.next(a, w)) {
         for (int n = 0; n < w.ntiles; ++n) {
-          const int row0 = w.orow0 + n * a.srow - TZ;  // GEMM row 0 of the tile
+          const int row0 = w.orow0 + (int)rank * OUTR + n * a.srow - TZ;  // GEMM row 0 of the tile
           for (int s = n == 0 ? 0 : nst - a.G; s < nst; ++s) {  // later tiles of a strip only load their newest stage group
             mbar_wait(a_empty + slot, ph ^ 1);
-            mbar_expect_tx(a_full + slot, (uint32_t)a.box_bytes);
             const CUtensorMap* src = a.st_src[s] ? &mapA1 : &mapA0;
+            if (PAIR) {  // both CTAs' boxes are counted on the leader's barrier, armed by the leader for both
+              if (rank == 0) mbar_expect_tx(a_full + slot, (uint32_t)a.box_bytes * 2);
+              tma2_load_3d(sA + slot * a.slot_bytes, src, a_full + slot, 0, row0 + a.st_off[s], w.b);
+              if (++slot == nslot) slot = 0, ph ^= 1;
+              continue;
+            }
+            if ((a.dbg & 1) && ph) {  // timing experiment: the ring keeps its first contents
+              mbar_arrive(a_full + slot);
+              if (++slot == nslot) slot = 0, ph ^= 1;
+              continue;
+            }
+            mbar_expect_tx(a_full + slot, (uint32_t)a.box_bytes);
             // 3D map {32 words, R, B}: rows outside [0, R) come back as zeros (the padding of the slowest axis)
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
@@ -190,9 +288,11 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
       }
     }
   } else if (warp == 1) {
+    if (!PAIR || rank == 0) {
     // ================================ MMA issuer ================================
-    const uint32_t idesc192 = (1u << 4) | ((192u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128
-    const uint32_t idesc96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t MM = PAIR ? 256u : 128u;
+    const uint32_t idesc192 = (1u << 4) | ((192u >> 3) << 17) | ((MM >> 4) << 24);  // f16 x f16 -> f32, K-major, M = 128 (256 per pair)
+    const uint32_t idesc96 = (1u << 4) | ((96u >> 3) << 17) | ((MM >> 4) << 24);
     const uint32_t idesc16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
     const uint32_t b_lo = ((smem_u32(sB) & 0x3FFFF) >> 4) | (1u << 16);
@@ -205,7 +305,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
       bslot += k;
       if (bslot >= nslot) bslot -= nslot, bph ^= 1;
     };
-    TzSched<OUTR> sched(a);
+    TzSched<SOUTR, NCTA> sched(a);
       TzItem w;
       while (sched.next(a, w)) {
       for (int n = 0; n < w.ntiles; ++n, ++ti, advance(G)) {
@@ -230,6 +330,13 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
 #pragma unroll
                 for (int u = 0; u < 4; ++u)  // xh k-steps against B1, xl k-steps against B2, all into the same 16 columns
                   tz_mma(d_main, desc_hi | (uint64_t)(wa + 2 * u), desc_hi | (uint64_t)(wb + 2 * u), idesc16, (s | k | u) == 0 ? 0u : 1u);
+              } else if (PAIR) {
+                const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE2 >> 4) + (blk & 1) * 4;  // this CTA's half of [wh | wl]
+                const uint32_t wc = wb + ((96 * 128) >> 4);                                          // this CTA's half of wh
+                tz_mma2(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, (s | k) == 0 ? 0u : 1u);
+                tz_mma2(d_main, desc_hi | (uint64_t)(wa + 2), desc_hi | (uint64_t)(wb + 2), idesc192, 1u);
+                tz_mma2(d_main + 96, desc_hi | (uint64_t)(wa + 4), desc_hi | (uint64_t)(wc + 0), idesc96, 1u);
+                tz_mma2(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wc + 2), idesc96, 1u);
               } else {
                 const uint32_t wb = b_lo + (uint32_t)(blk >> 1) * (TZ_BTILE >> 4) + (blk & 1) * 4;  // weight block
                 tz_mma(d_main, desc_hi | (uint64_t)(wa + 0), desc_hi | (uint64_t)(wb + 0), idesc192, (s | k) == 0 ? 0u : 1u);
@@ -238,14 +345,20 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
                 tz_mma(d_main + 96, desc_hi | (uint64_t)(wa + 6), desc_hi | (uint64_t)(wb + 2), idesc96, 1u);
               }
             }
-            if (s < G || last) tz_commit(a_empty + slot);  // the other boxes are stages s - G of the next tile of the strip
-            if (s == NST - 1) tz_commit(t_full + tb);
+            if (PAIR) {
+              if (s < G || last) tz_commit2(a_empty + slot);
+              if (s == NST - 1) tz_commit2(t_full + tb);
+            } else {
+              if (s < G || last) tz_commit(a_empty + slot);  // the other boxes are stages s - G of the next tile of the strip
+              if (s == NST - 1) tz_commit(t_full + tb);
+            }
           }
           __syncwarp();
           if (++slot == nslot) slot = 0, ph ^= 1;
         }
       }
       advance(nst - G);  // the strip's last tile consumed all of its entries
+    }
     }
   } else if (LAST) {
     // ================================ epilogue of the C -> 1 layer ================================
@@ -318,15 +431,24 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
     float* xq = xch + q * (3 * TZ * 32) + hf * 16;
     const float* xn = xch + ((q + 1) & 3) * (3 * TZ * 32) + hf * 16;
     uint32_t ti = 0;
-    TzSched<OUTR> sched(a);
+    TzSched<SOUTR, NCTA> sched(a);
       TzItem w;
       while (sched.next(a, w)) {
       for (int n = 0; n < w.ntiles; ++n, ++ti) {
         const uint32_t tb = ti & 1;
-        const int orow0 = w.orow0 + n * a.srow;  // first output row of the tile
+        const int orow0 = w.orow0 + (int)rank * OUTR + n * a.srow;  // first output row of the tile
         mbar_wait(t_full + tb, (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + tb * 256 + hf * 16;
+        if (a.dbg & 2) {  // timing experiment: free the accumulator at once
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_leader(t_empty + tb);
+            else mbar_arrive(t_empty + tb);
+          }
+          continue;
+        }
         float out[16];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {  // 8 output channels at a time
@@ -361,7 +483,14 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty + tb);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(t_empty + tb);
+          else mbar_arrive(t_empty + tb);
+        }
+        if (a.dbg & 4) {  // timing experiment: no staging, no store
+          if (out[0] == 123.456f) a.out_f32[0] = out[1];
+          continue;
+        }
         // previous tile's TMA store must have finished reading the staging tile before anyone overwrites it
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         named_bar_sync(1, 256);
@@ -446,12 +575,17 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (PAIR) {
+    cluster_sync_all();  // the leader's MMAs read this CTA's shared memory and write its TMEM until the pair's last tile
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  } else if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
 }
 
 // ---- host: one Toeplitz-N GEMM layer (TzLayer: conv3d_f16.cuh) ------------------------------------------------------------
-static size_t tz_smem_bytes(int nbtiles, int nslot, int slot_bytes, int tz) {
-  return (size_t)nbtiles * TZ_BTILE + 16384 + (size_t)nslot * slot_bytes + 4 * 3 * tz * 32 * 4 + 256 + 1024;
+static size_t tz_smem_bytes(int nbtiles, int nslot, int slot_bytes, int tz, bool pair = false) {
+  return (size_t)nbtiles * (pair ? TZ_BTILE2 : TZ_BTILE) + 16384 + (size_t)nslot * slot_bytes + 4 * 3 * tz * 32 * 4 + 256 + 1024;
 }
 
 int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
@@ -465,10 +599,16 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   a.box_bytes = L.box_rows * 128;
   a.slot_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   const int outr = 128 - 2 * L.tz;
+  const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1 && !L.last;
+  const bool is2dlast = L.tz == 1 && L.nstages == 3 && L.nshift == 1 && L.last;
+  if (!is3d && !is2d && !is2dlast) return LWS_ERR_UNSUPPORTED;
+  // CTA pairs (cta_group::2): the 32 -> 32 3D layers on the strip schedule; a schedule tile is the pair's 2 * outr rows
+  const bool pair = L.pair && is3d && !L.last && L.srow > 0;
+  const int soutr = pair ? 2 * outr : outr;
   a.nstages = L.nstages, a.nshift = L.nshift;
   if (L.srow > 0) {  // strips along the slowest tap axis
     a.G = L.G, a.srow = L.srow;
-    a.ct_per_sl = make_fastdiv((L.srow + outr - 1) / outr);
+    a.ct_per_sl = make_fastdiv((L.srow + soutr - 1) / soutr);
     a.strip_len = (L.R + L.srow - 1) / L.srow;
   } else {
     a.G = L.nstages, a.srow = L.R;
@@ -476,18 +616,29 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
     a.strip_len = 1;
   }
   a.total_tiles = L.B * a.ct_per_sl.d * a.strip_len;
+  a.dbg = opt(OPT_TZ_DEBUG);
+  const int grid = pair ? (2 * a.total_tiles < kNumSMs ? 2 * a.total_tiles : kNumSMs / 2 * 2) : (a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs);
+  if (a.strip_len > 1 && L.seg_mode && !pair) {
+    // segments per strip: the count that minimises the busiest CTA's tiles + box reloads (a segment start loads nstages - G boxes
+    // more than a tile inside a strip; counted as (nstages - G) / nstages of a tile)
+    double best = 1e30;
+    for (int sp = 1; sp <= a.strip_len && sp <= 16; ++sp) {
+      const int sl = (a.strip_len + sp - 1) / sp, spe = (a.strip_len + sl - 1) / sl;
+      const long long nseg = (long long)L.B * spe * a.ct_per_sl.d;
+      const double cost = (double)((nseg + grid - 1) / grid) * (sl + (double)(L.nstages - a.G) / L.nstages);
+      if (cost < best) best = cost, a.seg_len = sl, a.segs_per_strip = spe, a.nseg = (int)nseg;
+    }
+  }
   // ring: one tile's stages plus as many more as fit (at most 8)
   a.nslot = 8;
-  while (a.nslot > L.nstages && tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz) > 232448) --a.nslot;
-  const size_t smem = tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz);
+  while (a.nslot > L.nstages && tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz, pair) > 232448) --a.nslot;
+  const size_t smem = tz_smem_bytes(a.nbtiles, a.nslot, a.slot_bytes, L.tz, pair);
   if (smem > 232448 || a.nslot < L.nstages) return LWS_ERR_UNSUPPORTED;
-  const bool is3d = L.tz == 1 && L.nstages == 3 && L.nshift == 3, is2d = L.tz == 8 && L.nstages == 6 && L.nshift == 1 && !L.last;
-  const bool is2dlast = L.tz == 1 && L.nstages == 3 && L.nshift == 1 && L.last;
-  if (!is3d && !is2d && !is2dlast) return LWS_ERR_UNSUPPORTED;
   // every variant may use up to the 227 KB cap (the per-call size is `smem`): set once per variant and device
   if (is2dlast) LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 1, true>), 232448);
   else if (is2d) LWS_SET_SMEM_ONCE((tz_gemm_kernel<8, 6, 1, false>), 232448);
   else if (L.last) LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 3, true>), 232448);
+  else if (pair) LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 3, false, true>), 232448);
   else LWS_SET_SMEM_ONCE((tz_gemm_kernel<1, 3, 3, false>), 232448);
   cudaError_t e;
   a.bias = L.bias, a.scales = L.wtab + (L.last ? (size_t)nblk * 16 * 32 : (size_t)a.nbtiles * 192 * 32);
@@ -508,10 +659,32 @@ int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
   rc = make_tensor_map_f32(&mapOut, L.last ? L.src0 : L.out, 3, dimsA, strA, boxO, true);  // unused by the C -> 1 layer
   if (rc) return rc;
   const uint64_t dimsB[2] = {32, L.last ? (uint64_t)nblk * 16 : (uint64_t)a.nbtiles * 192}, strB[1] = {128};
-  const uint32_t boxB[2] = {32, L.last ? (uint32_t)nblk * 16 : 192u};
+  const uint32_t boxB[2] = {32, L.last ? (uint32_t)nblk * 16 : (pair ? 48u : 192u)};
   rc = make_tensor_map_f32(&mapB, L.wtab, 2, dimsB, strB, boxB, true);
   if (rc) return rc;
-  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(TZ_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    // a persistent grid must be co-resident: GPCs with an odd number of usable SMs leave one SM without a partner
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
+      int n = 0;
+      cfg.gridDim = dim3(kNumSMs / 2 * 2);
+      if (cudaOccupancyMaxActiveClusters(&n, tz_gemm_kernel<1, 3, 3, false, true>, &cfg) != cudaSuccess || n <= 0) n = kNumSMs / 2;
+      max_clusters[dev] = n;
+    }
+    const int maxc = dev >= 0 && dev < 64 ? max_clusters[dev] : kNumSMs / 2;
+    cfg.gridDim = dim3(grid < 2 * maxc ? grid : 2 * maxc);
+    e = cudaLaunchKernelEx(&cfg, tz_gemm_kernel<1, 3, 3, false, true>, mapA0, mapA1, mapB, mapOut, a);
+    return e == cudaSuccess ? LWS_OK : (int)e;
+  }
   if (is2dlast) tz_gemm_kernel<1, 3, 1, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   else if (is2d) tz_gemm_kernel<8, 6, 1, false><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
   else if (L.last) tz_gemm_kernel<1, 3, 3, true><<<grid, TZ_THREADS, smem, st>>>(mapA0, mapA1, mapB, mapOut, a);
@@ -930,6 +1103,8 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
     L.tz = 1, L.nstages = 3, L.nshift = 3, L.box_rows = 128 + 2 * Dp;
     for (int kh = 0; kh < 3; ++kh) L.st_off[kh] = (kh - 1) * Wp * Dp - Dp, L.st_src[kh] = 0;  // box starts one x column early
     for (int kw = 0; kw < 3; ++kw) L.shift_rows[kw] = kw * Dp;
+    // strips down y: a tile shares its ky = 0, 1 boxes with the tile above it (2: strips cut into segments dealt round-robin)
+    if (opt(OPT_TZ_STRIPS)) L.srow = Wp * Dp, L.G = 1, L.seg_mode = opt(OPT_TZ_STRIPS) == 2, L.pair = opt(OPT_TZ_STRIPS) == 3;
     L.out_split = 1, L.relu = 1;
     int rc = launch_tz_gemm(L, st);
     if (rc) return rc;

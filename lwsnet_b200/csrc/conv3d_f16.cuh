@@ -22,6 +22,8 @@ struct TzLayer {
   int srow;             // rows between consecutive taps of the slowest axis if the stages are ordered [tap][G sources] and
                         // st_off[tap*G + g] = (tap - 1) * srow + const (strip schedule with ring reuse); 0 = linear tiling
   int G;
+  int pair;             // strip schedule, 3D 32 -> 32 layers only: 1 = CTA pairs (tcgen05 cta_group::2, M = 256, weights split over the pair)
+  int seg_mode;         // strip schedule only: 1 = strips cut into segments dealt round-robin to the CTAs (TzSched), 0 = contiguous ranges
   int last;             // 1: the closing C -> 1 layer: wtab = [nstages*nshift blocks][16 rows][32 words] + scales[2], fp32 NCDHW
                         //    output out_f32 (+ skip) instead of rows
   const float* skip;

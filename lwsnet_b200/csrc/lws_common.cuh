@@ -35,6 +35,8 @@ enum {
   OPT_FUSED_TAIL,
   OPT_C8_GROUP,
   OPT_FUSE_VOLUME,
+  OPT_TZ_STRIPS,
+  OPT_TZ_DEBUG,
   OPT_COUNT
 };
 int opt(int id);

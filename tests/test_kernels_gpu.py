@@ -289,6 +289,28 @@ def test_first_conv_versions_bit_identical(C, B, D, H, W):
             assert torch.equal(net.run(x, add_skip=True), ref), ver
 
 
+@pytest.mark.parametrize("B,D,H,W", [(2, 24, 46, 154), (1, 24, 3, 40), (3, 12, 17, 70), (1, 48, 9, 70)])
+def test_tz_strips_bit_identical(B, D, H, W):
+    """C = 32 mid layers with the tiles walking down y in strips (two of the three ky boxes stay in the shared-memory ring) against
+    linear tiling (every tile loads its three boxes): the same MMAs on the same operands, identical bits."""
+    from oracle import lwsnet_torch as O
+    from lwsnet_b200.submodules import post_3dconvs
+    onet = O.post_3dconvs(4, 32)
+    holder = torch.nn.Module()
+    holder.net = onet
+    O.kaiming_normal_init_(holder, 51)
+    O.randomize_bn_(holder, 52)
+    net = post_3dconvs(4, 32)
+    net.load_state_dict(onet.state_dict(), strict=True)
+    net = net.cuda()
+    x = (rnd(53, B, D, H, W, scale=6.0).abs()).cuda()
+    with ops().options(tz_strips=0):
+        ref = net.run(x, add_skip=True).clone()
+    for mode in (1, 2, 3):  # contiguous tile ranges / segments dealt round-robin / CTA pairs (cta_group::2)
+        with ops().options(tz_strips=mode):
+            assert torch.equal(net.run(x, add_skip=True), ref), mode
+
+
 @pytest.mark.parametrize("B,Cf,D,H,W", [(2, 32, 24, 46, 154), (1, 32, 24, 7, 66), (3, 16, 12, 9, 130), (1, 32, 40, 5, 64), (1, 2, 3, 4, 6)])
 def test_fused_volume_first_conv_bit_identical(B, Cf, D, H, W):
     """Stage 1 as ONE call (lws_cost_volume_conv3d_stack_f32: the volume is built inside the first conv kernel's shared-memory
@@ -459,6 +481,23 @@ def test_refinement_chain_option_is_bit_identical():
             out = model._refine(left, pred3)
             torch.cuda.synchronize()
         assert torch.equal(out, ref), n
+
+
+def test_refinement_segment_schedule_is_bit_identical():
+    """The dense 64 -> 32 conv and the closing 32 -> 1 conv of the refinement with their strips cut into segments dealt round-robin
+    (option tz_strips = 2) == contiguous tile ranges, bitwise."""
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=True))
+    for (B, H, W) in ((2, 200, 328), (1, 368, 1232), (3, 40, 72)):
+        left = rnd(73, B, 3, H, W).cuda()
+        pred3 = (rnd(74, B, 1, H, W, scale=10.0) + 20.0).cuda()
+        with ops().options(tz_strips=0):
+            ref = model._refine(left, pred3).clone()
+        with ops().options(tz_strips=2):
+            out = model._refine(left, pred3)
+            torch.cuda.synchronize()
+        assert torch.equal(out, ref), (B, H, W)
 
 
 # ------------------------------------------------------------------------------------------------ n1 feature pyramid

@@ -33,6 +33,8 @@
 namespace lws {
 
 constexpr int TZ_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TZ_XS = 36;  // floats per row of the epilogue's boundary-row exchange: 32 + 4 so that the rows of a quarter-warp's 128-bit
+                           // accesses fall into different banks (a 32-float pitch put all of them into the same four: 8-way conflicts)
 constexpr int TZ_BTILE = 192 * 128;  // one weight tile: 192 rows x [block 2i | block 2i+1] x 32 halves
 
 struct TzArgs {
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
   uint8_t* sOut = sB + a.nbtiles * (PAIR ? TZ_BTILE2 : TZ_BTILE);  // [16384] staging tile
   uint8_t* sA = sOut + 16384;                            // [nslot][slot_bytes]
   uint8_t* tail = sA + a.nslot * a.slot_bytes;
-  float* xch = reinterpret_cast<float*>(tail);           // [4 quarters][3*TZ rows][32] boundary rows for the Toeplitz shifts
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4 * 3 * TZ * 32 * 4);
+  float* xch = reinterpret_cast<float*>(tail);           // [4 quarters][3*TZ rows][TZ_XS] boundary rows for the Toeplitz shifts
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 4 * 3 * TZ * TZ_XS * 4);
   uint64_t* a_full = bars;                 // [8]
   uint64_t* a_empty = a_full + 8;          // [8]
   uint64_t* b_full = a_empty + 8;          // [1]
@@ -428,8 +430,8 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
 #pragma unroll
     for (int c = 0; c < 16; ++c) bias[c] = __ldg(a.bias + hf * 16 + c) * a.bias_mul;
     // quarter q publishes for quarter q-1: rows [0,TZ) = e1 of lanes 0..TZ-1, rows [TZ,3TZ) = e2 of lanes 0..2TZ-1
-    float* xq = xch + q * (3 * TZ * 32) + hf * 16;
-    const float* xn = xch + ((q + 1) & 3) * (3 * TZ * 32) + hf * 16;
+    float* xq = xch + q * (3 * TZ * TZ_XS) + hf * 16;
+    const float* xn = xch + ((q + 1) & 3) * (3 * TZ * TZ_XS) + hf * 16;
     uint32_t ti = 0;
     TzSched<SOUTR, NCTA> sched(a);
       TzItem w;
@@ -472,10 +474,10 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
             out[cc * 8 + c] = e0 + (has1 ? s1 : 0.f) + (has2 ? s2 : 0.f);
           }
           if (lane < 2 * TZ) {  // rows the previous quarter needs
-            float4* d2 = reinterpret_cast<float4*>(xq + (TZ + lane) * 32 + cc * 8);
+            float4* d2 = reinterpret_cast<float4*>(xq + (TZ + lane) * TZ_XS + cc * 8);
             d2[0] = make_float4(m2[0], m2[1], m2[2], m2[3]), d2[1] = make_float4(m2[4], m2[5], m2[6], m2[7]);
             if (lane < TZ) {
-              float4* d1 = reinterpret_cast<float4*>(xq + lane * 32 + cc * 8);
+              float4* d1 = reinterpret_cast<float4*>(xq + lane * TZ_XS + cc * 8);
               d1[0] = make_float4(m1[0], m1[1], m1[2], m1[3]), d1[1] = make_float4(m1[4], m1[5], m1[6], m1[7]);
             }
           }
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         named_bar_sync(1, 256);
         if (q < 3) {  // rows of the next quarter (the last quarter's missing rows belong to the next tile)
           if (!has1) {
-            const float4* p1 = reinterpret_cast<const float4*>(xn + (lane + TZ - 32) * 32);
+            const float4* p1 = reinterpret_cast<const float4*>(xn + (lane + TZ - 32) * TZ_XS);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float4 v = p1[c];
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
             }
           }
           if (!has2) {
-            const float4* p2 = reinterpret_cast<const float4*>(xn + (TZ + lane + 2 * TZ - 32) * 32);
+            const float4* p2 = reinterpret_cast<const float4*>(xn + (TZ + lane + 2 * TZ - 32) * TZ_XS);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float4 v = p2[c];
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
 
 // ---- host: one Toeplitz-N GEMM layer (TzLayer: conv3d_f16.cuh) ------------------------------------------------------------
 static size_t tz_smem_bytes(int nbtiles, int nslot, int slot_bytes, int tz, bool pair = false) {
-  return (size_t)nbtiles * (pair ? TZ_BTILE2 : TZ_BTILE) + 16384 + (size_t)nslot * slot_bytes + 4 * 3 * tz * 32 * 4 + 256 + 1024;
+  return (size_t)nbtiles * (pair ? TZ_BTILE2 : TZ_BTILE) + 16384 + (size_t)nslot * slot_bytes + 4 * 3 * tz * TZ_XS * 4 + 256 + 1024;
 }
 
 int launch_tz_gemm(const TzLayer& L, cudaStream_t st) {
@@ -1104,7 +1106,7 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
     for (int kh = 0; kh < 3; ++kh) L.st_off[kh] = (kh - 1) * Wp * Dp - Dp, L.st_src[kh] = 0;  // box starts one x column early
     for (int kw = 0; kw < 3; ++kw) L.shift_rows[kw] = kw * Dp;
     // strips down y: a tile shares its ky = 0, 1 boxes with the tile above it (2: strips cut into segments dealt round-robin)
-    if (opt(OPT_TZ_STRIPS)) L.srow = Wp * Dp, L.G = 1, L.seg_mode = opt(OPT_TZ_STRIPS) == 2, L.pair = opt(OPT_TZ_STRIPS) == 3;
+    if (opt(OPT_TZ_STRIPS) & 3) L.srow = Wp * Dp, L.G = 1, L.seg_mode = (opt(OPT_TZ_STRIPS) & 3) == 2, L.pair = (opt(OPT_TZ_STRIPS) & 3) == 3;
     L.out_split = 1, L.relu = 1;
     int rc = launch_tz_gemm(L, st);
     if (rc) return rc;
@@ -1119,6 +1121,7 @@ int conv3d_stack_f16(const float* cost, const float* affine, const float* w_firs
     L.tz = 1, L.nstages = 3, L.nshift = 3, L.box_rows = 128 + 2 * Dp;
     for (int kh = 0; kh < 3; ++kh) L.st_off[kh] = (kh - 1) * Wp * Dp - Dp, L.st_src[kh] = 0;
     for (int kw = 0; kw < 3; ++kw) L.shift_rows[kw] = kw * Dp;
+    if (opt(OPT_TZ_STRIPS) & 4) L.srow = Wp * Dp, L.G = 1;
     L.last = 1, L.skip = add_skip ? cost : nullptr, L.out_f32 = out;
     int rc = launch_tz_gemm(L, st);
     if (rc) return rc;

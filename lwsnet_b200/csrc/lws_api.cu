@@ -45,9 +45,10 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"c8_group", 0, 0, 4096},         // C = 8 stacks: depth-first over groups of this many pairs (0 = whole batch layer by layer)
     {"fuse_volume", 1, 0, 2},         // stage 1 through lws_cost_volume_conv3d_stack_f32 (volume built inside the first conv kernel; the
                                       // model reads this, profiles/r02_fuse_volume_ab.txt): 0 = two calls, 1 = fused, 2 = fused with 8-disparity tiles
-    {"tz_strips", 1, 0, 3},           // C = 32 mid layers (profiles/r02_tz_strips_ab.txt): 0 = linear tiling (every tile loads its three ky boxes);
-                                      // 1 = tiles walk down y in strips, two of the three boxes stay in the shared-memory ring (default);
-                                      // 2 = strips cut into segments dealt round-robin (L2-friendlier, worse balance); 3 = CTA pairs (cta_group::2)
+    {"tz_strips", 5, 0, 7},           // C = 32 stack (profiles/r02_tz_strips_ab.txt).  Bits 0-1, the 32 -> 32 layers: 0 = linear tiling (every tile
+                                      // loads its three ky boxes); 1 = tiles walk down y in strips, two of the three boxes stay in the shared-memory
+                                      // ring (default); 2 = strips cut into segments dealt round-robin (L2-friendlier, worse balance); 3 = CTA pairs
+                                      // (cta_group::2).  Bit 2 (value 4): strips for the closing 32 -> 1 conv too (default)
     {"tz_debug", 0, 0, 7},            // TIMING EXPERIMENTS ONLY (results are wrong): Toeplitz GEMM kernels without A loads (1), epilogue (2), stores (4)
 };
 static std::atomic<int> g_opts[OPT_COUNT];

@@ -114,7 +114,7 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
     L.tz = 8, L.nstages = 6, L.nshift = 1, L.box_rows = 128, L.G = 2, L.srow = 8 * Wp;
     for (int s = 0; s < 6; ++s) L.st_off[s] = (s / 2 - 1) * 8 * Wp, L.st_src[s] = s & 1;
     L.out_split = 0, L.relu = 1;
-    L.seg_mode = opt(OPT_TZ_STRIPS) == 2;
+    L.seg_mode = (opt(OPT_TZ_STRIPS) & 3) == 2;
     if ((rc = launch_tz_gemm(L, st))) return rc;
   }
   // blocks 1..4 of refinement2: ping -> catL (free by now); the last block has no ReLU and feeds the closing conv (split-fp16 rows)
@@ -129,7 +129,7 @@ int refinement_tc(const float* left, const float* pred3, const RefTcWeights& wt,
     L.tz = 1, L.nstages = 3, L.nshift = 1, L.box_rows = 128, L.G = 1, L.srow = Wp;
     for (int s = 0; s < 3; ++s) L.st_off[s] = (s - 1) * Wp, L.st_src[s] = 0;
     L.last = 1, L.skip = pred3, L.out_f32 = pred4, L.out_mode = 1;
-    L.seg_mode = opt(OPT_TZ_STRIPS) == 2;
+    L.seg_mode = (opt(OPT_TZ_STRIPS) & 3) == 2;
     if ((rc = launch_tz_gemm(L, st))) return rc;
   }
   return LWS_OK;

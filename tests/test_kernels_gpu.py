@@ -306,7 +306,8 @@ def test_tz_strips_bit_identical(B, D, H, W):
     x = (rnd(53, B, D, H, W, scale=6.0).abs()).cuda()
     with ops().options(tz_strips=0):
         ref = net.run(x, add_skip=True).clone()
-    for mode in (1, 2, 3):  # contiguous tile ranges / segments dealt round-robin / CTA pairs (cta_group::2)
+    # contiguous tile ranges / segments dealt round-robin / CTA pairs (cta_group::2); +4 = strips for the closing 32 -> 1 conv too
+    for mode in (1, 2, 3, 4, 5, 7):
         with ops().options(tz_strips=mode):
             assert torch.equal(net.run(x, add_skip=True), ref), mode
 

@@ -37,6 +37,7 @@ enum {
   OPT_FUSE_VOLUME,
   OPT_TZ_STRIPS,
   OPT_TZ_DEBUG,
+  OPT_K5_INT,
   OPT_COUNT
 };
 int opt(int id);

@@ -112,6 +112,104 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Integer scales S = H/h = W/w in {2, 4, 8} (the three stages of the network): 1/S is exact in fp32, so away from the clamped image
+// borders the tap pattern is periodic -- the four pixels of a thread use low-resolution columns c, c+1 (, c+2, c+3) at fixed offsets
+// and the K5_ROWS rows of a block use rows r, .., r + K5_ROWS/S + 1 at fixed offsets.  The fast path loads that window once
+// ((K5_ROWS/S + 2) x NC scalars instead of 16 per output row), scales every value once and shares the horizontal blends between the
+// output rows of a low-resolution row pair: ~300 instead of ~1100 instructions per thread.  Every thread CHECKS the pattern against
+// the generic resize_tap() results and falls back to the generic loop where it does not hold (borders), and the blend is the same
+// sequence of rounded operations: bit-identical to scale_upsample_add_kernel.
+template <int S>
+__global__ void __launch_bounds__(128)
+    scale_upsample_add_int_kernel(const float* __restrict__ low, const float* __restrict__ prev, float* __restrict__ pred, int h, int w,
+                                  int H, int W, float fH, float rh, float sy, float sx) {
+  constexpr int NR = K5_ROWS / S + 2;           // low-resolution rows under K5_ROWS output rows
+  constexpr int NC = S == 2 ? 4 : (S == 4 ? 3 : 2);  // low-resolution columns under 4 output pixels
+  const int W4 = W >> 2;  // host: W % 4 == 0
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y0 = blockIdx.y * K5_ROWS;
+  const int b = blockIdx.z;
+  if (xq >= W4) return;
+  ResizeTap tx[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) tx[p] = resize_tap(xq * 4 + p, sx, w);
+  const int c0 = tx[0].i0;
+  bool fast = y0 + K5_ROWS <= H && c0 + NC - 1 < w;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int off = S == 2 ? (p + 1) / 2 : (S == 4 ? p / 2 : 0);
+    fast = fast && tx[p].i0 == c0 + off && tx[p].i1 == tx[p].i0 + 1;
+  }
+  const ResizeTap ty0 = resize_tap(y0, sy, h);
+  const int r0 = ty0.i0;
+  ResizeTap tyr[K5_ROWS];
+#pragma unroll
+  for (int r = 0; r < K5_ROWS; ++r) {
+    tyr[r] = resize_tap(min(y0 + r, H - 1), sy, h);
+    const int off = (2 * r + S) / (2 * S);  // floor((r + 0.5) / S + 0.5): rows r0, r0 + 1, .. in steps of S starting half a period in
+    fast = fast && tyr[r].i0 == r0 + off && tyr[r].i1 == tyr[r].i0 + 1;
+  }
+  fast = fast && r0 + NR - 1 < h;
+  const long long base0 = ((long long)b * H + y0) * W + xq * 4;
+  float4 pv[K5_ROWS];
+  if (prev) {
+#pragma unroll
+    for (int r = 0; r < K5_ROWS; ++r)
+      pv[r] = y0 + r < H ? __ldcs(reinterpret_cast<const float4*>(prev + base0 + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (fast) {
+    // horizontal blends of the NR low-resolution rows for the 4 pixels
+    float hb[NR][4];
+    const float* lp = low + ((long long)b * h + r0) * w + c0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      float c[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) c[j] = __fmul_rn(__fmul_rn(__ldg(lp + i * w + j), fH), rh);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int off = S == 2 ? (p + 1) / 2 : (S == 4 ? p / 2 : 0);
+        hb[i][p] = __fmaf_rn(tx[p].l1, c[off + 1], __fmul_rn(tx[p].l0, c[off]));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < K5_ROWS; ++r) {
+      const int off = (2 * r + S) / (2 * S);
+      float4 o;
+      o.x = __fmaf_rn(tyr[r].l1, hb[off + 1][0], __fmul_rn(tyr[r].l0, hb[off][0]));
+      o.y = __fmaf_rn(tyr[r].l1, hb[off + 1][1], __fmul_rn(tyr[r].l0, hb[off][1]));
+      o.z = __fmaf_rn(tyr[r].l1, hb[off + 1][2], __fmul_rn(tyr[r].l0, hb[off][2]));
+      o.w = __fmaf_rn(tyr[r].l1, hb[off + 1][3], __fmul_rn(tyr[r].l0, hb[off][3]));
+      if (prev) o.x = __fadd_rn(o.x, pv[r].x), o.y = __fadd_rn(o.y, pv[r].y), o.z = __fadd_rn(o.z, pv[r].z), o.w = __fadd_rn(o.w, pv[r].w);
+      *reinterpret_cast<float4*>(pred + base0 + (long long)r * W) = o;
+    }
+    return;
+  }
+  // generic path (image borders): as scale_upsample_add_kernel
+  for (int r = 0; r < K5_ROWS; ++r) {
+    const int y = y0 + r;
+    if (y >= H) break;
+    const ResizeTap ty = resize_tap(y, sy, h);
+    const float* l0 = low + ((long long)b * h + ty.i0) * w;
+    const float* l1 = low + ((long long)b * h + ty.i1) * w;
+    float out[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float a00 = __fmul_rn(__fmul_rn(__ldg(l0 + tx[p].i0), fH), rh);
+      const float a01 = __fmul_rn(__fmul_rn(__ldg(l0 + tx[p].i1), fH), rh);
+      const float a10 = __fmul_rn(__fmul_rn(__ldg(l1 + tx[p].i0), fH), rh);
+      const float a11 = __fmul_rn(__fmul_rn(__ldg(l1 + tx[p].i1), fH), rh);
+      out[p] = bilinear_blend(a00, a01, a10, a11, tx[p], ty);
+    }
+    float4 o = make_float4(out[0], out[1], out[2], out[3]);
+    if (prev) {
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(prev + base0 + (long long)r * W));
+      o.x = __fadd_rn(o.x, q.x), o.y = __fadd_rn(o.y, q.y), o.z = __fadd_rn(o.z, q.z), o.w = __fadd_rn(o.w, q.w);
+    }
+    *reinterpret_cast<float4*>(pred + base0 + (long long)r * W) = o;
+  }
+}
+
 // wflow[b,0,y,x] = (resize(pred_full)[y,x] * float(h)) * fl32(1/H)
 __global__ void __launch_bounds__(256)
     disp_to_scale_kernel(const float* __restrict__ pred, float* __restrict__ wflow, int H, int W, int h, int w,
@@ -305,8 +403,15 @@ extern "C" int lws_scale_upsample_add_f32(const float* low, const float* prev_or
   cudaStream_t st = (cudaStream_t)stream;
   const int W4 = (W + 3) / 4;
   dim3 grid(cdiv(W4, 128), cdiv(H, K5_ROWS), B);
-  scale_upsample_add_kernel<<<grid, 128, 0, st>>>(low, prev_or_null, pred, h, w, H, W, (float)H,
-                                                  (float)(1.0 / (double)h), (float)h / (float)H, (float)w / (float)W);
+  const float fH = (float)H, rh = (float)(1.0 / (double)h), sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int S = H / h;
+  if ((W & 3) == 0 && H == S * h && W == S * w && (S == 2 || S == 4 || S == 8) && opt(OPT_K5_INT)) {  // the network's three stages
+    if (S == 2) scale_upsample_add_int_kernel<2><<<grid, 128, 0, st>>>(low, prev_or_null, pred, h, w, H, W, fH, rh, sy, sx);
+    else if (S == 4) scale_upsample_add_int_kernel<4><<<grid, 128, 0, st>>>(low, prev_or_null, pred, h, w, H, W, fH, rh, sy, sx);
+    else scale_upsample_add_int_kernel<8><<<grid, 128, 0, st>>>(low, prev_or_null, pred, h, w, H, W, fH, rh, sy, sx);
+    LWS_RETURN_LAUNCH_STATUS();
+  }
+  scale_upsample_add_kernel<<<grid, 128, 0, st>>>(low, prev_or_null, pred, h, w, H, W, fH, rh, sy, sx);
   LWS_RETURN_LAUNCH_STATUS();
 }
 

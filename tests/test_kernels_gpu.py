@@ -170,6 +170,22 @@ def test_scale_upsample_add(B, h, w, H, W):
     close_rel(ops().scale_upsample_add(low.cuda(), prev.cuda(), H, W), S.scale_upsample_add(low.numpy(), prev.numpy(), H, W), 1e-5)
 
 
+@pytest.mark.parametrize("B,h,w,S", [(2, 46, 154, 8), (2, 92, 308, 4), (2, 184, 616, 2), (1, 5, 7, 2), (1, 3, 4, 4), (3, 2, 3, 8), (1, 13, 33, 2),
+                                     (1, 9, 16, 4)])
+def test_scale_upsample_add_integer_scale_path_bit_identical(B, h, w, S):
+    """K5's periodic-tap fast path for the integer scales 2 / 4 / 8 (option k5_int = 1, default) == the generic kernel, bitwise, with and
+    without the previous-stage skip, image borders and tiny images included."""
+    H, W = h * S, w * S
+    low = (rnd(81, B, 1, h, w, scale=5.0)).cuda()
+    prev = (rnd(82, B, 1, H, W, scale=9.0)).cuda()
+    for pv in (None, prev):
+        with ops().options(k5_int=0):
+            ref = ops().scale_upsample_add(low, pv, H, W).clone()
+        with ops().options(k5_int=1):
+            out = ops().scale_upsample_add(low, pv, H, W)
+        assert torch.equal(out, ref), (B, h, w, S, pv is None)
+
+
 @pytest.mark.parametrize("B,D,h,w,H,W,nhw,start", [
     (2, 24, 46, 154, 368, 1232, (92, 308), 0.0),     # stage 1 -> wflow of stage 2 (decimation 4)
     (1, 9, 92, 308, 368, 1232, (184, 616), -4.0),    # stage 2 -> wflow of stage 3 (decimation 2)

@@ -566,7 +566,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--probes-only", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not pin each rank to its GPU's NUMA-local CPU cores")
-    ap.add_argument("--probe-batch", type=int, default=16, help="pairs per launch in the streaming-kernel probes")
+    ap.add_argument("--probe-batch", type=int, default=24, help="pairs per launch in the streaming-kernel probes (default: the engine's micro-batch)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library option for A/B runs (lws_set_option, include/lws.h), e.g. --opt refine_chain=0")
     args = ap.parse_args()

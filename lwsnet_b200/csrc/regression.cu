@@ -133,39 +133,37 @@ __global__ void __launch_bounds__(128)
   ResizeTap tx[4];
 #pragma unroll
   for (int p = 0; p < 4; ++p) tx[p] = resize_tap(xq * 4 + p, sx, w);
-  const int c0 = tx[0].i0;
-  bool fast = y0 + K5_ROWS <= H && c0 + NC - 1 < w;
+  // With scale 1/S every operation of resize_tap() is exact, so src = (2 dst + 1 - S) / 2S exactly: unclamped from the second thread
+  // column / block row on, tap index = floor(src), weight l1 = ((2 dst + 1 - S) mod 2S) / 2S.  For the rows dst = y0 + r with
+  // y0 % 8 == 0, so index offsets AND weights are compile-time constants of r.
+  const int c0 = (8 * xq + 1 - S) / (2 * S), r0 = (2 * y0 + 1 - S) / (2 * S);
+  bool fast = xq >= 1 && y0 >= K5_ROWS && y0 + K5_ROWS <= H && c0 + NC - 1 < w && r0 + NR - 1 < h;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int p = 0; p < 4; ++p) {  // cheap cross-check of the closed form against the generic tap (always true)
     const int off = S == 2 ? (p + 1) / 2 : (S == 4 ? p / 2 : 0);
     fast = fast && tx[p].i0 == c0 + off && tx[p].i1 == tx[p].i0 + 1;
   }
-  const ResizeTap ty0 = resize_tap(y0, sy, h);
-  const int r0 = ty0.i0;
-  ResizeTap tyr[K5_ROWS];
-#pragma unroll
-  for (int r = 0; r < K5_ROWS; ++r) {
-    tyr[r] = resize_tap(min(y0 + r, H - 1), sy, h);
-    const int off = (2 * r + S) / (2 * S);  // floor((r + 0.5) / S + 0.5): rows r0, r0 + 1, .. in steps of S starting half a period in
-    fast = fast && tyr[r].i0 == r0 + off && tyr[r].i1 == tyr[r].i0 + 1;
-  }
-  fast = fast && r0 + NR - 1 < h;
   const long long base0 = ((long long)b * H + y0) * W + xq * 4;
-  float4 pv[K5_ROWS];
-  if (prev) {
-#pragma unroll
-    for (int r = 0; r < K5_ROWS; ++r)
-      pv[r] = y0 + r < H ? __ldcs(reinterpret_cast<const float4*>(prev + base0 + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   if (fast) {
+    // the low-resolution window first (needed first), then the previous-stage rows, then the arithmetic
+    float cw[NR][NC];
+    const float* lp = low + ((long long)b * h + r0) * w + c0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) cw[i][j] = __ldg(lp + i * w + j);
+    float4 pv[K5_ROWS];
+    if (prev) {
+#pragma unroll
+      for (int r = 0; r < K5_ROWS; ++r) pv[r] = __ldcs(reinterpret_cast<const float4*>(prev + base0 + (long long)r * W));
+    }
     // horizontal blends of the NR low-resolution rows for the 4 pixels
     float hb[NR][4];
-    const float* lp = low + ((long long)b * h + r0) * w + c0;
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       float c[NC];
 #pragma unroll
-      for (int j = 0; j < NC; ++j) c[j] = __fmul_rn(__fmul_rn(__ldg(lp + i * w + j), fH), rh);
+      for (int j = 0; j < NC; ++j) c[j] = __fmul_rn(__fmul_rn(cw[i][j], fH), rh);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int off = S == 2 ? (p + 1) / 2 : (S == 4 ? p / 2 : 0);
@@ -174,12 +172,13 @@ __global__ void __launch_bounds__(128)
     }
 #pragma unroll
     for (int r = 0; r < K5_ROWS; ++r) {
-      const int off = (2 * r + S) / (2 * S);
+      const int off = (2 * r + S) / (2 * S);  // floor((r + 0.5) / S + 0.5): rows r0, r0 + 1, .. in steps of S starting half a period in
+      const float yl1 = (float)((2 * r + 1 + S) % (2 * S)) * (0.5f / S), yl0 = 1.0f - yl1;  // exact: multiples of 1/16
       float4 o;
-      o.x = __fmaf_rn(tyr[r].l1, hb[off + 1][0], __fmul_rn(tyr[r].l0, hb[off][0]));
-      o.y = __fmaf_rn(tyr[r].l1, hb[off + 1][1], __fmul_rn(tyr[r].l0, hb[off][1]));
-      o.z = __fmaf_rn(tyr[r].l1, hb[off + 1][2], __fmul_rn(tyr[r].l0, hb[off][2]));
-      o.w = __fmaf_rn(tyr[r].l1, hb[off + 1][3], __fmul_rn(tyr[r].l0, hb[off][3]));
+      o.x = __fmaf_rn(yl1, hb[off + 1][0], __fmul_rn(yl0, hb[off][0]));
+      o.y = __fmaf_rn(yl1, hb[off + 1][1], __fmul_rn(yl0, hb[off][1]));
+      o.z = __fmaf_rn(yl1, hb[off + 1][2], __fmul_rn(yl0, hb[off][2]));
+      o.w = __fmaf_rn(yl1, hb[off + 1][3], __fmul_rn(yl0, hb[off][3]));
       if (prev) o.x = __fadd_rn(o.x, pv[r].x), o.y = __fadd_rn(o.y, pv[r].y), o.z = __fadd_rn(o.z, pv[r].z), o.w = __fadd_rn(o.w, pv[r].w);
       *reinterpret_cast<float4*>(pred + base0 + (long long)r * W) = o;
     }

@@ -3,7 +3,7 @@ import os, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02b"
 os.makedirs("gpurun_out", exist_ok=True)
 # second round of tools/run_stream_kernels.py: K4 launches 3..5, K5 launch 1 (ncu -s skips matching launches)
-kernels = {"k5_upsample": ("scale_upsample_add_kernel", 1), "k4_d9_s3": ("softmax_regression_kernel", 5), "k4_d24": ("softmax_regression_kernel", 3)}
+kernels = {"k5_upsample": ("scale_upsample_add", 1)}
 for name, (rx, skip) in kernels.items():
     rep = f"gpurun_out/full_{tag}_{name}.ncu-rep"
     cmd = ["ncu", "--set", "full", "--import-source", "on", "--clock-control", "none", "-k", "regex:" + rx, "-s", str(skip), "-c", "1",

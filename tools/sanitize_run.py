@@ -42,6 +42,22 @@ for C, shape in ((32, (1, 6, 9, 20)), (8, (2, 9, 16, 32)), (8, (1, 4, 6, 9)), (1
     for tc in (1, 0):
         with ops.options(conv3d_tc=tc):
             net.run(x, add_skip=True)
+# r02 additions: the fused stage-1 volume + first conv (both disparity tile widths), every C = 32 schedule (linear, strips, segments,
+# CTA pairs / cta_group::2, strips for the closing conv), the integer-scale K5 path at the three scales and the fused stage tail
+net32 = post_3dconvs(4, 32).to(dev)
+fl, fr = rnd(2, 16, 9, 66), rnd(2, 16, 9, 66)
+for mode in (1, 2):
+    with ops.options(fuse_volume=mode):
+        ops.cost_volume_conv3d_stack(fl, fr, 24, net32.packed(dev), 32, 4)
+x32 = rnd(2, 12, 7, 40).abs() * 6
+for mode in (0, 1, 2, 3, 5, 7):
+    with ops.options(tz_strips=mode):
+        net32.run(x32, add_skip=True)
+for S, (h, w) in ((2, (17, 24)), (4, (9, 12)), (8, (5, 7))):
+    ops.scale_upsample_add(rnd(1, 1, h, w), rnd(1, 1, h * S, w * S), h * S, w * S)
+    ops.scale_upsample_add(rnd(2, 1, h, w), None, h * S, w * S)
+with ops.options(fused_tail=1):
+    ops.regression_tail(rnd(1, 9, 16, 32) * 8, rnd(1, 1, 64, 128), 64, 128, -4.0, 1.0, next_hw=(32, 64))
 left, right = synthetic_pair(1, 64, 128, seed=5, max_disp=20.0)
 left, right = left.to(dev), right.to(dev)
 pred3 = torch.rand(1, 1, 64, 128, generator=g).to(dev) * 30

@@ -29,9 +29,18 @@ constexpr int DS_OFF_IN = DS_OFF_B + 8192;
 constexpr int DS_OFF_W = DS_OFF_IN + DS_NIN * DS_INBYTES;   // depthwise weights [9][32] fp32
 constexpr int DS_OFF_BAR = DS_OFF_W + 9 * 32 * 4;
 constexpr int DS_SMEM = DS_OFF_BAR + 256 + 1024 /*align slack*/;
-// the im2col modes (CIN > 0) have no input ring: their shared memory ends 100 KB earlier, which the SM gives to L1 -- the front end's
-// tap loads are L1 hits only if the few image lines in flight stay resident
-constexpr int DS_SMEM_IM2COL = DS_SMEM - DS_NIN * DS_INBYTES;
+// the im2col modes (CIN > 0) have no activation ring; instead the image lines arrive through a small TMA ring (DS_NIMG lines of
+// CIN x 136 floats: the 128 pixels of the tile + 4 columns each side -- the innermost start coordinate of a tiled TMA load has to be
+// 16-byte aligned (tools/tma_probe.cu: an unaligned one is an illegal instruction), so the box starts at x0 - 4, not x0 - 1) whose
+// out-of-bounds zero fill is the conv's zero padding
+constexpr int DS_NIMG = 16;
+constexpr int DS_IMG_ROW = 136;                     // floats per channel line in the ring
+constexpr int DS_IMG_X0 = 4;                        // image column of ring column 0, relative to the tile's first pixel: x - 4
+constexpr int DS_IMG_SLOT = 13 * 128;               // >= 3 * 136 * 4 bytes, 128-byte aligned
+constexpr int DS_OFF_IMGBAR = DS_OFF_IN + 9 * 32 * 4 + 256;  // after the CIN > 0 layout's weights + barriers (dwsep_f16_kernel)
+constexpr int DS_OFF_IMG = DS_OFF_IMGBAR + 256;
+constexpr int DS_SMEM_IM2COL = DS_OFF_IMG + DS_NIMG * DS_IMG_SLOT + 1024 /*align slack*/;
+static_assert(DS_OFF_IMG % 128 == 0, "TMA destination alignment");
 constexpr float DS_ACT_SCALE = kDwsepActScale;
 
 struct DsArgs {
@@ -46,6 +55,8 @@ struct DsArgs {
   int out_split;        // 1: write rows as [32 hi | 32 lo] halves of act * 2^-6 (operand format of conv3d_f16.cu) instead of fp32
   int nxt, rows_phase;     // x tiles per line; lines per row phase (max over phases)
   long long total_rows;     // B * nxt * dil * rows_phase tile-rows, split evenly (contiguously) over the CTAs
+  int img_tma;              // CIN > 0: image lines through the TMA ring (map_in = {W, H, B*CIN} fp32) instead of per-thread loads
+  int dbg;                  // option chain_debug, TIMING EXPERIMENTS ONLY: bit 2 (4) = the im2col front end does not read the image
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {

@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
   uint64_t* t_empty = t_full + DS_NT;       // [NT]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + DS_NT);
   float* sW = reinterpret_cast<float*>(smem + OFF_W);
+  uint64_t* img_full = reinterpret_cast<uint64_t*>(smem + DS_OFF_IMGBAR);  // CIN > 0 only: [NIMG] + [NIMG]
+  uint64_t* img_empty = img_full + DS_NIMG;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dil = a.dil;
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     for (int i = 0; i < DS_NIN; ++i) mbar_init(in_full + i, 1), mbar_init(in_empty + i, DS_DW_WARPS);
     for (int i = 0; i < DS_NA; ++i) mbar_init(a_full + i, DS_DW_WARPS), mbar_init(a_empty + i, 1);
     for (int i = 0; i < DS_NT; ++i) mbar_init(t_full + i, 1), mbar_init(t_empty + i, 4);
+    if (CIN > 0)
+      for (int i = 0; i < DS_NIMG; ++i) mbar_init(img_full + i, 1), mbar_init(img_empty + i, DS_DW_WARPS);
     mbar_fence_init();
     tma_prefetch_desc(&map_in);
     tma_prefetch_desc(&map_out);
@@ -118,6 +122,26 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 
   if (warp == DS_PROD_WARP) {
     // ================================ TMA producer ================================
+    if (CIN > 0 && a.img_tma && !(a.dbg & 4) && elect_one_sync()) {
+      // image lines yi0 - 1 .. yi0 + nrows of every (partial) strip, CIN channel lines of DS_IMG_ROW floats per ring slot; columns left of
+      // 0 / right of W - 1 and lines above 0 / below H - 1 are the TMA's zero fill = the conv's zero padding
+      uint32_t it = 0;
+      DsSched sched(a);
+      DsItem w;
+      while (sched.next(a, w)) {
+        for (int k = 0; k < w.nrows + 2; ++k, ++it) {
+          const uint32_t slot = it % DS_NIMG;
+          mbar_wait(img_empty + slot, ((it / DS_NIMG) & 1) ^ 1);
+          mbar_expect_tx(img_full + slot, (uint32_t)(CIN * DS_IMG_ROW * 4));
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                  smem_u32(smem + DS_OFF_IMG + slot * DS_IMG_SLOT)),
+              "l"(reinterpret_cast<uint64_t>(&map_in)), "r"(smem_u32(img_full + slot)), "r"(w.x0 - DS_RP - DS_IMG_X0), "r"(w.yi0 - 1 + k),
+              "r"(w.b * CIN)
+              : "memory");
+        }
+      }
+    }
     if (CIN == 0 && elect_one_sync()) {
       uint32_t it = 0;
       const uint32_t bytes = (uint32_t)(128 + 2 * dil) * 128;
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     const uint32_t a_base = smem_u32(smem + DS_OFF_A);
     const uint32_t row = (uint32_t)p * 128;
     const long long hw = (long long)a.H * a.W;
-    uint32_t t_ = 0;
+    uint32_t t_ = 0, it_img = 0;
     DsSched sched(a);
       DsItem w;
       while (sched.next(a, w)) {
@@ -274,9 +298,74 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
       // 16 + 3(c-5) + ky otherwise; slot 15 is padding), so each half warp owns whole columns and a step down the image is a
       // register shift: only the new bottom row (5 / 4 values per thread instead of 16) is loaded, and it is loaded PF steps
       // ahead through a register FIFO -- a new image line comes from DRAM (~1.5 us under load), longer than one step.
-      constexpr int PF = 3, NCOL = CIN * 3;
+      constexpr int PF = 4, NCOL = CIN * 3;
+      if (a.img_tma) {
+        // ---- image lines from the TMA ring: the line that becomes the window's bottom row is read from shared memory when it is needed
+        const uint32_t img_base = smem_u32(smem + DS_OFF_IMG) + (uint32_t)(p + DS_IMG_X0 - 1) * 4;  // tap kx = 0 of pixel p
+        auto take_row = [&](float (&r)[5]) {
+          const uint32_t slot = it_img % DS_NIMG;
+          if (!(a.dbg & 4)) mbar_wait(img_full + slot, (it_img / DS_NIMG) & 1);
+          const uint32_t sb = img_base + slot * DS_IMG_SLOT;
+#pragma unroll
+          for (int lc = 0; lc < 5; ++lc) {
+            const int c0 = lc, c1 = 5 + lc;  // both halves are unrolled and the warp-uniform h selects one
+            float v0 = 0.f, v1 = 0.f;
+            if (h == 0) {
+              if (c0 < NCOL) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(sb + (uint32_t)((c0 / 3) * DS_IMG_ROW + c0 % 3) * 4));
+            } else {
+              if (c1 < NCOL) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(sb + (uint32_t)((c1 / 3) * DS_IMG_ROW + c1 % 3) * 4));
+            }
+            r[lc] = h == 0 ? v0 : v1;
+          }
+          __syncwarp();
+          if (lane == 0 && !(a.dbg & 4)) mbar_arrive(img_empty + slot);
+          ++it_img;
+        };
+        float t[16];
+        {
+          float r0[5], r1[5];
+          take_row(r0);
+          take_row(r1);
+#pragma unroll
+          for (int lc = 0; lc < 5; ++lc) t[3 * lc] = 0.f, t[3 * lc + 1] = r0[lc], t[3 * lc + 2] = r1[lc];
+          t[15] = 0.f;
+        }
+        for (int i = 0; i < w.nrows; ++i, ++t_) {
+          float nr[5];
+          take_row(nr);
+#pragma unroll
+          for (int lc = 0; lc < 5; ++lc) t[3 * lc] = t[3 * lc + 1], t[3 * lc + 1] = t[3 * lc + 2], t[3 * lc + 2] = nr[lc];
+          float v[16];
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) v[kk] = t[kk] * DS_ACT_SCALE;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const __half2 hh = f2h2_sat(v[2 * k], v[2 * k + 1]);
+            const float2 f = __half22float2(hh);
+            const float2 d = split_lo2(v[2 * k], v[2 * k + 1], f);
+            hi[k] = h2_bits(hh), lo[k] = h2_bits(f2h2_sat(d.x, d.y));
+          }
+          const uint32_t ab = t_ % DS_NA;
+          mbar_wait(a_empty + ab, ((t_ / DS_NA) & 1) ^ 1);
+          const uint32_t dst = a_base + ab * DS_TILE + row;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {  // hi chunks 2h, 2h+1; lo chunks 4+2h, 4+2h+1
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((2 * h + c) ^ (p & 7)) << 4)), "r"(hi[4 * c]),
+                         "r"(hi[4 * c + 1]), "r"(hi[4 * c + 2]), "r"(hi[4 * c + 3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((4 + 2 * h + c) ^ (p & 7)) << 4)), "r"(lo[4 * c]),
+                         "r"(lo[4 * c + 1]), "r"(lo[4 * c + 2]), "r"(lo[4 * c + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + ab);
+        }
+        continue;
+      }
       auto load_row = [&](int yrow, float (&r)[5]) {
-        const bool oky = (unsigned)yrow < (unsigned)a.H;
+        const bool oky = (unsigned)yrow < (unsigned)a.H && !(a.dbg & 4);
         const float* src = src0 + (long long)yrow * a.W;
 #pragma unroll
         for (int lc = 0; lc < 5; ++lc) {
@@ -308,16 +397,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
 #pragma unroll
         for (int f = 0; f < PF; ++f) load_row(w.yi0 + 1 + f, fifo[f]);
       }
-      for (int i = 0; i < w.nrows; ++i, ++t_) {
+      // One step down the image.  `slot` holds the line that becomes the window's bottom row; it is consumed and then refilled with
+      // the line PF steps further down.  The FIFO is a ROTATION of PF statically named register sets (the row loop is unrolled by
+      // PF): shifting the values through registers instead would make every step wait for the load issued ONE step earlier (a move
+      // out of a load's destination register waits for that load), i.e. a prefetch distance of 1 whatever PF is -- that move was
+      // 23 % of the kernel's stall samples in profiles/r02_ncu_full_r02_dwsep_f16_3.txt.
+      auto step = [&](int i, float (&slot)[5]) {
         const int y = w.yi0 + i;
-        // slide the window one image line down and refill the FIFO PF lines ahead
 #pragma unroll
-        for (int lc = 0; lc < 5; ++lc) t[3 * lc] = t[3 * lc + 1], t[3 * lc + 1] = t[3 * lc + 2], t[3 * lc + 2] = fifo[0][lc];
-#pragma unroll
-        for (int f = 0; f + 1 < PF; ++f)
-#pragma unroll
-          for (int lc = 0; lc < 5; ++lc) fifo[f][lc] = fifo[f + 1][lc];
-        load_row(y + 1 + PF, fifo[PF - 1]);
+        for (int lc = 0; lc < 5; ++lc) t[3 * lc] = t[3 * lc + 1], t[3 * lc + 1] = t[3 * lc + 2], t[3 * lc + 2] = slot[lc];
+        load_row(y + 1 + PF, slot);
         float v[16];
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) v[kk] = t[kk] * DS_ACT_SCALE;
@@ -344,6 +433,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + ab);
+        ++t_;
+      };
+      for (int i = 0; i < w.nrows; i += PF) {
+        step(i, fifo[0]);
+        if (i + 1 < w.nrows) step(i + 1, fifo[1]);
+        if (i + 2 < w.nrows) step(i + 2, fifo[2]);
+        if (PF > 3 && i + 3 < w.nrows) step(i + 3, fifo[PF - 1]);
       }
     }
   } else {
@@ -482,14 +578,23 @@ int launch_conv0_f16(const float* img, float* out, const void* wtab, const float
   a.nxt = (a.Wp + 127) / 128;
   a.rows_phase = H;
   a.total_rows = (long long)B * a.nxt * H;
+  a.dbg = opt(OPT_CHAIN_DEBUG);
   const int grid = a.total_rows < kNumSMs ? (int)a.total_rows : kNumSMs;
-  CUtensorMap map_out;
+  CUtensorMap map_out, map_img;
   const uint64_t dims[3] = {32, (uint64_t)a.Wp, (uint64_t)B * a.Hp}, strides[2] = {128, (uint64_t)a.Wp * 128};
   const uint32_t box_out[3] = {32, 32, 1};
   int rc = make_tensor_map_f32(&map_out, out, 3, dims, strides, box_out, true);
   if (rc) return rc;
-  if (CIN == 3) dwsep_f16_kernel<3><<<grid, DS_THREADS, DS_SMEM_IM2COL, st>>>(map_out, map_out, a);
-  else dwsep_f16_kernel<1><<<grid, DS_THREADS, DS_SMEM_IM2COL, st>>>(map_out, map_out, a);
+  // image lines through TMA when the NCHW rows are 16-byte aligned (W % 4 == 0); otherwise the front end loads its taps itself
+  a.img_tma = (W % 4 == 0) && ((uintptr_t)img % 16 == 0) && W >= 4;
+  map_img = map_out;
+  if (a.img_tma) {
+    const uint64_t dimg[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)B * CIN}, simg[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    const uint32_t bimg[3] = {(uint32_t)DS_IMG_ROW, 1, (uint32_t)CIN};
+    if (make_tensor_map_f32(&map_img, img, 3, dimg, simg, bimg, false) != LWS_OK) a.img_tma = 0, map_img = map_out;
+  }
+  if (CIN == 3) dwsep_f16_kernel<3><<<grid, DS_THREADS, DS_SMEM_IM2COL, st>>>(map_img, map_out, a);
+  else dwsep_f16_kernel<1><<<grid, DS_THREADS, DS_SMEM_IM2COL, st>>>(map_img, map_out, a);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? LWS_OK : (int)e;
 }

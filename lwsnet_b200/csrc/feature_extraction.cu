@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "lws_common.cuh"
+#include "tma_utils.cuh"
 
 namespace lws {
 
@@ -257,6 +258,107 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
   }
 }
 
+// ---- fast path 1b: stride-1 3x3 conv (dilation DIL, pad = DIL) with its input tile delivered by ONE TMA load ------------------------
+// fe_conv_pipe_kernel above is bound by the latency of its per-thread global loads (ncu: 34 % of its stall samples on their
+// scoreboard at 16 resident warps, issue slots 45 % used).  Here a block owns a TH x (4 TQ) output tile (TQ * TH = 128 threads, one
+// 4-pixel quad each) and ONE tiled TMA load brings the (TH + 2 DIL) x (4 TQ + 8) window of all Cin input channels into shared memory:
+// no load instructions in the threads, out-of-bounds zero fill = the conv's zero padding, and the blocks resident on an SM overlap
+// each other's load.  The window starts at column x0 - 4 (the innermost start coordinate of a tiled TMA load must be 16-byte aligned,
+// tools/tma_probe.cu), so the three aligned 128-bit shared-memory reads per (ci, ky) are the same 12-float register window as above.
+// Needs 16-byte aligned rows (Wi % 4 == 0: the 1/2- and 1/4-resolution maps of KITTI; the 1/8 maps have W = 154).
+template <int COUT, int CT, int DIL, int TQ>
+__global__ void __launch_bounds__(128) fe_conv_tile_kernel(const __grid_constant__ CUtensorMap map_in, const FeConvArgs a) {
+  constexpr int TH = 128 / TQ, ROWS = TH + 2 * DIL, COLS = 4 * TQ + 8, NG = COUT / CT;
+  extern __shared__ __align__(128) uint8_t fe_smem[];
+  float* sIn = reinterpret_cast<float*>(fe_smem);                       // [Cin][ROWS][COLS]
+  float* sW = sIn + a.Cin * ROWS * COLS;                                // [Cin][9][COUT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sW + a.Cin * 9 * COUT);   // 8-byte aligned: all counts above are even
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z / NG, c0 = (blockIdx.z - b * NG) * CT;
+  const int tx0 = blockIdx.x * (4 * TQ), ty0 = blockIdx.y * TH;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (uint32_t)(a.Cin * ROWS * COLS * 4));
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(sIn)),
+                 "l"(reinterpret_cast<uint64_t>(&map_in)), "r"(smem_u32(bar)), "r"(tx0 - 4), "r"(ty0 - DIL), "r"(b * a.Cin)
+                 : "memory");
+  }
+  for (int i = tid; i < a.Cin * 9 * COUT; i += 128) sW[i] = __ldg(a.w + i);
+  __syncthreads();  // weights staged, barrier initialised
+  const int q = tid % TQ, ty = tid / TQ;
+  const int x0 = tx0 + 4 * q, yo = ty0 + ty;
+  mbar_wait(bar, 0);
+  if (x0 >= a.Wo || yo >= a.Ho) return;
+  float2 acc[4][CT / 2];  // float2 pairs: FFMA2 (fma.rn.f32x2, sm_100) does two output channels per issued instruction
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < CT / 2; ++c) acc[p][c] = make_float2(0.f, 0.f);
+  const float* tile = sIn + ty * COLS + 4 * q;
+  for (int ci = 0; ci < a.Cin; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float4* rp = reinterpret_cast<const float4*>(tile + (ci * ROWS + ky * DIL) * COLS);
+      const float4 v0 = rp[0], v1 = rp[1], v2 = rp[2];
+      const float w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wp = sW + (ci * 9 + ky * 3 + kx) * COUT + c0;
+#pragma unroll
+        for (int c = 0; c < CT; c += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + c);
+          const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = w[4 + p + (kx - 1) * DIL];
+            const float2 vv = make_float2(v, v);
+            acc[p][c / 2] = __ffma2_rn(vv, w01, acc[p][c / 2]);
+            acc[p][c / 2 + 1] = __ffma2_rn(vv, w23, acc[p][c / 2 + 1]);
+          }
+        }
+      }
+    }
+  }
+  const long long ohw = (long long)a.Ho * a.Wo;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    const float bias = __ldg(a.bias + c0 + c);
+    const long long o = ((long long)b * COUT + c0 + c) * ohw + (long long)yo * a.Wo + x0;
+    float r[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) r[p] = (c & 1 ? acc[p][c / 2].y : acc[p][c / 2].x) + bias;
+    if (a.res) {
+      const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
+      r[0] += rv.x, r[1] += rv.y, r[2] += rv.z, r[3] += rv.w;
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) r[p] = fmaxf(r[p], 0.f);
+    }
+    *reinterpret_cast<float4*>(a.out + o) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+template <int COUT, int CT, int DIL, int TQ>
+static int launch_tile(const FeConvArgs& a, int B, cudaStream_t st) {
+  constexpr int TH = 128 / TQ, ROWS = TH + 2 * DIL, COLS = 4 * TQ + 8;
+  const size_t smem = ((size_t)a.Cin * ROWS * COLS + (size_t)a.Cin * 9 * COUT) * sizeof(float) + 16;
+  if (smem > 100 * 1024 || ROWS > 256 || a.Cin > 256) return LWS_ERR_UNSUPPORTED;
+  CUtensorMap map;
+  const uint64_t dims[3] = {(uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)B * a.Cin};
+  const uint64_t strides[2] = {(uint64_t)a.Wi * 4, (uint64_t)a.Hi * a.Wi * 4};
+  const uint32_t box[3] = {(uint32_t)COLS, (uint32_t)ROWS, (uint32_t)a.Cin};
+  int rc = make_tensor_map_f32(&map, a.in, 3, dims, strides, box, false);
+  if (rc) return rc;
+  LWS_SET_SMEM_ONCE((fe_conv_tile_kernel<COUT, CT, DIL, TQ>), 100 * 1024);
+  dim3 g(cdiv(a.Wo, 4 * TQ), cdiv(a.Ho, TH), B * (COUT / CT));
+  fe_conv_tile_kernel<COUT, CT, DIL, TQ><<<g, 128, smem, st>>>(map, a);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? LWS_OK : (int)e;
+}
+
 // ---- fast path 2: 3x3 stride-2 transposed conv (pad 1, output_padding 1 -> exact 2x upsampling), Wi % 2 == 0 ------------------
 // yo = 2*yi - 1 + ky: an even output row sees only (yi = yo/2, ky = 1), an odd one (yi = (yo-1)/2, ky = 2) and (yi = (yo+1)/2,
 // ky = 0); same along x.  A thread owns the 2 x 4 outputs (rows 2i, 2i+1; columns 4j .. 4j+3) of 8 output channels: 6 input
@@ -367,6 +469,19 @@ static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
   const bool cin_even = (a.Cin & 1) == 0;
   const bool even = (a.Wi & 1) == 0 && (a.Wo & 1) == 0 && a.pad == a.dil && !a.transposed &&
                     (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.res) & 15) == 0;
+  // input tile through TMA: 16-byte aligned rows, a tile that does not waste most of its width, B * Cin within a grid dimension
+  const bool tma_ok = even && a.stride == 1 && a.Wo == a.Wi && (a.Wi & 3) == 0 && a.Wi >= 64 && opt(OPT_FE_TMA) &&
+                      (long long)B * cout <= 65535;
+  if (tma_ok) {
+    const bool wide = a.Wi % 128 == 0 || a.Wi >= 512;  // 128-pixel tiles; 64-pixel tiles for the narrower maps (308 = 4.8 x 64)
+    int rc = LWS_ERR_UNSUPPORTED;
+    if (cout == 16 && a.dil == 1) rc = wide ? launch_tile<16, 8, 1, 32>(a, B, st) : launch_tile<16, 8, 1, 16>(a, B, st);
+    else if (cout == 8 && a.dil == 1) rc = wide ? launch_tile<8, 8, 1, 32>(a, B, st) : launch_tile<8, 8, 1, 16>(a, B, st);
+    else if (cout == 8 && a.dil == 2) rc = wide ? launch_tile<8, 8, 2, 32>(a, B, st) : launch_tile<8, 8, 2, 16>(a, B, st);
+    else if (cout == 8 && a.dil == 4) rc = wide ? launch_tile<8, 8, 4, 32>(a, B, st) : launch_tile<8, 8, 4, 16>(a, B, st);
+    else if (cout == 4 && a.dil == 2) rc = wide ? launch_tile<4, 4, 2, 32>(a, B, st) : launch_tile<4, 4, 2, 16>(a, B, st);
+    if (rc != LWS_ERR_UNSUPPORTED) return rc;
+  }
   if (even && cin_even && a.stride == 1 && a.Wo == a.Wi) {
     if (cout == 16 && a.dil == 1) return launch_pipe<16, 8, 1, 1>(a, B, smem_w, st);
     if (cout == 8 && a.dil == 1) return launch_pipe<8, 8, 1, 1>(a, B, smem_w, st);

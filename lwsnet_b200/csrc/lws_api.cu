@@ -51,6 +51,7 @@ static const OptDesc kOpts[OPT_COUNT] = {
                                       // (cta_group::2).  Bit 2 (value 4): strips for the closing 32 -> 1 conv too (default)
     {"tz_debug", 0, 0, 7},            // TIMING EXPERIMENTS ONLY (results are wrong): Toeplitz GEMM kernels without A loads (1), epilogue (2), stores (4)
     {"k5_int", 1, 0, 1},              // K5 (rescale + upsample + skip): periodic-tap fast path for the integer scales 2 / 4 / 8 (0 = generic kernel)
+    {"fe_tma", 1, 0, 1},              // feature pyramid: stride-1 convs on 16-byte aligned maps read their input tile through one TMA load (0 = per-thread loads)
 };
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::atomic<bool> g_opts_init{false};

@@ -38,6 +38,7 @@ enum {
   OPT_TZ_STRIPS,
   OPT_TZ_DEBUG,
   OPT_K5_INT,
+  OPT_FE_TMA,
   OPT_COUNT
 };
 int opt(int id);

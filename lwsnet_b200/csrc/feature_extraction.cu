@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(128) fe_conv_pipe_kernel(const FeConvArgs a) {
   const long long hw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
   const int xi0 = x0 * STRIDE;  // the aligned WIN-wide window starts at input column xi0 - 4
   const float* in_b = a.in + (long long)b * a.Cin * hw + (xi0 - 4);
+  if (a.res && (threadIdx.x & 7) == 0) {  // the skip tensor is read by the epilogue: request its lines into L2 now
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + ((long long)b * COUT + c0 + c) * ohw + (long long)yo * a.Wo + x0));
+  }
   bool okc[NG], oky[3];
   int rowoff[3];
 #pragma unroll
@@ -276,19 +281,33 @@ __global__ void __launch_bounds__(128) fe_conv_tile_kernel(const __grid_constant
   const int tid = threadIdx.x;
   const int b = blockIdx.z / NG, c0 = (blockIdx.z - b * NG) * CT;
   const int tx0 = blockIdx.x * (4 * TQ), ty0 = blockIdx.y * TH;
+  // the layer's weights ride on the same barrier as one bulk copy when they are 16-byte aligned (they are inside the packed blob)
+  const bool wbulk = (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;
+  const uint32_t wbytes = (uint32_t)(a.Cin * 9 * COUT * 4);
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(bar, (uint32_t)(a.Cin * ROWS * COLS * 4));
+    mbar_expect_tx(bar, (uint32_t)(a.Cin * ROWS * COLS * 4) + (wbulk ? wbytes : 0u));
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                      smem_u32(sIn)),
                  "l"(reinterpret_cast<uint64_t>(&map_in)), "r"(smem_u32(bar)), "r"(tx0 - 4), "r"(ty0 - DIL), "r"(b * a.Cin)
                  : "memory");
+    if (wbulk)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sW)),
+                   "l"(a.w), "r"(wbytes), "r"(smem_u32(bar))
+                   : "memory");
   }
-  for (int i = tid; i < a.Cin * 9 * COUT; i += 128) sW[i] = __ldg(a.w + i);
-  __syncthreads();  // weights staged, barrier initialised
+  if (!wbulk)
+    for (int i = tid; i < a.Cin * 9 * COUT; i += 128) sW[i] = __ldg(a.w + i);
+  __syncthreads();  // barrier initialised (and, on the fallback path, weights staged)
   const int q = tid % TQ, ty = tid / TQ;
   const int x0 = tx0 + 4 * q, yo = ty0 + ty;
+  if (a.res && x0 < a.Wo && yo < a.Ho && (q & 7) == 0) {
+    // the skip tensor is read by the epilogue: request its lines (128 bytes = the outputs of 8 neighbouring threads) into L2 now
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + ((long long)b * COUT + c0 + c) * ((long long)a.Ho * a.Wo) + (long long)yo * a.Wo + x0));
+  }
   mbar_wait(bar, 0);
   if (x0 >= a.Wo || yo >= a.Ho) return;
   float2 acc[4][CT / 2];  // float2 pairs: FFMA2 (fma.rn.f32x2, sm_100) does two output channels per issued instruction
@@ -379,6 +398,13 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
   const long long ihw = (long long)a.Hi * a.Wi, ohw = (long long)a.Ho * a.Wo;
   const float* in_b = a.in + (long long)b * a.Cin * ihw + (long long)i * a.Wi + 2 * j;
   const bool r1 = i + 1 < a.Hi, c2 = 2 * j + 2 < a.Wi;
+  if (a.res && (threadIdx.x & 7) == 0) {  // the skip tensor is read by the epilogue: request its lines into L2 now
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + ((long long)b * COUT + cg * 8 + q) * ohw + (long long)(2 * i + r) * a.Wo + 4 * j));
+  }
 
   float2 acc[2][4][4];  // float2 pairs of output channels: FFMA2 (fma.rn.f32x2) halves the issued FMA instructions
 #pragma unroll
@@ -404,6 +430,115 @@ __global__ void __launch_bounds__(128) fe_deconv_kernel(const FeConvArgs a) {
   for (int ci = 0; ci < a.Cin; ++ci) {
     const float in0[3] = {nx0[0], nx0[1], nx0[2]}, in1[3] = {nx1[0], nx1[1], nx1[2]};
     if (ci + 1 < a.Cin) load6(ci + 1, nx0, nx1);
+    const float* wc = sW + ci * 9 * COUT + cg * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q += 4) {
+      float4 w[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(wc + k * COUT + q);
+      // x pattern for output columns 4j + {0,1,2,3}: (kx=1,c=0) | (kx=2,c=0)+(kx=0,c=1) | (kx=1,c=1) | (kx=2,c=1)+(kx=0,c=2)
+#define LWS_ROW(ACC, IN, KY)                                                                                            \
+  {                                                                                                                     \
+    const float4 k0 = w[(KY) * 3], k1 = w[(KY) * 3 + 1], k2 = w[(KY) * 3 + 2];                                           \
+    const float2 k0a = make_float2(k0.x, k0.y), k0b = make_float2(k0.z, k0.w);                                           \
+    const float2 k1a = make_float2(k1.x, k1.y), k1b = make_float2(k1.z, k1.w);                                           \
+    const float2 k2a = make_float2(k2.x, k2.y), k2b = make_float2(k2.z, k2.w);                                           \
+    const float2 i0 = make_float2(IN[0], IN[0]), i1 = make_float2(IN[1], IN[1]), i2 = make_float2(IN[2], IN[2]);         \
+    ACC[0][q / 2] = __ffma2_rn(i0, k1a, ACC[0][q / 2]), ACC[0][q / 2 + 1] = __ffma2_rn(i0, k1b, ACC[0][q / 2 + 1]);       \
+    ACC[1][q / 2] = __ffma2_rn(i0, k2a, __ffma2_rn(i1, k0a, ACC[1][q / 2]));                                             \
+    ACC[1][q / 2 + 1] = __ffma2_rn(i0, k2b, __ffma2_rn(i1, k0b, ACC[1][q / 2 + 1]));                                     \
+    ACC[2][q / 2] = __ffma2_rn(i1, k1a, ACC[2][q / 2]), ACC[2][q / 2 + 1] = __ffma2_rn(i1, k1b, ACC[2][q / 2 + 1]);       \
+    ACC[3][q / 2] = __ffma2_rn(i1, k2a, __ffma2_rn(i2, k0a, ACC[3][q / 2]));                                             \
+    ACC[3][q / 2 + 1] = __ffma2_rn(i1, k2b, __ffma2_rn(i2, k0b, ACC[3][q / 2 + 1]));                                     \
+  }
+      LWS_ROW(acc[0], in0, 1)  // even output row: ky = 1 on input row i
+      LWS_ROW(acc[1], in0, 2)  // odd output row: ky = 2 on input row i ...
+      LWS_ROW(acc[1], in1, 0)  // ... and ky = 0 on input row i + 1
+#undef LWS_ROW
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int co = cg * 8 + q;
+    const float bias = __ldg(a.bias + co);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long o = ((long long)b * COUT + co) * ohw + (long long)(2 * i + r) * a.Wo + 4 * j;
+      float v[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v[p] = (q & 1 ? acc[r][p][q / 2].y : acc[r][p][q / 2].x) + bias;
+      if (a.res) {
+        const float4 rv = *reinterpret_cast<const float4*>(a.res + o);
+        v[0] += rv.x, v[1] += rv.y, v[2] += rv.z, v[3] += rv.w;
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[p] = fmaxf(v[p], 0.f);
+      }
+      *reinterpret_cast<float4*>(a.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// ---- fast path 2b: the same transposed conv with its input tile delivered by ONE TMA load (Wi % 4 == 0) -------------------------------
+// fe_deconv_kernel is bound by the latency of its per-thread loads (ncu: 71 % of the stall samples on their scoreboard, issue slots
+// 27 % used).  A block owns 4 input rows x 64 input columns (8 x 128 outputs) of 8 output channels; one tiled TMA load brings the
+// 5 x 68 window of all Cin channels into shared memory (rows / columns past the map are the TMA's zero fill = the taps that do not
+// exist), the threads only read shared memory.  Same arithmetic as fe_deconv_kernel.
+template <int COUT>
+__global__ void __launch_bounds__(128) fe_deconv_tile_kernel(const __grid_constant__ CUtensorMap map_in, const FeConvArgs a) {
+  constexpr int TI = 4, TJ = 32, ROWS = TI + 1, COLS = 2 * TJ + 4, NG = COUT / 8;
+  extern __shared__ __align__(128) uint8_t fe_smem[];
+  float* sIn = reinterpret_cast<float*>(fe_smem);                      // [Cin][ROWS][COLS]
+  float* sW = sIn + a.Cin * ROWS * COLS;                               // [Cin][9][COUT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sW + a.Cin * 9 * COUT);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z / NG, cg = blockIdx.z - b * NG;
+  const int i0 = blockIdx.y * TI, jx0 = blockIdx.x * (2 * TJ);  // first input row / column of the tile
+  const bool wbulk = (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;  // weights as one bulk copy on the same barrier
+  const uint32_t wbytes = (uint32_t)(a.Cin * 9 * COUT * 4);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (uint32_t)(a.Cin * ROWS * COLS * 4) + (wbulk ? wbytes : 0u));
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(sIn)),
+                 "l"(reinterpret_cast<uint64_t>(&map_in)), "r"(smem_u32(bar)), "r"(jx0), "r"(i0), "r"(b * a.Cin)
+                 : "memory");
+    if (wbulk)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sW)),
+                   "l"(a.w), "r"(wbytes), "r"(smem_u32(bar))
+                   : "memory");
+  }
+  if (!wbulk)
+    for (int k = tid; k < a.Cin * 9 * COUT; k += 128) sW[k] = __ldg(a.w + k);
+  __syncthreads();
+  const int tj = tid % TJ, ti = tid / TJ;
+  const int i = i0 + ti, j = blockIdx.x * TJ + tj;  // input row; input column pair (columns 2j, 2j+1)
+  const long long ohw = (long long)a.Ho * a.Wo;
+  if (a.res && i < a.Hi && 2 * j < a.Wi && (tj & 7) == 0) {
+    // the skip tensor is read by the epilogue: request its lines (128 bytes = the outputs of 8 neighbouring threads) into L2 now
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + ((long long)b * COUT + cg * 8 + q) * ohw + (long long)(2 * i + r) * a.Wo + 4 * j));
+  }
+  mbar_wait(bar, 0);
+  if (i >= a.Hi || 2 * j >= a.Wi) return;
+  float2 acc[2][4][4];  // float2 pairs of output channels: FFMA2 (fma.rn.f32x2) halves the issued FMA instructions
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[r][p][q] = make_float2(0.f, 0.f);
+
+  const float* tp = sIn + ti * COLS + 2 * tj;
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    const float* p0 = tp + ci * ROWS * COLS;
+    const float2 a01 = *reinterpret_cast<const float2*>(p0), b01 = *reinterpret_cast<const float2*>(p0 + COLS);
+    const float in0[3] = {a01.x, a01.y, p0[2]}, in1[3] = {b01.x, b01.y, p0[COLS + 2]};
     const float* wc = sW + ci * 9 * COUT + cg * 8;
 #pragma unroll
     for (int q = 0; q < 8; q += 4) {
@@ -492,6 +627,27 @@ static int launch_fe(FeConvArgs a, int cout, int B, cudaStream_t st) {
   if (even && cin_even && a.stride == 2 && a.dil == 1 && a.Wi == 2 * a.Wo && cout == 16) return launch_pipe<16, 8, 1, 2>(a, B, smem_w, st);
   if (even && a.stride == 2 && a.dil == 2 && a.Wi == 2 * a.Wo && cout == 4) return launch_pipe<4, 4, 2, 2, 16, true>(a, B, smem_w, st);
   if (a.transposed && a.stride == 2 && a.pad == 1 && (a.Wi & 1) == 0 && a.Ho == 2 * a.Hi && a.Wo == 2 * a.Wi && (cout == 8 || cout == 16)) {
+    if ((a.Wi & 3) == 0 && a.Wi >= 32 && opt(OPT_FE_TMA) && (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.res) & 15) == 0 &&
+        (long long)B * cout <= 65535) {  // input tile through TMA
+      constexpr int ROWS = 5, COLS = 68;
+      const size_t smem = ((size_t)a.Cin * ROWS * COLS + (size_t)a.Cin * 9 * cout) * sizeof(float) + 16;
+      CUtensorMap map;
+      const uint64_t dims[3] = {(uint64_t)a.Wi, (uint64_t)a.Hi, (uint64_t)B * a.Cin};
+      const uint64_t strides[2] = {(uint64_t)a.Wi * 4, (uint64_t)a.Hi * a.Wi * 4};
+      const uint32_t box[3] = {COLS, ROWS, (uint32_t)a.Cin};
+      if (smem <= 100 * 1024 && a.Cin <= 256 && make_tensor_map_f32(&map, a.in, 3, dims, strides, box, false) == LWS_OK) {
+        dim3 g(cdiv(a.Wi, 64), cdiv(a.Hi, 4), B * (cout / 8));
+        if (cout == 8) {
+          LWS_SET_SMEM_ONCE(fe_deconv_tile_kernel<8>, 100 * 1024);
+          fe_deconv_tile_kernel<8><<<g, 128, smem, st>>>(map, a);
+        } else {
+          LWS_SET_SMEM_ONCE(fe_deconv_tile_kernel<16>, 100 * 1024);
+          fe_deconv_tile_kernel<16><<<g, 128, smem, st>>>(map, a);
+        }
+        cudaError_t e = cudaPeekAtLastError();
+        return e == cudaSuccess ? LWS_OK : (int)e;
+      }
+    }
     dim3 g(cdiv((a.Wi >> 1) * a.Hi * (cout / 8), 128), B);
     if (cout == 8) fe_deconv_kernel<8><<<g, 128, smem_w, st>>>(a);
     else fe_deconv_kernel<16><<<g, 128, smem_w, st>>>(a);

@@ -560,6 +560,16 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
           const uint32_t st = k / CP_L;
           const int i = (int)(k - st * CP_L), n = (int)(st - st0);
           const uint32_t tb = st % CP_NT;
+          // LAST: the output index and the skip value do not depend on the accumulator: fetch the skip before waiting for it
+          long long o_last = -1;
+          float sk = 0.f;
+          if (LAST && i < w.L) {
+            const int y = yj + n;
+            if (!xborder && y >= 1 && y <= a.H) {
+              o_last = (((long long)w.b * a.D + (w.dp0 + i - 1)) * a.H + (y - 1)) * a.W + (xj - 1);
+              if (a.skip) sk = __ldg(a.skip + o_last);
+            }
+          }
           mbar_wait(t_full + tb, (st / CP_NT) & 1);
           if (i >= w.L) {  // no such plane in this d group: only release the buffer
             __syncwarp();
@@ -591,11 +601,7 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
             }
             // a tile that runs past the end of its plane (y > H) would produce voxels of the next plane, which that plane's own
             // tile accumulates in a different kd order (other accumulator index): leave them to their owner so results are unique
-            const int y = yj + n;
-            if (!xborder && y >= 1 && y <= a.H) {
-              const long long o = (((long long)w.b * a.D + (w.dp0 + i - 1)) * a.H + (y - 1)) * a.W + (xj - 1);
-              a.out_f32[o] = v + (a.skip ? __ldg(a.skip + o) : 0.f);
-            }
+            if (o_last >= 0) a.out_f32[o_last] = v + sk;
             continue;
           }
           float m0[8], m1[8], m2[8], k0[8], k1[8], k2[8];

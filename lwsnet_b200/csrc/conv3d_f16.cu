@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
     const uint32_t shq[3] = {(uint32_t)a.shift_rows[0] * 8, (uint32_t)a.shift_rows[1] * 8, (uint32_t)a.shift_rows[2] * 8};
     const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFF) >> 4) | (1u << 16), slot16 = (uint32_t)a.slot_bytes >> 4;
     const int G = a.G;
+    // ONE elected lane runs the whole schedule: a per-stage elect + reconvergence costs ~100 cycles, which is nothing next to twelve
+    // 96-cycle MMAs but was half of a tile's time in the closing C -> 1 layers (12 small MMAs per tile)
+    if (elect_one_sync()) {
     mbar_wait(b_full, 0);
     uint32_t bslot = 0, bph = 0, ti = 0;  // ring position / phase of stage 0 of the current tile
     auto advance = [&](uint32_t k) {
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
         for (int s = 0; s < NST; ++s) {
           mbar_wait(a_full + slot, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (elect_one_sync()) {
+          {
             const uint32_t x_lo = a_lo0 + slot * slot16;
 #pragma unroll
             for (int k = 0; k < NSH; ++k) {
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
               const uint32_t wa = x_lo + shq[k];                                                  // window base (16-byte units)
               if (LAST) {
                 const uint32_t wb = b_lo + (uint32_t)blk * (2048 >> 4);
+                if (a.dbg & 8) continue;  // timing experiment: no MMAs, only the commits
 #pragma unroll
                 for (int u = 0; u < 4; ++u)  // xh k-steps against B1, xl k-steps against B2, all into the same 16 columns
                   tz_mma(d_main, desc_hi | (uint64_t)(wa + 2 * u), desc_hi | (uint64_t)(wb + 2 * u), idesc16, (s | k | u) == 0 ? 0u : 1u);
@@ -355,12 +359,13 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
               if (s == NST - 1) tz_commit(t_full + tb);
             }
           }
-          __syncwarp();
           if (++slot == nslot) slot = 0, ph ^= 1;
         }
       }
       advance(nst - G);  // the strip's last tile consumed all of its entries
     }
+    }
+    __syncwarp();
     }
   } else if (LAST) {
     // ================================ epilogue of the C -> 1 layer ================================
@@ -393,6 +398,12 @@ __global__ void __launch_bounds__(TZ_THREADS, 1)
           const float sk = (ok && a.skip) ? __ldg(a.skip + o) : 0.f;
           mbar_wait(t_full + grp, (ti >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (a.dbg & 2) {  // timing experiment: free the accumulator at once
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + grp);
+            continue;
+          }
           float m[8], k[8];
           tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + grp * 32, m);
           tz_ld8(tmem + ((uint32_t)(q * 32) << 16) + grp * 32 + 8, k);

@@ -49,7 +49,7 @@ static const OptDesc kOpts[OPT_COUNT] = {
                                       // loads its three ky boxes); 1 = tiles walk down y in strips, two of the three boxes stay in the shared-memory
                                       // ring (default); 2 = strips cut into segments dealt round-robin (L2-friendlier, worse balance); 3 = CTA pairs
                                       // (cta_group::2).  Bit 2 (value 4): strips for the closing 32 -> 1 conv too (default)
-    {"tz_debug", 0, 0, 7},            // TIMING EXPERIMENTS ONLY (results are wrong): Toeplitz GEMM kernels without A loads (1), epilogue (2), stores (4)
+    {"tz_debug", 0, 0, 15},            // TIMING EXPERIMENTS ONLY (results are wrong): Toeplitz GEMM kernels without A loads (1), epilogue (2), stores (4)
     {"k5_int", 1, 0, 1},              // K5 (rescale + upsample + skip): periodic-tap fast path for the integer scales 2 / 4 / 8 (0 = generic kernel)
     {"fe_tma", 1, 0, 1},              // feature pyramid: stride-1 convs on 16-byte aligned maps read their input tile through one TMA load (0 = per-thread loads)
 };

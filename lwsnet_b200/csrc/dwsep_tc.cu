@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);  // SBO, version, SW128
     const uint32_t b_lo = ((smem_u32(smem + DS_OFF_B) & 0x3FFFF) >> 4) | (1u << 16);
     uint32_t t = 0;
+    if (elect_one_sync()) {  // one lane runs the whole schedule (no per-tile elect + reconvergence on the tile's critical path)
     DsSched sched(a);
       DsItem w;
       while (sched.next(a, w)) {
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
         mbar_wait(t_empty + tb, ((t / DS_NT) & 1) ^ 1);
         mbar_wait(a_full + ab, (t / DS_NA) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one_sync()) {
+        {
           const uint32_t a_lo = ((smem_u32(smem + DS_OFF_A + ab * DS_TILE) & 0x3FFFF) >> 4) | (1u << 16);
           const uint32_t d = tmem + tb * 64;
 #pragma unroll
@@ -203,9 +204,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(t_full + tb))
                        : "memory");
         }
-        __syncwarp();
       }
     }
+    }
+    __syncwarp();
   } else if (warp >= DS_EPI_WARP0) {
     // ================================ epilogue (warps 8..11) ================================
     const int quarter = warp & 3;

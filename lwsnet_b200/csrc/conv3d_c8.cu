@@ -473,14 +473,18 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
     CPItem w;
     while (sched.next(pa, w)) {
       const long long base = (long long)w.b * a.vox_b + w.row0 - 1 + (long long)(pl - 1) * plane;  // GEMM row 0 (Toeplitz shift 1)
+      // the two zero planes that pad d (2 of the 15 plane reads of a D = 9 volume in groups of 3) are not streamed from DRAM: every
+      // copy of them reads the same 2 KB of the zeroed slack in front of the tensor, an L2 hit (the kernel runs at the DRAM roofline)
+      const int dpa = w.dp0 + pl - 1;
+      const bool zero_plane = dpa <= 0 || dpa > a.D;
       for (int n = 0; n < w.nsteps; ++n) {
         for (int kh = n == 0 ? 0 : 2; kh < 3; ++kh) {  // later steps of a strip only need the line below
           mbar_wait(g_empty + slot, ph ^ 1);
           if (lane == 0) mbar_expect_tx(g_full + slot, (uint32_t)(w.L + 2) * 4096);
           __syncwarp();
           if (lane < 2 * (w.L + 2))
-            bulk_load(sRing + slot * CP_GBYTES + pl * 4096 + part * 2048, src_plane + (base + (long long)(n + kh - 1) * a.Wp) * 16, 2048,
-                      g_full + slot);
+            bulk_load(sRing + slot * CP_GBYTES + pl * 4096 + part * 2048,
+                      zero_plane ? src_plane - 4096 : src_plane + (base + (long long)(n + kh - 1) * a.Wp) * 16, 2048, g_full + slot);
           if (++slot == CP_NG) slot = 0, ph ^= 1;
         }
       }

@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8_kernel(const C8Args a
 // Tiles are numbered k = CP_L * step + i and handled round robin by the four epilogue groups; TMEM holds two steps (2 x 192 columns).
 constexpr int CP_L = 3;                       // d planes per group.  The kernel is generic up to 5 (CP_L = 5, CP_NG = 5, CP_TCOLS = 256,
                                               // CP_NT = 2: D = 9 as groups of 5 + 4, 13 input planes per 9 outputs instead of 15) --
-                                              // measured equal within noise (stage-3 stack 434 vs 442 us, stage-2 165 vs 159 per 4 pairs)
+                                              // measured equal within noise (stage-3 stack 434 vs 442 us, stage-2 165 vs 159 per 4 pairs);
+                                              // re-measured after the zero planes stopped coming from DRAM: 350 instead of 416 MB of
+                                              // DRAM reads per stage-3 layer but 125 instead of 118 us (two step buffers in TMEM)
 constexpr int CP_NG = 6;                      // ring of line groups
 constexpr int CP_GBYTES = (CP_L + 2) * 4096;  // (L + 2) planes x (hi, lo) x 128 voxels x 16 B
 constexpr int CP_OFF_RING = 14336;

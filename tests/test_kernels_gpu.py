@@ -518,6 +518,23 @@ def test_refinement_segment_schedule_is_bit_identical():
 
 
 # ------------------------------------------------------------------------------------------------ n1 feature pyramid
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 368, 1232), (1, 40, 72), (3, 24, 160)])
+def test_feature_extraction_tma_tiles_match_per_thread_loads(B, H, W):
+    """The TMA-tile kernels of the feature pyramid (option fe_tma = 1, default: stride-1 convs and the 1/4 -> 1/2 transposed conv on
+    maps with 16-byte aligned rows) accumulate in the same (ci, ky, kx) order as the per-thread-load kernels they replace: identical
+    bits for all three feature maps, including shapes where only some layers qualify."""
+    from oracle import lwsnet_torch as O
+    from util import product_from_oracle
+    model = product_from_oracle(O.build_oracle(seed=0, random_bn=True))
+    img = rnd(45, B, 3, H, W).cuda()
+    with ops().options(fe_tma=0):
+        ref = [t.clone() for t in model.feature_extraction(img)]
+    with ops().options(fe_tma=1):
+        out = model.feature_extraction(img)
+    for o, r in zip(out, ref):
+        assert torch.equal(o, r)
+
+
 @pytest.mark.parametrize("B,H,W,random_bn", [(1, 64, 128, True), (2, 40, 72, True), (1, 368, 1232, False), (1, 24, 40, True)])
 def test_feature_extraction_vs_fp64_oracle(B, H, W, random_bn):
     """|d| <= 1e-4 * (1 + |y|) + 2e-6 * max|y| against the fp64 oracle (reference models/submodules.py:176-188)."""

@@ -62,8 +62,16 @@ LWS_API const char* lws_version(void);
  *                         in shared memory (default), 4 / 8 = C = 8 staged as well (measured slower; A/B)
  *   "fused_tail"      0   hint for hosts: run the stage tail through lws_regression_tail_f32 (one kernel) instead of the three
  *                         stand-alone entries.  Bit-identical; measured slower at 24 pairs per launch (profiles/r02_tail_ab.txt)
+ *   "fuse_volume"     1   hint for hosts: stage 1 through lws_cost_volume_conv3d_stack_f32 (volume built inside the first conv kernel);
+ *                         0 = two calls, 2 = fused with 8-disparity tiles.  Bit-identical (profiles/r02_fuse_volume_ab.txt)
+ *   "tz_strips"       5   C = 32 stack schedule.  Bits 0-1, the 32 -> 32 layers: 0 = every tile loads its three ky boxes, 1 = tiles walk
+ *                         down y in strips (default), 2 = strips in round-robin segments, 3 = CTA pairs (tcgen05 cta_group::2);
+ *                         bit 2: strips for the closing conv too.  All bit-identical (profiles/r02_tz_strips_ab.txt)
+ *   "k5_int"          1   lws_scale_upsample_add_f32: closed-form periodic taps for the integer scales 2 / 4 / 8 (0 = generic kernel)
+ *   "fe_tma"          1   feature pyramid: input tiles through TMA where the maps have 16-byte aligned rows (0 = per-thread loads)
+ *   "c8_group"        0   C = 8 stacks depth-first over groups of this many pairs (0 = whole batch layer by layer; measured slower)
  *   "c8_v1" 0, "c8_chunk" 0, "k1_dt" 8   developer A/B switches of the C = 8 stack and the stage-1 volume kernel
- *   "chain_debug"     0   TIMING EXPERIMENTS ONLY (wrong results): chain kernel without dependency waits */
+ *   "chain_debug" 0, "tz_debug" 0   TIMING EXPERIMENTS ONLY (wrong results): kernels with waits / loads / epilogues / stores switched off */
 LWS_API int lws_set_option(const char* key, int value);
 LWS_API int lws_get_option(const char* key, int* value);
 

@@ -124,6 +124,24 @@ def test_schedule_options_bit_identical_end_to_end(models):
             assert torch.equal(out[s], ref[s]), (kw, s)
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 64, 128), (2, 72, 136), (1, 104, 264), (3, 64, 520), (1, 200, 328), (1, 368, 1232), (2, 56, 72)])
+def test_round2_paths_bit_identical_across_shapes(models, B, H, W):
+    """Every round-2 fast path that has a switch (fused stage-1 volume, strip schedule of the C = 32 stack, integer-scale K5, TMA tiles
+    of the feature pyramid) only re-schedules the same arithmetic: with all of them off the four stage outputs have the same bits, at
+    shapes where different subsets of the paths qualify (row alignment, tile and strip remainders)."""
+    from lwsnet_b200 import ops
+    O, o32, o64, prod = models
+    left, right = O.synthetic_pair(B, H, W, seed=29, max_disp=20.0)
+    left, right = left.cuda(), right.cuda()
+    out = [t.clone() for t in prod(left, right)]
+    with ops.options(fuse_volume=0, tz_strips=0, k5_int=0, fe_tma=0):
+        ref = prod(left, right)
+        torch.cuda.synchronize()
+    for s in range(4):
+        assert torch.isfinite(out[s]).all()
+        assert torch.equal(out[s], ref[s]), s
+
+
 def test_exact_fp32_mode_end_to_end(models):
     """Options conv3d_tc=0 refine_tc=0 select the fp32 FFMA kernels everywhere: every stage within 2x the fp32 oracle's floor."""
     from lwsnet_b200 import ops

@@ -686,8 +686,10 @@ __global__ void __launch_bounds__(C8_THREADS, 1) conv3d_c8p_kernel(const CPArgs 
 // One thread = NV voxels that are neighbours in y (same padded x): the 27-tap window of the NV voxels is (NV + 2) rows x 3 x 3, so
 // the cost loads (coalesced along x) and the broadcast weight loads from shared memory are shared NV ways (NV = 8: 90 + 54 per 1728
 // FFMAs) and the 16-byte voxel stores of a warp are contiguous.  Grid = (pair x padded plane, NV-row group, 128-voxel x segment).
+// 8 resident blocks (64 registers, ~50 bytes of spills): the kernel is bound by the latency of its predicated global tap loads, and
+// 32 instead of 20 resident warps take it from 223 to 191 us per 8 pairs (6 blocks: 217; 10 blocks / 48 registers spill heavily: 345)
 template <int NV>
-__global__ void __launch_bounds__(128, NV == 4 ? 5 : 3)
+__global__ void __launch_bounds__(128, NV == 4 ? 8 : 3)
     conv3d_first_c8_kernel(const float* __restrict__ cost, const float* __restrict__ w /*[27][8]*/, const float* __restrict__ bias,
                            const float* __restrict__ affine, uint4* __restrict__ out_hi, uint4* __restrict__ out_lo, int D, int H,
                            int W) {

@@ -197,7 +197,7 @@ def kernel_probes(model, pk, B=16):
 
     s = sets(nsets(B * (2 * C + D) * h * w * 4), (B, C, h, w), (B, C, h, w))
     us = time_rotating(lambda i: ops.cost_volume_l1(s[i][0], s[i][1], D), len(s))
-    add(f"K1 cost_volume_l1 [{B},16,46,154] D=24", us, B * (2 * C + D) * h * w * 4)
+    add(f"K1 cost_volume_l1 [{B},16,46,154] D=24 (stand-alone entry; the model's default schedule builds this volume inside the first conv kernel, option fuse_volume)", us, B * (2 * C + D) * h * w * 4)
     # K2 stages 2 and 3
     for (h, w, C) in ((92, 308, 16), (184, 616, 8)):
         s = sets(nsets(B * (2 * C + 10) * h * w * 4), (B, C, h, w), (B, C, h, w))

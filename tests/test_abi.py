@@ -51,6 +51,19 @@ def test_status_strings_and_validation_without_gpu():
     assert lib.lws_refinement_f32(dummy, dummy, dummy, dummy, dummy, 0, 1, 8, 8, None) == -4
     assert lib.lws_conv3d_stack_workspace_bytes(2, 24, 46, 154, 32, 4) >= 2 * 2 * 32 * 24 * 46 * 154 * 4
     assert lib.lws_refinement_workspace_bytes(1, 368, 1232) >= 128 * 368 * 1232 * 4
+    # the fused stage-1 call (volume built inside the first conv kernel): host-side applicability and argument checks
+    sup = lib.lws_cost_volume_conv3d_stack_supported
+    assert sup(2, 32, 46, 154, 24, 32, 4) == 0                     # KITTI stage 1
+    assert sup(2, 32, 46, 153, 24, 32, 4) == -5                    # odd W: no 64-bit row loads
+    assert sup(2, 32, 46, 154, 24, 8, 4) == -5                     # C = 8 stack has no fused kernel
+    assert sup(2, 32, 46, 154, 24, 32, 0) == -1 and sup(0, 32, 46, 154, 24, 32, 4) == -1
+    assert sup(2, 32, 46, 154, 100, 32, 4) == -5                   # TMA box of 128 + 2 (D + 2) rows would exceed 256
+    fused = lib.lws_cost_volume_conv3d_stack_f32
+    assert fused(None, dummy, dummy, dummy, dummy, dummy, 1 << 40, 2, 32, 46, 154, 24, 32, 4, 1, None) == -3
+    assert fused(dummy, dummy, dummy, dummy, dummy, dummy, 0, 2, 32, 46, 154, 24, 32, 4, 1, None) == -4
+    assert fused(dummy, dummy, dummy, dummy, dummy, dummy, 1 << 40, 2, 32, 46, 153, 24, 32, 4, 1, None) == -5
+    for key, default in ((b"fuse_volume", 1), (b"tz_strips", 5), (b"k5_int", 1), (b"fe_tma", 1), (b"tz_debug", 0), (b"chain_debug", 0)):
+        assert lib.lws_get_option(key, ctypes.byref(v)) == 0 and v.value == default, key
 
 
 def test_pack_conv3d_stack_folds_bn():

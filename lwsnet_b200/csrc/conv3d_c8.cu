@@ -1,6 +1,7 @@
 // K3 (C = 8): the residual 3D-conv stacks of stages 2 and 3, post_3dconvs(4, 8) (reference models/submodules.py:190-221,
 // models/models.py:136-138), on tcgen05 with split-fp16 operands.  HBM/latency bound by nature (8 channels: 64 B of traffic and
-// 3456 flop per voxel and layer); the design minimises the number of MMAs, each of which costs ~40 + N/2 cycles.
+// 3456 flop per voxel and layer); the design minimises the number of MMAs (an SS MMA at small N is bound by the shared-memory port:
+// max(N/2, (4096 + 32 N) / 128) cycles, tools/umma_ts_bench.cu).
 //
 // Layout: two planes per tensor, hi and lo, each  act[b][d+2][y+2][x+2][8] fp16  (one voxel = one 16-byte row; zero border in
 // all three axes; x*2^-6 = hi + lo*2^-11, see conv3d_f16.cu for the numerics).  With SWIZZLE_NONE K-major UMMA descriptors a

@@ -8,8 +8,9 @@
 // products of two 11-bit significands are exact in fp32, the dropped xl*wl term is 2^-22 relative: fp32-grade results at the
 // fp16 tensor rate (plain TF32/BF16 operands move stage-1 disparities by whole pixels).
 //
-// Cost model (tools/umma_bench.cu): one tcgen05.mma with both operands in shared memory takes ~40 + N/2 cycles at M = 128,
-// whatever the kind, so the work is arranged as few, wide MMAs ("Toeplitz-N"):
+// Cost model (tools/umma_ts_bench.cu, r02): one tcgen05.mma with both operands in shared memory takes max(N/2, (4096 + 32 N) / 128)
+// cycles at M = 128, K = 16 -- the tensor pipe's N/2 once N >= 128, the shared-memory port (4 KB A slice + 32 N bytes of B) below --
+// so the work is arranged as few, wide MMAs ("Toeplitz-N"):
 //   * a GEMM row is one voxel = 128 bytes [32 hi | 32 lo] halves; voxels are stored with the Toeplitz axis fastest
 //     (3D stack: act[b][y][x][d], d padded by one zero voxel each side, x padded, y padding = TMA out-of-bounds zero fill);
 //   * the three taps along the fastest axis are folded into N: D[r', t*32+co] = sum_ci x[r', ci] * w[t][ci][co], t = 0..2, and
@@ -17,9 +18,11 @@
 //     With the hi/lo weight halves side by side, N = 192 for the xh operand and N = 96 (accumulated onto the wl columns) for
 //     the xl operand: 4 MMAs per (stage, window) instead of 24;
 //   * the taps along the middle axis are row-shifted windows (UMMA descriptor offsets) of ONE TMA box per stage, the taps
-//     along the slowest axis are the stages: 3 TMA loads of 23 KB per 126 output voxels for the 3D stack;
+//     along the slowest axis are the stages; tiles walk down the slowest axis in strips, so two of a tile's three boxes are already
+//     in the shared-memory ring: 1 TMA load of 23 KB per 126 output voxels for the 3D stack;
 //   * all weights of the layer (27 x 32 x 32 hi + lo = 108 KB) stay resident in shared memory.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (2 accumulators x 192 columns),
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (ONE elected lane runs the whole schedule) + TMEM owner (2
+// accumulators x 192 columns),
 // warps 2-9 = epilogue, two per TMEM lane quarter, 16 output channels each (tcgen05.ld, Toeplitz row shifts by warp shuffles + a small shared-memory exchange at the warp
 // boundaries, bias + ReLU, border zeroing, re-split into hi/lo, staged through shared memory into one TMA store).
 #include <cuda_fp16.h>

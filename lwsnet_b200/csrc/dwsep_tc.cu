@@ -11,7 +11,8 @@
 //   * MMA warp: the 32x32 pointwise product as 4 tcgen05.mma kind::f16 (M=128): hi x [wh | wl] (N=64) and lo x wh (N=32,
 //     accumulated onto the hi*wl columns, both carry the 2^-11 weight); products of 11-bit significands are exact in the
 //     fp32 accumulator, so the result has the accuracy of an fp32 FMA chain (the dropped lo*lo term is 2^-22 relative).
-//     One tcgen05.mma costs ~40 + N/2 cycles with both operands in shared memory (tools/umma_bench.cu), hence few, wide MMAs.
+//     At these small N an SS MMA is bound by the shared-memory port (max(N/2, (4096 + 32 N) / 128) cycles, tools/umma_ts_bench.cu),
+//     hence few, wide MMAs; one elected lane runs the warp's whole schedule.
 //   * 4 epilogue warps: tcgen05.ld, rescale + bias + ReLU, zero the x border; every warp stages its own 32 x 128 B quarter in
 //     shared memory and TMA-stores it (clipped at the line end by the tensor map), so the tile's critical path has no
 //     cross-warp barrier.
@@ -302,8 +303,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1)
       const float* src0 = a.img + (long long)w.b * CIN * hw + x;
       // K slots are ordered by tap column c = ci*3 + kx with the three ky taps of a column adjacent (slot = 3c + ky for c < 5,
       // 16 + 3(c-5) + ky otherwise; slot 15 is padding), so each half warp owns whole columns and a step down the image is a
-      // register shift: only the new bottom row (5 / 4 values per thread instead of 16) is loaded, and it is loaded PF steps
-      // ahead through a register FIFO -- a new image line comes from DRAM (~1.5 us under load), longer than one step.
+      // register shift: only the new bottom row (5 / 4 values per thread instead of 16) is read per step -- from the TMA ring of
+      // image lines when the rows are 16-byte aligned (a.img_tma), otherwise from global memory PF steps ahead through a rotating
+      // register FIFO (a new image line comes from DRAM, ~1.5 us under load, longer than one step).
       constexpr int PF = 4, NCOL = CIN * 3;
       if (a.img_tma) {
         // ---- image lines from the TMA ring: the line that becomes the window's bottom row is read from shared memory when it is needed
